@@ -1,0 +1,146 @@
+/*
+ * srb200.h -- C-ABI of libsrb200.so, the B200 (sm_100a) engine behind the conv / deconv /
+ * PReLU / PixelShuffle stacks of the reference's base_networks.py.
+ *
+ * The reference is pure Python: its "FFI" for this path is the implicit ATen dispatch of
+ *   torch.nn.Conv2d            base_networks.py:42,112-113,156   (cudnn_convolution fwd/bwd)
+ *   torch.nn.ConvTranspose2d   base_networks.py:77, fsrcnn.py:33 (cudnn_convolution_transpose)
+ *   torch.nn.PixelShuffle      base_networks.py:157              (pixel_shuffle / pixel_unshuffle)
+ *   ReLU/PReLU/LeakyReLU       base_networks.py:51-56, fsrcnn.py:26
+ *   torch.add (skip)           base_networks.py:149, vdsr.py:31, edsr.py:42, srgan.py:39
+ * Each entry point below names the reference call it replaces.  All functions are plain C:
+ * raw device pointers, sizes, strides; no torch types.  Return 0 on success, a negative
+ * srb_status otherwise (message via srb_last_error(), thread local).  Nothing here ever falls
+ * back to a CPU or library (cuDNN/cuBLAS) path: unsupported == error.
+ *
+ * Tensors are fp32, logical NCHW with explicit element strides, so NCHW-contiguous and
+ * channels_last (NHWC) memory are both accepted.  The tensor-core kernels (math = SRB_MATH_TF32)
+ * require channels_last activations (sc == 1) with C % 32 == 0; everything else runs on the
+ * generic fp32 CUDA-core kernels of the same library.
+ *
+ * Threading: re-entrant, no global mutable state besides a thread-local error string.  All work
+ * is enqueued on the given stream; no cudaMalloc / device synchronisation on any hot entry point
+ * (CUDA-graph capturable).  Memory is owned by the caller.
+ */
+#ifndef SRB200_H_
+#define SRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB200_VERSION 100
+
+typedef enum srb_status {
+  SRB_OK = 0,
+  SRB_EINVAL = -1,       /* bad argument / shape */
+  SRB_EUNSUPPORTED = -2, /* valid request this build cannot run (never a silent fallback) */
+  SRB_ECUDA = -3,        /* CUDA runtime / driver error */
+  SRB_EWORKSPACE = -4    /* workspace too small */
+} srb_status;
+
+typedef enum srb_act { SRB_ACT_NONE = 0, SRB_ACT_RELU = 1, SRB_ACT_PRELU = 2, SRB_ACT_LRELU = 3 } srb_act;
+
+typedef enum srb_math {
+  SRB_MATH_FP32 = 0, /* CUDA-core fp32 FMA, fp32 accumulate (exact-order independent reference quality) */
+  SRB_MATH_TF32 = 1, /* tcgen05 kind::tf32, operands RN-rounded to tf32, fp32 accumulate in TMEM */
+  SRB_MATH_AUTO = 2  /* TF32 tensor path when the layer qualifies, FP32 otherwise */
+} srb_math;
+
+/* Logical NCHW view with element strides (like torch.Tensor.stride()). */
+typedef struct srb_tensor4 {
+  void *data;
+  int64_t sn, sc, sh, sw;
+} srb_tensor4;
+
+/*
+ * One convolution layer = torch.nn.Conv2d(Cin, Cout*ps*ps, (kh,kw), stride, pad) [transposed == 0]
+ *                      or torch.nn.ConvTranspose2d(Cin, Cout, (kh,kw), stride, pad, out_pad) [transposed == 1]
+ * followed (fused) by bias, activation, residual add and PixelShuffle(ps):
+ *     z = conv(x) + bias;  a = act(z);  y = PixelShuffle_ps(a) + residual
+ * (activation is elementwise with one scalar slope, so it commutes with the shuffle; this is
+ *  PSBlock.forward base_networks.py:177-185, ConvBlock.forward :62-71, ResnetBlock.forward :134-150).
+ * N,H,W: input batch / height / width.  Cout: channels of y AFTER the shuffle (conv emits Cout*ps*ps).
+ */
+typedef struct srb_conv_params {
+  int32_t N, Cin, H, W;
+  int32_t Cout, kh, kw;
+  int32_t stride, pad, out_pad;
+  int32_t transposed;
+  int32_t ps;   /* PixelShuffle factor r, 1 = none */
+  int32_t act;  /* srb_act */
+  float slope;  /* LeakyReLU negative slope (0.2 in base_networks.py:56); ignored otherwise */
+  int32_t math; /* srb_math */
+} srb_conv_params;
+
+int srb_version(void);
+const char *srb_last_error(void);
+
+/* Output spatial size of the conv itself (before PixelShuffle).  Returns SRB_EINVAL on bad params. */
+int srb_conv_out_hw(const srb_conv_params *p, int32_t *Ho, int32_t *Wo);
+
+/* Which path a call with these params and these layouts will take: 1 = tcgen05 tensor path,
+ * 0 = fp32 CUDA-core path.  pass: 0 fprop, 1 dgrad, 2 wgrad.  x_cl / y_cl: channels_last flags. */
+int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int y_cl);
+
+/* Bytes of scratch the call needs (may be 0).  pass as above. */
+size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass);
+
+/*
+ * Forward.  Replaces Conv2d/ConvTranspose2d forward + bias + act + PixelShuffle + torch.add.
+ *   x        (N,Cin,H,W)
+ *   w        Conv2d: (Cout*ps*ps, Cin, kh, kw) contiguous; ConvTranspose2d: (Cin, Cout, kh, kw) contiguous
+ *   bias     (Cout*ps*ps) or NULL
+ *   alpha    device pointer to the single PReLU slope (nn.PReLU() default, base_networks.py:54) or NULL
+ *   residual same shape as y, or NULL
+ *   y        (N,Cout,Ho*ps,Wo*ps)
+ *   preact   optional, same shape as y: receives PixelShuffle(z) (needed by PReLU backward), or NULL
+ */
+int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
+                   const float *alpha, const srb_tensor4 *residual, const srb_tensor4 *y,
+                   const srb_tensor4 *preact, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * Activation backward (threshold_backward / _prelu_kernel_backward / leaky_relu_backward):
+ *   dz = dy * act'(.)   elementwise over the (N,Cout,Ho*ps,Wo*ps) tensor; for PReLU also
+ *   *dalpha += sum(dy * z * [z <= 0]).   `ref` is y for RELU/LRELU and the saved preact z for PRELU.
+ * dz is written RN-rounded to tf32 when p->math selects the tensor path for the following kernels.
+ */
+int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tensor4 *ref, const float *alpha,
+                const srb_tensor4 *dz, float *dalpha, void *stream);
+
+/*
+ * Data gradient.  Replaces cudnn_convolution_backward_input (and, for transposed == 1, the
+ * backward of ConvTranspose2d).  dz is the gradient w.r.t. PixelShuffle(z), i.e. in y's layout;
+ * the un-shuffle is folded into the load addressing.   dx (N,Cin,H,W).
+ */
+int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *dx,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * Weight + bias gradient.  Replaces cudnn_convolution_backward_weight + the bias aten::sum.
+ *   dw   same shape as w (fp32, contiguous), overwritten (accumulate == 0) or added to (accumulate != 0)
+ *   db   (Cout*ps*ps) or NULL, same accumulate rule
+ *   scale multiplies the result before it is stored/added (1/world_size for data parallel).
+ */
+int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_tensor4 *dz, float *dw, float *db,
+                   float scale, int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* Stand-alone PReLU (the raw nn.PReLU() of fsrcnn.py:26): y = x > 0 ? x : alpha*x over n contiguous floats. */
+int srb_prelu_fwd(const float *x, const float *alpha, float *y, int64_t n, void *stream);
+int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx, float *dalpha, int64_t n,
+                  void *stream);
+
+/* Round n contiguous floats to tf32 (round-to-nearest, ties away) in place or out of place. */
+int srb_round_tf32(const float *x, float *y, int64_t n, void *stream);
+
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t srb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H_ */

@@ -1,0 +1,318 @@
+// extern "C" surface of libsrb200.so (see include/srb200.h) + the small elementwise kernels.
+#include "srb_common.cuh"
+#include <atomic>
+#include <string.h>
+
+namespace srb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+// dz = dy * act'(ref);  PReLU: dalpha += sum(dy * z * [z<=0]) (ATen _prelu_kernel_backward semantics)
+// Iterates in dz's memory order: channels_last -> (n,h,w,c), else (n,c,h,w).
+__global__ void k_act_bwd(T4 dy, T4 ref, T4 dz, int N, int C, int H, int W, int act, float slope_in,
+                          const float *__restrict__ alpha, float *dalpha, int cl, int rnd) {
+  const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : slope_in;
+  long long total = (long long)N * C * H * W;
+  float da = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n, c, h, w;
+    long long t = i;
+    if (cl) { c = (int)(t % C); t /= C; w = (int)(t % W); t /= W; h = (int)(t % H); n = (int)(t / H); }
+    else    { w = (int)(t % W); t /= W; h = (int)(t % H); t /= H; c = (int)(t % C); n = (int)(t / C); }
+    float g = __ldg(dy.p + n * dy.sn + c * dy.sc + h * dy.sh + w * dy.sw);
+    float r = __ldg(ref.p + n * ref.sn + c * ref.sc + h * ref.sh + w * ref.sw);
+    float o;
+    if (act == SRB_ACT_RELU) o = r > 0.f ? g : 0.f;
+    else {
+      o = r > 0.f ? g : g * slope;
+      if (act == SRB_ACT_PRELU && !(r > 0.f)) da += g * r;
+    }
+    if (rnd) o = round_tf32(o);
+    dz.p[n * dz.sn + c * dz.sc + h * dz.sh + w * dz.sw] = o;
+  }
+  if (act == SRB_ACT_PRELU && dalpha) {
+    for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    __shared__ float red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      da = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+      if (threadIdx.x == 0) atomicAdd(dalpha, da);
+    }
+  }
+}
+
+__global__ void k_prelu_fwd(const float *__restrict__ x, const float *__restrict__ alpha, float *y, long long n) {
+  const float a = __ldg(alpha);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    y[i] = v > 0.f ? v : v * a;
+  }
+}
+
+__global__ void k_prelu_bwd(const float *__restrict__ x, const float *__restrict__ dy, const float *__restrict__ alpha,
+                            float *dx, float *dalpha, long long n) {
+  const float a = __ldg(alpha);
+  float da = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i], g = dy[i];
+    dx[i] = v > 0.f ? g : g * a;
+    if (!(v > 0.f)) da += g * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    da = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    if (threadIdx.x == 0 && dalpha) atomicAdd(dalpha, da);
+  }
+}
+
+__global__ void k_round_tf32(const float *__restrict__ x, float *y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = round_tf32(x[i]);
+}
+
+inline unsigned ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int check_params(const srb_conv_params *p) {
+  SRB_REQUIRE(p != nullptr, SRB_EINVAL, "null params");
+  SRB_REQUIRE(p->N >= 0 && p->Cin > 0 && p->Cout > 0 && p->H > 0 && p->W > 0, SRB_EINVAL, "bad tensor dims");
+  SRB_REQUIRE(p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0 && p->out_pad >= 0, SRB_EINVAL,
+              "bad kernel/stride/pad");
+  SRB_REQUIRE(p->ps >= 1, SRB_EINVAL, "ps must be >= 1");
+  SRB_REQUIRE(p->act >= SRB_ACT_NONE && p->act <= SRB_ACT_LRELU, SRB_EINVAL, "bad activation %d", p->act);
+  SRB_REQUIRE(p->math >= SRB_MATH_FP32 && p->math <= SRB_MATH_AUTO, SRB_EINVAL, "bad math mode %d", p->math);
+  SRB_REQUIRE(!(p->transposed && p->ps != 1), SRB_EUNSUPPORTED, "PixelShuffle fused with ConvTranspose2d");
+  SRB_REQUIRE(p->transposed || p->out_pad == 0, SRB_EINVAL, "out_pad only for transposed");
+  SRB_REQUIRE(!p->transposed || p->out_pad < p->stride, SRB_EINVAL, "out_pad must be < stride");
+  return SRB_OK;
+}
+
+// Geometry in "gather" orientation (see srb_common.cuh).
+int make_geom(const srb_conv_params *p, Geom *g) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  int Ho, Wo;
+  if (!p->transposed) {
+    Ho = (p->H + 2 * p->pad - p->kh) / p->stride + 1;
+    Wo = (p->W + 2 * p->pad - p->kw) / p->stride + 1;
+    SRB_REQUIRE(p->H + 2 * p->pad >= p->kh && p->W + 2 * p->pad >= p->kw, SRB_EINVAL, "kernel larger than padded input");
+    *g = Geom{p->N, p->Cin, p->H, p->W, p->Cout * p->ps * p->ps, Ho, Wo, p->kh, p->kw, p->stride, p->pad, p->ps};
+  } else {
+    Ho = (p->H - 1) * p->stride - 2 * p->pad + p->kh + p->out_pad;
+    Wo = (p->W - 1) * p->stride - 2 * p->pad + p->kw + p->out_pad;
+    SRB_REQUIRE(Ho > 0 && Wo > 0, SRB_EINVAL, "transposed conv output empty");
+    // big = y (Ci := Cout), small = x (Co := Cin)
+    *g = Geom{p->N, p->Cout, Ho, Wo, p->Cin, p->H, p->W, p->kh, p->kw, p->stride, p->pad, 1};
+  }
+  return SRB_OK;
+}
+
+Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, const srb_tensor4 *residual,
+             const srb_tensor4 *preact, int round_out) {
+  Epi e;
+  e.bias = bias;
+  e.alpha = alpha;
+  e.act = p->act;
+  e.slope = p->slope;
+  e.residual = to_t4(residual);
+  e.preact = to_t4(preact);
+  e.round_tf32 = round_out;
+  return e;
+}
+
+inline bool is_cl(const T4 &t, int C) { return t.sc == 1 && t.sw == C; }
+
+// Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 32 == 0)
+inline int want_round(const srb_conv_params *p, const T4 &t, int C) {
+  return (p->math != SRB_MATH_FP32 && is_cl(t, C) && (C % 32) == 0) ? 1 : 0;
+}
+
+}  // namespace
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" {
+
+int srb_version(void) { return SRB200_VERSION; }
+const char *srb_last_error(void) { return g_err; }
+int64_t srb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int srb_conv_out_hw(const srb_conv_params *p, int32_t *Ho, int32_t *Wo) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  if (!p->transposed) { *Ho = g.Ho; *Wo = g.Wo; }
+  else                { *Ho = g.Hi; *Wo = g.Wi; }
+  return SRB_OK;
+}
+
+int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int y_cl) {
+  Geom g;
+  if (make_geom(p, &g)) return 0;
+  if (p->math == SRB_MATH_FP32 || p->transposed) return 0;
+  // fake dense views with the requested layouts
+  T4 x{nullptr, 0, 0, 0, 0}, y{nullptr, 0, 0, 0, 0};
+  if (x_cl) { x.sc = 1; x.sw = g.Ci; x.sh = (long long)g.Wi * g.Ci; x.sn = x.sh * g.Hi; }
+  else      { x.sw = 1; x.sh = g.Wi; x.sc = (long long)g.Hi * g.Wi; x.sn = x.sc * g.Ci; }
+  int Cy = p->Cout, Hy = g.Ho * g.ps, Wy = g.Wo * g.ps;
+  if (y_cl) { y.sc = 1; y.sw = Cy; y.sh = (long long)Wy * Cy; y.sn = y.sh * Hy; }
+  else      { y.sw = 1; y.sh = Wy; y.sc = (long long)Hy * Wy; y.sn = y.sc * Cy; }
+  x.p = y.p = (float *)16;
+  if (pass == 0) return tc_conv_supported(g, x, y, false) ? 1 : 0;
+  if (pass == 1) {
+    if (g.ps != 1 || g.st != 1 || g.kh != g.kw) return 0;
+    Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+    return tc_conv_supported(gd, y, x, true) ? 1 : 0;
+  }
+  return tc_wgrad_supported(g, y, x) ? 1 : 0;
+}
+
+size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
+  Geom g;
+  if (make_geom(p, &g)) return 0;
+  size_t a = 0, b = 0;
+  if (pass == 2) { a = simt_wgrad_ws_bytes(g); b = tc_wgrad_ws_bytes(g); }
+  else           { b = tc_conv_ws_bytes(g); }
+  return (a > b ? a : b) + 256;
+}
+
+int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
+                   const float *alpha, const srb_tensor4 *residual, const srb_tensor4 *y, const srb_tensor4 *preact,
+                   void *ws, size_t ws_bytes, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(x && x->data && w && y && y->data, SRB_EINVAL, "null tensor");
+  SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
+  cudaStream_t st = (cudaStream_t)stream;
+  T4 tx = to_t4(x), ty = to_t4(y);
+  if (!p->transposed) {
+    Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
+    if (p->math != SRB_MATH_FP32 && tc_conv_supported(g, tx, ty, false))
+      return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
+    return simt_conv_gather(g, tx, w, ty, e, st);
+  }
+  Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
+  return simt_conv_scatter(g, tx, w, ty, e, st);
+}
+
+int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tensor4 *ref, const float *alpha,
+                const srb_tensor4 *dz, float *dalpha, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(dy && ref && dz && dy->data && ref->data && dz->data, SRB_EINVAL, "null tensor");
+  SRB_REQUIRE(p->act != SRB_ACT_NONE, SRB_EINVAL, "act_bwd with act none");
+  SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
+  int C = p->Cout, H, W;
+  if (!p->transposed) { H = g.Ho * g.ps; W = g.Wo * g.ps; }
+  else                { H = g.Hi; W = g.Wi; }
+  T4 tdz = to_t4(dz);
+  long long total = (long long)p->N * C * H * W;
+  if (total == 0) return SRB_OK;
+  int cl = (tdz.sc == 1) ? 1 : 0;
+  k_act_bwd<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dy), to_t4(ref), tdz, p->N, C, H, W, p->act,
+                                                                 p->slope, alpha, dalpha, cl,
+                                                                 want_round(p, tdz, C));
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *dx, void *ws,
+                   size_t ws_bytes, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(dz && dz->data && w && dx && dx->data, SRB_EINVAL, "null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  T4 tdz = to_t4(dz), tdx = to_t4(dx);
+  Epi e;
+  memset(&e, 0, sizeof(e));
+  e.act = SRB_ACT_NONE;
+  e.round_tf32 = want_round(p, tdx, p->Cin);
+  if (!p->transposed) {
+    if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
+      // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
+      Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+      if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true))
+        return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
+    }
+    return simt_conv_scatter(g, tdz, w, tdx, e, st);
+  }
+  // ConvTranspose2d backward-data is a plain gather conv of dz (big side) producing dx (small side)
+  return simt_conv_gather(g, tdz, w, tdx, e, st);
+}
+
+int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_tensor4 *dz, float *dw, float *db,
+                   float scale, int accumulate, void *ws, size_t ws_bytes, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  T4 tx = to_t4(x), tdz = to_t4(dz);
+  if (!p->transposed) {
+    if (p->math != SRB_MATH_FP32 && tc_wgrad_supported(g, tdz, tx))
+      return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    return simt_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+  }
+  // transposed: small = x (Co := Cin), big = dz (Ci := Cout); db is a channel sum over the big side
+  rc = simt_conv_wgrad(g, tx, tdz, dw, nullptr, scale, accumulate, ws, ws_bytes, st);
+  if (rc) return rc;
+  if (db) return channel_sum(tdz, g.N, g.Ci, g.Hi, g.Wi, db, scale, accumulate, st);
+  return SRB_OK;
+}
+
+int srb_prelu_fwd(const float *x, const float *alpha, float *y, int64_t n, void *stream) {
+  SRB_REQUIRE(x && alpha && y && n >= 0, SRB_EINVAL, "bad prelu args");
+  if (n == 0) return SRB_OK;
+  k_prelu_fwd<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, alpha, y, n);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx, float *dalpha, int64_t n,
+                  void *stream) {
+  SRB_REQUIRE(x && dy && alpha && dx && n >= 0, SRB_EINVAL, "bad prelu args");
+  if (n == 0) return SRB_OK;
+  k_prelu_bwd<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, alpha, dx, dalpha, n);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_round_tf32(const float *x, float *y, int64_t n, void *stream) {
+  SRB_REQUIRE(x && y && n >= 0, SRB_EINVAL, "bad round args");
+  if (n == 0) return SRB_OK;
+  k_round_tf32<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,496 @@
+// fp32 CUDA-core implicit-GEMM convolution kernels (generic shapes / strides / layouts).
+//
+// These are the exact-fp32 kernels of the engine: they run every layer the tcgen05 path does not
+// take (Cin = 3 network inputs, Cout = 3 gradients, strided / transposed convolutions, 1x1 with tiny
+// channel counts) and serve as the on-device cross-check for the tensor-core kernels.
+// Three GEMM shapes, all smem-tiled with register blocking, im2col only as index arithmetic:
+//   gather  : small[n,co,oy,ox] = sum_{ci,r,s} big[n,ci,oy*st-pad+r,ox*st-pad+s] * w[co,ci,r,s]
+//             (Conv2d fprop, base_networks.py:42,66;  ConvTranspose2d dgrad)
+//   scatter : big[n,ci,iy,ix]   = sum_{co,r,s} small[n,co,(iy+pad-r)/st,(ix+pad-s)/st] * w[co,ci,r,s]
+//             (Conv2d dgrad;  ConvTranspose2d fprop, base_networks.py:77, fsrcnn.py:33)
+//   wgrad   : dw[co,ci,r,s]     = sum_{n,oy,ox} small[n,co,oy,ox] * big[n,ci,oy*st-pad+r,ox*st-pad+s]
+//             (+ db[co] = sum small, as one extra GEMM column), split-K over pixels, deterministic reduce.
+#include "srb_common.cuh"
+
+namespace srb {
+
+namespace {
+
+constexpr int BK = 16;
+
+template <int BM, int BN, int TM, int TN>
+struct Tile {
+  static constexpr int NT = (BM / TM) * (BN / TN);
+  static constexpr int LDA = BM + 4;
+  static constexpr int LDB = BN + 4;
+};
+
+// ---------------------------------------------------------------------------------------------
+// gather: M = (n,oy,ox), N = co, K = (r,s,ci)
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_gather(Geom g, T4 in, const float *__restrict__ w, T4 out, Epi epi) {
+  using TL = Tile<BM, BN, TM, TN>;
+  constexpr int NT = TL::NT;
+  __shared__ float As[BK][TL::LDA];
+  __shared__ float Bs[BK][TL::LDB];
+
+  const int tid = threadIdx.x;
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const int K = g.kh * g.kw * g.Ci;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-load assignment: one pixel per thread (mi fixed), BK/(NT/BM) k's.
+  static_assert(NT % BM == 0 || BM % NT == 0, "tile/threads mismatch");
+  constexpr int A_KSTEP = (NT >= BM) ? NT / BM : 1;
+  constexpr int A_MREP = (NT >= BM) ? 1 : BM / NT;
+  int a_n[A_MREP], a_iy0[A_MREP], a_ix0[A_MREP];
+  bool a_ok[A_MREP];
+#pragma unroll
+  for (int q = 0; q < A_MREP; ++q) {
+    int mi = (tid % BM) + q * NT;
+    long long m = m0 + mi;
+    a_ok[q] = m < M;
+    long long mm = a_ok[q] ? m : 0;
+    int ox = (int)(mm % g.Wo);
+    long long t = mm / g.Wo;
+    int oy = (int)(t % g.Ho);
+    a_n[q] = (int)(t / g.Ho);
+    a_iy0[q] = oy * g.st - g.pad;
+    a_ix0[q] = ox * g.st - g.pad;
+  }
+  const int a_k0 = (NT >= BM) ? tid / BM : 0;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // ---- A tile
+#pragma unroll
+    for (int kk = a_k0; kk < BK; kk += A_KSTEP) {
+      int k = k0 + kk;
+      int tap = k / g.Ci, ci = k - tap * g.Ci;
+      int r = tap / g.kw, s = tap - r * g.kw;
+#pragma unroll
+      for (int q = 0; q < A_MREP; ++q) {
+        float v = 0.f;
+        int iy = a_iy0[q] + r, ix = a_ix0[q] + s;
+        if (k < K && a_ok[q] && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+          v = __ldg(in.p + a_n[q] * in.sn + ci * in.sc + iy * in.sh + ix * in.sw);
+        As[kk][(tid % BM) + q * NT] = v;
+      }
+    }
+    // ---- B tile: element (kk, ni) = w[co=n0+ni][ci][r][s]
+    for (int e = tid; e < BK * BN; e += NT) {
+      int ni = e % BN, kk = e / BN;
+      int k = k0 + kk, co = n0 + ni;
+      float v = 0.f;
+      if (k < K && co < g.Co) {
+        int tap = k / g.Ci, ci = k - tap * g.Ci;
+        v = __ldg(w + ((long long)co * g.Ci + ci) * (g.kh * g.kw) + tap);
+      }
+      Bs[kk][ni] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias -> act -> (+residual) -> store at the pixel-shuffled address
+  const float slope = (epi.act == SRB_ACT_PRELU) ? __ldg(epi.alpha) : epi.slope;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int ox = (int)(m % g.Wo);
+    long long t = m / g.Wo;
+    int oy = (int)(t % g.Ho);
+    int n = (int)(t / g.Ho);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = n0 + tx * TN + j;
+      if (co >= g.Co) continue;
+      float z = acc[i][j] + (epi.bias ? __ldg(epi.bias + co) : 0.f);
+      long long off = ps_offset(out, g.ps, n, co, oy, ox);
+      if (epi.preact.p) epi.preact.p[ps_offset(epi.preact, g.ps, n, co, oy, ox)] = z;
+      float y = apply_act(z, epi.act, slope);
+      if (epi.residual.p) y += __ldg(epi.residual.p + ps_offset(epi.residual, g.ps, n, co, oy, ox));
+      if (epi.round_tf32) y = round_tf32(y);
+      out.p[off] = y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter: M = (n,iy,ix) of the big tensor, N = ci, K = (r,s,co)
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_scatter(Geom g, T4 in, const float *__restrict__ w, T4 out, Epi epi) {
+  using TL = Tile<BM, BN, TM, TN>;
+  constexpr int NT = TL::NT;
+  __shared__ float As[BK][TL::LDA];
+  __shared__ float Bs[BK][TL::LDB];
+
+  const int tid = threadIdx.x;
+  const long long M = (long long)g.N * g.Hi * g.Wi;
+  const int K = g.kh * g.kw * g.Co;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  constexpr int A_KSTEP = (NT >= BM) ? NT / BM : 1;
+  constexpr int A_MREP = (NT >= BM) ? 1 : BM / NT;
+  int a_n[A_MREP], a_y[A_MREP], a_x[A_MREP];
+  bool a_ok[A_MREP];
+#pragma unroll
+  for (int q = 0; q < A_MREP; ++q) {
+    int mi = (tid % BM) + q * NT;
+    long long m = m0 + mi;
+    a_ok[q] = m < M;
+    long long mm = a_ok[q] ? m : 0;
+    int ix = (int)(mm % g.Wi);
+    long long t = mm / g.Wi;
+    int iy = (int)(t % g.Hi);
+    a_n[q] = (int)(t / g.Hi);
+    a_y[q] = iy + g.pad;
+    a_x[q] = ix + g.pad;
+  }
+  const int a_k0 = (NT >= BM) ? tid / BM : 0;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int kk = a_k0; kk < BK; kk += A_KSTEP) {
+      int k = k0 + kk;
+      int tap = k / g.Co, co = k - tap * g.Co;
+      int r = tap / g.kw, s = tap - r * g.kw;
+#pragma unroll
+      for (int q = 0; q < A_MREP; ++q) {
+        float v = 0.f;
+        int ty_ = a_y[q] - r, tx_ = a_x[q] - s;
+        if (k < K && a_ok[q] && ty_ >= 0 && tx_ >= 0) {
+          int oy = ty_ / g.st, ox = tx_ / g.st;
+          if (oy * g.st == ty_ && ox * g.st == tx_ && oy < g.Ho && ox < g.Wo)
+            v = __ldg(in.p + ps_offset(in, g.ps, a_n[q], co, oy, ox));
+        }
+        As[kk][(tid % BM) + q * NT] = v;
+      }
+    }
+    for (int e = tid; e < BK * BN; e += NT) {
+      int ni = e % BN, kk = e / BN;
+      int k = k0 + kk, ci = n0 + ni;
+      float v = 0.f;
+      if (k < K && ci < g.Ci) {
+        int tap = k / g.Co, co = k - tap * g.Co;
+        v = __ldg(w + ((long long)co * g.Ci + ci) * (g.kh * g.kw) + tap);
+      }
+      Bs[kk][ni] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const float slope = (epi.act == SRB_ACT_PRELU) ? __ldg(epi.alpha) : epi.slope;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int ix = (int)(m % g.Wi);
+    long long t = m / g.Wi;
+    int iy = (int)(t % g.Hi);
+    int n = (int)(t / g.Hi);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int ci = n0 + tx * TN + j;
+      if (ci >= g.Ci) continue;
+      float z = acc[i][j] + (epi.bias ? __ldg(epi.bias + ci) : 0.f);
+      long long off = n * out.sn + ci * out.sc + iy * out.sh + ix * out.sw;
+      if (epi.preact.p) epi.preact.p[n * epi.preact.sn + ci * epi.preact.sc + iy * epi.preact.sh + ix * epi.preact.sw] = z;
+      float y = apply_act(z, epi.act, slope);
+      if (epi.residual.p)
+        y += __ldg(epi.residual.p + n * epi.residual.sn + ci * epi.residual.sc + iy * epi.residual.sh + ix * epi.residual.sw);
+      if (epi.round_tf32) y = round_tf32(y);
+      out.p[off] = y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: M = co, N = (ci,r,s) [+1 column of ones -> db], K = (n,oy,ox) split over blockIdx.z
+// partial[z][co][NN]  with NN = Ci*kh*kw + 1
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_wgrad(Geom g, T4 sm, T4 big, float *__restrict__ partial, long long kchunk) {
+  using TL = Tile<BM, BN, TM, TN>;
+  constexpr int NT = TL::NT;
+  __shared__ float As[BK][TL::LDA];
+  __shared__ float Bs[BK][TL::LDB];
+
+  const int tid = threadIdx.x;
+  const long long Kp = (long long)g.N * g.Ho * g.Wo;
+  const int CRS = g.Ci * g.kh * g.kw;
+  const int NN = CRS + 1;
+  const int m0 = blockIdx.x * BM;  // co
+  const int n0 = blockIdx.y * BN;  // column
+  const long long kbeg = (long long)blockIdx.z * kchunk;
+  long long kend = kbeg + kchunk;
+  if (kend > Kp) kend = Kp;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+  // B-load: this thread always loads the same column(s); pre-decode (ci,r,s).
+  constexpr int B_KSTEP = (NT >= BN) ? NT / BN : 1;
+  constexpr int B_NREP = (NT >= BN) ? 1 : BN / NT;
+  int b_ci[B_NREP], b_r[B_NREP], b_s[B_NREP], b_kind[B_NREP];  // kind: 0 invalid, 1 data, 2 ones
+#pragma unroll
+  for (int q = 0; q < B_NREP; ++q) {
+    int col = n0 + (tid % BN) + q * NT;
+    if (col < CRS) {
+      b_kind[q] = 1;
+      b_ci[q] = col / (g.kh * g.kw);
+      int rs = col - b_ci[q] * (g.kh * g.kw);
+      b_r[q] = rs / g.kw;
+      b_s[q] = rs - b_r[q] * g.kw;
+    } else {
+      b_kind[q] = (col == CRS) ? 2 : 0;
+      b_ci[q] = b_r[q] = b_s[q] = 0;
+    }
+  }
+  const int b_k0 = (NT >= BN) ? tid / BN : 0;
+
+  for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+    // A tile: (kk, mi) = small[n, co=m0+mi, oy, ox]; kk fastest over threads (pixels contiguous in NCHW)
+    for (int e = tid; e < BK * BM; e += NT) {
+      int kk = e % BK, mi = e / BK;
+      long long k = k0 + kk;
+      int co = m0 + mi;
+      float v = 0.f;
+      if (k < kend && co < g.Co) {
+        int ox = (int)(k % g.Wo);
+        long long t = k / g.Wo;
+        int oy = (int)(t % g.Ho);
+        int n = (int)(t / g.Ho);
+        v = __ldg(sm.p + ps_offset(sm, g.ps, n, co, oy, ox));
+      }
+      As[kk][mi] = v;
+    }
+#pragma unroll
+    for (int kk = b_k0; kk < BK; kk += B_KSTEP) {
+      long long k = k0 + kk;
+      bool kok = k < kend;
+      long long kc = kok ? k : 0;
+      int ox = (int)(kc % g.Wo);
+      long long t = kc / g.Wo;
+      int oy = (int)(t % g.Ho);
+      int n = (int)(t / g.Ho);
+#pragma unroll
+      for (int q = 0; q < B_NREP; ++q) {
+        float v = 0.f;
+        if (kok && b_kind[q] == 1) {
+          int iy = oy * g.st - g.pad + b_r[q], ix = ox * g.st - g.pad + b_s[q];
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+            v = __ldg(big.p + n * big.sn + b_ci[q] * big.sc + iy * big.sh + ix * big.sw);
+        } else if (kok && b_kind[q] == 2) {
+          v = 1.f;
+        }
+        Bs[kk][(tid % BN) + q * NT] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float *dst = partial + (long long)blockIdx.z * g.Co * NN;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int co = m0 + ty * TM + i;
+    if (co >= g.Co) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int col = n0 + tx * TN + j;
+      if (col < NN) dst[(long long)co * NN + col] = acc[i][j];
+    }
+  }
+}
+
+// Sum the split-K partials in a fixed order (deterministic), scale, store / accumulate.
+__global__ void k_wgrad_reduce(const float *__restrict__ partial, int splits, int Co, int CRS, float *dw, float *db,
+                               float scale, int accumulate) {
+  const int NN = CRS + 1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Co * NN;
+  if (idx >= total) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + idx];
+  s *= scale;
+  int co = (int)(idx / NN), col = (int)(idx - (long long)co * NN);
+  if (col < CRS) {
+    float *d = dw + (long long)co * CRS + col;
+    *d = accumulate ? (*d + s) : s;
+  } else if (db) {
+    db[co] = accumulate ? (db[co] + s) : s;
+  }
+}
+
+// out[c] (=|+=) scale * sum_{n,h,w} t[n,c,h,w]   (bias gradient of a transposed conv)
+__global__ void k_channel_sum(T4 t, int N, int C, int H, int W, float *out, float scale, int accumulate) {
+  int c = blockIdx.x;
+  long long total = (long long)N * H * W;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    int x = (int)(i % W);
+    long long q = i / W;
+    int y = (int)(q % H);
+    int n = (int)(q / H);
+    s += __ldg(t.p + n * t.sn + c * t.sc + y * t.sh + x * t.sw);
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[c] = accumulate ? (out[c] + s * scale) : s * scale;
+  }
+}
+
+}  // namespace
+
+int simt_conv_gather(const Geom &g, const T4 &in, const float *w, const T4 &out, const Epi &epi, cudaStream_t st) {
+  long long M = (long long)g.N * g.Ho * g.Wo;
+  if (M == 0 || g.Co == 0) return SRB_OK;
+  if (g.Co <= 8) {
+    constexpr int BM = 128, BN = 8, TM = 2, TN = 4;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (g.Co + BN - 1) / BN);
+    k_gather<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g, in, w, out, epi);
+  } else {
+    constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (g.Co + BN - 1) / BN);
+    k_gather<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g, in, w, out, epi);
+  }
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int simt_conv_scatter(const Geom &g, const T4 &in_small, const float *w, const T4 &out_big, const Epi &epi,
+                      cudaStream_t st) {
+  long long M = (long long)g.N * g.Hi * g.Wi;
+  if (M == 0 || g.Ci == 0) return SRB_OK;
+  if (g.Ci <= 8) {
+    constexpr int BM = 128, BN = 8, TM = 2, TN = 4;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (g.Ci + BN - 1) / BN);
+    k_scatter<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g, in_small, w, out_big, epi);
+  } else {
+    constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (g.Ci + BN - 1) / BN);
+    k_scatter<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g, in_small, w, out_big, epi);
+  }
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+static int wgrad_splits(const Geom &g) {
+  long long Kp = (long long)g.N * g.Ho * g.Wo;
+  int NN = g.Ci * g.kh * g.kw + 1;
+  long long tiles = (long long)((g.Co + 63) / 64) * ((NN + 63) / 64);
+  long long want = (148LL * 4 + tiles - 1) / tiles;  // ~4 waves worth of CTAs
+  long long maxs = (Kp + 255) / 256;                  // at least 256 pixels per split
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  return (int)want;
+}
+
+size_t simt_wgrad_ws_bytes(const Geom &g) {
+  int NN = g.Ci * g.kh * g.kw + 1;
+  return (size_t)wgrad_splits(g) * g.Co * NN * sizeof(float);
+}
+
+int simt_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
+                    int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
+  long long Kp = (long long)g.N * g.Ho * g.Wo;
+  int CRS = g.Ci * g.kh * g.kw, NN = CRS + 1;
+  int splits = wgrad_splits(g);
+  size_t need = (size_t)splits * g.Co * NN * sizeof(float);
+  SRB_REQUIRE(ws && ws_bytes >= need, SRB_EWORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);
+  long long kchunk = (Kp + splits - 1) / splits;
+  kchunk = (kchunk + BK - 1) / BK * BK;
+  constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
+  dim3 grid((g.Co + BM - 1) / BM, (NN + BN - 1) / BN, splits);
+  k_wgrad<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g, small, big, (float *)ws, kchunk);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  long long total = (long long)g.Co * NN;
+  k_wgrad_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float *)ws, splits, g.Co, CRS, dw, db_small,
+                                                                   scale, accumulate);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int channel_sum(const T4 &t, int N, int C, int H, int W, float *out, float scale, int accumulate, cudaStream_t st) {
+  if (C == 0) return SRB_OK;
+  k_channel_sum<<<C, 256, 0, st>>>(t, N, C, H, W, out, scale, accumulate);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+}  // namespace srb

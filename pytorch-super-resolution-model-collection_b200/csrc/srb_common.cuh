@@ -1,0 +1,108 @@
+// Shared declarations for libsrb200 (sm_100a).  Internal; the public surface is include/srb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "srb200.h"
+
+namespace srb {
+
+// Thread-local error string (srb_last_error) and the process-wide launch counter.
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define SRB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      srb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));    \
+      return SRB_ECUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+
+#define SRB_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      srb::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// Device-side strided NCHW view.
+struct T4 {
+  float *p;
+  long long sn, sc, sh, sw;
+};
+static inline T4 to_t4(const srb_tensor4 *t) {
+  T4 r;
+  if (t) { r.p = (float *)t->data; r.sn = t->sn; r.sc = t->sc; r.sh = t->sh; r.sw = t->sw; }
+  else   { r.p = nullptr; r.sn = r.sc = r.sh = r.sw = 0; }
+  return r;
+}
+
+// Geometry of one "gather" convolution:  small[n,co,oy,ox] <-> big[n,ci,oy*st-pad+r,ox*st-pad+s].
+//   Conv2d:           big = x (Ci=Cin, Hi=H, Wi=W),  small = conv output (Co=Cout*ps*ps, Ho, Wo)
+//   ConvTranspose2d:  big = y (Ci=Cout, Hi=Ho_t, Wi=Wo_t), small = x (Co=Cin, Ho=H, Wo=W)
+// Weight element for (co,ci,r,s) sits at w[((co*Ci + ci)*kh + r)*kw + s] in both cases
+// (Conv2d OIHW; ConvTranspose2d (Cin,Cout,kh,kw) with co=Cin index, ci=Cout index).
+struct Geom {
+  int N, Ci, Hi, Wi;
+  int Co, Ho, Wo;
+  int kh, kw, st, pad;
+  int ps;  // PixelShuffle factor applied to the *small* side tensor addressing (Conv2d only)
+};
+
+struct Epi {
+  const float *bias;   // indexed by channel of the written tensor (pre-shuffle channel), or null
+  const float *alpha;  // PReLU slope (device scalar) or null
+  int act;
+  float slope;
+  T4 residual;  // p == null -> none
+  T4 preact;    // p == null -> none
+  int round_tf32;  // store y RN-rounded to tf32 (feeds a tensor-core consumer)
+};
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float apply_act(float z, int act, float slope) {
+  // ATen semantics: relu(z)=max(z,0); prelu/lrelu take the slope branch at z<=0 (value identical at 0).
+  if (act == SRB_ACT_NONE) return z;
+  if (act == SRB_ACT_RELU) return z > 0.f ? z : 0.f;
+  return z > 0.f ? z : z * slope;
+}
+
+// Address of logical (n, k, oy, ox) of a conv output whose memory holds PixelShuffle_r of it:
+//   out[n, c, oy*r+i, ox*r+j] = conv[n, c*r*r + i*r + j, oy, ox]      (base_networks.py:157; ATen pixel_shuffle)
+__device__ __forceinline__ long long ps_offset(const T4 &t, int r, int n, int k, int oy, int ox) {
+  if (r == 1) return n * t.sn + k * t.sc + oy * t.sh + ox * t.sw;
+  int rr = r * r;
+  int c = k / rr, ij = k - c * rr;
+  int i = ij / r, j = ij - i * r;
+  return n * t.sn + c * t.sc + (long long)(oy * r + i) * t.sh + (long long)(ox * r + j) * t.sw;
+}
+
+// Entry points implemented in the .cu files (host side).
+int simt_conv_gather(const Geom &g, const T4 &in, const float *w, const T4 &out, const Epi &epi, cudaStream_t st);
+int simt_conv_scatter(const Geom &g, const T4 &in_small, const float *w, const T4 &out_big, const Epi &epi,
+                      cudaStream_t st);
+size_t simt_wgrad_ws_bytes(const Geom &g);
+int simt_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
+                    int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
+int channel_sum(const T4 &t, int N, int C, int H, int W, float *out, float scale, int accumulate, cudaStream_t st);
+
+// Tensor-core (tcgen05) path, tc_conv.cu.
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_as_gather);
+size_t tc_conv_ws_bytes(const Geom &g);
+int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
+                   void *ws, size_t ws_bytes, cudaStream_t st);
+bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);
+size_t tc_wgrad_ws_bytes(const Geom &g);
+int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace srb

@@ -1,0 +1,16 @@
+"""srb200 -- B200-native (sm_100a) engine for the conv + PixelShuffle hot path of
+togheppi/pytorch-super-resolution-model-collection (base_networks.py blocks).
+
+Importing this package loads libsrb200.so; if the CUDA library is not built the import fails
+(no CPU / torch fallback exists on the product path)."""
+from . import _lib  # noqa: F401  (raises ImportError when the engine is missing)
+from ._lib import launch_count, SrbError, LIB_PATH
+from . import functional
+from .functional import conv2d, conv_transpose2d, prelu, set_math, get_math, set_grad_scale
+from . import base_networks
+from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBlock, Upsample2xBlock
+from .convert import convert, PReLU, ConvTranspose2d, Conv2d
+from .ddp import GradBucket
+from . import models, host
+
+__version__ = "0.1.0"

@@ -1,0 +1,218 @@
+"""Drop-in for the reference's base_networks.py: same class names, constructor signatures, defaults,
+child-module names (conv / deconv / conv1 / conv2 / ps / bn / act / fc / upsample -> identical state_dict
+keys) and forward semantics, with the Conv2d / ConvTranspose2d / PixelShuffle / ReLU /
+PReLU / LeakyReLU / residual-add stacks executed by libsrb200's fused sm_100a kernels instead of ATen.
+
+Usage (reference model files untouched; they do `from base_networks import *`, e.g. srcnn.py:5):
+    import sys, srb200.base_networks as bn; sys.modules['base_networks'] = bn
+or rewrite an already-built model with srb200.convert(net).
+
+The parameter holders stay torch.nn.Conv2d / ConvTranspose2d / PReLU modules so that
+utils.weights_init_* (class-name matching, utils.py:76-113), optimizers and checkpoints keep working;
+only their forward is bypassed.  BatchNorm / InstanceNorm / Linear / tanh / sigmoid stay on torch
+(SURVEY.md 8f "next" rows).
+"""
+import torch  # re-exported on purpose: the model files get `torch` through the star import (srcnn.py:13)
+
+from . import functional as F
+
+__all__ = ["torch", "DenseBlock", "ConvBlock", "DeconvBlock", "ResnetBlock", "PSBlock", "Upsample2xBlock"]
+
+_FUSABLE = (None, "relu", "prelu", "lrelu")
+
+
+def _make_norm(norm_arg, self_norm, ctor2d, num):
+    # mirrors the reference's quirk: ResnetBlock/PSBlock test the ctor argument for 'instance' (base_networks.py:118,162)
+    if self_norm == "batch":
+        return torch.nn.BatchNorm2d(num)
+    if norm_arg == "instance":
+        return torch.nn.InstanceNorm2d(num)
+    return None
+
+
+def _make_act(activation):
+    if activation == "relu":
+        return torch.nn.ReLU(True)
+    if activation == "prelu":
+        return torch.nn.PReLU()
+    if activation == "lrelu":
+        return torch.nn.LeakyReLU(0.2, True)
+    if activation == "tanh":
+        return torch.nn.Tanh()
+    if activation == "sigmoid":
+        return torch.nn.Sigmoid()
+    return None
+
+
+class _ActMixin:
+    def _fused_act(self):
+        """(activation code, alpha) if the block's activation can be fused into the conv epilogue."""
+        if self.activation in _FUSABLE:
+            return self.activation, (self.act.weight if self.activation == "prelu" else None)
+        return None, None
+
+    def _post(self, out, fused):
+        # activation the conv kernel could not fuse (after a norm layer, or tanh/sigmoid)
+        if self.activation is not None and not fused:
+            if self.activation == "prelu":
+                return F.prelu(out, self.act.weight)
+            return self.act(out)
+        return out
+
+
+class DenseBlock(torch.nn.Module):
+    """base_networks.py:4-36 -- Linear (+BN1d) (+act); stays on torch."""
+
+    def __init__(self, input_size, output_size, bias=True, activation='relu', norm='batch'):
+        super(DenseBlock, self).__init__()
+        self.fc = torch.nn.Linear(input_size, output_size, bias=bias)
+        self.norm = norm
+        if self.norm == 'batch':
+            self.bn = torch.nn.BatchNorm1d(output_size)
+        elif self.norm == 'instance':
+            self.bn = torch.nn.InstanceNorm1d(output_size)
+        self.activation = activation
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+
+    def forward(self, x):
+        out = self.bn(self.fc(x)) if self.norm is not None else self.fc(x)
+        return self.act(out) if self.activation is not None else out
+
+
+class ConvBlock(torch.nn.Module, _ActMixin):
+    """base_networks.py:39-71 -- act(bn?(Conv2d(x))).  norm=None: one fused kernel."""
+
+    def __init__(self, input_size, output_size, kernel_size=4, stride=2, padding=1, bias=True, activation='relu',
+                 norm='batch'):
+        super(ConvBlock, self).__init__()
+        self.conv = torch.nn.Conv2d(input_size, output_size, kernel_size, stride, padding, bias=bias)
+        self.norm = norm
+        bn = _make_norm(norm, self.norm, None, output_size) if norm in ('batch', 'instance') else None
+        if bn is not None:
+            self.bn = bn
+        self.activation = activation
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+
+    def forward(self, x):
+        c = self.conv
+        if self.norm is not None:
+            out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0]))
+            return self._post(out, fused=False)
+        a, alpha = self._fused_act()
+        out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha)
+        return self._post(out, fused=self.activation in _FUSABLE)
+
+
+class DeconvBlock(torch.nn.Module, _ActMixin):
+    """base_networks.py:74-106 -- act(bn?(ConvTranspose2d(x)))."""
+
+    def __init__(self, input_size, output_size, kernel_size=4, stride=2, padding=1, bias=True, activation='relu',
+                 norm='batch'):
+        super(DeconvBlock, self).__init__()
+        self.deconv = torch.nn.ConvTranspose2d(input_size, output_size, kernel_size, stride, padding, bias=bias)
+        self.norm = norm
+        bn = _make_norm(norm, self.norm, None, output_size) if norm in ('batch', 'instance') else None
+        if bn is not None:
+            self.bn = bn
+        self.activation = activation
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+
+    def forward(self, x):
+        d = self.deconv
+        if self.norm is not None:
+            out = self.bn(F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0]))
+            return self._post(out, fused=False)
+        a, alpha = self._fused_act()
+        out = F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0],
+                                 activation=a, alpha=alpha)
+        return self._post(out, fused=self.activation in _FUSABLE)
+
+
+class ResnetBlock(torch.nn.Module, _ActMixin):
+    """base_networks.py:109-150 -- x + bn?(conv2(act(bn?(conv1(x))))); ONE bn module shared by both convs (:137,145).
+    norm=None: two fused kernels (conv1+act, conv2+residual add)."""
+
+    def __init__(self, num_filter, kernel_size=3, stride=1, padding=1, bias=True, activation='relu', norm='batch'):
+        super(ResnetBlock, self).__init__()
+        self.conv1 = torch.nn.Conv2d(num_filter, num_filter, kernel_size, stride, padding, bias=bias)
+        self.conv2 = torch.nn.Conv2d(num_filter, num_filter, kernel_size, stride, padding, bias=bias)
+        self.norm = norm
+        if self.norm == 'batch':
+            self.bn = torch.nn.BatchNorm2d(num_filter)
+        elif norm == 'instance':
+            self.bn = torch.nn.InstanceNorm2d(num_filter)
+        self.activation = activation
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+
+    def forward(self, x):
+        c1, c2 = self.conv1, self.conv2
+        if self.norm is not None:
+            out = self.bn(F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0]))
+            out = self._post(out, fused=False)
+            out = self.bn(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0]))
+            return torch.add(out, x)
+        a, alpha = self._fused_act()
+        out = F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0], activation=a, alpha=alpha)
+        out = self._post(out, fused=self.activation in _FUSABLE)
+        return F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0], residual=x)
+
+
+class PSBlock(torch.nn.Module, _ActMixin):
+    """base_networks.py:153-185 -- act?(bn?(PixelShuffle_r(Conv2d(in -> out*r*r)))).
+    The shuffle is never a kernel: it is the store addressing of the conv epilogue (bit-exact permutation)."""
+
+    def __init__(self, input_size, output_size, scale_factor, kernel_size=3, stride=1, padding=1, bias=True,
+                 activation='relu', norm='batch'):
+        super(PSBlock, self).__init__()
+        self.conv = torch.nn.Conv2d(input_size, output_size * scale_factor ** 2, kernel_size, stride, padding,
+                                    bias=bias)
+        self.ps = torch.nn.PixelShuffle(scale_factor)
+        self.norm = norm
+        if self.norm == 'batch':
+            self.bn = torch.nn.BatchNorm2d(output_size)
+        elif norm == 'instance':
+            self.bn = torch.nn.InstanceNorm2d(output_size)
+        self.activation = activation
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+
+    def forward(self, x):
+        c = self.conv
+        r = self.ps.upscale_factor
+        if self.norm is not None:
+            out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], pixel_shuffle=r))
+            return self._post(out, fused=False)
+        a, alpha = self._fused_act()
+        out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha, pixel_shuffle=r)
+        return self._post(out, fused=self.activation in _FUSABLE)
+
+
+class Upsample2xBlock(torch.nn.Module):
+    """base_networks.py:188-214 -- 'deconv' (k4 s2 p1) | 'ps' (r=2) | 'rnc' (nearest x2 + conv3)."""
+
+    def __init__(self, input_size, output_size, bias=True, upsample='deconv', activation='relu', norm='batch'):
+        super(Upsample2xBlock, self).__init__()
+        scale_factor = 2
+        if upsample == 'deconv':
+            self.upsample = DeconvBlock(input_size, output_size, kernel_size=4, stride=2, padding=1, bias=bias,
+                                        activation=activation, norm=norm)
+        elif upsample == 'ps':
+            self.upsample = PSBlock(input_size, output_size, scale_factor=scale_factor, bias=bias,
+                                    activation=activation, norm=norm)
+        elif upsample == 'rnc':
+            self.upsample = torch.nn.Sequential(
+                torch.nn.Upsample(scale_factor=scale_factor, mode='nearest'),
+                ConvBlock(input_size, output_size, kernel_size=3, stride=1, padding=1, bias=bias,
+                          activation=activation, norm=norm))
+
+    def forward(self, x):
+        return self.upsample(x)

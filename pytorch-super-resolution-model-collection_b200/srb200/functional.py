@@ -1,0 +1,218 @@
+"""autograd.Functions over the libsrb200 C-ABI: the fused conv (+bias +act +residual +PixelShuffle),
+the transposed conv, and the stand-alone PReLU.  Replaces the ATen ops behind base_networks.py's
+blocks (Conv2d :42, ConvTranspose2d :77, PixelShuffle :157, ReLU/PReLU/LeakyReLU :51-56, torch.add :149).
+
+No torch compute op is used on the data path: torch only allocates the tensors and provides the
+stream.  A CUDA tensor is required; CPU tensors raise (there is no CPU fallback by design).
+"""
+import ctypes
+import torch
+
+from . import _lib
+from ._lib import lib, check, t4, ConvParams
+
+_ACT_CODES = {None: _lib.ACT_NONE, "relu": _lib.ACT_RELU, "prelu": _lib.ACT_PRELU, "lrelu": _lib.ACT_LRELU}
+
+_state = {"math": _lib.MATH_AUTO, "grad_scale": 1.0}
+
+
+def set_math(mode):
+    """'auto' (default): tcgen05 TF32 tensor path where a layer qualifies; 'fp32': CUDA-core fp32 everywhere."""
+    _state["math"] = {"auto": _lib.MATH_AUTO, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}[mode]
+
+
+def get_math():
+    return {_lib.MATH_AUTO: "auto", _lib.MATH_TF32: "tf32", _lib.MATH_FP32: "fp32"}[_state["math"]]
+
+
+def set_grad_scale(s):
+    """Factor folded by the wgrad kernels into gradients they write straight into a GradBucket slot
+    (1/world_size under data parallel).  Gradients returned through autograd are never scaled here."""
+    _state["grad_scale"] = float(s)
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Per-(device, stream) scratch owned by torch's caching allocator, grown geometrically."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dense(t):
+    """Return t as NCHW-contiguous or channels_last-contiguous memory (whichever it already is, else NCHW)."""
+    if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return t.contiguous()
+
+
+def _is_cl(t):
+    return t.shape[1] > 1 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _out_format(channels):
+    # activations that can feed the tensor-core kernels live in NHWC; skinny (3-channel) edges stay NCHW
+    return torch.channels_last if channels % 32 == 0 else torch.contiguous_format
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("srb200 kernels need CUDA float32 tensors (got %s %s); there is no CPU path"
+                               % (t.device, t.dtype))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _params(x, weight, stride, pad, out_pad, transposed, ps, act, slope):
+    N, Cin, H, W = x.shape
+    if transposed:
+        assert weight.shape[0] == Cin, "ConvTranspose2d weight is (Cin, Cout, kh, kw)"
+        Cout = weight.shape[1]
+    else:
+        assert weight.shape[1] == Cin, "Conv2d weight is (Cout*ps*ps, Cin, kh, kw)"
+        assert weight.shape[0] % (ps * ps) == 0
+        Cout = weight.shape[0] // (ps * ps)
+    return ConvParams(N, Cin, H, W, Cout, weight.shape[2], weight.shape[3], stride, pad, out_pad,
+                      1 if transposed else 0, ps, _ACT_CODES[act], float(slope), _state["math"])
+
+
+class _FusedConv(torch.autograd.Function):
+    """y = PixelShuffle_ps(act(conv(x, w) + b)) + residual   (one kernel forward; act_bwd + wgrad + dgrad backward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope):
+        _require_cuda(x, weight, bias, alpha, residual)
+        x = _dense(x)
+        weight = weight.contiguous()
+        p = _params(x, weight, stride, pad, out_pad, transposed, ps, act, slope)
+        ho, wo = ctypes.c_int32(), ctypes.c_int32()
+        check(lib.srb_conv_out_hw(ctypes.byref(p), ctypes.byref(ho), ctypes.byref(wo)))
+        oshape = (p.N, p.Cout, ho.value * ps, wo.value * ps)
+        fmt = _out_format(p.Cout)
+        y = torch.empty(oshape, dtype=torch.float32, device=x.device, memory_format=fmt)
+        # PReLU backward needs z itself; relu/lrelu can use sign(y) unless a residual was added on top
+        need_preact = act == "prelu" or (act is not None and residual is not None)
+        preact = torch.empty_like(y) if need_preact else None
+        if residual is not None:
+            assert tuple(residual.shape) == oshape, "residual must match the block output"
+            residual = _dense(residual)
+        ws = _workspace(x.device, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_FPROP))
+        tx, ty = t4(x), t4(y)
+        tr = t4(residual) if residual is not None else None
+        tp = t4(preact) if preact is not None else None
+        check(lib.srb_conv_fprop(ctypes.byref(p), ctypes.byref(tx), _ptr(weight), _ptr(bias), _ptr(alpha),
+                                 ctypes.byref(tr) if tr is not None else None, ctypes.byref(ty),
+                                 ctypes.byref(tp) if tp is not None else None,
+                                 _ptr(ws), ws.numel(), _stream(x.device)))
+        ctx.p = p
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.params = (weight, bias)  # GradBucket direct-write targets (ddp.py)
+        ctx.save_for_backward(x, weight, alpha, preact if need_preact else (y if act is not None else None))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, alpha, ref = ctx.saved_tensors
+        p = ctx.p
+        dev = x.device
+        st = _stream(dev)
+        dy = _dense(dy)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        dalpha = None
+        if ctx.act is not None:
+            dz = torch.empty(dy.shape, dtype=torch.float32, device=dev, memory_format=_out_format(p.Cout))
+            if ctx.act == "prelu":
+                dalpha = torch.zeros_like(alpha)
+            tdy, tref, tdz = t4(dy), t4(ref), t4(dz)
+            check(lib.srb_act_bwd(ctypes.byref(p), ctypes.byref(tdy), ctypes.byref(tref), _ptr(alpha),
+                                  ctypes.byref(tdz), _ptr(dalpha), st))
+        else:
+            dz = dy
+        tdz, tx = t4(dz), t4(x)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            wparam, bparam = ctx.params
+            direct = getattr(wparam, "_srb_direct", False) and wparam.grad is not None and \
+                (bparam is None or (getattr(bparam, "_srb_direct", False) and bparam.grad is not None))
+            if direct:
+                # the wgrad kernel overwrites the parameter's slot of the flat gradient bucket, pre-scaled
+                dw_t, db_t, scale = wparam.grad, (bparam.grad if bparam is not None else None), _state["grad_scale"]
+            else:
+                dw_t = dw = torch.empty_like(weight)
+                db_t = db = torch.empty(weight.shape[1] if p.transposed else weight.shape[0], dtype=torch.float32,
+                                        device=dev) if ctx.has_bias else None
+                scale = 1.0
+            ws = _workspace(dev, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_WGRAD))
+            check(lib.srb_conv_wgrad(ctypes.byref(p), ctypes.byref(tx), ctypes.byref(tdz), _ptr(dw_t), _ptr(db_t),
+                                     ctypes.c_float(scale), 0, _ptr(ws), ws.numel(), st))
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=torch.float32, device=dev,
+                             memory_format=torch.channels_last if _is_cl(x) else torch.contiguous_format)
+            tdx = t4(dx)
+            ws = _workspace(dev, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_DGRAD))
+            check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight), ctypes.byref(tdx),
+                                     _ptr(ws), ws.numel(), st))
+        return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, activation=None, alpha=None, slope=0.2, residual=None,
+           pixel_shuffle=1):
+    """Fused Conv2d -> +bias -> act -> PixelShuffle(r) -> +residual.
+
+    activation: None | 'relu' | 'prelu' (alpha = the nn.PReLU weight, shape (1,)) | 'lrelu' (slope).
+    """
+    if activation == "prelu":
+        assert alpha is not None and alpha.numel() == 1, "base_networks.py uses nn.PReLU() with one shared slope"
+    return _FusedConv.apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
+                            int(stride), int(padding), 0, False, int(pixel_shuffle), activation, slope)
+
+
+def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, activation=None, alpha=None,
+                     slope=0.2, residual=None):
+    """Fused ConvTranspose2d -> +bias -> act -> +residual (weight is (Cin, Cout, kh, kw) like torch)."""
+    return _FusedConv.apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
+                            int(stride), int(padding), int(output_padding), True, 1, activation, slope)
+
+
+class _PReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha):
+        _require_cuda(x, alpha)
+        x = _dense(x)
+        y = torch.empty_like(x)
+        check(lib.srb_prelu_fwd(_ptr(x), _ptr(alpha), _ptr(y), x.numel(), _stream(x.device)))
+        ctx.save_for_backward(x, alpha)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, alpha = ctx.saved_tensors
+        if _is_cl(x):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        else:
+            dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dalpha = torch.zeros_like(alpha)
+        check(lib.srb_prelu_bwd(_ptr(x), _ptr(dy), _ptr(alpha), _ptr(dx), _ptr(dalpha), x.numel(),
+                                _stream(x.device)))
+        return dx, dalpha
+
+
+def prelu(x, alpha):
+    """Stand-alone PReLU with one shared slope (fsrcnn.py:26)."""
+    assert alpha.numel() == 1
+    return _PReLU.apply(x, alpha)

@@ -1,0 +1,327 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI (ctypes) behind the block API, against
+(1) the golden vectors produced from the unmodified reference, (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star: 1e-3 relative fp32; PixelShuffle permutation bit-exact):
+  math='fp32' (CUDA-core kernels)      rel-L2 <= 2e-5 (summation order only)
+  math='auto' (tcgen05 TF32 kernels)   rel-L2 <= 1e-3 per op and on the shallow golden nets
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+pytestmark = pytest.mark.gpu
+
+import srb200
+from srb200 import models as M
+from oracle import torch_ref as R
+from util import load_golden, load_state, rel_l2
+
+DEV = "cuda:0"
+TOL = {"fp32": 2e-5, "auto": 1e-3}
+
+
+@pytest.fixture(autouse=True)
+def _reset_math():
+    srb200.set_math("auto")
+    srb200.set_grad_scale(1.0)
+    yield
+    srb200.set_math("auto")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+
+
+BLOCKS = {
+    "convblock_k3_relu": lambda: srb200.ConvBlock(8, 16, 3, 1, 1, activation="relu", norm=None),
+    "convblock_k5_p0_prelu": lambda: srb200.ConvBlock(3, 12, 5, 1, 0, activation="prelu", norm=None),
+    "convblock_k3_s2_lrelu": lambda: srb200.ConvBlock(6, 10, 3, 2, 1, activation="lrelu", norm=None),
+    "convblock_default_k4s2_nobias": lambda: srb200.ConvBlock(4, 8, bias=False, activation=None, norm=None),
+    "psblock_r4": lambda: srb200.PSBlock(8, 3, 4, 3, 1, 0, activation=None, norm=None),
+    "psblock_r2_prelu": lambda: srb200.PSBlock(8, 8, 2, activation="prelu", norm=None),
+    "resnetblock_relu": lambda: srb200.ResnetBlock(8, norm=None),
+    "resnetblock_prelu": lambda: srb200.ResnetBlock(8, activation="prelu", norm=None),
+    "deconvblock_k4s2": lambda: srb200.DeconvBlock(6, 4, activation="relu", norm=None),
+    "upsample2x_ps": lambda: srb200.Upsample2xBlock(8, 8, upsample="ps", activation=None, norm=None),
+    "upsample2x_deconv": lambda: srb200.Upsample2xBlock(4, 4, upsample="deconv", activation="lrelu", norm=None),
+    "fsrcnn_tail": lambda: torch.nn.Sequential(srb200.PReLU(), srb200.ConvTranspose2d(6, 3, 9, 4, 3, output_padding=1)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BLOCKS))
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+def test_block_matches_reference_golden(name, math):
+    _need_gpu()
+    srb200.set_math(math)
+    g = load_golden("block_" + name)
+    blk = BLOCKS[name]()
+    load_state(blk, g)
+    blk.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    y = blk(x)
+    y.backward(torch.from_numpy(g["gy"]).to(DEV))
+    tol = TOL[math]
+    assert tuple(y.shape) == g["y"].shape
+    assert rel_l2(y.detach(), g["y"]) < tol
+    assert rel_l2(x.grad, g["gx"]) < tol
+    for k, p in blk.named_parameters():
+        assert rel_l2(p.grad, g["grad:" + k]) < tol, k
+
+
+NETS = {"srcnn": "l2", "espcn": "l2", "fsrcnn": "l2", "vdsr": "l2", "edsr": "l1", "srgan_g": "l2"}
+
+
+@pytest.mark.parametrize("name", sorted(NETS))
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+def test_net_matches_reference_golden(name, math):
+    _need_gpu()
+    srb200.set_math(math)
+    g = load_golden("net_" + name)
+    net = M.MODELS[name](*[int(v) for v in g["args"]])
+    load_state(net, g)
+    net.to(DEV).train()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    tgt = torch.from_numpy(g["target"]).to(DEV)
+    y = net(x)
+    loss = TF.l1_loss(y, tgt) if NETS[name] == "l1" else TF.mse_loss(y, tgt)
+    loss.backward()
+    tol = 1e-4 if math == "fp32" else 1e-3
+    assert rel_l2(y.detach(), g["y"]) < tol
+    assert abs(loss.item() - float(g["loss"])) < tol * abs(float(g["loss"]))
+    gtol = tol * (3 if name == "edsr" else 1)  # L1 loss: sign(y - t) flips amplify rounding on a few pixels
+    for k, p in net.named_parameters():
+        ref = g["grad:" + k]
+        if np.abs(ref).max() < 1e-12:
+            continue
+        assert rel_l2(p.grad, ref) < gtol, k
+
+
+# ---- op-level sweep against the CPU oracle ---------------------------------------------------------
+#        Cin Cout k  s  p  act      res    ps  H   W   N
+SWEEP = [
+    (3, 64, 9, 1, 0, "relu", False, 1, 20, 22, 2),     # SRCNN first layer
+    (64, 32, 5, 1, 0, "relu", False, 1, 14, 15, 2),    # SRCNN second
+    (32, 3, 5, 1, 0, None, False, 1, 12, 12, 2),       # SRCNN last
+    (3, 64, 5, 1, 0, "relu", False, 1, 18, 17, 2),     # ESPCN first
+    (64, 32, 3, 1, 0, "relu", False, 1, 16, 16, 3),    # ESPCN second
+    (32, 3, 3, 1, 0, None, False, 4, 13, 14, 2),       # ESPCN PSBlock (32 -> 48 -> PS4)
+    (64, 64, 3, 1, 1, "relu", False, 1, 16, 16, 2),    # VDSR / EDSR body
+    (64, 64, 3, 1, 1, None, True, 1, 12, 20, 2),       # ResnetBlock conv2 + skip
+    (64, 3, 3, 1, 1, None, True, 1, 16, 16, 2),        # VDSR output conv + global residual
+    (64, 64, 3, 1, 1, "prelu", False, 2, 8, 8, 2),     # SRGAN/EDSR upsampler (64 -> 256 -> PS2)
+    (64, 3, 9, 1, 4, None, False, 1, 16, 16, 1),       # SRGAN output conv
+    (64, 64, 3, 2, 1, "lrelu", False, 1, 16, 16, 2),   # SRGAN D stride-2
+    (128, 128, 3, 2, 1, "lrelu", False, 1, 8, 8, 2),
+    (56, 12, 1, 1, 0, "prelu", False, 1, 10, 10, 2),   # FSRCNN shrink
+    (12, 12, 3, 1, 1, None, False, 1, 10, 10, 2),      # FSRCNN map
+    (12, 56, 1, 1, 0, "prelu", False, 1, 10, 10, 2),   # FSRCNN expand
+    (32, 32, 3, 1, 1, "relu", False, 1, 7, 5, 1),      # ragged: smaller than one tile
+    (96, 160, 3, 1, 1, "relu", False, 1, 9, 9, 1),     # non power-of-two channel counts
+    (256, 256, 3, 1, 1, "relu", False, 1, 8, 8, 1),    # EDSR-256 body
+    (64, 64, 1, 1, 0, None, False, 1, 5, 6, 2),
+]
+
+
+def _ref_op(x, w, b, alpha, res, k, s, p, act, ps):
+    z = TF.conv2d(x, w, b, s, p)
+    if act == "relu":
+        z = TF.relu(z)
+    elif act == "prelu":
+        z = TF.prelu(z, alpha)
+    elif act == "lrelu":
+        z = TF.leaky_relu(z, 0.2)
+    if ps > 1:
+        z = TF.pixel_shuffle(z, ps)
+    if res is not None:
+        z = z + res
+    return z
+
+
+@pytest.mark.parametrize("case", SWEEP)
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+@pytest.mark.parametrize("cl", [False, True])
+def test_fused_conv_vs_oracle(case, math, cl):
+    _need_gpu()
+    srb200.set_math(math)
+    Cin, Cout, k, s, p, act, res, ps, H, W, N = case
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, H, W, generator=gen)
+    w = torch.randn(Cout * ps * ps, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout * ps * ps, generator=gen) * 0.1
+    alpha = torch.tensor([0.25])
+    xr = x.clone().requires_grad_(True)
+    wr, br, ar = w.clone().requires_grad_(True), b.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    y0 = TF.conv2d(x, w, b, s, p)
+    oshape = (N, Cout, y0.shape[2] * ps, y0.shape[3] * ps)
+    r = torch.randn(oshape, generator=gen) if res else None
+    rr = r.clone().requires_grad_(True) if res else None
+    yref = _ref_op(xr, wr, br, ar, rr, k, s, p, act, ps)
+    gy = torch.randn(oshape, generator=gen)
+    yref.backward(gy)
+
+    xg = x.to(DEV)
+    if cl:
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_(True)
+    wg, bg, ag = (t.to(DEV).requires_grad_(True) for t in (w, b, alpha))
+    rg = r.to(DEV).requires_grad_(True) if res else None
+    y = srb200.conv2d(xg, wg, bg, s, p, activation=act, alpha=ag if act == "prelu" else None, residual=rg,
+                      pixel_shuffle=ps)
+    y.backward(gy.to(DEV))
+    tol = TOL[math]
+    assert rel_l2(y.detach(), yref.detach()) < tol
+    assert rel_l2(xg.grad, xr.grad) < tol
+    assert rel_l2(wg.grad, wr.grad) < tol
+    assert rel_l2(bg.grad, br.grad) < tol
+    if act == "prelu":
+        assert abs(ag.grad.item() - ar.grad.item()) < max(tol * 10 * abs(ar.grad.item()), 1e-4)
+    if res:
+        assert torch.equal(rg.grad.cpu(), gy)
+
+
+@pytest.mark.parametrize("k,s,p,op,Ci,Co", [(9, 4, 3, 1, 56, 3), (4, 2, 1, 0, 16, 8), (3, 1, 1, 0, 8, 8), (5, 3, 2, 2, 6, 5)])
+def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co):
+    _need_gpu()
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(2, Ci, 7, 6, generator=gen)
+    w = torch.randn(Ci, Co, k, k, generator=gen) * 0.1
+    b = torch.randn(Co, generator=gen)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    yref = TF.conv_transpose2d(xr, wr, br, s, p, op)
+    gy = torch.randn(yref.shape, generator=gen)
+    yref.backward(gy)
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = srb200.conv_transpose2d(xg, wg, bg, s, p, op)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y.detach(), yref.detach()) < 2e-5
+    assert rel_l2(xg.grad, xr.grad) < 2e-5
+    assert rel_l2(wg.grad, wr.grad) < 2e-5
+    assert rel_l2(bg.grad, br.grad) < 2e-5
+
+
+@pytest.mark.parametrize("r,C,H,W", [(2, 64, 8, 8), (4, 3, 9, 7), (3, 5, 4, 6), (2, 256, 4, 4)])
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+def test_pixel_shuffle_permutation_bit_exact(r, C, H, W, math):
+    """1x1 conv with an identity filter: the fused store must reproduce nn.PixelShuffle bit for bit
+    (values are tf32-representable small integers, so the tensor path is exact too)."""
+    _need_gpu()
+    srb200.set_math(math)
+    cin = C * r * r
+    x = torch.randint(-64, 64, (2, cin, H, W)).float()
+    w = torch.eye(cin).reshape(cin, cin, 1, 1)
+    for cl in (False, True):
+        xg = x.to(DEV)
+        if cl:
+            xg = xg.contiguous(memory_format=torch.channels_last)
+        y = srb200.conv2d(xg, w.to(DEV), None, 1, 0, pixel_shuffle=r)
+        assert torch.equal(y.cpu(), TF.pixel_shuffle(x, r))
+        # and the un-shuffle in backward
+        xg = xg.detach().requires_grad_(True)
+        y = srb200.conv2d(xg, w.to(DEV), None, 1, 0, pixel_shuffle=r)
+        gy = torch.randint(-8, 8, tuple(y.shape)).float()
+        y.backward(gy.to(DEV))
+        assert torch.equal(xg.grad.cpu(), TF.pixel_unshuffle(gy, r))
+
+
+def test_act_corner_cases_at_zero():
+    """z == 0: ReLU grad is 0, PReLU/LeakyReLU take the slope branch (ATen semantics)."""
+    _need_gpu()
+    srb200.set_math("fp32")
+    x = torch.zeros(1, 1, 4, 4)
+    x[0, 0, 0, 0], x[0, 0, 1, 1] = 1.0, -2.0
+    w = torch.ones(1, 1, 1, 1)
+    gy = torch.ones(1, 1, 4, 4)
+    for act, mod in (("relu", torch.nn.ReLU()), ("prelu", torch.nn.PReLU()), ("lrelu", torch.nn.LeakyReLU(0.2))):
+        xr = x.clone().requires_grad_(True)
+        mod(TF.conv2d(xr, w)).backward(gy)
+        xg = x.to(DEV).requires_grad_(True)
+        alpha = torch.tensor([0.25], device=DEV, requires_grad=True)
+        y = srb200.conv2d(xg, w.to(DEV), None, 1, 0, activation=act, alpha=alpha if act == "prelu" else None)
+        y.backward(gy.to(DEV))
+        assert torch.equal(xg.grad.cpu(), xr.grad), act
+        if act == "prelu":
+            assert abs(alpha.grad.item() - mod.weight.grad.item()) < 1e-6
+
+
+def test_empty_batch_and_tiny_images():
+    _need_gpu()
+    w = torch.randn(8, 4, 3, 3, device=DEV)
+    y = srb200.conv2d(torch.zeros(0, 4, 8, 8, device=DEV), w, None, 1, 1)
+    assert tuple(y.shape) == (0, 8, 8, 8)
+    x = torch.randn(1, 4, 3, 3, device=DEV)
+    y = srb200.conv2d(x, w, None, 1, 0)
+    assert tuple(y.shape) == (1, 8, 1, 1)
+    assert rel_l2(y, TF.conv2d(x.cpu(), w.cpu())) < 2e-5
+    with pytest.raises(srb200.SrbError):
+        srb200.conv2d(torch.zeros(1, 4, 2, 2, device=DEV), w, None, 1, 0)  # kernel larger than input
+
+
+# ---- size-independent properties at the BASELINE.json sizes ------------------------------------------
+def test_espcn_cfg2_full_size_properties():
+    """ESPCN x4, batch 128, 64x64 LR (BASELINE cfg2): adjointness <conv(x),g> == <x,dgrad(g)> and
+    <dW,W> == <conv_W(x),g> (conv is linear in x and in W), plus the shuffle checksum."""
+    _need_gpu()
+    torch.manual_seed(0)
+    net = M.ESPCN(3, 64, 4).to(DEV)
+    R.init_normal(net)
+    x = torch.rand(128, 3, 64, 64, device=DEV)
+    y = net(x)
+    assert tuple(y.shape) == (128, 3, 224, 224)
+    # last block alone (linear: no activation): adjoint identities
+    blk = net.layers[2]
+    h = net.layers[1](net.layers[0](x)).detach().requires_grad_(True)
+    out = blk(h)
+    g = torch.randn_like(out)
+    out.backward(g)
+    lhs = (out.detach().double() * g.double()).sum().item()
+    bias_term = (TF.pixel_shuffle(blk.conv.bias.detach().view(1, 48, 1, 1).expand(128, 48, 56, 56), 4).double()
+                 * g.double()).sum().item()
+    dx_term = (h.detach().double() * h.grad.double()).sum().item()
+    dw_term = (blk.conv.weight.detach().double() * blk.conv.weight.grad.double()).sum().item()
+    scale = abs(lhs) + abs(bias_term) + 1.0
+    assert abs((lhs - bias_term) - dx_term) / scale < 2e-3
+    assert abs((lhs - bias_term) - dw_term) / scale < 2e-3
+    db_ref = TF.pixel_unshuffle(g, 4).sum(dim=(0, 2, 3))
+    assert rel_l2(blk.conv.bias.grad, db_ref) < 1e-4
+
+
+def test_vdsr_body_layer_full_size_linearity():
+    """64->64 k3 p1 at 128x128 (BASELINE cfg3 body layer, batch reduced to 8): conv(a*x1+b*x2) == a*conv(x1)+b*conv(x2)."""
+    _need_gpu()
+    torch.manual_seed(1)
+    w = torch.randn(64, 64, 3, 3, device=DEV) / 24.0
+    x1 = torch.randn(8, 64, 128, 128, device=DEV).contiguous(memory_format=torch.channels_last)
+    x2 = torch.randn_like(x1)
+    y1 = srb200.conv2d(x1, w, None, 1, 1)
+    y2 = srb200.conv2d(x2, w, None, 1, 1)
+    y12 = srb200.conv2d(2.0 * x1 - 0.5 * x2, w, None, 1, 1)
+    assert rel_l2(y12, 2.0 * y1 - 0.5 * y2) < 1e-3
+    # spot-check one image against the oracle
+    ref = TF.conv2d(x1[:1].cpu().contiguous(), w.cpu(), None, 1, 1)
+    assert rel_l2(y1[:1], ref) < 1e-3
+
+
+def test_training_steps_track_the_oracle():
+    """Restated loop body (espcn.py:126-131, vdsr.py:142-150 incl. clipping): 3 optimizer steps, parameters stay
+    within tolerance of the CPU oracle's trajectory."""
+    _need_gpu()
+    for name, args, xs in (("espcn", (3, 64, 4), (4, 3, 20, 20)), ("vdsr", (3, 64, 3), (2, 3, 16, 16))):
+        ref = R.build(name, args, seed=0)
+        ours = M.MODELS[name](*args)
+        ours.load_state_dict(ref.state_dict())
+        ours.to(DEV)
+        lr = 1e-5 if name == "espcn" else 1e-2  # Adam's g/sqrt(v) turns rounding of ~0 gradients into +-lr steps
+        oref = R.make_optimizer(name, ref.parameters(), lr=lr)
+        oours = R.make_optimizer(name, ours.parameters(), lr=lr)
+        gen = torch.Generator().manual_seed(3)
+        for _ in range(3):
+            x = torch.rand(xs, generator=gen)
+            t = torch.rand(R.output_shape(name, args, xs), generator=gen)
+            l0 = R.train_step(name, ref, oref, x, t)
+            l1 = R.train_step(name, ours, oours, x.to(DEV), t.to(DEV))
+            assert abs(l0.item() - l1.item()) < 1e-3 * abs(l0.item())
+        for (k, a), (_, b) in zip(ref.state_dict().items(), ours.state_dict().items()):
+            assert rel_l2(b, a) < 1e-3, (name, k)
