@@ -205,6 +205,7 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
+  if (p->N == 0) return SRB_OK;  // empty batch: nothing to compute
   SRB_REQUIRE(x && x->data && w && y && y->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
@@ -224,6 +225,7 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
+  if (p->N == 0) return SRB_OK;
   SRB_REQUIRE(dy && ref && dz && dy->data && ref->data && dz->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(p->act != SRB_ACT_NONE, SRB_EINVAL, "act_bwd with act none");
   SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
@@ -247,6 +249,7 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
+  if (p->N == 0) return SRB_OK;
   SRB_REQUIRE(dz && dz->data && w && dx && dx->data, SRB_EINVAL, "null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   T4 tdz = to_t4(dz), tdx = to_t4(dx);
@@ -272,8 +275,17 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
-  SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->N == 0) {  // empty batch: the gradient is exactly zero
+    SRB_REQUIRE(dw, SRB_EINVAL, "null tensor");
+    if (!accumulate) {
+      size_t wn = (size_t)p->Cin * p->Cout * p->ps * p->ps * p->kh * p->kw;
+      SRB_CHECK_CUDA(cudaMemsetAsync(dw, 0, wn * sizeof(float), st));
+      if (db) SRB_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)p->Cout * p->ps * p->ps * sizeof(float), st));
+    }
+    return SRB_OK;
+  }
+  SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
   T4 tx = to_t4(x), tdz = to_t4(dz);
   if (!p->transposed) {
     if (p->math != SRB_MATH_FP32 && tc_wgrad_supported(g, tdz, tx))
