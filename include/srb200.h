@@ -129,6 +129,14 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
 int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_tensor4 *dz, float *dw, float *db,
                    float scale, int accumulate, void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * pixel_unshuffle into channels_last (the inverse of the fused PixelShuffle store, ATen pixel_unshuffle):
+ *   out[n, c*r*r + i*r + j, h, w] = dz[n, c, h*r+i, w*r+j],   out must be NHWC (sc == 1), values RN-rounded
+ * to tf32.  Used by the backward of PixelShuffle layers so that their dgrad/wgrad can run on the tensor
+ * path with p->ps = 1, Cout = Cout*r*r.  dz is (N,Cout,Ho*ps,Wo*ps); out is (N,Cout*ps*ps,Ho,Wo).
+ */
+int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const srb_tensor4 *out, void *stream);
+
 /* Stand-alone PReLU (the raw nn.PReLU() of fsrcnn.py:26): y = x > 0 ? x : alpha*x over n contiguous floats. */
 int srb_prelu_fwd(const float *x, const float *alpha, float *y, int64_t n, void *stream);
 int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx, float *dalpha, int64_t n,

@@ -55,6 +55,51 @@ __global__ void k_act_bwd(T4 dy, T4 ref, T4 dz, int N, int C, int H, int W, int 
   }
 }
 
+// out[n, k, h, w] (NHWC) = dz[n, c, h*r+i, w*r+j] with k = c*r*r + i*r + j, rounded to tf32
+__global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int r) {
+  const long long total = (long long)N * H * W * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long t = i / K;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    float v = __ldg(dz.p + ps_offset(dz, r, n, k, h, w));
+    out.p[n * out.sn + (long long)h * out.sh + (long long)w * out.sw + k] = round_tf32(v);
+  }
+}
+
+// Same-layout dense tensors: flat float4 walk (the common case: dy, ref, dz all NHWC- or all NCHW-contiguous)
+__global__ void k_act_bwd_flat(const float4 *__restrict__ dy, const float4 *__restrict__ ref, float4 *dz, long long n4,
+                               int act, float slope_in, const float *__restrict__ alpha, float *dalpha, int rnd) {
+  const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : (act == SRB_ACT_RELU ? 0.f : slope_in);
+  float da = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g = __ldg(dy + i), r = __ldg(ref + i);
+    float4 o;
+    o.x = r.x > 0.f ? g.x : g.x * slope; o.y = r.y > 0.f ? g.y : g.y * slope;
+    o.z = r.z > 0.f ? g.z : g.z * slope; o.w = r.w > 0.f ? g.w : g.w * slope;
+    if (act == SRB_ACT_PRELU) {
+      da += (r.x > 0.f ? 0.f : g.x * r.x) + (r.y > 0.f ? 0.f : g.y * r.y) + (r.z > 0.f ? 0.f : g.z * r.z) +
+            (r.w > 0.f ? 0.f : g.w * r.w);
+    }
+    if (rnd) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    dz[i] = o;
+  }
+  if (act == SRB_ACT_PRELU && dalpha) {
+    for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    __shared__ float red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      da = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+      if (threadIdx.x == 0) atomicAdd(dalpha, da);
+    }
+  }
+}
+
 __global__ void k_prelu_fwd(const float *__restrict__ x, const float *__restrict__ alpha, float *y, long long n) {
   const float a = __ldg(alpha);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -235,6 +280,24 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
   T4 tdz = to_t4(dz);
   long long total = (long long)p->N * C * H * W;
   if (total == 0) return SRB_OK;
+  {
+    T4 a = to_t4(dy), b = to_t4(ref);
+    auto dense = [&](const T4 &t) {
+      bool nchw = t.sw == 1 && t.sh == W && t.sc == (long long)H * W && t.sn == (long long)C * H * W;
+      bool nhwc = t.sc == 1 && t.sw == C && t.sh == (long long)W * C && t.sn == (long long)H * W * C;
+      return nchw ? 1 : (nhwc ? 2 : 0);
+    };
+    int la = dense(a), lb = dense(b), lc = dense(tdz);
+    if (la && la == lb && la == lc && (total & 3) == 0 &&
+        ((((uintptr_t)a.p) | ((uintptr_t)b.p) | ((uintptr_t)tdz.p)) & 15) == 0) {
+      k_act_bwd_flat<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
+          (const float4 *)a.p, (const float4 *)b.p, (float4 *)tdz.p, total / 4, p->act, p->slope, alpha, dalpha,
+          want_round(p, tdz, C));
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+      return SRB_OK;
+    }
+  }
   int cl = (tdz.sc == 1) ? 1 : 0;
   k_act_bwd<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dy), to_t4(ref), tdz, p->N, C, H, W, p->act,
                                                                  p->slope, alpha, dalpha, cl,
@@ -296,6 +359,22 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   rc = simt_conv_wgrad(g, tx, tdz, dw, nullptr, scale, accumulate, ws, ws_bytes, st);
   if (rc) return rc;
   if (db) return channel_sum(tdz, g.N, g.Ci, g.Hi, g.Wi, db, scale, accumulate, st);
+  return SRB_OK;
+}
+
+int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const srb_tensor4 *out, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(!p->transposed && p->ps > 1, SRB_EINVAL, "pixel_unshuffle needs a PixelShuffle conv");
+  if (p->N == 0) return SRB_OK;
+  SRB_REQUIRE(dz && dz->data && out && out->data, SRB_EINVAL, "null tensor");
+  SRB_REQUIRE(out->sc == 1, SRB_EINVAL, "pixel_unshuffle writes channels_last");
+  long long total = (long long)g.N * g.Ho * g.Wo * g.Co;
+  k_pixel_unshuffle<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, g.Co, g.Ho, g.Wo,
+                                                                         g.ps);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
 }
 

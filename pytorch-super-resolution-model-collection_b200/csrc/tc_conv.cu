@@ -11,8 +11,7 @@
 // * tcgen05.mma kind::tf32, M=128 x N<=256 x K=8, fp32 accumulators in TMEM (MT x N columns).
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue
 //   (tcgen05.ld -> bias -> ReLU/PReLU/LeakyReLU -> +residual -> store at the pixel-shuffled address).
-#include "srb_common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace srb {
 
@@ -22,39 +21,6 @@ constexpr int kThreads = 192;
 constexpr int kChunkC = 32;             // channels per K-block: 32 fp32 = 128 B = one swizzle row
 constexpr int kABytes = 128 * 128;      // one A stage tile: 128 pixels x 128 B
 constexpr int kMaxSmem = 227 * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
@@ -111,7 +77,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   const int n0 = blockIdx.y * a.NT;
   int mt_valid = a.num_tiles - tile0;
   if (mt_valid > a.MT) mt_valid = a.MT;
-  const int chunks = a.Cin / kChunkC;
+  const int chunks = (a.Cin + kChunkC - 1) / kChunkC;  // a ragged last chunk is zero-filled by TMA (A) / packing (B)
   const int kblocks = a.kh * a.kw * chunks;
 
   if (warp == 0 && lane == 0) {
@@ -133,14 +99,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    {
       int tn[4], toh[4], tow[4];
-      for (int t = 0; t < mt_valid; ++t) {
-        int tile = tile0 + t;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        int tile = tile0 + (t < mt_valid ? t : 0);
         int tw_i = tile % a.tiles_w;
         int q = tile / a.tiles_w;
         int th_i = q % a.tiles_h;
@@ -157,35 +124,46 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t *sa = smem + (size_t)st * stage_bytes;
-          mbar_expect_tx(&full_bar[st], tx_bytes);
-          for (int t = 0; t < mt_valid; ++t)
-            tma_load_4d(&mapA, &full_bar[st], sa + t * kABytes, c * kChunkC, tow[t] + s, toh[t] + r, tn[t]);
-          tma_load_3d(&mapB, &full_bar[st], sa + a.MT * kABytes, c * kChunkC, n0, tap);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[st], tx_bytes);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (t < mt_valid)
+                tma_load_4d(&mapA, &full_bar[st], sa + t * kABytes, c * kChunkC, tow[t] + s, toh[t] + r, tn[t]);
+            tma_load_3d(&mapB, &full_bar[st], sa + a.MT * kABytes, c * kChunkC, n0, tap);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t d_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
       for (int kb = 0; kb < kblocks; ++kb) {
         const int st = kb % a.stages;
         const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-        const uint64_t bdesc0 = make_kmajor_sw128_desc(sa + a.MT * kABytes);
-        for (int t = 0; t < mt_valid; ++t) {
-          const uint64_t adesc0 = make_kmajor_sw128_desc(sa + t * kABytes);
+        const uint32_t a_lo0 = ((sa >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t b_lo0 = (((sa + a.MT * kABytes) >> 4) & 0x3FFF) | (1u << 16);
+        if (elect_one()) {
+          uint32_t a_lo = a_lo0, tcol = tmem_base;
+          for (int t = 0; t < mt_valid; ++t, a_lo += (uint32_t)(kABytes >> 4), tcol += (uint32_t)a.NT) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) inside the 128 B swizzle row
-            umma_tf32(tmem_base + (uint32_t)(t * a.NT), adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2), idesc,
-                      (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) inside the 128 B swizzle row
+              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 2 * k),
+                        ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
+        __syncwarp();
       }
-      umma_commit(accum_bar);  // all accumulators complete
+      if (elect_one()) umma_commit(accum_bar);  // all accumulators complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: warps 2..5 -> TMEM lanes 32*(warp%4) .. +31 =====================
@@ -216,35 +194,64 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         if (!pix_ok) continue;
         const int cbase = n0 + j0;
         if (cbase >= a.Co) continue;
-        const bool vec = (a.ps == 1) && (a.out.sc == 1) && (cbase + 16 <= a.Co) && ((a.Co & 3) == 0) &&
-                         (!a.epi.residual.p || a.epi.residual.sc == 1) && (!a.epi.preact.p || a.epi.preact.sc == 1);
-        if (vec) {
-          float *op = a.out.p + n * a.out.sn + (long long)oy * a.out.sh + (long long)ox * a.out.sw + cbase;
-          const float *rp = a.epi.residual.p ? a.epi.residual.p + n * a.epi.residual.sn +
-                                                   (long long)oy * a.epi.residual.sh + (long long)ox * a.epi.residual.sw + cbase
-                                             : nullptr;
-          float *pp = a.epi.preact.p ? a.epi.preact.p + n * a.epi.preact.sn + (long long)oy * a.epi.preact.sh +
-                                           (long long)ox * a.epi.preact.sw + cbase
-                                     : nullptr;
+        // Store modes (16 accumulator columns = conv channels cbase .. cbase+15 of this pixel):
+        //   0: NHWC, no shuffle           -> 4 x float4 at channel cbase + 4q
+        //   1: PixelShuffle(4) into NCHW  -> one output channel c = cbase/16; quad q = sub-row i: 4 contiguous j
+        //   2: PixelShuffle(2) into NHWC  -> 4 output channels cbase/4 ..+3; quad q = sub-pixel (i,j)
+        //   3: anything else              -> scalar stores through ps_offset()
+        const bool full = (cbase + 16 <= a.Co);
+        const bool lay0 = a.out.sc == 1 && (!a.epi.residual.p || a.epi.residual.sc == 1) &&
+                          (!a.epi.preact.p || a.epi.preact.sc == 1);
+        const bool lay1 = a.out.sw == 1 && (!a.epi.residual.p || a.epi.residual.sw == 1) &&
+                          (!a.epi.preact.p || a.epi.preact.sw == 1);
+        int mode = 3;
+        if (full && a.ps == 1 && lay0 && (a.Co & 3) == 0) mode = 0;
+        else if (full && a.ps == 4 && lay1 && (a.out.sh & 3) == 0) mode = 1;
+        else if (full && a.ps == 2 && lay0 && ((a.Co >> 2) & 3) == 0) mode = 2;
+        if (mode != 3) {
+          float z[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 z;
-            z.x = __uint_as_float(v[j + 0]); z.y = __uint_as_float(v[j + 1]);
-            z.z = __uint_as_float(v[j + 2]); z.w = __uint_as_float(v[j + 3]);
-            if (a.epi.bias) {
-              float4 b = __ldg((const float4 *)(a.epi.bias + cbase + j));
-              z.x += b.x; z.y += b.y; z.z += b.z; z.w += b.w;
+            float4 b = a.epi.bias ? __ldg((const float4 *)(a.epi.bias + cbase + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            z[j] = __uint_as_float(v[j]) + b.x; z[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+            z[j + 2] = __uint_as_float(v[j + 2]) + b.z; z[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            long long off_o, off_r = 0, off_p = 0;
+            float4 zq;
+            if (mode == 0) {
+              zq = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+              off_o = n * a.out.sn + (long long)oy * a.out.sh + (long long)ox * a.out.sw + cbase + 4 * q4;
+              if (a.epi.residual.p)
+                off_r = n * a.epi.residual.sn + (long long)oy * a.epi.residual.sh + (long long)ox * a.epi.residual.sw + cbase + 4 * q4;
+              if (a.epi.preact.p)
+                off_p = n * a.epi.preact.sn + (long long)oy * a.epi.preact.sh + (long long)ox * a.epi.preact.sw + cbase + 4 * q4;
+            } else if (mode == 1) {
+              zq = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+              const int c = cbase >> 4;
+              const long long yy = (long long)oy * 4 + q4, xx = (long long)ox * 4;
+              off_o = n * a.out.sn + c * a.out.sc + yy * a.out.sh + xx;
+              if (a.epi.residual.p) off_r = n * a.epi.residual.sn + c * a.epi.residual.sc + yy * a.epi.residual.sh + xx;
+              if (a.epi.preact.p) off_p = n * a.epi.preact.sn + c * a.epi.preact.sc + yy * a.epi.preact.sh + xx;
+            } else {
+              zq = make_float4(z[q4], z[4 + q4], z[8 + q4], z[12 + q4]);
+              const int c = cbase >> 2;
+              const long long yy = (long long)oy * 2 + (q4 >> 1), xx = (long long)ox * 2 + (q4 & 1);
+              off_o = n * a.out.sn + yy * a.out.sh + xx * a.out.sw + c;
+              if (a.epi.residual.p) off_r = n * a.epi.residual.sn + yy * a.epi.residual.sh + xx * a.epi.residual.sw + c;
+              if (a.epi.preact.p) off_p = n * a.epi.preact.sn + yy * a.epi.preact.sh + xx * a.epi.preact.sw + c;
             }
-            if (pp) *(float4 *)(pp + j) = z;
+            if (a.epi.preact.p) *(float4 *)(a.epi.preact.p + off_p) = zq;
             float4 y;
-            y.x = apply_act(z.x, a.epi.act, slope); y.y = apply_act(z.y, a.epi.act, slope);
-            y.z = apply_act(z.z, a.epi.act, slope); y.w = apply_act(z.w, a.epi.act, slope);
-            if (rp) {
-              float4 rr = __ldg((const float4 *)(rp + j));
+            y.x = apply_act(zq.x, a.epi.act, slope); y.y = apply_act(zq.y, a.epi.act, slope);
+            y.z = apply_act(zq.z, a.epi.act, slope); y.w = apply_act(zq.w, a.epi.act, slope);
+            if (a.epi.residual.p) {
+              const float4 rr = __ldg((const float4 *)(a.epi.residual.p + off_r));
               y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
             }
             if (a.epi.round_tf32) { y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w); }
-            *(float4 *)(op + j) = y;
+            *(float4 *)(a.out.p + off_o) = y;
           }
         } else {
 #pragma unroll
@@ -276,18 +283,18 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // Repack weights (Conv2d OIHW, tf32 RN) into the GEMM B operand [tap][Co_pad][Cin]:
 //   flip == 0 (fprop):  B[r*kw+s][co][ci] = w[co][ci][r][s]                       (N = Co, K = Ci)
 //   flip == 1 (dgrad):  B[(kh-1-r)*kw + (kw-1-s)][ci][co] = w[co][ci][r][s]        (N = Ci, K = Co)
-// Rows n >= N_real are zero.
+// Rows n >= N_real and columns k >= K_real (K is padded to a multiple of 32) are zero.
 __global__ void k_pack_weights(const float *__restrict__ w, float *__restrict__ out, int Co, int Ci, int kh, int kw,
-                               int Npad, int flip) {
+                               int Npad, int Kpad, int flip) {
   const int N = flip ? Ci : Co, K = flip ? Co : Ci;
-  const long long total = (long long)kh * kw * Npad * K;
+  const long long total = (long long)kh * kw * Npad * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(i % K);
-    long long q = i / K;
+    int k = (int)(i % Kpad);
+    long long q = i / Kpad;
     int n = (int)(q % Npad);
     int tap = (int)(q / Npad);
     float v = 0.f;
-    if (n < N) {
+    if (n < N && k < K) {
       int r = tap / kw, s = tap - r * kw;
       if (flip) { r = kh - 1 - r; s = kw - 1 - s; }
       int co = flip ? k : n, ci = flip ? n : k;
@@ -295,25 +302,6 @@ __global__ void k_pack_weights(const float *__restrict__ w, float *__restrict__ 
     }
     out[i] = v;
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int encode_tiled(CUtensorMap *map, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                 const cuuint32_t *box) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides_bytes,
-                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    const char *msg = nullptr;
-    cuGetErrorString(r, &msg);
-    set_error("cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
-    return SRB_ECUDA;
-  }
-  return SRB_OK;
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -368,7 +356,7 @@ bool make_plan(const Geom &g, Plan *p) {
 
 bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/) {
   if (g.st != 1 || g.N <= 0) return false;
-  if (g.Ci % kChunkC != 0) return false;
+  if (g.Ci % 4 != 0 || g.Ci < 16) return false;                        // TMA: 16-byte pixel stride; ragged K chunk is zero-filled
   if (in.sc != 1) return false;                                       // channels_last activations
   if ((in.sw % 4) || (in.sh % 4) || (in.sn % 4)) return false;       // TMA strides: multiples of 16 B
   if (((uintptr_t)in.p) & 15) return false;
@@ -379,17 +367,17 @@ bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*
 }
 
 size_t tc_conv_ws_bytes(const Geom &g) {
-  int a = round_up(g.Co, 16), b = round_up(g.Ci, 16);
-  int npad = a > b ? a : b;
-  int k = g.Co > g.Ci ? g.Co : g.Ci;
-  return (size_t)g.kh * g.kw * npad * k * sizeof(float) + 256;
+  int a = round_up(g.Co, 32), b = round_up(g.Ci, 32);
+  int m = a > b ? a : b;
+  return (size_t)g.kh * g.kw * m * m * sizeof(float) + 512;
 }
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
                    void *ws, size_t ws_bytes, cudaStream_t st) {
   Plan p;
   SRB_REQUIRE(make_plan(g, &p), SRB_EUNSUPPORTED, "tc_conv: no tile plan");
-  size_t need = (size_t)g.kh * g.kw * p.Npad * g.Ci * sizeof(float);
+  const int Kpad = round_up(g.Ci, kChunkC);
+  size_t need = (size_t)g.kh * g.kw * p.Npad * Kpad * sizeof(float);
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_conv workspace: need %zu bytes", need + 256);
   float *wp = (float *)wsp;
@@ -398,13 +386,13 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   //    g here is already the *gather* geometry, so the stored filter is w[co_orig][ci_orig] with
   //    co_orig = g.Ci (K side) and ci_orig = g.Co (N side) when flip_transpose is set.
   {
-    long long total = (long long)g.kh * g.kw * p.Npad * g.Ci;
+    long long total = (long long)g.kh * g.kw * p.Npad * Kpad;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (!flip_transpose)
-      k_pack_weights<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, p.Npad, 0);
+      k_pack_weights<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, p.Npad, Kpad, 0);
     else
-      k_pack_weights<<<blocks, 256, 0, st>>>(w, wp, /*Co_orig=*/g.Ci, /*Ci_orig=*/g.Co, g.kh, g.kw, p.Npad, 1);
+      k_pack_weights<<<blocks, 256, 0, st>>>(w, wp, /*Co_orig=*/g.Ci, /*Ci_orig=*/g.Co, g.kh, g.kw, p.Npad, Kpad, 1);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
@@ -419,8 +407,8 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)g.Ci, (cuuint64_t)p.Npad, (cuuint64_t)(g.kh * g.kw)};
-    cuuint64_t strides[2] = {(cuuint64_t)g.Ci * 4, (cuuint64_t)g.Ci * p.Npad * 4};
+    cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)p.Npad, (cuuint64_t)(g.kh * g.kw)};
+    cuuint64_t strides[2] = {(cuuint64_t)Kpad * 4, (cuuint64_t)Kpad * p.Npad * 4};
     cuuint32_t box[3] = {(cuuint32_t)kChunkC, (cuuint32_t)p.NT, 1};
     int rc = encode_tiled(&mapB, wp, 3, dims, strides, box);
     if (rc) return rc;
@@ -444,14 +432,6 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
-}
-
-// ---- wgrad on tensor cores: not built yet (falls to the fp32 CUDA-core wgrad) ----
-bool tc_wgrad_supported(const Geom &, const T4 &, const T4 &) { return false; }
-size_t tc_wgrad_ws_bytes(const Geom &) { return 0; }
-int tc_conv_wgrad(const Geom &, const T4 &, const T4 &, float *, float *, float, int, void *, size_t, cudaStream_t) {
-  set_error("tensor-core wgrad not built");
-  return SRB_EUNSUPPORTED;
 }
 
 }  // namespace srb

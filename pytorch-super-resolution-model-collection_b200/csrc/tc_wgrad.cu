@@ -1,0 +1,429 @@
+// tcgen05 weight-gradient kernel for sm_100a (stride-1 Conv2d, NHWC fp32 activations holding tf32 values).
+//
+//   dW[co][ci][r][s] = sum_{n,oy,ox} dz[n,oy,ox,co] * x[n,oy+r-pad,ox+s-pad,ci]
+//
+// as a GEMM whose K dimension is the PIXEL index:  D[(s,ci), co] += sum_p X_{r,s}[p, ci] * dZ[p, co].
+// Both operands are "MN-major" (channels contiguous, K = pixel rows of 128 B), which for tf32 needs the
+// 128B swizzle with 32B atoms (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type 1).
+//
+// * A band of TH output rows x the FULL padded width BW = Wo+kw-1 is loaded ONCE per 32-channel block as a
+//   halo tile (TMA zero-fills the padding and everything outside the image); the kh*kw filter taps are not
+//   separate loads but SHIFTED VIEWS of that tile: tap (r,s) starts (r*BW+s) pixel slots = (r*BW+s)*128 B
+//   later.  One tcgen05.mma covers 4 consecutive s-taps at once (the 4 M-blocks of 32 channels are 128 B
+//   apart: leading-byte-offset = 128 B), so a 3x3 filter needs 3 accumulators per 32-channel block.
+// * dz is loaded with the same flattened pitch BW; its columns >= Wo are out of bounds => zero, which is
+//   what keeps the wrapped-around x slots of the flattened view from contributing.
+// * Each CTA walks a contiguous range of bands accumulating in TMEM (fp32), then dumps its partial dW to
+//   a workspace; k_wgrad_finish sums the partials in a fixed order (deterministic), scales, and writes OIHW.
+#include "tc_common.cuh"
+
+namespace srb {
+
+namespace {
+
+constexpr int kWgThreads = 192;
+
+struct WgArgs {
+  int N, Ho, Wo, Ci, Co;
+  int kh, kw, pad;
+  int TH, BW, BH;       // band rows; flattened pitch; x box height = TH + RG - 1
+  int bands_per_img, num_bands, bands_per_cta;
+  int CIB, RG, SG, NT;  // ci-blocks per CTA; filter rows per CTA; ceil(kw/4); co tile (multiple of 32)
+  int n_cig, n_rg, n_cot;
+  int stages, tmem_cols;
+  int x_slots, dz_slots;  // allocated 128-B pixel slots per 32-channel block (zero tail included)
+  int ksteps;             // ceil(TH*BW / 8)
+  float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
+};
+
+// MN-major operand, 128B swizzle with 32B atoms: 4 K-rows x 128 B per atom (SBO = 512 B between atoms along K),
+// LBO = byte distance between consecutive 32-channel blocks along M/N.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ, WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nb = a.NT / 32;
+  const int x_bytes = a.x_slots * 128, dz_bytes = a.dz_slots * 128;
+  const int stage_bytes = a.CIB * x_bytes + nb * dz_bytes;
+  uint64_t *full_bar = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
+  uint64_t *empty_bar = full_bar + a.stages;
+  uint64_t *accum_bar = empty_bar + a.stages;
+  uint32_t *tmem_slot = (uint32_t *)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // grid.y -> (ci group, filter-row group, co tile)
+  int by = blockIdx.y;
+  const int cot = by % a.n_cot; by /= a.n_cot;
+  const int rgi = by % a.n_rg;
+  const int cig = by / a.n_rg;
+  const int r0 = rgi * a.RG;
+  const int rg_valid = min(a.RG, a.kh - r0);
+  const int band0 = blockIdx.x * a.bands_per_cta;
+  const int band1 = min(band0 + a.bands_per_cta, a.num_bands);
+  const int ACC = a.RG * a.SG * a.CIB;
+
+  // zero all stage buffers once: the tails past each TMA box must read as 0.0f forever
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 *p = (uint4 *)smem;
+    const int n16 = a.stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += kWgThreads) p[i] = z;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZ) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer: one halo band per stage =====================
+    {
+      const uint32_t tx_bytes = (uint32_t)(a.CIB * a.BH * a.BW * 128 + nb * a.TH * a.BW * 128);
+      int it = 0;
+      for (int band = band0; band < band1; ++band, ++it) {
+        const int st = it % a.stages;
+        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        const int n = band / a.bands_per_img;
+        const int oh0 = (band - n * a.bands_per_img) * a.TH;
+        uint8_t *sx = smem + (size_t)st * stage_bytes;
+        uint8_t *sz = sx + a.CIB * x_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[st], tx_bytes);
+          for (int cb = 0; cb < a.CIB; ++cb)
+            tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, -a.pad, oh0 - a.pad + r0, n);
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * 32, 0, oh0, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    {
+      // D=f32, A=B=tf32, both MN-major (bits 15,16), N>>3 at bit 17, M=128>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
+      // descriptor high words are loop invariant; low word = (addr >> 4) | LBO << 16
+      const uint32_t a_hi = (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
+      const uint32_t a_lbo = (128u >> 4) << 16;
+      const uint32_t b_lbo = (((uint32_t)dz_bytes >> 4) & 0x3FFF) << 16;
+      const uint32_t x_step = (uint32_t)x_bytes >> 4, row_step = (uint32_t)a.BW * 8u;  // 128 B per slot >> 4
+      int it = 0;
+      for (int band = band0; band < band1; ++band, ++it) {
+        const int st = it % a.stages;
+        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sx = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t x_lo = ((sx >> 4) & 0x3FFF) | a_lbo;
+        const uint32_t z_lo = (((sx + a.CIB * x_bytes) >> 4) & 0x3FFF) | b_lbo;
+        if (elect_one()) {
+          for (int ks = 0; ks < a.ksteps; ++ks) {
+            const uint64_t bdesc = ((uint64_t)a_hi << 32) | (uint64_t)(z_lo + ks * 64);
+            const uint32_t accflag = (it | ks) ? 1u : 0u;
+            uint32_t lo_r = x_lo + ks * 64;
+            uint32_t tcol = tmem_base;
+            for (int rl = 0; rl < rg_valid; ++rl, lo_r += row_step) {
+              uint32_t lo_s = lo_r;
+              for (int sg = 0; sg < a.SG; ++sg, lo_s += 32u) {
+                uint32_t lo = lo_s;
+                for (int cb = 0; cb < a.CIB; ++cb, lo += x_step, tcol += (uint32_t)a.NT)
+                  umma_tf32_ss(tcol, ((uint64_t)a_hi << 32) | (uint64_t)lo, bdesc, idesc, accflag);
+              }
+            }
+          }
+          umma_commit_arrive(&empty_bar[st]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit_arrive(accum_bar);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: dump the partial dW tile =====================
+    const int lane_grp = warp & 3;
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = lane_grp * 32 + lane;
+    float *dst = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * ACC * 128 * a.NT;
+    for (int acc = 0; acc < ACC; ++acc) {
+      const int rl = acc / (a.SG * a.CIB);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.NT);
+      float *row = dst + ((size_t)acc * 128 + m) * a.NT;
+      for (int j0 = 0; j0 < a.NT; j0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)j0, v);
+        if (rl >= rg_valid || band0 >= band1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *(uint4 *)(row + j0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+// dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order)
+__global__ void k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float scale, int accumulate) {
+  const long long total = (long long)a.Co * a.Ci * a.kh * a.kw;
+  const int ACC = a.RG * a.SG * a.CIB;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int s = (int)(i % a.kw);
+    long long q = i / a.kw;
+    int r = (int)(q % a.kh); q /= a.kh;
+    int ci = (int)(q % a.Ci);
+    int co = (int)(q / a.Ci);
+    int cot = co / a.NT, n = co - cot * a.NT;
+    int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
+    int rgi = r / a.RG, rl = r - rgi * a.RG;
+    int sg = s >> 2, sl = s & 3;
+    int by = (cig * a.n_rg + rgi) * a.n_cot + cot;
+    int acc = (rl * a.SG + sg) * a.CIB + cb;
+    int m = sl * 32 + (ci & 31);
+    const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
+    const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
+    float sum = 0.f;
+    for (int z = 0; z < splits; ++z) sum += p[(size_t)z * split_stride];
+    sum *= scale;
+    dw[i] = accumulate ? dw[i] + sum : sum;
+  }
+}
+
+// db[c] partial sums over pixel chunks of a dense-in-C NHWC tensor: part[block][C].
+// Each block takes a contiguous range of pixels; thread t owns channel group (t % (C/4)) as a float4 and
+// strides over pixels by blockDim/(C/4); a shared-memory tree folds the pixel lanes.  C % 4 == 0.
+__global__ void __launch_bounds__(256)
+k_colsum_nhwc_partial(T4 t, int N, int H, int W, int C, float *part, long long pix_per_block) {
+  __shared__ float4 red[256];
+  const long long P = (long long)N * H * W;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > P) p1 = P;
+  const int c4n = C >> 2;                 // float4 groups per pixel
+  const int lanes = 256 / c4n;            // pixel lanes per block (>= 1 for C <= 1024)
+  const int cg = threadIdx.x % c4n, pl = threadIdx.x / c4n;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < lanes) {
+    long long p = p0 + pl;
+    // incremental (n,y,x) instead of div/mod per pixel
+    int x = (int)(p % W);
+    long long q = p / W;
+    int y = (int)(q % H);
+    int n = (int)(q / H);
+    for (; p < p1; p += lanes) {
+      const float4 v = __ldg((const float4 *)(t.p + n * t.sn + (long long)y * t.sh + (long long)x * t.sw) + cg);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      x += lanes;
+      while (x >= W) { x -= W; if (++y == H) { y = 0; ++n; } }
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    float4 acc = red[threadIdx.x];
+    for (int l = 1; l < lanes; ++l) {
+      const float4 v = red[l * c4n + threadIdx.x];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *(float4 *)(part + (size_t)blockIdx.x * C + 4 * threadIdx.x) = acc;
+  }
+}
+__global__ void k_colsum_finish(const float *part, int blocks, int C, float *db, float scale, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[(size_t)b * C + c];
+  s *= scale;
+  db[c] = accumulate ? db[c] + s : s;
+}
+
+struct WgPlan {
+  WgArgs a;
+  size_t smem;
+  dim3 grid;
+  int db_blocks;
+  size_t partial_floats, db_floats;
+};
+
+bool make_wg_plan(const Geom &g, WgPlan *pl) {
+  WgArgs &a = pl->a;
+  a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
+  a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
+  a.BW = g.Wo + g.kw - 1;
+  if (a.BW > 256) return false;
+  a.SG = (g.kw + 3) / 4;
+  const int cblocks = g.Ci / 32;
+  const int co_pad = round_up_i(g.Co, 32);
+  int best_score = -1;
+  WgArgs best = a;
+  size_t best_smem = 0;
+  // enumerate (NT, CIB, RG, TH); prefer: fits, >= 2 stages, most MMA work per loaded byte, enough CTAs
+  for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
+    if (co_pad % NT) continue;
+    for (int CIB = cblocks; CIB >= 1; --CIB) {
+      if (cblocks % CIB) continue;
+      for (int RG = g.kh; RG >= 1; --RG) {
+        int acc = RG * a.SG * CIB;
+        if (acc * NT > 512) continue;
+        for (int TH = 8; TH >= 1; --TH) {
+          if (TH > g.Ho && TH > 1) continue;
+          int BH = TH + RG - 1;
+          if (BH > 256) continue;
+          int x_slots = round_up_i(BH * a.BW + 4 * a.SG + 8, 8);
+          int dz_slots = round_up_i(TH * a.BW, 8);
+          size_t stage = (size_t)CIB * x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
+          int stages = (int)((kMaxSmemBytes - 4096) / stage);
+          if (stages < 2) continue;
+          if (stages > 4) stages = 4;
+          // score: useful K rows per stage (amortises halo + barrier cost) x N width x accumulators
+          int n_rg = (g.kh + RG - 1) / RG;
+          int gy = (cblocks / CIB) * n_rg * (co_pad / NT);
+          int score = TH * 1000 / BH * 8 + (acc * NT >= 128 ? 400 : 0) + (NT >= 64 ? 100 : 0) - gy * 2 + TH;
+          if (score > best_score) {
+            best_score = score;
+            best = a;
+            best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
+            best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
+            best.n_cig = cblocks / CIB; best.n_rg = n_rg; best.n_cot = co_pad / NT;
+            best_smem = (size_t)stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
+          }
+        }
+      }
+    }
+  }
+  if (best_score < 0) return false;
+  a = best;
+  a.bands_per_img = (g.Ho + a.TH - 1) / a.TH;
+  a.num_bands = g.N * a.bands_per_img;
+  a.ksteps = (a.TH * a.BW + 7) / 8;
+  int gy = a.n_cig * a.n_rg * a.n_cot;
+  int target = (148 + gy - 1) / gy;  // one wave of CTAs (1 CTA/SM: big smem)
+  if (target < 1) target = 1;
+  a.bands_per_cta = (a.num_bands + target - 1) / target;
+  int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
+  int cols = a.RG * a.SG * a.CIB * a.NT, tc = 32;
+  while (tc < cols) tc <<= 1;
+  a.tmem_cols = tc;
+  pl->grid = dim3(gx, gy);
+  pl->smem = best_smem;
+  pl->partial_floats = (size_t)gx * gy * a.RG * a.SG * a.CIB * 128 * a.NT;
+  long long P = (long long)g.N * g.Ho * g.Wo;
+  pl->db_blocks = (int)((P + 2047) / 2048);
+  if (pl->db_blocks > 1184) pl->db_blocks = 1184;
+  pl->db_floats = (size_t)pl->db_blocks * g.Co;
+  return true;
+}
+
+}  // namespace
+
+// small = dz (N,Co,Ho,Wo) NHWC, big = x (N,Ci,Hi,Wi) NHWC
+bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
+  if (g.st != 1 || g.ps != 1 || g.N <= 0) return false;
+  if (g.Ci % 32 != 0 || g.Co % 4 != 0 || g.Co > 1024) return false;
+  if (small.sc != 1 || big.sc != 1) return false;
+  if ((big.sw % 4) || (big.sh % 4) || (big.sn % 4) || (small.sw % 4) || (small.sh % 4) || (small.sn % 4)) return false;
+  if ((((uintptr_t)big.p) | ((uintptr_t)small.p)) & 15) return false;
+  if (g.kh > 16 || g.kw > 16) return false;
+  WgPlan pl;
+  return make_wg_plan(g, &pl);
+}
+
+size_t tc_wgrad_ws_bytes(const Geom &g) {
+  WgPlan pl;
+  if (g.st != 1 || g.ps != 1 || g.Ci % 32 != 0 || !make_wg_plan(g, &pl)) return 0;
+  return (pl.partial_floats + pl.db_floats) * sizeof(float) + 512;
+}
+
+int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
+  WgPlan pl;
+  SRB_REQUIRE(make_wg_plan(g, &pl), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
+  size_t need = (pl.partial_floats + pl.db_floats) * sizeof(float);
+  uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+  SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_wgrad workspace: need %zu bytes, have %zu",
+              need, ws_bytes);
+  WgArgs &a = pl.a;
+  a.partial = (float *)wsp;
+  float *db_part = a.partial + pl.partial_floats;
+
+  CUtensorMap mapX, mapZ;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)big.sw * 4, (cuuint64_t)big.sh * 4, (cuuint64_t)big.sn * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    int rc = encode_tiled(&mapX, big.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)small.sw * 4, (cuuint64_t)small.sh * 4, (cuuint64_t)small.sn * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.TH, 1};
+    int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+    attr_set = true;
+  }
+  k_tc_wgrad<<<pl.grid, kWgThreads, pl.smem, st>>>(mapX, mapZ, a);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  {
+    long long total = (long long)g.Co * g.Ci * g.kh * g.kw;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_wgrad_finish<<<blocks, 256, 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, scale, accumulate);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (db_small) {
+    long long P = (long long)g.N * g.Ho * g.Wo;
+    long long ppb = (P + pl.db_blocks - 1) / pl.db_blocks;
+    k_colsum_nhwc_partial<<<pl.db_blocks, 256, 0, st>>>(small, g.N, g.Ho, g.Wo, g.Co, db_part, ppb);
+    count_launch();
+    k_colsum_finish<<<(g.Co + 127) / 128, 128, 0, st>>>(db_part, pl.db_blocks, g.Co, db_small, scale, accumulate);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SRB_OK;
+}
+
+}  // namespace srb

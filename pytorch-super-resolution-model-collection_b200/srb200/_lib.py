@@ -43,6 +43,7 @@ SYMBOLS = {
     "srb_conv_dgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _vp, ctypes.c_size_t, _vp]),
     "srb_conv_wgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _vp, ctypes.c_float,
                                       ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
+    "srb_pixel_unshuffle": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp]),
     "srb_prelu_fwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_prelu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_round_tf32": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),

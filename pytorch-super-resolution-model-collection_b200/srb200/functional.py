@@ -142,6 +142,17 @@ class _FusedConv(torch.autograd.Function):
                                   ctypes.byref(tdz), _ptr(dalpha), st))
         else:
             dz = dy
+        if p.ps > 1 and p.math != _lib.MATH_FP32 and x.shape[1] % 32 == 0 and _is_cl(x):
+            # PixelShuffle layer on the tensor path: undo the shuffle once (NHWC, tf32) and run dgrad/wgrad as a
+            # plain conv with Cout*r*r output channels
+            r = p.ps
+            dzu = torch.empty((p.N, p.Cout * r * r, dz.shape[2] // r, dz.shape[3] // r), dtype=torch.float32,
+                              device=dev, memory_format=torch.channels_last)
+            tdz0, tdzu = t4(dz), t4(dzu)
+            check(lib.srb_pixel_unshuffle(ctypes.byref(p), ctypes.byref(tdz0), ctypes.byref(tdzu), st))
+            p = ConvParams(p.N, p.Cin, p.H, p.W, p.Cout * r * r, p.kh, p.kw, p.stride, p.pad, 0, 0, 1, p.act,
+                           p.slope, p.math)
+            dz = dzu
         tdz, tx = t4(dz), t4(x)
         dw = db = dx = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
