@@ -151,12 +151,18 @@ k_tc_conv(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const uint32_t a_lo0 = ((sa >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t b_lo0 = (((sa + a.MT * kABytes) >> 4) & 0x3FFF) | (1u << 16);
         if (elect_one()) {
-          uint32_t a_lo = a_lo0, tcol = tmem_base;
-          for (int t = 0; t < mt_valid; ++t, a_lo += (uint32_t)(kABytes >> 4), tcol += (uint32_t)a.NT) {
+          const uint32_t acc0 = kb ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) inside the 128 B swizzle row
-              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 2 * k),
-                        ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int t = 0; t < 4; ++t) {
+            if (t < mt_valid) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)(t * (kABytes >> 4));
+              const uint32_t tcol = tmem_base + (uint32_t)(t * a.NT);
+              // 4 x (K = 8 tf32 = 32 B) inside the 128 B swizzle row
+              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 0), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 0), idesc, acc0);
+              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 2), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 2), idesc, 1u);
+              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 4), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 4), idesc, 1u);
+              umma_tf32(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(a_lo + 6), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 + 6), idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
         }

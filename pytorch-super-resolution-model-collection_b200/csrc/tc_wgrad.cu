@@ -22,6 +22,7 @@ namespace srb {
 namespace {
 
 constexpr int kWgThreads = 192;
+constexpr int kMaxAcc = 8;  // accumulators (M=128 tiles) per CTA the unrolled issue loop supports
 
 struct WgArgs {
   int N, Ho, Wo, Ci, Co;
@@ -145,19 +146,35 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const uint32_t x_lo = ((sx >> 4) & 0x3FFF) | a_lbo;
         const uint32_t z_lo = (((sx + a.CIB * x_bytes) >> 4) & 0x3FFF) | b_lbo;
         if (elect_one()) {
-          for (int ks = 0; ks < a.ksteps; ++ks) {
-            const uint64_t bdesc = ((uint64_t)a_hi << 32) | (uint64_t)(z_lo + ks * 64);
-            const uint32_t accflag = (it | ks) ? 1u : 0u;
-            uint32_t lo_r = x_lo + ks * 64;
-            uint32_t tcol = tmem_base;
+          // per-accumulator A start (low descriptor word) for this stage; fully unrolled, branch-uniform issue
+          uint32_t lo[kMaxAcc];
+          {
+            int i = 0;
+            uint32_t lo_r = x_lo;
             for (int rl = 0; rl < rg_valid; ++rl, lo_r += row_step) {
               uint32_t lo_s = lo_r;
               for (int sg = 0; sg < a.SG; ++sg, lo_s += 32u) {
-                uint32_t lo = lo_s;
-                for (int cb = 0; cb < a.CIB; ++cb, lo += x_step, tcol += (uint32_t)a.NT)
-                  umma_tf32_ss(tcol, ((uint64_t)a_hi << 32) | (uint64_t)lo, bdesc, idesc, accflag);
+                uint32_t l = lo_s;
+                for (int cb = 0; cb < a.CIB; ++cb, l += x_step, ++i)
+#pragma unroll
+                  for (int j = 0; j < kMaxAcc; ++j)
+                    if (j == i) lo[j] = l;
               }
             }
+#pragma unroll
+            for (int j = 0; j < kMaxAcc; ++j)
+              if (j >= i) lo[j] = x_lo;
+          }
+          const int nacc = rg_valid * a.SG * a.CIB;
+          uint32_t ko = 0;
+          for (int ks = 0; ks < a.ksteps; ++ks, ko += 64u) {
+            const uint64_t bdesc = ((uint64_t)a_hi << 32) | (uint64_t)(z_lo + ko);
+            const uint32_t accflag = (it | ks) ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < kMaxAcc; ++j)
+              if (j < nacc)
+                umma_tf32_ss(tmem_base + (uint32_t)(j * a.NT), ((uint64_t)a_hi << 32) | (uint64_t)(lo[j] + ko), bdesc, idesc,
+                             accflag);
           }
           umma_commit_arrive(&empty_bar[st]);
         }
@@ -291,18 +308,21 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   a.SG = (g.kw + 3) / 4;
   const int cblocks = g.Ci / 32;
   const int co_pad = round_up_i(g.Co, 32);
-  int best_score = -1;
+  double best_score = -1.0;
   WgArgs best = a;
   size_t best_smem = 0;
-  // enumerate (NT, CIB, RG, TH); prefer: fits, >= 2 stages, most MMA work per loaded byte, enough CTAs
+  // Enumerate (NT, CIB, RG, TH) and minimise a per-output-row time model summed over the CTAs of grid.y:
+  //   MMA cycles  = accumulators * cost(NT) * (BW / 8 K-steps),   cost(N) = max(32 + N/4, N/2)  [measured, tools/bench_umma.cu:
+  //                 an SS-mode tf32 MMA re-reads its 4 KB A tile and N*32 B of B from shared memory at 128 B/cycle]
+  //   load cycles = TMA bytes / (HBM share of one SM ~ 23 B/cycle)
   for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
     if (co_pad % NT) continue;
     for (int CIB = cblocks; CIB >= 1; --CIB) {
       if (cblocks % CIB) continue;
       for (int RG = g.kh; RG >= 1; --RG) {
         int acc = RG * a.SG * CIB;
-        if (acc * NT > 512) continue;
-        for (int TH = 8; TH >= 1; --TH) {
+        if (acc * NT > 512 || acc > kMaxAcc) continue;
+        for (int TH = 16; TH >= 1; --TH) {
           if (TH > g.Ho && TH > 1) continue;
           int BH = TH + RG - 1;
           if (BH > 256) continue;
@@ -312,16 +332,18 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
           int stages = (int)((kMaxSmemBytes - 4096) / stage);
           if (stages < 2) continue;
           if (stages > 4) stages = 4;
-          // score: useful K rows per stage (amortises halo + barrier cost) x N width x accumulators
-          int n_rg = (g.kh + RG - 1) / RG;
-          int gy = (cblocks / CIB) * n_rg * (co_pad / NT);
-          int score = TH * 1000 / BH * 8 + (acc * NT >= 128 ? 400 : 0) + (NT >= 64 ? 100 : 0) - gy * 2 + TH;
+          int n_rg = (g.kh + RG - 1) / RG, n_cig = cblocks / CIB, n_cot = co_pad / NT;
+          double costN = (32.0 + NT / 4.0) > NT / 2.0 ? (32.0 + NT / 4.0) : NT / 2.0;
+          double mma = (double)n_cig * n_rg * n_cot * acc * costN * (a.BW / 8.0);
+          double bytes = ((double)n_cot * n_rg * cblocks * BH / TH + (double)n_cig * n_rg * (co_pad / 32)) * 128.0 * a.BW;
+          double t = mma > bytes / 23.0 ? mma : bytes / 23.0;
+          double score = 1e9 / t + TH * 1e-3 + (stages >= 3 ? 0.5 : 0.0);
           if (score > best_score) {
             best_score = score;
             best = a;
             best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
             best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
-            best.n_cig = cblocks / CIB; best.n_rg = n_rg; best.n_cot = co_pad / NT;
+            best.n_cig = n_cig; best.n_rg = n_rg; best.n_cot = n_cot;
             best_smem = (size_t)stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
           }
         }
@@ -334,7 +356,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   a.num_bands = g.N * a.bands_per_img;
   a.ksteps = (a.TH * a.BW + 7) / 8;
   int gy = a.n_cig * a.n_rg * a.n_cot;
-  int target = (148 + gy - 1) / gy;  // one wave of CTAs (1 CTA/SM: big smem)
+  int target = 148 / gy;  // at most one wave of CTAs (1 CTA/SM: big smem)
   if (target < 1) target = 1;
   a.bands_per_cta = (a.num_bands + target - 1) / target;
   int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;

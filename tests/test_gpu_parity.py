@@ -107,6 +107,10 @@ def test_net_matches_reference_golden(name, math):
         if math == "fp32":
             gtol = tol * (3 if name == "edsr" else 1)  # L1 loss: sign(y - t) flips on a few pixels
             assert rel_l2(p.grad, ref) < gtol, k
+        elif ref.size == 1:
+            # one shared PReLU slope: d(alpha) = sum(dy*z*[z<=0]) cancels to ~1e-4 of its terms; gate it
+            # against the gradient scale of the net instead of against itself
+            assert abs(p.grad.item() - float(ref.reshape(-1)[0])) < 2e-3 * gscale, k
         else:
             a = p.grad.detach().double().cpu().flatten()
             b = torch.from_numpy(ref).double().flatten()
@@ -315,7 +319,7 @@ def test_espcn_cfg2_full_size_properties():
     assert abs((lhs - bias_term) - dx_term) / scale < 2e-3
     assert abs((lhs - bias_term) - dw_term) / scale < 2e-3
     db_ref = TF.pixel_unshuffle(g, 4).sum(dim=(0, 2, 3))
-    assert rel_l2(blk.conv.bias.grad, db_ref) < 1e-4
+    assert rel_l2(blk.conv.bias.grad, db_ref) < 1e-3  # sum of tf32-rounded dz over 401k pixels
 
 
 def test_vdsr_body_layer_full_size_linearity():
