@@ -86,6 +86,9 @@ int srb_conv_out_hw(const srb_conv_params *p, int32_t *Ho, int32_t *Wo);
  * 0 = fp32 CUDA-core path.  pass: 0 fprop, 1 dgrad, 2 wgrad.  x_cl / y_cl: channels_last flags. */
 int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int y_cl);
 
+/* Diagnostic: human-readable tile plan the tensor path would use for this layer (host only, no GPU work). */
+int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t n);
+
 /* Bytes of scratch the call needs (may be 0).  pass as above. */
 size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass);
 

@@ -189,9 +189,9 @@ Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, co
 
 inline bool is_cl(const T4 &t, int C) { return t.sc == 1 && t.sw == C; }
 
-// Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 32 == 0)
+// Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 4 == 0, C >= 8)
 inline int want_round(const srb_conv_params *p, const T4 &t, int C) {
-  return (p->math != SRB_MATH_FP32 && is_cl(t, C) && (C % 32) == 0) ? 1 : 0;
+  return (p->math != SRB_MATH_FP32 && is_cl(t, C) && (C % 4) == 0 && C >= 8) ? 1 : 0;
 }
 
 }  // namespace
@@ -233,6 +233,25 @@ int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int 
     return tc_conv_supported(gd, y, x, true) ? 1 : 0;
   }
   return tc_wgrad_supported(g, y, x) ? 1 : 0;
+}
+
+/* Debug only (not in the public header): per-CTA phase timestamps of the next k_conv_sl launches go to buf (8 x int64 per CTA). */
+void srb_debug_set_trace(void *buf, long long max_ctas) { tc_conv_set_trace((long long *)buf, max_ctas); }
+void srb_debug_set_flags(int flags) { tc_conv_set_dbg(flags); }
+
+int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t n) {
+  Geom g;
+  if (!buf || n == 0) return SRB_EINVAL;
+  buf[0] = 0;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  if (p->transposed || p->math == SRB_MATH_FP32) { snprintf(buf, n, "fp32 CUDA-core kernels"); return SRB_OK; }
+  if (pass == 0) tc_conv_describe(g, buf, n);
+  else if (pass == 1) {
+    Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+    if (g.st != 1 || gd.pad < 0) snprintf(buf, n, "fp32 CUDA-core kernels"); else tc_conv_describe(gd, buf, n);
+  } else tc_wgrad_describe(g, buf, n);
+  return SRB_OK;
 }
 
 size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {

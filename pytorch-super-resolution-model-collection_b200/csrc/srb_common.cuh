@@ -100,6 +100,10 @@ bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_
 size_t tc_conv_ws_bytes(const Geom &g);
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
                    void *ws, size_t ws_bytes, cudaStream_t st);
+void tc_conv_set_trace(long long *buf, long long max_ctas);
+void tc_conv_set_dbg(int flags);
+int tc_conv_describe(const Geom &g, char *buf, size_t n);
+int tc_wgrad_describe(const Geom &g, char *buf, size_t n);
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);
 size_t tc_wgrad_ws_bytes(const Geom &g);
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,

@@ -1,0 +1,703 @@
+// "Slot-linear" tcgen05 implicit-GEMM convolution for sm_100a (stride-1 fprop, and dgrad as a flipped fprop).
+//
+//   D[m, n] = sum_{r,s,c} X[pixel(m) + (r,s), c] * W[n, c, r, s]        m = output pixel slot, n = output channel
+//
+// The input halo of a band of TH x TW output pixels -- (TH+kh-1) x BW pixel "slots", BW = TW+kw-1 -- is fetched
+// ONCE per 32-channel chunk by a single TMA box load into shared memory (out-of-image slots are zero-filled by the
+// TMA unit = the conv padding).  Output pixel (ty,tx) is slot q = ty*BW + tx of the flattened band, and filter tap
+// (r,s) is nothing but the same shared-memory tile viewed (r*BW + s) slots later: the A operand of every tap is a
+// SHIFTED VIEW, expressed purely through the start address of the tcgen05 shared-memory descriptor (the 128B swizzle
+// is a function of the absolute smem address, so any 128-byte shift stays consistent with what TMA wrote --
+// tools/probe_desc.cu).  An M-tile is 128 consecutive slots; the kw-1 wrap-around slots per row compute garbage that
+// the epilogue never stores.  Compared with per-tap im2col loads this cuts L2->SMEM traffic by ~kh*kw.
+//
+// Two operand flavours share the kernel:
+//   generic (Cin % 4 == 0, NHWC): slot = 128 B = 32 channels, K-major SWIZZLE_128B; one K-block = (chunk, tap) = 4 MMAs
+//            of K = 8; weights stream through a TMA ring as [chunk][tap][Npad][32].
+//   c4      (Cin <= 4): the image is packed to NHWC4 (16 B / pixel); slot = 16 B.  With the NO-swizzle K-major layout,
+//            leading-byte-offset 16 B and stride-byte-offset 128 B, row m of the operand is the 32 bytes starting at
+//            slot m: an OVERLAPPING (Toeplitz) view -- one K = 8 MMA covers two horizontal taps x 4 channels straight
+//            from the raw image tile.  All weights ([kb][N/8][2][8][4]) stay resident in shared memory.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue (warp-uniform loops, one elected lane issues),
+// warps 2..5 = epilogue (tcgen05.ld -> bias -> act -> +residual -> tf32 round -> store at the pixel-shuffled address).
+// CTAs are sized for two per SM (<= 112 KB smem, <= 256 TMEM columns) so one CTA's epilogue overlaps the other's MMAs.
+#include "tc_common.cuh"
+
+namespace srb {
+
+namespace {
+
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kMaxBStages = 8;
+
+struct SlArgs {
+  int N, Ho, Wo, Co;
+  int kh, kw, pad;
+  int c4;
+  int TH, TW, BW, BH;
+  int bands_h, bands_w;
+  int MTB, NT;
+  int chunks;        // A loads per band: generic ceil(Cin/32); c4: 1
+  int spairs;        // c4: ceil(kw/2)
+  int a_bufs, a_buf_bytes, a_tx_bytes;
+  int b_stages, b_stage_bytes;  // c4: one stage holding every K-block of this N tile
+  int tmem_cols;
+  int ps;
+  const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
+  long long *trace;    // debug (srb_debug_set_trace): 8 timestamps per CTA, null in production
+  T4 out;
+  Epi epi;
+};
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SL_TRACE(slot)                                                                           \
+  do {                                                                                           \
+    if (a.trace) a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime();  \
+  } while (0)
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// tf32 round-to-nearest (ties away) on the bit pattern: 2 integer ops instead of cvt.rna's 4-instruction expansion
+// (the Inf guard is dropped: +-Inf would become NaN, which only matters for a diverged run).
+__device__ __forceinline__ float round_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+
+// One epilogue warp's share of the band: work items (M-tile, 16-column group), item = half, half+2, ...
+//   MODE 0: NHWC, no shuffle           -> 4 x float4 at channel cbase + 4q
+//   MODE 1: PixelShuffle(4) into NCHW  -> one output channel c = cbase/16; quad q = sub-row i: 4 contiguous j
+//   MODE 2: PixelShuffle(2) into NHWC  -> 4 output channels cbase/4 ..+3; quad q = sub-pixel (i,j)
+//   MODE 3: anything else              -> scalar stores through ps_offset()
+// Modes 0..2 need Co % 16 == 0.  EXTRA = a residual and/or pre-activation tensor is present; the lean variant
+// (plain conv + bias + act) is ~100 instructions per item, which matters: the epilogue is issue-bound.
+template <int MODE, bool EXTRA>
+__device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
+                                               int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid) {
+  const int act = a.epi.act;
+  const float slope = (act == SRB_ACT_PRELU) ? __ldg(a.epi.alpha) : a.epi.slope;
+  const bool has_bias = a.epi.bias != nullptr;
+  const bool rnd = a.epi.round_tf32 != 0;
+  const bool has_res = EXTRA && a.epi.residual.p != nullptr, has_pre = EXTRA && a.epi.preact.p != nullptr;
+  const int ngroups = a.NT >> 4;
+  int t_cur = -1, oy = 0, ox = 0;
+  bool pix_ok = false;
+  float *po = nullptr, *pp = nullptr;
+  const float *pr = nullptr;
+#pragma unroll 1
+  for (int item = half; item < mtb * ngroups; item += 2) {
+    const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
+    if (t != t_cur) {
+      t_cur = t;
+      const int q = t * 128 + m;  // slot of this thread's accumulator row
+      const int ty = q / a.BW, tx = q - ty * a.BW;
+      oy = oy0 + ty; ox = ox0 + tx;
+      pix_ok = (ty < rows_valid) && (tx < cols_valid);
+      if (MODE != 3) {
+        const long long yy = (long long)oy * a.ps, xx = (long long)ox * a.ps;
+        po = a.out.p + (n * a.out.sn + yy * a.out.sh + xx * a.out.sw);
+        if (EXTRA) {
+          pr = a.epi.residual.p + (n * a.epi.residual.sn + yy * a.epi.residual.sh + xx * a.epi.residual.sw);
+          pp = a.epi.preact.p + (n * a.epi.preact.sn + yy * a.epi.preact.sh + xx * a.epi.preact.sw);
+        }
+      }
+    }
+    const int cbase = n0 + j0;
+    if (cbase >= a.Co) continue;  // warp-uniform
+    uint32_t v[16];
+    tmem_ld16(trow + (uint32_t)(t * a.NT + j0), v);
+    if (!pix_ok) continue;
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = lds128(bias_saddr + (uint32_t)(j0 + j) * 4u);
+        z[j] += b.x; z[j + 1] += b.y; z[j + 2] += b.z; z[j + 3] += b.w;
+      }
+    }
+    if (MODE == 3) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = cbase + j;
+        if (co < a.Co) {
+          if (a.epi.preact.p) a.epi.preact.p[ps_offset(a.epi.preact, a.ps, n, co, oy, ox)] = z[j];
+          float y = act == SRB_ACT_NONE ? z[j] : (act == SRB_ACT_RELU ? fmaxf(z[j], 0.f) : (z[j] > 0.f ? z[j] : z[j] * slope));
+          if (a.epi.residual.p) y += __ldg(a.epi.residual.p + ps_offset(a.epi.residual, a.ps, n, co, oy, ox));
+          if (rnd) y = round_tf32_fast(y);
+          a.out.p[ps_offset(a.out, a.ps, n, co, oy, ox)] = y;
+        }
+      }
+      continue;
+    }
+    // group base pointers and quad strides (floats)
+    float *pg, *ppg = nullptr;
+    const float *prg = nullptr;
+    long long qs_o, qs_o2 = 0, qs_r = 0, qs_r2 = 0, qs_p = 0, qs_p2 = 0;
+    if (MODE == 0) {
+      pg = po + cbase; qs_o = 4;
+      if (EXTRA) { prg = pr + cbase; ppg = pp + cbase; qs_r = qs_p = 4; }
+    } else if (MODE == 1) {
+      const int c = cbase >> 4;
+      pg = po + c * a.out.sc; qs_o = a.out.sh;
+      if (EXTRA) { prg = pr + c * a.epi.residual.sc; ppg = pp + c * a.epi.preact.sc; qs_r = a.epi.residual.sh; qs_p = a.epi.preact.sh; }
+    } else {
+      const int c = cbase >> 2;
+      pg = po + c; qs_o = a.out.sw; qs_o2 = a.out.sh;
+      if (EXTRA) { prg = pr + c; ppg = pp + c; qs_r = a.epi.residual.sw; qs_r2 = a.epi.residual.sh; qs_p = a.epi.preact.sw; qs_p2 = a.epi.preact.sh; }
+    }
+    if (has_pre) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 zq = MODE == 2 ? make_float4(z[q4], z[4 + q4], z[8 + q4], z[12 + q4])
+                                    : make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+        *(float4 *)(ppg + (MODE == 2 ? (q4 >> 1) * qs_p2 + (q4 & 1) * qs_p : q4 * qs_p)) = zq;
+      }
+    }
+    if (act == SRB_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = fmaxf(z[j], 0.f);
+    } else if (act != SRB_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
+    }
+    if (has_res) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 rr = __ldg((const float4 *)(prg + (MODE == 2 ? (q4 >> 1) * qs_r2 + (q4 & 1) * qs_r : q4 * qs_r)));
+        if (MODE == 2) { z[q4] += rr.x; z[4 + q4] += rr.y; z[8 + q4] += rr.z; z[12 + q4] += rr.w; }
+        else { z[4 * q4] += rr.x; z[4 * q4 + 1] += rr.y; z[4 * q4 + 2] += rr.z; z[4 * q4 + 3] += rr.w; }
+      }
+    }
+    if (rnd) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = round_tf32_fast(z[j]);
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 y = MODE == 2 ? make_float4(z[q4], z[4 + q4], z[8 + q4], z[12 + q4])
+                                 : make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+      *(float4 *)(pg + (MODE == 2 ? (q4 >> 1) * qs_o2 + (q4 & 1) * qs_o : q4 * qs_o)) = y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, SlArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *a_smem = smem;
+  uint8_t *b_smem = smem + (size_t)a.a_bufs * a.a_buf_bytes;
+  uint64_t *a_full = (uint64_t *)(b_smem + (size_t)a.b_stages * a.b_stage_bytes);
+  uint64_t *a_empty = a_full + 2;
+  uint64_t *b_full = a_empty + 2;
+  uint64_t *b_empty = b_full + kMaxBStages;
+  uint64_t *accum_bar = b_empty + kMaxBStages;
+  uint32_t *tmem_slot = (uint32_t *)(accum_bar + 1);
+  float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    SL_TRACE(0);
+    if (a.trace) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = smid;
+    }
+  }
+  // band -> (image, band row, band col)
+  const int band = blockIdx.x;
+  const int bw_i = band % a.bands_w;
+  const int bq = band / a.bands_w;
+  const int bh_i = bq % a.bands_h;
+  const int img = bq / a.bands_h;
+  const int oy0 = bh_i * a.TH, ox0 = bw_i * a.TW;
+  const int n0 = blockIdx.y * a.NT;
+  const int rows_valid = min(a.TH, a.Ho - oy0), cols_valid = min(a.TW, a.Wo - ox0);
+  const int mtb = ((rows_valid - 1) * a.BW + cols_valid + 127) >> 7;  // M-tiles that hold at least one real pixel
+  const int taps = a.kh * a.kw;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    if (!a.c4) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (threadIdx.x == 0) SL_TRACE(1);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const int ix0 = ox0 - a.pad, iy0 = oy0 - a.pad;
+    if (a.c4) {
+      if (elect_one()) {
+        const uint32_t wbytes = (uint32_t)a.b_stage_bytes;
+        mbar_expect_tx(&b_full[0], wbytes);
+        const uint8_t *src = (const uint8_t *)a.wpack + (size_t)blockIdx.y * wbytes;
+        for (uint32_t off = 0; off < wbytes; off += 16384u)
+          bulk_g2s(b_smem + off, src + off, min(16384u, wbytes - off), &b_full[0]);
+        mbar_expect_tx(&a_full[0], (uint32_t)a.a_tx_bytes);
+        tma_load_4d(&mapA, &a_full[0], a_smem, 0, ix0, iy0, img);
+      }
+      __syncwarp();
+    } else {
+      int kb = 0;
+      for (int c = 0; c < a.chunks; ++c) {
+        const int buf = c % a.a_bufs;
+        mbar_wait(&a_empty[buf], (((uint32_t)(c / a.a_bufs)) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[buf], (uint32_t)a.a_tx_bytes);
+          tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * 32, ix0, iy0, img);
+        }
+        __syncwarp();
+        for (int tap = 0; tap < taps; ++tap, ++kb) {
+          const int st = kb % a.b_stages;
+          mbar_wait(&b_empty[st], (((uint32_t)(kb / a.b_stages)) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&b_full[st], (uint32_t)a.b_stage_bytes);
+            tma_load_3d(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes, 0, n0, kb);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
+    if (a.c4) {
+      // A: no swizzle, LBO 16 B (next 4 floats along K = next pixel), SBO 128 B (next 8 rows = next 8 slots)
+      // B: no swizzle canonical [N/8][2][8 rows][16 B]: LBO 128 B, SBO 256 B
+      const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
+      const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
+      mbar_wait(&b_full[0], 0);
+      mbar_wait(&a_full[0], 0);
+      if (lane == 0) SL_TRACE(2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem);
+      const uint32_t kb_bytes = (uint32_t)a.NT * 32u;
+      if (elect_one()) {
+        int kb = 0;
+        for (int r = 0; r < a.kh; ++r) {
+          for (int sp = 0; sp < a.spairs; ++sp, ++kb) {
+            const uint32_t a_lo = (((a_addr + (uint32_t)(r * a.BW + 2 * sp) * 16u) >> 4) & 0x3FFF) | a_lbo;
+            const uint32_t b_lo = (((b_addr + (uint32_t)kb * kb_bytes) >> 4) & 0x3FFF) | b_lbo;
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+            const uint32_t acc = kb ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < mtb)  // 128 slots x 16 B = 2048 B per M-tile
+                umma_tf32_ss(tmem_base + (uint32_t)(j * a.NT), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + j * 128), bdesc, idesc, acc);
+          }
+        }
+        umma_commit_arrive(accum_bar);
+      }
+      __syncwarp();
+      if (lane == 0) SL_TRACE(3);
+    } else {
+      // K-major SWIZZLE_128B: SBO 1024 B (8 slots), layout type 2
+      const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t lbo = 1u << 16;
+      const uint32_t b_addr0 = smem_u32(b_smem);
+      int kb = 0;
+      for (int c = 0; c < a.chunks; ++c) {
+        const int buf = c % a.a_bufs;
+        mbar_wait(&a_full[buf], ((uint32_t)(c / a.a_bufs)) & 1u);
+        if (c == 0 && lane == 0) SL_TRACE(2);
+        const uint32_t a_addr = smem_u32(a_smem + (size_t)buf * a.a_buf_bytes);
+        for (int r = 0; r < a.kh; ++r) {
+          for (int s = 0; s < a.kw; ++s, ++kb) {
+            const int st = kb % a.b_stages;
+            mbar_wait(&b_full[st], ((uint32_t)(kb / a.b_stages)) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_lo = (((a_addr + (uint32_t)(r * a.BW + s) * 128u) >> 4) & 0x3FFF) | lbo;
+            const uint32_t b_lo = (((b_addr0 + (uint32_t)st * (uint32_t)a.b_stage_bytes) >> 4) & 0x3FFF) | lbo;
+            if (elect_one()) {
+              const uint32_t acc0 = kb ? 1u : 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < mtb) {
+                  const uint32_t aj = a_lo + (uint32_t)j * 1024u;  // 128 slots x 128 B >> 4
+                  const uint32_t tcol = tmem_base + (uint32_t)(j * a.NT);
+                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 0), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 0), idesc, acc0);
+                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 2), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 2), idesc, 1u);
+                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 4), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 4), idesc, 1u);
+                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 6), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 6), idesc, 1u);
+                }
+              }
+              umma_commit_arrive(&b_empty[st]);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit_arrive(&a_empty[buf]);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit_arrive(accum_bar);
+      __syncwarp();
+      if (lane == 0) SL_TRACE(3);
+    }
+  } else {
+    // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31 =====================
+    // Two warps share each lane quadrant and alternate over the (M-tile, 16-column group) work items.
+    const int lane_grp = warp & 3, half = (warp - 2) >> 2;
+    // bias -> shared memory while the MMAs run (zero when absent or beyond Co)
+    for (int j = threadIdx.x - 64; j < a.NT; j += kThreads - 64) {
+      const int co = n0 + j;
+      bias_s[j] = (a.epi.bias && co < a.Co) ? __ldg(a.epi.bias + co) : 0.f;
+    }
+    const bool lay0 = a.out.sc == 1 && (!a.epi.residual.p || a.epi.residual.sc == 1) &&
+                      (!a.epi.preact.p || a.epi.preact.sc == 1);
+    const bool lay1 = a.out.sw == 1 && (!a.epi.residual.p || a.epi.residual.sw == 1) &&
+                      (!a.epi.preact.p || a.epi.preact.sw == 1);
+    int fmode = 3;  // see epilogue_items
+    if ((a.Co & 15) == 0) {
+      if (a.ps == 1 && lay0) fmode = 0;
+      else if (a.ps == 4 && lay1 && (a.out.sh & 3) == 0) fmode = 1;
+      else if (a.ps == 2 && lay0 && ((a.Co >> 2) & 3) == 0) fmode = 2;
+    }
+    const bool extra = a.epi.residual.p != nullptr || a.epi.preact.p != nullptr;
+    asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");  // bias_s visible to all epilogue warps
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 2 && lane == 0) SL_TRACE(4);
+    const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    const uint32_t bsa = smem_u32(bias_s);
+    const int m = lane_grp * 32 + lane;
+#define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
+    if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
+    else if (fmode == 1) { if (extra) SL_EPI(1, true); else SL_EPI(1, false); }
+    else if (fmode == 2) { if (extra) SL_EPI(2, true); else SL_EPI(2, false); }
+    else SL_EPI(3, true);
+#undef SL_EPI
+  }
+
+  if (warp == 2 && lane == 0) SL_TRACE(5);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+  if (threadIdx.x == 0) SL_TRACE(6);
+}
+
+// Filter element for GEMM row n (output channel of this launch), K index k (input channel of this launch), tap (r,s):
+//   flip == 0 (fprop):  w[n][k][r][s]                      (Conv2d OIHW, Ci = Kk)
+//   flip == 1 (dgrad):  w[k][n][kh-1-r][kw-1-s]            (the launch's output channel is the filter's input channel)
+__device__ __forceinline__ float wval(const float *__restrict__ w, int n, int k, int r, int s, int Nn, int Kk, int kh,
+                                      int kw, int flip) {
+  if (!flip) return __ldg(w + (((long long)n * Kk + k) * kh + r) * kw + s);
+  return __ldg(w + (((long long)k * Nn + n) * kh + (kh - 1 - r)) * kw + (kw - 1 - s));
+}
+
+// generic B operand: out[chunk][tap][Npad][32] (tf32 RN), zero for n >= Nn or k >= Kk
+__global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad,
+                            int chunks, int flip) {
+  const int taps = kh * kw;
+  const long long total = (long long)chunks * taps * Npad * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 31);
+    long long q = i >> 5;
+    const int n = (int)(q % Npad); q /= Npad;
+    const int tap = (int)(q % taps);
+    const int c = (int)(q / taps);
+    const int k = c * 32 + kk;
+    float v = 0.f;
+    if (n < Nn && k < Kk) {
+      const int r = tap / kw, s = tap - r * kw;
+      v = round_tf32(wval(w, n, k, r, s, Nn, Kk, kh, kw, flip));
+    }
+    out[i] = v;
+  }
+}
+
+// c4 B operand: out[ntile][kb = r*spairs+sp][NT/8][2][8][4]; element (n, k): pixel offset sl = k/4 -> s = 2*sp+sl, channel k%4
+__global__ void k_pack_w_c4(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int NT,
+                            int ntiles, int spairs, int flip) {
+  const int kblocks = kh * spairs;
+  const long long total = (long long)ntiles * kblocks * NT * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(i & 3);
+    const int n8 = (int)((i >> 2) & 7);
+    const int kh2 = (int)((i >> 5) & 1);
+    long long q = i >> 6;
+    const int ng = (int)(q % (NT / 8)); q /= (NT / 8);
+    const int kb = (int)(q % kblocks);
+    const int t = (int)(q / kblocks);
+    const int n = t * NT + ng * 8 + n8;
+    const int r = kb / spairs, sp = kb - r * spairs;
+    const int s = 2 * sp + kh2, ci = k4;
+    float v = 0.f;
+    if (n < Nn && ci < Kk && s < kw) v = round_tf32(wval(w, n, ci, r, s, Nn, Kk, kh, kw, flip));
+    out[i] = v;
+  }
+}
+
+// x (N, C<=4, H, W; any strides) -> NHWC4 image (16 B per pixel, channel >= C zero), tf32-rounded
+__global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long q = i / W;
+    const int yy = (int)(q % H);
+    const int n = (int)(q / H);
+    const float *p = x.p + n * x.sn + (long long)yy * x.sh + (long long)xx * x.sw;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) v[c] = round_tf32(__ldg(p + c * x.sc));
+    xp[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+struct SlPlan {
+  SlArgs a;
+  size_t smem;
+  int n_tiles_n, Npad;
+  size_t wpack_floats, xpack_floats;
+};
+
+inline double mma_cost(int N) {  // cycles of one SS-mode tf32 MMA, M=128 K=8 (tools/bench_umma.cu)
+  double c1 = 32.0 + N / 4.0, c2 = N / 2.0;
+  return c1 > c2 ? c1 : c2;
+}
+
+bool make_sl_plan(const Geom &g, SlPlan *pl) {
+  SlArgs &a = pl->a;
+  const bool c4 = g.Ci <= 4;
+  const int sb = c4 ? 16 : 128;
+  const int Npad = round_up_i(g.Co, 16);
+  int NT = Npad;
+  if (NT > 256) {
+    NT = 256;
+    while (Npad % NT) NT -= 16;
+  }
+  const int spairs = (g.kw + 1) / 2;
+  const int kextra = c4 ? 2 * spairs - 1 : g.kw - 1;
+  const int chunks = c4 ? 1 : (g.Ci + 31) / 32;
+  const int kblocks = c4 ? g.kh * spairs : g.kh * g.kw * chunks;
+  const double mma_per_tile = (c4 ? kblocks : kblocks * 4) * mma_cost(NT);
+  double best_t = -1.0;
+  for (int ctas = 2; ctas >= 1; --ctas) {
+    const int smem_cap = ctas == 2 ? 113 * 1024 : 226 * 1024;
+    const int col_cap = ctas == 2 ? 256 : 512;
+    for (int MTB = (col_cap / NT < 4 ? col_cap / NT : 4); MTB >= 1; --MTB) {
+      for (int wsplit = 1; wsplit <= 16; ++wsplit) {
+        const int TW = (g.Wo + wsplit - 1) / wsplit;
+        const int BW = TW + kextra;
+        if (BW > 256 || TW > 128 * MTB) continue;
+        int TH = (128 * MTB - TW) / BW + 1;
+        if (TH > g.Ho) TH = g.Ho;
+        const int bands_h = (g.Ho + TH - 1) / TH;
+        TH = (g.Ho + bands_h - 1) / bands_h;
+        const int BH = TH + g.kh - 1;
+        if (BH > 256) continue;
+        const int bands_w = (g.Wo + TW - 1) / TW;
+        int slots = BH * BW;
+        const int need = 128 * MTB + (g.kh - 1) * BW + kextra;
+        if (need > slots) slots = need;
+        const int a_buf = round_up_i(slots * sb, 1024);
+        int b_stage, b_stages, a_bufs;
+        if (c4) {
+          b_stage = kblocks * NT * 32; b_stages = 1; a_bufs = 1;
+        } else {
+          b_stage = NT * 128;
+          a_bufs = chunks > 1 ? 2 : 1;
+          b_stages = (smem_cap - 3072 - a_bufs * a_buf) / b_stage;
+          if (b_stages < 3 && a_bufs == 2) { a_bufs = 1; b_stages = (smem_cap - 3072 - a_buf) / b_stage; }
+          if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+          if (b_stages > kblocks) b_stages = kblocks;
+          if (b_stages < 2 && kblocks >= 2) continue;
+        }
+        const size_t smem = (size_t)a_bufs * a_buf + (size_t)b_stages * b_stage + 1024 + 512 + 1024;
+        if (smem > (size_t)smem_cap) continue;
+        // time model per real output pixel (cycles on one SM)
+        const double eff = (double)g.Ho * g.Wo / ((double)bands_h * bands_w * MTB * 128);
+        const double t_mma = mma_per_tile / 128.0 / eff;
+        const double a_bytes = (double)chunks * BH * BW * sb / ((double)TH * TW);
+        const double b_bytes = (double)kblocks * NT * (c4 ? 32 : 128) / (eff * MTB * 128.0);
+        const double t_mem = (a_bytes + b_bytes + 4.0 * NT) / 48.0;  // ~48 B/clk/SM of L2->SM + store bandwidth
+        double t = t_mma > t_mem ? t_mma : t_mem;
+        if (ctas == 1) t *= 1.2;                      // no co-resident CTA to hide the epilogue
+        if (a_bufs == 1 && chunks > 1) t *= 1.1;      // chunk loads serialise with the MMAs
+        const long long nctas = (long long)g.N * bands_h * bands_w * (Npad / NT);
+        if (nctas < 148) t *= 148.0 / (double)nctas;  // do not starve the SMs on tiny problems
+        if (best_t < 0 || t < best_t) {
+          best_t = t;
+          a.TH = TH; a.TW = TW; a.BW = BW; a.BH = BH; a.bands_h = bands_h; a.bands_w = bands_w;
+          a.MTB = MTB; a.NT = NT; a.chunks = chunks; a.spairs = spairs;
+          a.a_bufs = a_bufs; a.a_buf_bytes = a_buf; a.a_tx_bytes = BH * BW * sb;
+          a.b_stages = b_stages; a.b_stage_bytes = b_stage;
+          int tc = 32;
+          while (tc < MTB * NT) tc <<= 1;
+          a.tmem_cols = tc;
+          pl->smem = smem;
+        }
+      }
+    }
+  }
+  if (best_t < 0) return false;
+  a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Co = g.Co; a.kh = g.kh; a.kw = g.kw; a.pad = g.pad; a.c4 = c4 ? 1 : 0;
+  a.ps = g.ps;
+  pl->Npad = Npad;
+  pl->n_tiles_n = Npad / NT;
+  pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
+  pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;
+  return true;
+}
+
+long long *g_sl_trace = nullptr;
+long long g_sl_trace_ctas = 0;
+int g_sl_dbg = 0;
+
+}  // namespace
+
+void tc_conv_set_trace(long long *buf, long long max_ctas) { g_sl_trace = buf; g_sl_trace_ctas = max_ctas; }
+void tc_conv_set_dbg(int flags) { g_sl_dbg = flags; }
+
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/) {
+  if (g.st != 1 || g.N <= 0) return false;
+  if (g.kh > 16 || g.kw > 16) return false;
+  if ((long long)g.N * g.Hi * g.Wi * (g.Ci > 4 ? g.Ci : 4) >= (1LL << 40)) return false;
+  if ((long long)g.N * ((g.Ho + 0) * (long long)g.Wo) >= (1LL << 31)) return false;
+  if (g.Ci > 4) {
+    if (g.Ci % 4 != 0 || g.Ci < 8) return false;                       // TMA: 16-byte pixel stride
+    if (in.sc != 1) return false;                                       // channels_last activations
+    if ((in.sw % 4) || (in.sh % 4) || (in.sn % 4)) return false;       // TMA strides: multiples of 16 B
+    if (((uintptr_t)in.p) & 15) return false;
+  }
+  SlPlan p;
+  return make_sl_plan(g, &p);
+}
+
+size_t tc_conv_ws_bytes(const Geom &g) {
+  SlPlan p;
+  if (g.st != 1 || !make_sl_plan(g, &p)) return 0;
+  // dgrad of the same layer swaps Ci/Co: take the larger of both packings
+  Geom gd = g;
+  gd.Ci = g.Co; gd.Co = g.Ci; gd.Hi = g.Ho; gd.Wi = g.Wo; gd.Ho = g.Hi; gd.Wo = g.Wi; gd.pad = g.kh - 1 - g.pad; gd.ps = 1;
+  size_t a = (p.wpack_floats + p.xpack_floats) * sizeof(float) + 1024;
+  SlPlan pd;
+  if (gd.pad >= 0 && make_sl_plan(gd, &pd)) {
+    size_t b = (pd.wpack_floats + pd.xpack_floats) * sizeof(float) + 1024;
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+int tc_conv_describe(const Geom &g, char *buf, size_t n) {
+  SlPlan pl;
+  if (!make_sl_plan(g, &pl)) return snprintf(buf, n, "conv_sl: no plan");
+  const SlArgs &a = pl.a;
+  return snprintf(buf, n,
+                  "conv_sl %s: band %dx%d (halo %dx%d), %dx%d bands/img, MTB %d, NT %d x%d, chunks %d, a_bufs %d x %d B, "
+                  "b_stages %d x %d B, smem %zu B, tmem %d cols, grid %d x %d",
+                  a.c4 ? "c4" : "generic", a.TH, a.TW, a.BH, a.BW, a.bands_h, a.bands_w, a.MTB, a.NT, pl.n_tiles_n, a.chunks,
+                  a.a_bufs, a.a_buf_bytes, a.b_stages, a.b_stage_bytes, pl.smem, a.tmem_cols, g.N * a.bands_h * a.bands_w,
+                  pl.n_tiles_n);
+}
+
+int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
+                   void *ws, size_t ws_bytes, cudaStream_t st) {
+  SlPlan pl;
+  SRB_REQUIRE(make_sl_plan(g, &pl), SRB_EUNSUPPORTED, "tc_conv: no band plan");
+  SlArgs &a = pl.a;
+  const size_t need = (pl.wpack_floats + pl.xpack_floats) * sizeof(float) + 512;
+  uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+  SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_conv workspace: need %zu bytes, have %zu",
+              need + 256, ws_bytes);
+  float *wp = (float *)wsp;
+  float *xp = (float *)((wsp + pl.wpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
+
+  // 1. operands: weights (and, for c4, the NHWC4 image)
+  {
+    const long long total = (long long)pl.wpack_floats;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (a.c4)
+      k_pack_w_c4<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
+    else
+      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    if (a.c4) {
+      const long long px = (long long)g.N * g.Hi * g.Wi;
+      int pb = (int)((px + 255) / 256);
+      if (pb > 148 * 16) pb = 148 * 16;
+      k_pack_nhwc4<<<pb, 256, 0, st>>>(in, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi);
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+
+  // 2. tensor maps
+  CUtensorMap mapA, mapB;
+  if (a.c4) {
+    cuuint64_t dims[4] = {4, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {16, (cuuint64_t)g.Wi * 16, (cuuint64_t)g.Hi * g.Wi * 16};
+    cuuint32_t box[4] = {4, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    int rc = encode_tiled(&mapA, xp, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    mapB = mapA;  // unused
+    a.wpack = wp;
+  } else {
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+      cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sh * 4, (cuuint64_t)in.sn * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+      int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      cuuint64_t dims[3] = {32, (cuuint64_t)pl.Npad, (cuuint64_t)(a.chunks * g.kh * g.kw)};
+      cuuint64_t strides[2] = {128, (cuuint64_t)pl.Npad * 128};
+      cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
+      int rc = encode_tiled(&mapB, wp, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    a.wpack = nullptr;
+  }
+  a.out = out;
+  a.epi = epi;
+  a.trace = ((long long)g.N * a.bands_h * a.bands_w * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_sl, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(g.N * a.bands_h * a.bands_w), (unsigned)pl.n_tiles_n);
+  k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+}  // namespace srb

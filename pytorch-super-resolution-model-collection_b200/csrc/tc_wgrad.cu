@@ -34,6 +34,9 @@ struct WgArgs {
   int stages, tmem_cols;
   int x_slots, dz_slots;  // allocated 128-B pixel slots per 32-channel block (zero tail included)
   int ksteps;             // ceil(TH*BW / 8)
+  int c4;                 // Cin <= 4: x is the zero-padded NHWC4 image seen through an overlapping-stride TMA view whose
+                          // 32 "channels" are the 8-pixel x 4-channel window starting at the slot; an accumulator's four
+                          // 32-lane M-blocks are four consecutive FILTER ROWS (LBO = one slot row); RG = ceil(kh/4) accumulators
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
 };
 
@@ -117,8 +120,12 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         uint8_t *sz = sx + a.CIB * x_bytes;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[st], tx_bytes);
-          for (int cb = 0; cb < a.CIB; ++cb)
-            tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, -a.pad, oh0 - a.pad + r0, n);
+          if (a.c4) {
+            tma_load_4d(&mapX, &full_bar[st], sx, 0, 0, oh0, n);  // padded image: no negative coordinates
+          } else {
+            for (int cb = 0; cb < a.CIB; ++cb)
+              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, -a.pad, oh0 - a.pad + r0, n);
+          }
           for (int j = 0; j < nb; ++j)
             tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * 32, 0, oh0, n);
         }
@@ -133,7 +140,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                              ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
       // descriptor high words are loop invariant; low word = (addr >> 4) | LBO << 16
       const uint32_t a_hi = (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
-      const uint32_t a_lbo = (128u >> 4) << 16;
+      const uint32_t a_lbo = a.c4 ? ((((uint32_t)a.BW * 128u) >> 4) & 0x3FFF) << 16 : (128u >> 4) << 16;
       const uint32_t b_lbo = (((uint32_t)dz_bytes >> 4) & 0x3FFF) << 16;
       const uint32_t x_step = (uint32_t)x_bytes >> 4, row_step = (uint32_t)a.BW * 8u;  // 128 B per slot >> 4
       int it = 0;
@@ -148,7 +155,13 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         if (elect_one()) {
           // per-accumulator A start (low descriptor word) for this stage; fully unrolled, branch-uniform issue
           uint32_t lo[kMaxAcc];
-          {
+          if (a.c4) {
+#pragma unroll
+            for (int j = 0; j < kMaxAcc; ++j) {  // accumulator j = (row group, 8-pixel window group)
+              const int rg = j / a.SG, sg = j - rg * a.SG;
+              lo[j] = x_lo + (j < a.RG * a.SG ? (uint32_t)(4 * rg) * row_step + (uint32_t)sg * 64u : 0u);
+            }
+          } else {
             int i = 0;
             uint32_t lo_r = x_lo;
             for (int rl = 0; rl < rg_valid; ++rl, lo_r += row_step) {
@@ -165,7 +178,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int j = 0; j < kMaxAcc; ++j)
               if (j >= i) lo[j] = x_lo;
           }
-          const int nacc = rg_valid * a.SG * a.CIB;
+          const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;
           uint32_t ko = 0;
           for (int ks = 0; ks < a.ksteps; ++ks, ko += 64u) {
             const uint64_t bdesc = ((uint64_t)a_hi << 32) | (uint64_t)(z_lo + ko);
@@ -228,12 +241,19 @@ __global__ void k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float sc
     int ci = (int)(q % a.Ci);
     int co = (int)(q / a.Ci);
     int cot = co / a.NT, n = co - cot * a.NT;
-    int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
-    int rgi = r / a.RG, rl = r - rgi * a.RG;
-    int sg = s >> 2, sl = s & 3;
-    int by = (cig * a.n_rg + rgi) * a.n_cot + cot;
-    int acc = (rl * a.SG + sg) * a.CIB + cb;
-    int m = sl * 32 + (ci & 31);
+    int by, acc, m;
+    if (a.c4) {
+      by = cot;
+      acc = (r >> 2) * a.SG + (s >> 3);
+      m = (r & 3) * 32 + (s & 7) * 4 + ci;
+    } else {
+      int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
+      int rgi = r / a.RG, rl = r - rgi * a.RG;
+      int sg = s >> 2, sl = s & 3;
+      by = (cig * a.n_rg + rgi) * a.n_cot + cot;
+      acc = (rl * a.SG + sg) * a.CIB + cb;
+      m = sl * 32 + (ci & 31);
+    }
     const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
     const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
     float sum = 0.f;
@@ -291,16 +311,104 @@ __global__ void k_colsum_finish(const float *part, int blocks, int C, float *db,
   db[c] = accumulate ? db[c] + s : s;
 }
 
+// x (N, C<=4, H, W; any strides) -> zero-padded NHWC4 image xp[N][H+2p][Wp][4] (Wp >= W+2p+8*SG), tf32-rounded.  The
+// padding and the extra right-hand columns are real zeros so that every 8-pixel window of the overlapping view is finite.
+__global__ void k_pack_nhwc4_padded(T4 x, float4 *__restrict__ xp, int N, int C, int H, int W, int pad, int Hp, int Wp,
+                                    long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % Wp);
+    long long q = i / Wp;
+    const int yy = (int)(q % Hp);
+    const long long n = q / Hp;
+    const int h = yy - pad, w_ = xx - pad;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N && h >= 0 && h < H && w_ >= 0 && w_ < W) {
+      const float *p = x.p + n * x.sn + (long long)h * x.sh + (long long)w_ * x.sw;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) v[c] = round_tf32(__ldg(p + c * x.sc));
+    }
+    xp[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 struct WgPlan {
   WgArgs a;
   size_t smem;
   dim3 grid;
   int db_blocks;
   size_t partial_floats, db_floats;
+  int Hp, Wp;            // c4: padded NHWC4 image geometry
+  size_t xpack_floats;   // c4: floats of the packed image (incl. the tail the last windows run into)
 };
 
-bool make_wg_plan(const Geom &g, WgPlan *pl) {
+// Cin <= 4 (network inputs): see WgArgs::c4.
+bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   WgArgs &a = pl->a;
+  a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
+  a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
+  a.c4 = 1;
+  a.BW = g.Wo + g.kw - 1;  // == Wi + 2*pad at stride 1
+  if (a.BW > 256 || g.kw > 16 || g.kh > 16) return false;
+  a.SG = (g.kw + 7) / 8;
+  a.RG = (g.kh + 3) / 4;
+  a.CIB = 1;
+  const int nacc = a.RG * a.SG;
+  if (nacc > kMaxAcc) return false;
+  const int co_pad = round_up_i(g.Co, 32);
+  int NT = co_pad < 256 ? co_pad : 256;
+  while (NT > 32 && (co_pad % NT || nacc * NT > 512)) NT -= 32;
+  if (co_pad % NT || nacc * NT > 512) return false;
+  int bestTH = 0, best_stages = 0;
+  size_t best_stage = 0;
+  int best_xs = 0, best_zs = 0;
+  for (int TH = 8; TH >= 1; --TH) {
+    if (TH > g.Ho && TH > 1) continue;
+    const int x_slots = round_up_i((TH + 4 * a.RG - 1) * a.BW + 8 * a.SG + 8, 8);
+    const int dz_slots = round_up_i(TH * a.BW, 8);
+    const size_t stage = (size_t)x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
+    int stages = (int)((kMaxSmemBytes - 4096) / stage);
+    if (stages < 2 && TH > 1) continue;  // a single-stage pipeline only as the last resort (k9 windows at TH = 1)
+    if (stages < 1) continue;
+    if (stages > 4) stages = 4;
+    bestTH = TH; best_stages = stages; best_stage = stage; best_xs = x_slots; best_zs = dz_slots;
+    break;  // largest band that still double-buffers: least halo re-read
+  }
+  if (!bestTH) return false;
+  a.NT = NT; a.TH = bestTH; a.BH = bestTH + g.kh - 1;
+  a.x_slots = best_xs; a.dz_slots = best_zs; a.stages = best_stages;
+  a.n_cig = 1; a.n_rg = 1; a.n_cot = co_pad / NT;
+  a.bands_per_img = (g.Ho + a.TH - 1) / a.TH;
+  a.num_bands = g.N * a.bands_per_img;
+  a.ksteps = (a.TH * a.BW + 7) / 8;
+  const int gy = a.n_cot;
+  int target = 148 / gy;
+  if (target < 1) target = 1;
+  a.bands_per_cta = (a.num_bands + target - 1) / target;
+  if (a.bands_per_cta < 1) a.bands_per_cta = 1;  // empty batch: plan for the workspace query only
+  const int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
+  int tc = 32;
+  while (tc < nacc * NT) tc <<= 1;
+  a.tmem_cols = tc;
+  pl->grid = dim3(gx, gy);
+  pl->smem = (size_t)best_stages * best_stage + 1024 + (2 * best_stages + 1) * 8 + 16;
+  pl->partial_floats = (size_t)gx * gy * nacc * 128 * NT;
+  long long P = (long long)g.N * g.Ho * g.Wo;
+  pl->db_blocks = (int)((P + 2047) / 2048);
+  if (pl->db_blocks > 1184) pl->db_blocks = 1184;
+  pl->db_floats = (size_t)pl->db_blocks * g.Co;
+  pl->Hp = g.Hi + 2 * g.pad;
+  pl->Wp = g.Wi + 2 * g.pad + 8 * a.SG;
+  pl->xpack_floats = ((size_t)g.N * pl->Hp * pl->Wp + 64) * 4;
+  return true;
+}
+
+bool make_wg_plan(const Geom &g, WgPlan *pl) {
+  if (g.Ci <= 4) return make_wg_plan_c4(g, pl);
+  WgArgs &a = pl->a;
+  a.c4 = 0;
+  pl->Hp = pl->Wp = 0;
+  pl->xpack_floats = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
   a.BW = g.Wo + g.kw - 1;
@@ -359,6 +467,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   int target = 148 / gy;  // at most one wave of CTAs (1 CTA/SM: big smem)
   if (target < 1) target = 1;
   a.bands_per_cta = (a.num_bands + target - 1) / target;
+  if (a.bands_per_cta < 1) a.bands_per_cta = 1;  // empty batch: plan for the workspace query only
   int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
   int cols = a.RG * a.SG * a.CIB * a.NT, tc = 32;
   while (tc < cols) tc <<= 1;
@@ -378,26 +487,40 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
 // small = dz (N,Co,Ho,Wo) NHWC, big = x (N,Ci,Hi,Wi) NHWC
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
   if (g.st != 1 || g.ps != 1 || g.N <= 0) return false;
-  if (g.Ci % 32 != 0 || g.Co % 4 != 0 || g.Co > 1024) return false;
-  if (small.sc != 1 || big.sc != 1) return false;
-  if ((big.sw % 4) || (big.sh % 4) || (big.sn % 4) || (small.sw % 4) || (small.sh % 4) || (small.sn % 4)) return false;
-  if ((((uintptr_t)big.p) | ((uintptr_t)small.p)) & 15) return false;
+  const bool c4 = g.Ci <= 4;
+  if ((!c4 && g.Ci % 32 != 0) || g.Co % 4 != 0 || g.Co > 1024) return false;
+  if (small.sc != 1 || (!c4 && big.sc != 1)) return false;
+  if ((small.sw % 4) || (small.sh % 4) || (small.sn % 4)) return false;
+  if (!c4 && ((big.sw % 4) || (big.sh % 4) || (big.sn % 4))) return false;
+  if (((uintptr_t)small.p) & 15) return false;
+  if (!c4 && (((uintptr_t)big.p) & 15)) return false;
   if (g.kh > 16 || g.kw > 16) return false;
   WgPlan pl;
   return make_wg_plan(g, &pl);
 }
 
+int tc_wgrad_describe(const Geom &g, char *buf, size_t n) {
+  WgPlan pl;
+  if (g.st != 1 || g.ps != 1 || (g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl)) return snprintf(buf, n, "tc_wgrad: no plan");
+  const WgArgs &a = pl.a;
+  return snprintf(buf, n,
+                  "tc_wgrad: band TH %d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
+                  "stages %d, smem %zu B, tmem %d cols, grid %d x %d, ksteps %d",
+                  a.TH, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
+                  pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
+}
+
 size_t tc_wgrad_ws_bytes(const Geom &g) {
   WgPlan pl;
-  if (g.st != 1 || g.ps != 1 || g.Ci % 32 != 0 || !make_wg_plan(g, &pl)) return 0;
-  return (pl.partial_floats + pl.db_floats) * sizeof(float) + 512;
+  if (g.st != 1 || g.ps != 1 || (g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl)) return 0;
+  return (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 1024;
 }
 
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
   WgPlan pl;
   SRB_REQUIRE(make_wg_plan(g, &pl), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
-  size_t need = (pl.partial_floats + pl.db_floats) * sizeof(float);
+  size_t need = (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 256;
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_wgrad workspace: need %zu bytes, have %zu",
               need, ws_bytes);
@@ -406,7 +529,21 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   float *db_part = a.partial + pl.partial_floats;
 
   CUtensorMap mapX, mapZ;
-  {
+  if (a.c4) {
+    float *xp = (float *)(((uintptr_t)(db_part + pl.db_floats) + 255) & ~(uintptr_t)255);
+    const long long total = (long long)(pl.xpack_floats / 4);
+    int pb = (int)((total + 255) / 256);
+    if (pb > 148 * 16) pb = 148 * 16;
+    k_pack_nhwc4_padded<<<pb, 256, 0, st>>>(big, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi, g.pad, pl.Hp, pl.Wp, total);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    // overlapping view: "channel" c of slot x is float 4*x + c of the padded row -> 8 pixels x 4 channels per slot
+    cuuint64_t dims[4] = {32, (cuuint64_t)a.BW, (cuuint64_t)pl.Hp, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {16, (cuuint64_t)pl.Wp * 16, (cuuint64_t)pl.Hp * pl.Wp * 16};
+    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    int rc = encode_tiled(&mapX, xp, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)big.sw * 4, (cuuint64_t)big.sh * 4, (cuuint64_t)big.sn * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};

@@ -61,7 +61,7 @@ def _is_cl(t):
 
 def _out_format(channels):
     # activations that can feed the tensor-core kernels live in NHWC; skinny (3-channel) edges stay NCHW
-    return torch.channels_last if channels % 32 == 0 else torch.contiguous_format
+    return torch.channels_last if (channels % 4 == 0 and channels >= 8) else torch.contiguous_format
 
 
 def _require_cuda(*ts):
@@ -142,7 +142,7 @@ class _FusedConv(torch.autograd.Function):
                                   ctypes.byref(tdz), _ptr(dalpha), st))
         else:
             dz = dy
-        if p.ps > 1 and p.math != _lib.MATH_FP32 and x.shape[1] % 32 == 0 and _is_cl(x):
+        if p.ps > 1 and p.math != _lib.MATH_FP32 and x.shape[1] % 4 == 0 and x.shape[1] >= 8 and _is_cl(x):
             # PixelShuffle layer on the tensor path: undo the shuffle once (NHWC, tf32) and run dgrad/wgrad as a
             # plain conv with Cout*r*r output channels
             r = p.ps

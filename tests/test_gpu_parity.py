@@ -212,9 +212,13 @@ def test_fused_conv_vs_oracle(case, math, cl):
         assert torch.equal(rg.grad.cpu(), gy)
 
 
+@pytest.mark.parametrize("math", ["fp32", "auto"])
 @pytest.mark.parametrize("k,s,p,op,Ci,Co", [(9, 4, 3, 1, 56, 3), (4, 2, 1, 0, 16, 8), (3, 1, 1, 0, 8, 8), (5, 3, 2, 2, 6, 5)])
-def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co):
+def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co, math):
     _need_gpu()
+    srb200.set_math(math)
+    # fp32 mode: exact-order-independent fp32; auto: NHWC outputs with C % 4 == 0 are stored tf32-rounded (2^-11 relative)
+    tol = 2e-5 if math == "fp32" else 1e-3
     gen = torch.Generator().manual_seed(12)
     x = torch.randn(2, Ci, 7, 6, generator=gen)
     w = torch.randn(Ci, Co, k, k, generator=gen) * 0.1
@@ -226,10 +230,10 @@ def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co):
     xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
     y = srb200.conv_transpose2d(xg, wg, bg, s, p, op)
     y.backward(gy.to(DEV))
-    assert rel_l2(y.detach(), yref.detach()) < 2e-5
-    assert rel_l2(xg.grad, xr.grad) < 2e-5
-    assert rel_l2(wg.grad, wr.grad) < 2e-5
-    assert rel_l2(bg.grad, br.grad) < 2e-5
+    assert rel_l2(y.detach(), yref.detach()) < tol
+    assert rel_l2(xg.grad, xr.grad) < tol
+    assert rel_l2(wg.grad, wr.grad) < tol
+    assert rel_l2(bg.grad, br.grad) < tol
 
 
 @pytest.mark.parametrize("r,C,H,W", [(2, 64, 8, 8), (4, 3, 9, 7), (3, 5, 4, 6), (2, 256, 4, 4)])
@@ -288,7 +292,7 @@ def test_empty_batch_and_tiny_images():
     x = torch.randn(1, 4, 3, 3, device=DEV)
     y = srb200.conv2d(x, w, None, 1, 0)
     assert tuple(y.shape) == (1, 8, 1, 1)
-    assert rel_l2(y, TF.conv2d(x.cpu(), w.cpu())) < 2e-5
+    assert rel_l2(y, TF.conv2d(x.cpu(), w.cpu())) < 1e-3  # Cin = 4 runs on the tf32 tensor path in 'auto' mode
     with pytest.raises(srb200.SrbError):
         srb200.conv2d(torch.zeros(1, 4, 2, 2, device=DEV), w, None, 1, 0)  # kernel larger than input
 
