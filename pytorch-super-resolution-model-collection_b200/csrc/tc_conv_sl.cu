@@ -42,9 +42,11 @@ struct SlArgs {
   int spairs;        // c4: ceil(kw/2)
   int a_bufs, a_buf_bytes, a_tx_bytes;
   int b_stages, b_stage_bytes;  // c4: one stage holding every K-block of this N tile
-  int tmem_cols;
+  int b_resident;               // generic: b_stages == K-blocks, every weight tile is loaded once per CTA and stays
+  int t_bufs, tmem_cols;  // accumulator buffers in TMEM (2: epilogue of band i overlaps the MMAs of band i+1)
   int ps;
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
+  int dbg;             // debug knobs (srb_debug_set_flags): 1 = epilogue does nothing, 2 = A tiles are loaded only once per buffer
   long long *trace;    // debug (srb_debug_set_trace): 8 timestamps per CTA, null in production
   T4 out;
   Epi epi;
@@ -196,6 +198,103 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   }
 }
 
+
+// Ring positions of the MMA warp (buffer index + phase bit each; no divisions in the issue loop).
+struct MmaState {
+  uint32_t a_buf, a_phase, b_st, b_phase, t_buf, t_phase;
+};
+
+// (Called by the ONE elected thread of the MMA warp: every wait, MMA and commit of the band is issued by it.)
+// All MMAs of one band, generic operands: for every 32-channel chunk and filter tap, K = 4 x 8 over MTB_ M-tiles.
+// K-step outer / M-tile inner so that consecutive MMAs write different accumulators.
+template <int MTB_>
+__device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, uint64_t *a_full, uint64_t *a_empty,
+                                                 uint64_t *b_full, uint64_t *b_empty, uint32_t a_base, uint32_t b_base,
+                                                 uint32_t tacc, uint32_t idesc) {
+  // K-major SWIZZLE_128B: SBO 1024 B (8 slots), layout type 2; LBO field = 1 (unused)
+  const uint64_t d_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+  const uint32_t lbo = 1u << 16;
+  const uint32_t row_step = (uint32_t)(a.BW - a.kw) * 8u;  // desc units (16 B) from the end of one filter row to the next
+  const uint32_t b_stage16 = (uint32_t)a.b_stage_bytes >> 4;
+  uint32_t tcol[MTB_];
+#pragma unroll
+  for (int j = 0; j < MTB_; ++j) tcol[j] = tacc + (uint32_t)(j * a.NT);
+  uint32_t b_res = ((b_base >> 4) & 0x3FFF) | lbo;  // resident weights: K-block kb lives at stage kb
+  uint32_t first_kb = 0;                             // 0 for the very first K-block of the band: overwrite the accumulators
+  for (int c = 0; c < a.chunks; ++c) {
+    mbar_wait(&a_full[ms.a_buf], ms.a_phase);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t a_tap = (((a_base + ms.a_buf * (uint32_t)a.a_buf_bytes) >> 4) & 0x3FFF) | lbo;
+    for (int r = 0; r < a.kh; ++r) {
+      for (int s = 0; s < a.kw; ++s) {
+        uint32_t b_lo;
+        if (a.b_resident) {
+          b_lo = b_res;
+          b_res += b_stage16;
+        } else {
+          mbar_wait(&b_full[ms.b_st], ms.b_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          b_lo = (((b_base >> 4) + ms.b_st * b_stage16) & 0x3FFF) | lbo;
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+          for (int j = 0; j < MTB_; ++j)
+            umma_tf32_ss(tcol[j], d_hi | (uint64_t)(a_tap + (uint32_t)(j * 1024 + 2 * k4)), d_hi | (uint64_t)(b_lo + 2u * k4), idesc,
+                         k4 ? 1u : first_kb);
+        }
+        if (!a.b_resident) umma_commit_arrive(&b_empty[ms.b_st]);  // frees this weight stage once its MMAs have read it
+        first_kb = 1u;
+        a_tap += 8u;  // next tap in the row: one slot (128 B) later
+        if (!a.b_resident && ++ms.b_st == (uint32_t)a.b_stages) { ms.b_st = 0; ms.b_phase ^= 1u; }
+      }
+      a_tap += row_step;
+    }
+    umma_commit_arrive(&a_empty[ms.a_buf]);
+    if (++ms.a_buf == (uint32_t)a.a_bufs) { ms.a_buf = 0; ms.a_phase ^= 1u; }
+  }
+}
+
+// All MMAs of one band, c4 operands: one K = 8 MMA per (filter row, tap pair) and M-tile.
+//   A: no swizzle, LBO 16 B (next 4 floats along K = next pixel), SBO 128 B (next 8 rows = next 8 slots)
+//   B: no swizzle canonical [N/8][2][8 rows][16 B]: LBO 128 B, SBO 256 B
+template <int MTB_>
+__device__ __forceinline__ void mma_band_c4(const SlArgs &a, MmaState &ms, uint64_t *a_full, uint64_t *a_empty, uint32_t a_base,
+                                            uint32_t b_base, uint32_t tacc, uint32_t idesc) {
+  const uint64_t a_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32, b_hi = (uint64_t)((256u >> 4) | (1u << 14)) << 32;
+  const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
+  uint32_t tcol[MTB_];
+#pragma unroll
+  for (int j = 0; j < MTB_; ++j) tcol[j] = tacc + (uint32_t)(j * a.NT);
+  mbar_wait(&a_full[ms.a_buf], ms.a_phase);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t a_tap = (((a_base + ms.a_buf * (uint32_t)a.a_buf_bytes) >> 4) & 0x3FFF) | a_lbo;
+  uint32_t b_lo = ((b_base >> 4) & 0x3FFF) | b_lbo;
+  const uint32_t kb16 = (uint32_t)a.NT * 2u;                          // NT * 32 B per K-block, in 16-byte units
+  const uint32_t row_step = (uint32_t)(a.BW - 2 * a.spairs);          // slots (16 B) to the next filter row
+  uint32_t acc = 0;
+  for (int r = 0; r < a.kh; ++r) {
+    for (int sp = 0; sp < a.spairs; ++sp) {
+#pragma unroll
+      for (int j = 0; j < MTB_; ++j)  // 128 slots x 16 B = 2048 B per M-tile
+        umma_tf32_ss(tcol[j], a_hi | (uint64_t)(a_tap + (uint32_t)(j * 128)), b_hi | (uint64_t)b_lo, idesc, acc);
+      acc = 1u;
+      a_tap += 2u;   // two pixels (32 B) to the right
+      b_lo += kb16;
+    }
+    a_tap += row_step;
+  }
+  umma_commit_arrive(&a_empty[ms.a_buf]);
+  if (++ms.a_buf == (uint32_t)a.a_bufs) { ms.a_buf = 0; ms.a_phase ^= 1u; }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: CTA (x, y) walks bands x, x + gridDim.x, ... of N tile y.  Every ring (A chunk buffers, B stages, TMEM
+// accumulator buffers) is tracked by a running counter, so the TMA producer runs ahead into the next band while the
+// MMAs of the current one are still in flight, and the epilogue of band i overlaps the MMAs of band i+1.
 __global__ void __launch_bounds__(kThreads)
 k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, SlArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -206,8 +305,9 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   uint64_t *a_empty = a_full + 2;
   uint64_t *b_full = a_empty + 2;
   uint64_t *b_empty = b_full + kMaxBStages;
-  uint64_t *accum_bar = b_empty + kMaxBStages;
-  uint32_t *tmem_slot = (uint32_t *)(accum_bar + 1);
+  uint64_t *t_full = b_empty + kMaxBStages;
+  uint64_t *t_empty = t_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(t_empty + 2);
   float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,24 +319,19 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = smid;
     }
   }
-  // band -> (image, band row, band col)
-  const int band = blockIdx.x;
-  const int bw_i = band % a.bands_w;
-  const int bq = band / a.bands_w;
-  const int bh_i = bq % a.bands_h;
-  const int img = bq / a.bands_h;
-  const int oy0 = bh_i * a.TH, ox0 = bw_i * a.TW;
+  const int num_bands = a.N * a.bands_h * a.bands_w;
   const int n0 = blockIdx.y * a.NT;
-  const int rows_valid = min(a.TH, a.Ho - oy0), cols_valid = min(a.TW, a.Wo - ox0);
-  const int mtb = ((rows_valid - 1) * a.BW + cols_valid + 127) >> 7;  // M-tiles that hold at least one real pixel
   const int taps = a.kh * a.kw;
+  const int acc_cols = a.MTB * a.NT;  // TMEM columns of one accumulator buffer
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     if (!a.c4) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
+      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], (kThreads - 64) / 32);
+    }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -251,38 +346,63 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) SL_TRACE(1);
 
+// band index -> image, origin and number of M-tiles holding at least one real pixel
+#define SL_BAND_GEOM(band)                                                                 \
+  const int bw_i = (band) % a.bands_w;                                                     \
+  const int bq_ = (band) / a.bands_w;                                                      \
+  const int bh_i = bq_ % a.bands_h;                                                        \
+  const int img = bq_ / a.bands_h;                                                         \
+  const int oy0 = bh_i * a.TH, ox0 = bw_i * a.TW;                                          \
+  const int rows_valid = min(a.TH, a.Ho - oy0), cols_valid = min(a.TW, a.Wo - ox0);        \
+  const int mtb = ((rows_valid - 1) * a.BW + cols_valid + 127) >> 7;
+
   if (warp == 0) {
     // ===================== TMA producer =====================
-    const int ix0 = ox0 - a.pad, iy0 = oy0 - a.pad;
     if (a.c4) {
-      if (elect_one()) {
+      if (elect_one()) {  // every K-block of this N tile stays resident
         const uint32_t wbytes = (uint32_t)a.b_stage_bytes;
         mbar_expect_tx(&b_full[0], wbytes);
         const uint8_t *src = (const uint8_t *)a.wpack + (size_t)blockIdx.y * wbytes;
         for (uint32_t off = 0; off < wbytes; off += 16384u)
           bulk_g2s(b_smem + off, src + off, min(16384u, wbytes - off), &b_full[0]);
-        mbar_expect_tx(&a_full[0], (uint32_t)a.a_tx_bytes);
-        tma_load_4d(&mapA, &a_full[0], a_smem, 0, ix0, iy0, img);
       }
       __syncwarp();
-    } else {
-      int kb = 0;
-      for (int c = 0; c < a.chunks; ++c) {
-        const int buf = c % a.a_bufs;
-        mbar_wait(&a_empty[buf], (((uint32_t)(c / a.a_bufs)) & 1u) ^ 1u);
+    }
+    if (!a.c4 && a.b_resident) {
+      if (elect_one()) {
+        mbar_expect_tx(&b_full[0], (uint32_t)(a.b_stages * a.b_stage_bytes));
+        for (int kb = 0; kb < a.b_stages; ++kb)
+          tma_load_3d(&mapB, &b_full[0], b_smem + (size_t)kb * a.b_stage_bytes, 0, n0, kb);
+      }
+      __syncwarp();
+    }
+    uint32_t ac = 0, kb = 0;  // running A-chunk / K-block counters
+    for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+      SL_BAND_GEOM(band)
+      (void)mtb;
+      const int ix0 = ox0 - a.pad, iy0 = oy0 - a.pad;
+      for (int c = 0; c < a.chunks; ++c, ++ac) {
+        const uint32_t buf = ac % (uint32_t)a.a_bufs;
+        mbar_wait(&a_empty[buf], ((ac / (uint32_t)a.a_bufs) & 1u) ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[buf], (uint32_t)a.a_tx_bytes);
-          tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * 32, ix0, iy0, img);
+          if ((a.dbg & 2) && ac >= (uint32_t)a.a_bufs) {
+            mbar_arrive(&a_full[buf]);
+          } else {
+            mbar_expect_tx(&a_full[buf], (uint32_t)a.a_tx_bytes);
+            tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * 32, ix0, iy0, img);
+          }
         }
         __syncwarp();
-        for (int tap = 0; tap < taps; ++tap, ++kb) {
-          const int st = kb % a.b_stages;
-          mbar_wait(&b_empty[st], (((uint32_t)(kb / a.b_stages)) & 1u) ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(&b_full[st], (uint32_t)a.b_stage_bytes);
-            tma_load_3d(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes, 0, n0, kb);
+        if (!a.c4 && !a.b_resident) {
+          for (int tap = 0; tap < taps; ++tap, ++kb) {
+            const uint32_t st = kb % (uint32_t)a.b_stages;
+            mbar_wait(&b_empty[st], ((kb / (uint32_t)a.b_stages) & 1u) ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[st], (uint32_t)a.b_stage_bytes);
+              tma_load_3d(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes, 0, n0, c * taps + tap);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -290,83 +410,47 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
-    if (a.c4) {
-      // A: no swizzle, LBO 16 B (next 4 floats along K = next pixel), SBO 128 B (next 8 rows = next 8 slots)
-      // B: no swizzle canonical [N/8][2][8 rows][16 B]: LBO 128 B, SBO 256 B
-      const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
-      const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
-      mbar_wait(&b_full[0], 0);
-      mbar_wait(&a_full[0], 0);
-      if (lane == 0) SL_TRACE(2);
+    const long long clk0 = clock64();
+    const long long gt0 = gtime();
+    MmaState ms;
+    ms.a_buf = 0; ms.a_phase = 0; ms.b_st = 0; ms.b_phase = 0; ms.t_buf = 0; ms.t_phase = 0;
+    if (a.c4 || a.b_resident) mbar_wait(&b_full[0], 0);
+    bool first = true;
+    if (elect_one())
+    for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+      SL_BAND_GEOM(band)
+      (void)img;
+      mbar_wait(&t_empty[ms.t_buf], ms.t_phase ^ 1u);  // epilogue has drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem);
-      const uint32_t kb_bytes = (uint32_t)a.NT * 32u;
-      if (elect_one()) {
-        int kb = 0;
-        for (int r = 0; r < a.kh; ++r) {
-          for (int sp = 0; sp < a.spairs; ++sp, ++kb) {
-            const uint32_t a_lo = (((a_addr + (uint32_t)(r * a.BW + 2 * sp) * 16u) >> 4) & 0x3FFF) | a_lbo;
-            const uint32_t b_lo = (((b_addr + (uint32_t)kb * kb_bytes) >> 4) & 0x3FFF) | b_lbo;
-            const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
-            const uint32_t acc = kb ? 1u : 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < mtb)  // 128 slots x 16 B = 2048 B per M-tile
-                umma_tf32_ss(tmem_base + (uint32_t)(j * a.NT), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + j * 128), bdesc, idesc, acc);
-          }
-        }
-        umma_commit_arrive(accum_bar);
+      const uint32_t tacc = tmem_base + ms.t_buf * (uint32_t)acc_cols;
+      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+      if (first) SL_TRACE(2);
+      first = false;
+      // straight-line issue code per M-tile count (no per-MMA predicates, descriptors stay in uniform registers)
+      if (a.c4) {
+        if (mtb == 1) mma_band_c4<1>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 2) mma_band_c4<2>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 3) mma_band_c4<3>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
+        else mma_band_c4<4>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
+      } else {
+        if (mtb == 1) mma_band_generic<1>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 2) mma_band_generic<2>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 3) mma_band_generic<3>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else mma_band_generic<4>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
       }
-      __syncwarp();
-      if (lane == 0) SL_TRACE(3);
-    } else {
-      // K-major SWIZZLE_128B: SBO 1024 B (8 slots), layout type 2
-      const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t lbo = 1u << 16;
-      const uint32_t b_addr0 = smem_u32(b_smem);
-      int kb = 0;
-      for (int c = 0; c < a.chunks; ++c) {
-        const int buf = c % a.a_bufs;
-        mbar_wait(&a_full[buf], ((uint32_t)(c / a.a_bufs)) & 1u);
-        if (c == 0 && lane == 0) SL_TRACE(2);
-        const uint32_t a_addr = smem_u32(a_smem + (size_t)buf * a.a_buf_bytes);
-        for (int r = 0; r < a.kh; ++r) {
-          for (int s = 0; s < a.kw; ++s, ++kb) {
-            const int st = kb % a.b_stages;
-            mbar_wait(&b_full[st], ((uint32_t)(kb / a.b_stages)) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_lo = (((a_addr + (uint32_t)(r * a.BW + s) * 128u) >> 4) & 0x3FFF) | lbo;
-            const uint32_t b_lo = (((b_addr0 + (uint32_t)st * (uint32_t)a.b_stage_bytes) >> 4) & 0x3FFF) | lbo;
-            if (elect_one()) {
-              const uint32_t acc0 = kb ? 1u : 0u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (j < mtb) {
-                  const uint32_t aj = a_lo + (uint32_t)j * 1024u;  // 128 slots x 128 B >> 4
-                  const uint32_t tcol = tmem_base + (uint32_t)(j * a.NT);
-                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 0), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 0), idesc, acc0);
-                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 2), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 2), idesc, 1u);
-                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 4), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 4), idesc, 1u);
-                  umma_tf32_ss(tcol, ((uint64_t)d_hi << 32) | (uint64_t)(aj + 6), ((uint64_t)d_hi << 32) | (uint64_t)(b_lo + 6), idesc, 1u);
-                }
-              }
-              umma_commit_arrive(&b_empty[st]);
-            }
-            __syncwarp();
-          }
-        }
-        if (elect_one()) umma_commit_arrive(&a_empty[buf]);
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit_arrive(accum_bar);
-      __syncwarp();
-      if (lane == 0) SL_TRACE(3);
+      umma_commit_arrive(&t_full[ms.t_buf]);  // this band's accumulators are complete
+      if (++ms.t_buf == (uint32_t)a.t_bufs) { ms.t_buf = 0; ms.t_phase ^= 1u; }
+    }
+    __syncwarp();
+    if (lane == 0 && a.trace) {  // slot 3: MMA-loop duration in ns (low 32 bits) and in SM cycles (high 32 bits)
+      const long long dc = clock64() - clk0, dt = gtime() - gt0;
+      a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 3] = (dc << 32) | (dt & 0xffffffffLL);
     }
   } else {
     // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31 =====================
     // Two warps share each lane quadrant and alternate over the (M-tile, 16-column group) work items.
     const int lane_grp = warp & 3, half = (warp - 2) >> 2;
-    // bias -> shared memory while the MMAs run (zero when absent or beyond Co)
+    // bias -> shared memory while the first MMAs run (zero when absent or beyond Co)
     for (int j = threadIdx.x - 64; j < a.NT; j += kThreads - 64) {
       const int co = n0 + j;
       bias_s[j] = (a.epi.bias && co < a.Co) ? __ldg(a.epi.bias + co) : 0.f;
@@ -383,21 +467,32 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
     const bool extra = a.epi.residual.p != nullptr || a.epi.preact.p != nullptr;
     asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");  // bias_s visible to all epilogue warps
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp == 2 && lane == 0) SL_TRACE(4);
-    const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;
+    uint32_t wi = 0;
+    for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++wi) {
+      SL_BAND_GEOM(band)
+      const uint32_t tb = wi % (uint32_t)a.t_bufs;
+      mbar_wait(&t_full[tb], (wi / (uint32_t)a.t_bufs) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (wi == 0 && warp == 2 && lane == 0) SL_TRACE(4);
+      const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + tb * (uint32_t)acc_cols;
 #define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
-    if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
-    else if (fmode == 1) { if (extra) SL_EPI(1, true); else SL_EPI(1, false); }
-    else if (fmode == 2) { if (extra) SL_EPI(2, true); else SL_EPI(2, false); }
-    else SL_EPI(3, true);
+      if (a.dbg & 1) {}
+      else if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
+      else if (fmode == 1) { if (extra) SL_EPI(1, true); else SL_EPI(1, false); }
+      else if (fmode == 2) { if (extra) SL_EPI(2, true); else SL_EPI(2, false); }
+      else SL_EPI(3, true);
 #undef SL_EPI
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): hand the buffer back
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[tb]);
+      if (wi == 0 && warp == 2 && lane == 0) SL_TRACE(5);
+    }
   }
+#undef SL_BAND_GEOM
 
-  if (warp == 2 && lane == 0) SL_TRACE(5);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -480,7 +575,7 @@ __global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H,
 struct SlPlan {
   SlArgs a;
   size_t smem;
-  int n_tiles_n, Npad;
+  int n_tiles_n, Npad, ctas_per_sm, grid_x;
   size_t wpack_floats, xpack_floats;
 };
 
@@ -506,59 +601,71 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   const double mma_per_tile = (c4 ? kblocks : kblocks * 4) * mma_cost(NT);
   double best_t = -1.0;
   for (int ctas = 2; ctas >= 1; --ctas) {
-    const int smem_cap = ctas == 2 ? 113 * 1024 : 226 * 1024;
+    const int smem_cap = ctas == 2 ? 111 * 1024 : 226 * 1024;
     const int col_cap = ctas == 2 ? 256 : 512;
-    for (int MTB = (col_cap / NT < 4 ? col_cap / NT : 4); MTB >= 1; --MTB) {
-      for (int wsplit = 1; wsplit <= 16; ++wsplit) {
-        const int TW = (g.Wo + wsplit - 1) / wsplit;
-        const int BW = TW + kextra;
-        if (BW > 256 || TW > 128 * MTB) continue;
-        int TH = (128 * MTB - TW) / BW + 1;
-        if (TH > g.Ho) TH = g.Ho;
-        const int bands_h = (g.Ho + TH - 1) / TH;
-        TH = (g.Ho + bands_h - 1) / bands_h;
-        const int BH = TH + g.kh - 1;
-        if (BH > 256) continue;
-        const int bands_w = (g.Wo + TW - 1) / TW;
-        int slots = BH * BW;
-        const int need = 128 * MTB + (g.kh - 1) * BW + kextra;
-        if (need > slots) slots = need;
-        const int a_buf = round_up_i(slots * sb, 1024);
-        int b_stage, b_stages, a_bufs;
-        if (c4) {
-          b_stage = kblocks * NT * 32; b_stages = 1; a_bufs = 1;
-        } else {
-          b_stage = NT * 128;
-          a_bufs = chunks > 1 ? 2 : 1;
-          b_stages = (smem_cap - 3072 - a_bufs * a_buf) / b_stage;
-          if (b_stages < 3 && a_bufs == 2) { a_bufs = 1; b_stages = (smem_cap - 3072 - a_buf) / b_stage; }
-          if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-          if (b_stages > kblocks) b_stages = kblocks;
-          if (b_stages < 2 && kblocks >= 2) continue;
-        }
-        const size_t smem = (size_t)a_bufs * a_buf + (size_t)b_stages * b_stage + 1024 + 512 + 1024;
-        if (smem > (size_t)smem_cap) continue;
-        // time model per real output pixel (cycles on one SM)
-        const double eff = (double)g.Ho * g.Wo / ((double)bands_h * bands_w * MTB * 128);
-        const double t_mma = mma_per_tile / 128.0 / eff;
-        const double a_bytes = (double)chunks * BH * BW * sb / ((double)TH * TW);
-        const double b_bytes = (double)kblocks * NT * (c4 ? 32 : 128) / (eff * MTB * 128.0);
-        const double t_mem = (a_bytes + b_bytes + 4.0 * NT) / 48.0;  // ~48 B/clk/SM of L2->SM + store bandwidth
-        double t = t_mma > t_mem ? t_mma : t_mem;
-        if (ctas == 1) t *= 1.2;                      // no co-resident CTA to hide the epilogue
-        if (a_bufs == 1 && chunks > 1) t *= 1.1;      // chunk loads serialise with the MMAs
-        const long long nctas = (long long)g.N * bands_h * bands_w * (Npad / NT);
-        if (nctas < 148) t *= 148.0 / (double)nctas;  // do not starve the SMs on tiny problems
-        if (best_t < 0 || t < best_t) {
-          best_t = t;
-          a.TH = TH; a.TW = TW; a.BW = BW; a.BH = BH; a.bands_h = bands_h; a.bands_w = bands_w;
-          a.MTB = MTB; a.NT = NT; a.chunks = chunks; a.spairs = spairs;
-          a.a_bufs = a_bufs; a.a_buf_bytes = a_buf; a.a_tx_bytes = BH * BW * sb;
-          a.b_stages = b_stages; a.b_stage_bytes = b_stage;
-          int tc = 32;
-          while (tc < MTB * NT) tc <<= 1;
-          a.tmem_cols = tc;
-          pl->smem = smem;
+    for (int t_bufs = 2; t_bufs >= 1; --t_bufs) {
+      for (int MTB = (col_cap / (t_bufs * NT) < 4 ? col_cap / (t_bufs * NT) : 4); MTB >= 1; --MTB) {
+        for (int wsplit = 1; wsplit <= 16; ++wsplit) {
+          const int TW = (g.Wo + wsplit - 1) / wsplit;
+          const int BW = TW + kextra;
+          if (BW > 256 || TW > 128 * MTB) continue;
+          int TH = (128 * MTB - TW) / BW + 1;
+          if (TH > g.Ho) TH = g.Ho;
+          const int bands_h = (g.Ho + TH - 1) / TH;
+          TH = (g.Ho + bands_h - 1) / bands_h;
+          const int BH = TH + g.kh - 1;
+          if (BH > 256) continue;
+          const int bands_w = (g.Wo + TW - 1) / TW;
+          int slots = BH * BW;
+          const int need = 128 * MTB + (g.kh - 1) * BW + kextra;
+          if (need > slots) slots = need;
+          const int a_buf = round_up_i(slots * sb, 1024);
+          int b_stage, b_stages, a_bufs = 2;  // two A buffers: the next chunk / next band loads under the current MMAs
+          int b_res = 0;
+          if (c4) {
+            b_stage = kblocks * NT * 32; b_stages = 1;
+          } else {
+            b_stage = NT * 128;
+            b_stages = (smem_cap - 3072 - a_bufs * a_buf) / b_stage;
+            if (b_stages >= kblocks) { b_stages = kblocks; b_res = 1; }  // all weights stay resident
+            else {
+              if (b_stages < 4) { a_bufs = 1; b_stages = (smem_cap - 3072 - a_buf) / b_stage; }
+              if (b_stages >= kblocks) { b_stages = kblocks; b_res = 1; }
+              else if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+              if (b_stages < 2) continue;
+            }
+          }
+          const size_t smem = (size_t)a_bufs * a_buf + (size_t)b_stages * b_stage + 1024 + 512 + 1024;
+          if (smem > (size_t)smem_cap) continue;
+          // time model per real output pixel (cycles on one SM)
+          const double eff = (double)g.Ho * g.Wo / ((double)bands_h * bands_w * MTB * 128);
+          double t_mma = mma_per_tile / 128.0 / eff;
+          if (!c4 && !b_res) {  // a streamed weight ring delivers one K-block per (TMA round trip / stages)
+            const double ring = 2400.0 / b_stages * kblocks / (MTB * 128.0) / eff;
+            if (ring > t_mma) t_mma = ring;
+          }
+          const double a_bytes = (double)chunks * BH * BW * sb / ((double)TH * TW);
+          const double b_bytes = (c4 || b_res) ? 0.0 : (double)kblocks * NT * 128 / (eff * MTB * 128.0);
+          const double t_mem = (a_bytes + b_bytes + 4.0 * NT) / 48.0;  // ~48 B/clk/SM of L2->SM + store bandwidth
+          double t = t_mma > t_mem ? t_mma : t_mem;
+          t += 600.0 / ((double)TH * TW);  // per-band hand-offs (accumulator swap, first-MMA latency)
+          if (t_bufs == 1) t *= (ctas == 2 ? 1.1 : 1.3);  // the epilogue is only hidden by a co-resident CTA, if any
+          if (a_bufs == 1) t *= 1.15;                       // operand loads serialise with the MMAs
+          const long long work = (long long)g.N * bands_h * bands_w * (Npad / NT);
+          if (work < 148) t *= 148.0 / (double)(work > 0 ? work : 1);  // do not starve the SMs on tiny problems
+          if (best_t < 0 || t < best_t) {
+            best_t = t;
+            a.TH = TH; a.TW = TW; a.BW = BW; a.BH = BH; a.bands_h = bands_h; a.bands_w = bands_w;
+            a.MTB = MTB; a.NT = NT; a.chunks = chunks; a.spairs = spairs;
+            a.a_bufs = a_bufs; a.a_buf_bytes = a_buf; a.a_tx_bytes = BH * BW * sb;
+            a.b_stages = b_stages; a.b_stage_bytes = b_stage; a.b_resident = b_res;
+            a.t_bufs = t_bufs;
+            int tc = 32;
+            while (tc < t_bufs * MTB * NT) tc <<= 1;
+            a.tmem_cols = tc;
+            pl->smem = smem;
+            pl->ctas_per_sm = ctas;
+          }
         }
       }
     }
@@ -568,6 +675,16 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   a.ps = g.ps;
   pl->Npad = Npad;
   pl->n_tiles_n = Npad / NT;
+  {  // persistent grid: as many CTAs as fit on the chip, bands split evenly
+    const long long num_bands = (long long)g.N * a.bands_h * a.bands_w;
+    long long slots = (long long)pl->ctas_per_sm * 148 / pl->n_tiles_n;
+    if (slots < 1) slots = 1;
+    long long P = num_bands < slots ? num_bands : slots;
+    if (P < 1) P = 1;
+    const long long per = (num_bands + P - 1) / P;
+    pl->grid_x = (int)(per > 0 ? (num_bands + per - 1) / per : 1);
+    if (pl->grid_x < 1) pl->grid_x = 1;
+  }
   pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
   pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;
   return true;
@@ -618,10 +735,10 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n) {
   const SlArgs &a = pl.a;
   return snprintf(buf, n,
                   "conv_sl %s: band %dx%d (halo %dx%d), %dx%d bands/img, MTB %d, NT %d x%d, chunks %d, a_bufs %d x %d B, "
-                  "b_stages %d x %d B, smem %zu B, tmem %d cols, grid %d x %d",
+                  "b_stages %d%s x %d B, smem %zu B, tmem %d cols (%d acc bufs), %d bands on grid %d x %d (%d CTA/SM)",
                   a.c4 ? "c4" : "generic", a.TH, a.TW, a.BH, a.BW, a.bands_h, a.bands_w, a.MTB, a.NT, pl.n_tiles_n, a.chunks,
-                  a.a_bufs, a.a_buf_bytes, a.b_stages, a.b_stage_bytes, pl.smem, a.tmem_cols, g.N * a.bands_h * a.bands_w,
-                  pl.n_tiles_n);
+                  a.a_bufs, a.a_buf_bytes, a.b_stages, (a.c4 || a.b_resident) ? " (resident)" : "", a.b_stage_bytes, pl.smem, a.tmem_cols, a.t_bufs,
+                  g.N * a.bands_h * a.bands_w, pl.grid_x, pl.n_tiles_n, pl.ctas_per_sm);
 }
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
@@ -686,14 +803,16 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   }
   a.out = out;
   a.epi = epi;
-  a.trace = ((long long)g.N * a.bands_h * a.bands_w * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;
+  a.dbg = g_sl_dbg;
+  a.trace = ((long long)pl.grid_x * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;
 
   static bool attr_set = false;
   if (!attr_set) {
     SRB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_sl, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_sl, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  dim3 grid((unsigned)(g.N * a.bands_h * a.bands_w), (unsigned)pl.n_tiles_n);
+  dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles_n);
   k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());

@@ -12,7 +12,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
-__global__ void __launch_bounds__(128, 1) k(int N, int mn_major, int iters, int ctas_share, long long *out) {
+__global__ void __launch_bounds__(128, 1) k(int N, int mn_major, int iters, int ctas_share, long long *out, int a_shift) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint64_t *bar = (uint64_t *)(smem + 160 * 1024);
@@ -39,12 +39,12 @@ __global__ void __launch_bounds__(128, 1) k(int N, int mn_major, int iters, int 
     if (mn_major) {
       idesc |= (1u << 15) | (1u << 16);
       hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
-      a_lo = ((smem_u32(smem) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+      a_lo = (((smem_u32(smem) + a_shift) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
       b_lo = ((smem_u32(smem + 64 * 1024) >> 4) & 0x3FFF) | ((16384u >> 4) << 16);
       step = 64;  // 1 KB per K-step
     } else {
       hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-      a_lo = ((smem_u32(smem) >> 4) & 0x3FFF) | (1u << 16);
+      a_lo = (((smem_u32(smem) + a_shift) >> 4) & 0x3FFF) | (1u << 16);
       b_lo = ((smem_u32(smem + 64 * 1024) >> 4) & 0x3FFF) | (1u << 16);
       step = 2;  // 32 B per K-step inside the swizzle row
     }
@@ -78,15 +78,17 @@ int main() {
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   int Ns[] = {16, 32, 48, 64, 128, 256};
+  int shifts[] = {0, 128, 640, 1024};
+  for (int si = 0; si < 4; ++si)
   for (int mn = 0; mn < 2; ++mn)
     for (int share = 1; share <= 2; ++share)
       for (int ni = 0; ni < 6; ++ni) {
         int N = Ns[ni], iters = 2000;
-        k<<<1, 128, 200 * 1024>>>(N, mn, iters, share, d);
+        k<<<1, 128, 200 * 1024>>>(N, mn, iters, share, d, shifts[si]);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("%s N=%3d accumulators=%d : issue %.1f cyc/mma, complete %.1f cyc/mma (math floor %.0f)\n", mn ? "MN-major" : "K-major ", N,
+        printf("A shift %4d B  %s N=%3d accumulators=%d : issue %.1f cyc/mma, complete %.1f cyc/mma (math floor %.0f)\n", shifts[si], mn ? "MN-major" : "K-major ", N,
                share, (double)h[0] / iters, (double)h[1] / iters, 128.0 * N / 256.0);
       }
   return 0;

@@ -34,8 +34,11 @@ def run(name, N, Ci, H, W, Co, k, p, ps=1, act="relu"):
     t0 = t[:, 0].min()
     d = lambda a, b: (t[:, b] - t[:, a]) / 1e3
     print("%s: %d CTAs, call %.1f us (incl. pack kernels), kernel span %.1f us" % (name, len(t), e0.elapsed_time(e1) * 1e3, (t[:, 6].max() - t0) / 1e3))
-    for lbl, a_, b_ in (("setup (alloc+init+sync)", 0, 1), ("wait first operands", 1, 2), ("MMA issue loop", 2, 3), ("issue end -> accum done", 3, 4),
-                        ("epilogue", 4, 5), ("teardown", 5, 6), ("CTA lifetime", 0, 6)):
+    cyc = (t[:, 3] >> 32).astype(np.float64)
+    ns = (t[:, 3] & 0xffffffff).astype(np.float64)
+    print("   MMA loop: mean %.2f us, %.0f SM cycles -> effective SM clock %.0f MHz" % (ns.mean() / 1e3, cyc.mean(), (cyc / ns).mean() * 1e3))
+    for lbl, a_, b_ in (("setup (alloc+init+sync)", 0, 1), ("wait first operands", 1, 2),
+                        ("first band epilogue", 4, 5), ("CTA lifetime", 0, 6)):
         v = d(a_, b_)
         print("   %-26s mean %7.2f us  p10 %7.2f  p50 %7.2f  p90 %7.2f" % (lbl, v.mean(), np.percentile(v, 10), np.percentile(v, 50), np.percentile(v, 90)))
     # concurrency per SM
@@ -44,6 +47,18 @@ def run(name, N, Ci, H, W, Co, k, p, ps=1, act="relu"):
     print("   CTAs/SM %.1f, sum(lifetime)/SM/span = %.2f resident CTAs on average" % (len(t) / len(set(sm.tolist())), life.sum() / len(set(sm.tolist())) / ((t[:, 6].max() - t0) / 1e3)))
 
 if __name__ == "__main__":
+    dbg = _lib.lib.srb_debug_set_flags
+    dbg.argtypes = [ctypes.c_int]
+    dbg.restype = None
+    if len(sys.argv) > 1:
+        for flags in (0, 1, 2, 3):
+            dbg(flags)
+            print("#### debug flags %d (1: empty epilogue, 2: A tiles loaded once)" % flags)
+            run("espcn L1 (c4)", 128, 3, 64, 64, 64, 5, 0)
+            run("espcn L2", 128, 64, 60, 60, 32, 3, 0)
+            run("vdsr body", 64, 64, 128, 128, 64, 3, 1)
+        dbg(0)
+        sys.exit(0)
     run("espcn L1 (c4)", 128, 3, 64, 64, 64, 5, 0)
     run("espcn L2", 128, 64, 60, 60, 32, 3, 0)
     run("espcn L3 +PS4", 128, 32, 58, 58, 3, 3, 0, ps=4, act=None)
