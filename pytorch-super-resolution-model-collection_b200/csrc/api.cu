@@ -70,6 +70,51 @@ __global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int
   }
 }
 
+// Tiled pixel_unshuffle for row-contiguous dz (sw == 1): one block per output row (n, h).  The C*r source rows
+// (W*r floats each, fully coalesced reads) are staged in shared memory, then written as the W*K contiguous floats of the
+// NHWC output row (fully coalesced stores).  Row pitch W*r + 4 keeps the (i, j) gather off a single bank.
+__global__ void __launch_bounds__(256)
+k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r) {
+  extern __shared__ float srow[];
+  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+  const int Wr = W * r, pitch = Wr + 4, rows = C * r, K = C * r * r;
+  // load: rows x Wr floats
+  if ((Wr & 3) == 0 && (dz.sh & 3) == 0 && (dz.sc & 3) == 0 && (dz.sn & 3) == 0 && ((uintptr_t)dz.p & 15) == 0) {
+    const int w4 = Wr >> 2;
+    for (int e = threadIdx.x; e < rows * w4; e += blockDim.x) {
+      const int row = e / w4, x4 = e - row * w4;
+      const int c = row / r, i = row - c * r;
+      const float4 v = __ldg((const float4 *)(dz.p + n * dz.sn + c * dz.sc + (long long)(h * r + i) * dz.sh) + x4);
+      *(float4 *)(srow + row * pitch + 4 * x4) = v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < rows * Wr; e += blockDim.x) {
+      const int row = e / Wr, x = e - row * Wr;
+      const int c = row / r, i = row - c * r;
+      srow[row * pitch + x] = __ldg(dz.p + n * dz.sn + c * dz.sc + (long long)(h * r + i) * dz.sh + x);
+    }
+  }
+  __syncthreads();
+  float *orow = out.p + n * out.sn + (long long)h * out.sh;
+  if (r == 4 && out.sw == K) {
+    // one float4 = the 4 j's of (w, c, i): smem s[c*4+i][4w .. 4w+3] -> out[w*K + c*16 + i*4 ..]
+    const int q = K >> 2;  // float4 per pixel
+    for (int e = threadIdx.x; e < W * q; e += blockDim.x) {
+      const int w = e / q, ci = e - w * q;  // ci = c*4 + i
+      float4 v = *(const float4 *)(srow + ci * pitch + 4 * w);
+      v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+      *(float4 *)(orow + (long long)w * K + 4 * ci) = v;
+    }
+  } else {
+    const int rr = r * r;
+    for (int e = threadIdx.x; e < W * K; e += blockDim.x) {
+      const int w = e / K, k = e - w * K;
+      const int c = k / rr, ij = k - c * rr, i = ij / r, j = ij - i * r;
+      orow[(long long)w * out.sw + k] = round_tf32(srow[(c * r + i) * pitch + w * r + j]);
+    }
+  }
+}
+
 // Same-layout dense tensors: flat float4 walk (the common case: dy, ref, dz all NHWC- or all NCHW-contiguous)
 __global__ void k_act_bwd_flat(const float4 *__restrict__ dy, const float4 *__restrict__ ref, float4 *dz, long long n4,
                                int act, float slope_in, const float *__restrict__ alpha, float *dalpha, int rnd) {
@@ -390,6 +435,14 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
   SRB_REQUIRE(dz && dz->data && out && out->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(out->sc == 1, SRB_EINVAL, "pixel_unshuffle writes channels_last");
   long long total = (long long)g.N * g.Ho * g.Wo * g.Co;
+  const size_t row_smem = (size_t)p->Cout * g.ps * ((size_t)g.Wo * g.ps + 4) * sizeof(float);
+  if (dz->sw == 1 && row_smem <= 48 * 1024 && (long long)g.N * g.Ho < (1LL << 31)) {
+    k_pixel_unshuffle_rows<<<(unsigned)(g.N * g.Ho), 256, row_smem, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, p->Cout,
+                                                                                            g.Ho, g.Wo, g.ps);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    return SRB_OK;
+  }
   k_pixel_unshuffle<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, g.Co, g.Ho, g.Wo,
                                                                          g.ps);
   count_launch();

@@ -38,6 +38,7 @@ struct WgArgs {
                           // 32 "channels" are the 8-pixel x 4-channel window starting at the slot; an accumulator's four
                           // 32-lane M-blocks are four consecutive FILTER ROWS (LBO = one slot row); RG = ceil(kh/4) accumulators
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
+  float *db_part;         // bias gradient partials [gridDim.x][4 warps][n_cot * NT], or null
 };
 
 // MN-major operand, 128B swizzle with 32B atoms: 4 K-rows x 128 B per atom (SBO = 512 B between atoms along K),
@@ -75,6 +76,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   const int band0 = blockIdx.x * a.bands_per_cta;
   const int band1 = min(band0 + a.bands_per_cta, a.num_bands);
   const int ACC = a.RG * a.SG * a.CIB;
+  // the CTAs of the first (ci group, filter-row group) also reduce dz over pixels: db[co] = sum_p dz[p][co]
+  const bool do_db = a.db_part != nullptr && cig == 0 && rgi == 0;
 
   // zero all stage buffers once: the tails past each TMA box must read as 0.0f forever
   {
@@ -89,7 +92,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZ) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_db ? 5 : 1);  // MMA commit (+ the four column-sum warps)
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -199,6 +202,32 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   } else {
     // ===================== epilogue: dump the partial dW tile =====================
     const int lane_grp = warp & 3;
+    if (do_db) {
+      // While the MMAs run, these warps walk the same stages and sum the dz tiles over pixels (rows of 128 B holding
+      // 32 channels; 128B_ATOM_32B swizzle: 32-byte atom index XOR (row & 3)).  Warp w takes rows w, w+4, ...
+      float dbs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dbs[j] = 0.f;
+      const int rows = a.TH * a.BW;
+      int it = 0;
+      for (int band = band0; band < band1; ++band, ++it) {
+        const int st = it % a.stages;
+        mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
+        const uint8_t *sz = smem + (size_t)st * stage_bytes + (size_t)a.CIB * x_bytes;
+        for (int q = lane_grp; q < rows; q += 4) {
+          const uint32_t off = (uint32_t)q * 128u + (((uint32_t)lane * 4u) ^ (((uint32_t)q & 3u) << 5));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < nb) dbs[j] += *(const float *)(sz + (size_t)j * dz_bytes + off);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[st])) : "memory");
+      }
+      float *dp = a.db_part + ((size_t)blockIdx.x * 4 + lane_grp) * (size_t)(a.n_cot * a.NT) + (size_t)cot * a.NT;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nb) dp[j * 32 + lane] = dbs[j];
+    }
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = lane_grp * 32 + lane;
@@ -230,17 +259,30 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   }
 }
 
-// dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order)
-__global__ void k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float scale, int accumulate) {
+// dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order => deterministic)
+// blockDim = (32 elements, 8 split lanes): lane y sums splits y, y+8, ... ; the 8 lane sums are folded in shared memory
+// in a fixed order.  Element index runs co-fastest so that the partial reads (n contiguous) coalesce.
+__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
+  __shared__ float red[8][33];
   const long long total = (long long)a.Co * a.Ci * a.kh * a.kw;
   const int ACC = a.RG * a.SG * a.CIB;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int s = (int)(i % a.kw);
-    long long q = i / a.kw;
-    int r = (int)(q % a.kh); q /= a.kh;
-    int ci = (int)(q % a.Ci);
-    int co = (int)(q / a.Ci);
-    int cot = co / a.NT, n = co - cot * a.NT;
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  float sum = 0.f;
+  long long dst = 0;
+  const bool is_db = db != nullptr && i >= total && i < total + a.Co;
+  if (is_db) {  // bias gradient: splits x 4 warp partials per channel
+    const int co = (int)(i - total);
+    const size_t pitch = (size_t)(a.n_cot * a.NT);
+    for (int z = threadIdx.y; z < splits * 4; z += 8) sum += a.db_part[(size_t)z * pitch + co];
+  }
+  if (i < total) {
+    const int co = (int)(i % a.Co);
+    long long q = i / a.Co;
+    const int s = (int)(q % a.kw); q /= a.kw;
+    const int r = (int)(q % a.kh);
+    const int ci = (int)(q / a.kh);
+    dst = (((long long)co * a.Ci + ci) * a.kh + r) * a.kw + s;
+    const int cot = co / a.NT, n = co - cot * a.NT;
     int by, acc, m;
     if (a.c4) {
       by = cot;
@@ -256,59 +298,18 @@ __global__ void k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float sc
     }
     const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
     const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
-    float sum = 0.f;
-    for (int z = 0; z < splits; ++z) sum += p[(size_t)z * split_stride];
-    sum *= scale;
-    dw[i] = accumulate ? dw[i] + sum : sum;
+    for (int z = threadIdx.y; z < splits; z += 8) sum += p[(size_t)z * split_stride];
   }
-}
-
-// db[c] partial sums over pixel chunks of a dense-in-C NHWC tensor: part[block][C].
-// Each block takes a contiguous range of pixels; thread t owns channel group (t % (C/4)) as a float4 and
-// strides over pixels by blockDim/(C/4); a shared-memory tree folds the pixel lanes.  C % 4 == 0.
-__global__ void __launch_bounds__(256)
-k_colsum_nhwc_partial(T4 t, int N, int H, int W, int C, float *part, long long pix_per_block) {
-  __shared__ float4 red[256];
-  const long long P = (long long)N * H * W;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > P) p1 = P;
-  const int c4n = C >> 2;                 // float4 groups per pixel
-  const int lanes = 256 / c4n;            // pixel lanes per block (>= 1 for C <= 1024)
-  const int cg = threadIdx.x % c4n, pl = threadIdx.x / c4n;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (pl < lanes) {
-    long long p = p0 + pl;
-    // incremental (n,y,x) instead of div/mod per pixel
-    int x = (int)(p % W);
-    long long q = p / W;
-    int y = (int)(q % H);
-    int n = (int)(q / H);
-    for (; p < p1; p += lanes) {
-      const float4 v = __ldg((const float4 *)(t.p + n * t.sn + (long long)y * t.sh + (long long)x * t.sw) + cg);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      x += lanes;
-      while (x >= W) { x -= W; if (++y == H) { y = 0; ++n; } }
-    }
-  }
-  red[threadIdx.x] = s;
+  red[threadIdx.y][threadIdx.x] = sum;
   __syncthreads();
-  if (threadIdx.x < c4n) {
-    float4 acc = red[threadIdx.x];
-    for (int l = 1; l < lanes; ++l) {
-      const float4 v = red[l * c4n + threadIdx.x];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    *(float4 *)(part + (size_t)blockIdx.x * C + 4 * threadIdx.x) = acc;
+  if (threadIdx.y == 0 && (i < total || is_db)) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
+    t *= scale;
+    float *d = is_db ? db + (i - total) : dw + dst;
+    *d = accumulate ? *d + t : t;
   }
-}
-__global__ void k_colsum_finish(const float *part, int blocks, int C, float *db, float scale, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += part[(size_t)b * C + c];
-  s *= scale;
-  db[c] = accumulate ? db[c] + s : s;
 }
 
 // x (N, C<=4, H, W; any strides) -> zero-padded NHWC4 image xp[N][H+2p][Wp][4] (Wp >= W+2p+8*SG), tf32-rounded.  The
@@ -393,10 +394,8 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   pl->grid = dim3(gx, gy);
   pl->smem = (size_t)best_stages * best_stage + 1024 + (2 * best_stages + 1) * 8 + 16;
   pl->partial_floats = (size_t)gx * gy * nacc * 128 * NT;
-  long long P = (long long)g.N * g.Ho * g.Wo;
-  pl->db_blocks = (int)((P + 2047) / 2048);
-  if (pl->db_blocks > 1184) pl->db_blocks = 1184;
-  pl->db_floats = (size_t)pl->db_blocks * g.Co;
+  pl->db_blocks = 0;
+  pl->db_floats = (size_t)gx * 4 * a.n_cot * NT;
   pl->Hp = g.Hi + 2 * g.pad;
   pl->Wp = g.Wi + 2 * g.pad + 8 * a.SG;
   pl->xpack_floats = ((size_t)g.N * pl->Hp * pl->Wp + 64) * 4;
@@ -475,10 +474,8 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   pl->grid = dim3(gx, gy);
   pl->smem = best_smem;
   pl->partial_floats = (size_t)gx * gy * a.RG * a.SG * a.CIB * 128 * a.NT;
-  long long P = (long long)g.N * g.Ho * g.Wo;
-  pl->db_blocks = (int)((P + 2047) / 2048);
-  if (pl->db_blocks > 1184) pl->db_blocks = 1184;
-  pl->db_floats = (size_t)pl->db_blocks * g.Co;
+  pl->db_blocks = 0;
+  pl->db_floats = (size_t)gx * 4 * a.n_cot * a.NT;
   return true;
 }
 
@@ -527,6 +524,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   WgArgs &a = pl.a;
   a.partial = (float *)wsp;
   float *db_part = a.partial + pl.partial_floats;
+  a.db_part = db_small ? db_part : nullptr;
 
   CUtensorMap mapX, mapZ;
   if (a.c4) {
@@ -567,18 +565,8 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   SRB_CHECK_CUDA(cudaGetLastError());
   {
     long long total = (long long)g.Co * g.Ci * g.kh * g.kw;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_wgrad_finish<<<blocks, 256, 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, scale, accumulate);
-    count_launch();
-    SRB_CHECK_CUDA(cudaGetLastError());
-  }
-  if (db_small) {
-    long long P = (long long)g.N * g.Ho * g.Wo;
-    long long ppb = (P + pl.db_blocks - 1) / pl.db_blocks;
-    k_colsum_nhwc_partial<<<pl.db_blocks, 256, 0, st>>>(small, g.N, g.Ho, g.Wo, g.Co, db_part, ppb);
-    count_launch();
-    k_colsum_finish<<<(g.Co + 127) / 128, 128, 0, st>>>(db_part, pl.db_blocks, g.Co, db_small, scale, accumulate);
+    if (db_small) total += g.Co;
+    k_wgrad_finish<<<(unsigned)((total + 31) / 32), dim3(32, 8), 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
