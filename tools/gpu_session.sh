@@ -1,0 +1,49 @@
+#!/bin/bash
+# One gpurun call = tests + smoke + bench lines + ncu launch list + one ncu --set full capture.
+# Usage (from the repo root, on the GPU box):  bash tools/gpu_session.sh <tag> [parts]
+#   parts: any of  tests smoke bench bench_more ref cudnn launches full   (default: all)
+set -u
+TAG=${1:-r1}
+PARTS=${2:-"tests smoke bench bench_more ref cudnn launches full"}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+has() { [[ " $PARTS " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
+
+if has tests; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+  echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log"
+fi
+if has smoke; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
+  echo "smoke exit $?" >> "$OUT/smoke.log"; tail -3 "$OUT/smoke.log"
+fi
+if has bench; then
+  timeout 600 python bench.py > "$OUT/bench_espcn.json" 2> "$OUT/bench_espcn.err"
+  echo "bench exit $?"; cat "$OUT/bench_espcn.json"
+fi
+if has bench_more; then
+  for wl in vdsr_b64_128 edsr64_x4_b32_lr32 srcnn_x2_b16; do
+    timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
+    echo "bench $wl exit $?"; cut -c1-600 "$OUT/bench_$wl.json"
+  done
+fi
+if has ref; then
+  timeout 400 python bench.py --impl reference --steps 10 --warmup 3 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"
+  cat "$OUT/bench_reference.json"
+fi
+if has cudnn; then
+  timeout 600 python tools/cudnn_baseline.py > "$OUT/cudnn_baseline.jsonl" 2> "$OUT/cudnn_baseline.err"
+  cat "$OUT/cudnn_baseline.jsonl"
+fi
+if has launches; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file "$OUT/launches_espcn.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/launches_run.log" 2>&1
+  echo "ncu launches exit $?"
+fi
+if has full; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_conv_sl|k_tc_wgrad" \
+      --launch-skip 16 -c 10 -f -o "$OUT/espcn_full" python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/full_run.log" 2>&1
+  echo "ncu full exit $?"
+  ls -la "$OUT"
+fi
