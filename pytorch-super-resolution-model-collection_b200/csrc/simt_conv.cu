@@ -409,6 +409,158 @@ __global__ void k_channel_sum(T4 t, int N, int C, int H, int W, float *out, floa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// wgrad for skinny outputs (Co <= 4: the 64->3 / 32->3 tail layers of SRCNN / VDSR / EDSR / SRGAN-G), stride 1,
+// channels_last x.  The GEMM tiling above would waste 61 of 64 rows; this kernel is a direct reduction instead:
+//   thread (ci, r) owns dw[0..CO)[ci][r][0..KW)  (KW*CO accumulators in registers)
+// and walks the INPUT rows of its band: input row iy pairs with output row oy = iy - r + pad, so every x element is
+// fetched from global once per CTA (the kh filter-row warps hit the same lines in L1) with ci contiguous across the
+// warp (128-byte coalesced), while the CO dz values of a pixel are warp-uniform broadcast loads kept in a KW-deep
+// register window.  One partial dW per band goes to the workspace in k_wgrad's [co][NN] layout (db = column CRS);
+// k_wgrad_reduce_par sums the bands in a fixed order.
+// ---------------------------------------------------------------------------------------------
+template <int KW, int CO>
+__global__ void __launch_bounds__(1024)
+k_wgrad_smallco(Geom g, T4 sm, T4 big, float *__restrict__ partial, int TH, int bands_per_img, int ci_tile, int r_db) {
+  const int band = blockIdx.x;
+  const int n = band / bands_per_img;
+  const int iy0 = (band - n * bands_per_img) * TH;
+  const int iy1 = min(iy0 + TH, g.Hi);
+  const int ci = blockIdx.y * ci_tile + (int)(threadIdx.x % ci_tile);
+  const int r = threadIdx.x / ci_tile;
+  const bool ci_ok = ci < g.Ci;
+  const bool do_db = (ci == 0) && (r == r_db);
+  float acc[KW][CO];
+  float dbs[CO];
+#pragma unroll
+  for (int s = 0; s < KW; ++s)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[s][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) dbs[c] = 0.f;
+
+  for (int iy = iy0; iy < iy1; ++iy) {
+    const int oy = iy - r + g.pad;
+    if (oy < 0 || oy >= g.Ho) continue;  // uniform per warp (ci_tile is a multiple of 32)
+    const float *xr = big.p + n * big.sn + (long long)iy * big.sh + (ci_ok ? ci : 0) * big.sc;
+    const float *zr = sm.p + n * sm.sn + (long long)oy * sm.sh;
+    float win[CO][KW];  // win[c][ix % KW] = dz[c][oy][ix + pad]
+#pragma unroll
+    for (int s = 1; s < KW; ++s) {
+      const int ox = g.pad - s;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        const float v = (ox >= 0 && ox < g.Wo) ? __ldg(zr + c * sm.sc + (long long)ox * sm.sw) : 0.f;
+        win[c][KW - s] = v;
+        dbs[c] += v;
+      }
+    }
+    for (int ix0 = 0; ix0 < g.Wi; ix0 += KW) {
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        const int ix = ix0 + j;
+        if (ix < g.Wi) {
+          const float v = ci_ok ? __ldg(xr + (long long)ix * big.sw) : 0.f;
+          const int oxn = ix + g.pad;
+#pragma unroll
+          for (int c = 0; c < CO; ++c) {
+            const float z = (oxn < g.Wo) ? __ldg(zr + c * sm.sc + (long long)oxn * sm.sw) : 0.f;
+            win[c][j] = z;
+            dbs[c] += z;
+          }
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[s][c] = fmaf(v, win[c][(j - s + KW) % KW], acc[s][c]);
+        }
+      }
+    }
+  }
+  const int CRS = g.Ci * g.kh * KW, NN = CRS + 1;
+  float *dst = partial + (long long)band * CO * NN;
+  if (ci_ok) {
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+#pragma unroll
+      for (int s = 0; s < KW; ++s) dst[(long long)c * NN + (ci * g.kh + r) * KW + s] = acc[s][c];
+  }
+  if (do_db) {
+#pragma unroll
+    for (int c = 0; c < CO; ++c) dst[(long long)c * NN + CRS] = dbs[c];
+  }
+}
+
+// Parallel, deterministic version of k_wgrad_reduce for many splits: block = (32 outputs, 8 split lanes), lane y sums
+// splits y, y+8, ...; the eight lane sums are folded in a fixed order.
+__global__ void __launch_bounds__(256)
+k_wgrad_reduce_par(const float *__restrict__ partial, int splits, int Co, int CRS, float *dw, float *db, float scale,
+                   int accumulate) {
+  __shared__ float red[8][33];
+  const int NN = CRS + 1;
+  const long long total = (long long)Co * NN;
+  const long long idx = (long long)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (idx < total)
+    for (int z = threadIdx.y; z < splits; z += 8) s += partial[(long long)z * total + idx];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < total) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
+    t *= scale;
+    const int co = (int)(idx / NN), col = (int)(idx - (long long)co * NN);
+    if (col < CRS) {
+      float *d = dw + (long long)co * CRS + col;
+      *d = accumulate ? (*d + t) : t;
+    } else if (db) {
+      db[co] = accumulate ? (db[co] + t) : t;
+    }
+  }
+}
+
+struct SmallCoPlan {
+  int TH, bands_per_img, bands, ci_tile, ci_tiles, r_db;
+};
+
+// Applies to: Conv2d-orientation wgrad, stride 1, no PixelShuffle, Co <= 4, kw in {1,3,5,9}, channels_last x,
+// and padding no larger than "same" (so that one filter row sees every output row: the db column).
+bool smallco_plan(const Geom &g, const T4 &big, SmallCoPlan *p) {
+  if (g.st != 1 || g.ps != 1 || g.Co > 4 || g.Co < 1 || g.N <= 0) return false;
+  if (g.kw != 1 && g.kw != 3 && g.kw != 5 && g.kw != 9) return false;
+  if (big.p && big.sc != 1) return false;
+  if (2 * g.pad > g.kh - 1 || g.pad > g.kw - 1) return false;
+  int ci_tile = g.Ci >= 64 ? 64 : 32;
+  while (ci_tile * g.kh > 1024 && ci_tile > 32) ci_tile >>= 1;
+  if (ci_tile * g.kh > 1024) return false;
+  p->ci_tile = ci_tile;
+  p->ci_tiles = (g.Ci + ci_tile - 1) / ci_tile;
+  p->r_db = g.pad;
+  const long long rows = (long long)g.N * g.Hi;
+  long long target = 148LL * 8 / p->ci_tiles;  // ~8 CTAs per SM in flight
+  if (target < 1) target = 1;
+  int TH = (int)((rows + target - 1) / target);
+  if (TH < 1) TH = 1;
+  if (TH > g.Hi) TH = g.Hi;
+  p->TH = TH;
+  p->bands_per_img = (g.Hi + TH - 1) / TH;
+  p->bands = g.N * p->bands_per_img;
+  return true;
+}
+
+template <int KW>
+void launch_smallco(const Geom &g, const T4 &small, const T4 &big, float *partial, const SmallCoPlan &p, cudaStream_t st) {
+  dim3 grid((unsigned)p.bands, (unsigned)p.ci_tiles);
+  const int threads = p.ci_tile * g.kh;
+  switch (g.Co) {
+    case 1: k_wgrad_smallco<KW, 1><<<grid, threads, 0, st>>>(g, small, big, partial, p.TH, p.bands_per_img, p.ci_tile, p.r_db); break;
+    case 2: k_wgrad_smallco<KW, 2><<<grid, threads, 0, st>>>(g, small, big, partial, p.TH, p.bands_per_img, p.ci_tile, p.r_db); break;
+    case 3: k_wgrad_smallco<KW, 3><<<grid, threads, 0, st>>>(g, small, big, partial, p.TH, p.bands_per_img, p.ci_tile, p.r_db); break;
+    default: k_wgrad_smallco<KW, 4><<<grid, threads, 0, st>>>(g, small, big, partial, p.TH, p.bands_per_img, p.ci_tile, p.r_db); break;
+  }
+}
+
 }  // namespace
 
 int simt_conv_gather(const Geom &g, const T4 &in, const float *w, const T4 &out, const Epi &epi, cudaStream_t st) {
@@ -460,13 +612,39 @@ static int wgrad_splits(const Geom &g) {
 
 size_t simt_wgrad_ws_bytes(const Geom &g) {
   int NN = g.Ci * g.kh * g.kw + 1;
-  return (size_t)wgrad_splits(g) * g.Co * NN * sizeof(float);
+  size_t a = (size_t)wgrad_splits(g) * g.Co * NN * sizeof(float);
+  SmallCoPlan sp;
+  T4 none{nullptr, 0, 0, 0, 0};
+  if (smallco_plan(g, none, &sp)) {
+    size_t b = (size_t)sp.bands * g.Co * NN * sizeof(float);
+    if (b > a) a = b;
+  }
+  return a;
 }
 
 int simt_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                     int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
   long long Kp = (long long)g.N * g.Ho * g.Wo;
   int CRS = g.Ci * g.kh * g.kw, NN = CRS + 1;
+  SmallCoPlan sp;
+  if (smallco_plan(g, big, &sp)) {
+    size_t need_s = (size_t)sp.bands * g.Co * NN * sizeof(float);
+    SRB_REQUIRE(ws && ws_bytes >= need_s, SRB_EWORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need_s, ws_bytes);
+    switch (g.kw) {
+      case 1: launch_smallco<1>(g, small, big, (float *)ws, sp, st); break;
+      case 3: launch_smallco<3>(g, small, big, (float *)ws, sp, st); break;
+      case 5: launch_smallco<5>(g, small, big, (float *)ws, sp, st); break;
+      default: launch_smallco<9>(g, small, big, (float *)ws, sp, st); break;
+    }
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    const long long total_s = (long long)g.Co * NN;
+    k_wgrad_reduce_par<<<(unsigned)((total_s + 31) / 32), dim3(32, 8), 0, st>>>((const float *)ws, sp.bands, g.Co, CRS, dw,
+                                                                                 db_small, scale, accumulate);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    return SRB_OK;
+  }
   int splits = wgrad_splits(g);
   size_t need = (size_t)splits * g.Co * NN * sizeof(float);
   SRB_REQUIRE(ws && ws_bytes >= need, SRB_EWORKSPACE, "wgrad workspace: need %zu bytes, got %zu", need, ws_bytes);

@@ -209,16 +209,28 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < 8; ++j) dbs[j] = 0.f;
       const int rows = a.TH * a.BW;
+      // this lane's byte offset inside a 128-B row, for rows q with q % 4 == i (swizzle: 32-byte atom index XOR (q & 3))
+      uint32_t lane_off[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lane_off[i] = ((uint32_t)lane * 4u) ^ ((uint32_t)i << 5);
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
         mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
-        const uint8_t *sz = smem + (size_t)st * stage_bytes + (size_t)a.CIB * x_bytes;
-        for (int q = lane_grp; q < rows; q += 4) {
-          const uint32_t off = (uint32_t)q * 128u + (((uint32_t)lane * 4u) ^ (((uint32_t)q & 3u) << 5));
+        const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)a.CIB * x_bytes);
+        // four consecutive rows per warp and step; rows .. round_up(rows, 4) lie in the tile's zero tail (dz_slots % 8 == 0)
+        for (int q0 = lane_grp * 4; q0 < rows; q0 += 16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nb) dbs[j] += *(const float *)(sz + (size_t)j * dz_bytes + off);
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t off = sz + (uint32_t)(q0 + i) * 128u + lane_off[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nb) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(off + (uint32_t)j * (uint32_t)dz_bytes));
+                dbs[j] += v;
+              }
+          }
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[st])) : "memory");

@@ -141,6 +141,11 @@ SWEEP = [
     (96, 160, 3, 1, 1, "relu", False, 1, 9, 9, 1),     # non power-of-two channel counts
     (256, 256, 3, 1, 1, "relu", False, 1, 8, 8, 1),    # EDSR-256 body
     (64, 64, 1, 1, 0, None, False, 1, 5, 6, 2),
+    (40, 2, 3, 1, 1, "relu", False, 1, 45, 9, 2),      # skinny-output wgrad: ragged channel tile, several row bands
+    (64, 4, 3, 1, 0, None, False, 1, 11, 13, 3),       # skinny-output wgrad, no padding
+    (16, 1, 1, 1, 0, None, False, 1, 6, 7, 2),         # 1x1, single output channel
+    (64, 64, 3, 1, 1, "relu", False, 1, 6, 150, 1),    # wide rows (column-tiled wgrad bands)
+    (32, 64, 3, 1, 1, None, False, 1, 20, 140, 1),
 ]
 
 
