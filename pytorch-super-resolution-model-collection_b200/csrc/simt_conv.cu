@@ -421,8 +421,10 @@ __global__ void k_channel_sum(T4 t, int N, int C, int H, int W, float *out, floa
 // k_wgrad_reduce_par sums the bands in a fixed order.
 // ---------------------------------------------------------------------------------------------
 template <int KW, int CO>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(KW == 9 ? 288 : 64 * KW, KW == 3 ? 3 : (KW == 1 ? 6 : 1))
 k_wgrad_smallco(Geom g, T4 sm, T4 big, float *__restrict__ partial, int TH, int bands_per_img, int ci_tile, int r_db) {
+  constexpr int U = KW == 9 ? 9 : (KW == 5 ? 10 : 12);  // pixels per chunk: all loads of a chunk are issued before its FMAs
+  constexpr int KC = KW > 1 ? KW - 1 : 1;
   const int band = blockIdx.x;
   const int n = band / bands_per_img;
   const int iy0 = (band - n * bands_per_img) * TH;
@@ -443,38 +445,49 @@ k_wgrad_smallco(Geom g, T4 sm, T4 big, float *__restrict__ partial, int TH, int 
   for (int iy = iy0; iy < iy1; ++iy) {
     const int oy = iy - r + g.pad;
     if (oy < 0 || oy >= g.Ho) continue;  // uniform per warp (ci_tile is a multiple of 32)
+    // row-local offsets fit 32 bits (one image row of one tensor); the row bases carry the 64-bit part
     const float *xr = big.p + n * big.sn + (long long)iy * big.sh + (ci_ok ? ci : 0) * big.sc;
-    const float *zr = sm.p + n * sm.sn + (long long)oy * sm.sh;
-    float win[CO][KW];  // win[c][ix % KW] = dz[c][oy][ix + pad]
+    const float *zrow[CO];
 #pragma unroll
-    for (int s = 1; s < KW; ++s) {
-      const int ox = g.pad - s;
+    for (int c = 0; c < CO; ++c) zrow[c] = sm.p + n * sm.sn + (long long)oy * sm.sh + c * sm.sc;
+    const int xsw = (int)big.sw, zsw = (int)sm.sw;
+    float zc[CO][KC];  // carried window: zc[c][t] = dz[c][oy][ix0 + pad - (KW-1) + t]
+#pragma unroll
+    for (int t = 0; t < KW - 1; ++t) {
+      const int ox = g.pad - (KW - 1) + t;
 #pragma unroll
       for (int c = 0; c < CO; ++c) {
-        const float v = (ox >= 0 && ox < g.Wo) ? __ldg(zr + c * sm.sc + (long long)ox * sm.sw) : 0.f;
-        win[c][KW - s] = v;
+        const float v = (ox >= 0 && ox < g.Wo) ? __ldg(zrow[c] + ox * zsw) : 0.f;
+        zc[c][t] = v;
         dbs[c] += v;
       }
     }
-    for (int ix0 = 0; ix0 < g.Wi; ix0 += KW) {
+    for (int ix0 = 0; ix0 < g.Wi; ix0 += U) {
+      float xv[U], zv[CO][U + KW - 1];
 #pragma unroll
-      for (int j = 0; j < KW; ++j) {
-        const int ix = ix0 + j;
-        if (ix < g.Wi) {
-          const float v = ci_ok ? __ldg(xr + (long long)ix * big.sw) : 0.f;
-          const int oxn = ix + g.pad;
+      for (int j = 0; j < U; ++j) {
+        const int ix = ix0 + j, ox = ix + g.pad;
+        xv[j] = (ix < g.Wi && ci_ok) ? __ldg(xr + ix * xsw) : 0.f;
 #pragma unroll
-          for (int c = 0; c < CO; ++c) {
-            const float z = (oxn < g.Wo) ? __ldg(zr + c * sm.sc + (long long)oxn * sm.sw) : 0.f;
-            win[c][j] = z;
-            dbs[c] += z;
-          }
-#pragma unroll
-          for (int s = 0; s < KW; ++s)
-#pragma unroll
-            for (int c = 0; c < CO; ++c) acc[s][c] = fmaf(v, win[c][(j - s + KW) % KW], acc[s][c]);
-        }
+        for (int c = 0; c < CO; ++c) zv[c][KW - 1 + j] = (ix < g.Wi && ox < g.Wo) ? __ldg(zrow[c] + ox * zsw) : 0.f;
       }
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+#pragma unroll
+        for (int t = 0; t < KW - 1; ++t) zv[c][t] = zc[c][t];
+#pragma unroll
+        for (int j = 0; j < U; ++j) dbs[c] += zv[c][KW - 1 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+#pragma unroll
+        for (int s = 0; s < KW; ++s)
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[s][c] = fmaf(xv[j], zv[c][KW - 1 + j - s], acc[s][c]);
+#pragma unroll
+      for (int c = 0; c < CO; ++c)
+#pragma unroll
+        for (int t = 0; t < KW - 1; ++t) zc[c][t] = zv[c][U + t];
     }
   }
   const int CRS = g.Ci * g.kh * KW, NN = CRS + 1;
@@ -528,12 +541,10 @@ struct SmallCoPlan {
 // and padding no larger than "same" (so that one filter row sees every output row: the db column).
 bool smallco_plan(const Geom &g, const T4 &big, SmallCoPlan *p) {
   if (g.st != 1 || g.ps != 1 || g.Co > 4 || g.Co < 1 || g.N <= 0) return false;
-  if (g.kw != 1 && g.kw != 3 && g.kw != 5 && g.kw != 9) return false;
+  if (g.kh != g.kw || (g.kw != 1 && g.kw != 3 && g.kw != 5 && g.kw != 9)) return false;
   if (big.p && big.sc != 1) return false;
   if (2 * g.pad > g.kh - 1 || g.pad > g.kw - 1) return false;
-  int ci_tile = g.Ci >= 64 ? 64 : 32;
-  while (ci_tile * g.kh > 1024 && ci_tile > 32) ci_tile >>= 1;
-  if (ci_tile * g.kh > 1024) return false;
+  const int ci_tile = (g.Ci >= 64 && g.kw < 9) ? 64 : 32;  // threads = ci_tile * kh <= the kernel's launch bound
   p->ci_tile = ci_tile;
   p->ci_tiles = (g.Ci + ci_tile - 1) / ci_tile;
   p->r_db = g.pad;

@@ -27,7 +27,9 @@ constexpr int kMaxAcc = 8;  // accumulators (M=128 tiles) per CTA the unrolled i
 struct WgArgs {
   int N, Ho, Wo, Ci, Co;
   int kh, kw, pad;
-  int TH, BW, BH;       // band rows; flattened pitch; x box height = TH + RG - 1
+  int TH, BW, BH;       // band rows; flattened pitch (= x box width); x box height = TH + RG - 1
+  int TW, bands_w;      // output columns per band and column tiles per image (1: the band spans the full row)
+  int dz_rowwise;       // bands_w > 1: dz is loaded one row per TMA (TW slots) at pitch BW; the kw-1 slots between rows stay zero
   int bands_per_img, num_bands, bands_per_cta;
   int CIB, RG, SG, NT;  // ci-blocks per CTA; filter rows per CTA; ceil(kw/4); co tile (multiple of 32)
   int n_cig, n_rg, n_cot;
@@ -111,14 +113,16 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer: one halo band per stage =====================
     {
-      const uint32_t tx_bytes = (uint32_t)(a.CIB * a.BH * a.BW * 128 + nb * a.TH * a.BW * 128);
+      const uint32_t tx_bytes = (uint32_t)(a.CIB * a.BH * a.BW * 128 + nb * a.TH * (a.dz_rowwise ? a.TW : a.BW) * 128);
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
         const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
         mbar_wait(&empty_bar[st], ph ^ 1u);
         const int n = band / a.bands_per_img;
-        const int oh0 = (band - n * a.bands_per_img) * a.TH;
+        const int rem = band - n * a.bands_per_img;
+        const int bh = rem / a.bands_w;
+        const int oh0 = bh * a.TH, ox0 = (rem - bh * a.bands_w) * a.TW;
         uint8_t *sx = smem + (size_t)st * stage_bytes;
         uint8_t *sz = sx + a.CIB * x_bytes;
         if (elect_one()) {
@@ -127,10 +131,16 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             tma_load_4d(&mapX, &full_bar[st], sx, 0, 0, oh0, n);  // padded image: no negative coordinates
           } else {
             for (int cb = 0; cb < a.CIB; ++cb)
-              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, -a.pad, oh0 - a.pad + r0, n);
+              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, ox0 - a.pad, oh0 - a.pad + r0, n);
           }
-          for (int j = 0; j < nb; ++j)
-            tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * 32, 0, oh0, n);
+          if (a.dz_rowwise) {
+            for (int t = 0; t < a.TH; ++t)  // rows past the image (and columns past Wo) arrive as zeros
+              for (int j = 0; j < nb; ++j)
+                tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, cot * a.NT + j * 32, ox0, oh0 + t, n);
+          } else {
+            for (int j = 0; j < nb; ++j)
+              tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * 32, 0, oh0, n);
+          }
         }
         __syncwarp();
       }
@@ -361,6 +371,7 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
   a.c4 = 1;
+  a.TW = g.Wo; a.bands_w = 1; a.dz_rowwise = 0;
   a.BW = g.Wo + g.kw - 1;  // == Wi + 2*pad at stride 1
   if (a.BW > 256 || g.kw > 16 || g.kh > 16) return false;
   a.SG = (g.kw + 7) / 8;
@@ -422,48 +433,60 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   pl->xpack_floats = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
-  a.BW = g.Wo + g.kw - 1;
-  if (a.BW > 256) return false;
   a.SG = (g.kw + 3) / 4;
   const int cblocks = g.Ci / 32;
   const int co_pad = round_up_i(g.Co, 32);
   double best_score = -1.0;
   WgArgs best = a;
   size_t best_smem = 0;
-  // Enumerate (NT, CIB, RG, TH) and minimise a per-output-row time model summed over the CTAs of grid.y:
-  //   MMA cycles  = accumulators * cost(NT) * (BW / 8 K-steps),   cost(N) = max(32 + N/4, N/2)  [measured, tools/bench_umma.cu:
+  // Enumerate (column split, NT, CIB, RG, TH) and minimise a time model per image row, summed over the CTAs of grid.y:
+  //   MMA cycles  = accumulators * cost(NT) * (pitch / 8 K-steps),   cost(N) = max(32 + N/4, N/2)  [measured, tools/bench_umma.cu:
   //                 an SS-mode tf32 MMA re-reads its 4 KB A tile and N*32 B of B from shared memory at 128 B/cycle]
-  //   load cycles = TMA bytes / (HBM share of one SM ~ 23 B/cycle)
-  for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
-    if (co_pad % NT) continue;
-    for (int CIB = cblocks; CIB >= 1; --CIB) {
-      if (cblocks % CIB) continue;
-      for (int RG = g.kh; RG >= 1; --RG) {
-        int acc = RG * a.SG * CIB;
-        if (acc * NT > 512 || acc > kMaxAcc) continue;
-        for (int TH = 16; TH >= 1; --TH) {
-          if (TH > g.Ho && TH > 1) continue;
-          int BH = TH + RG - 1;
-          if (BH > 256) continue;
-          int x_slots = round_up_i(BH * a.BW + 4 * a.SG + 8, 8);
-          int dz_slots = round_up_i(TH * a.BW, 8);
-          size_t stage = (size_t)CIB * x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
-          int stages = (int)((kMaxSmemBytes - 4096) / stage);
-          if (stages < 2) continue;
-          if (stages > 4) stages = 4;
-          int n_rg = (g.kh + RG - 1) / RG, n_cig = cblocks / CIB, n_cot = co_pad / NT;
-          double costN = (32.0 + NT / 4.0) > NT / 2.0 ? (32.0 + NT / 4.0) : NT / 2.0;
-          double mma = (double)n_cig * n_rg * n_cot * acc * costN * (a.BW / 8.0);
-          double bytes = ((double)n_cot * n_rg * cblocks * BH / TH + (double)n_cig * n_rg * (co_pad / 32)) * 128.0 * a.BW;
-          double t = mma > bytes / 23.0 ? mma : bytes / 23.0;
-          double score = 1e9 / t + TH * 1e-3 + (stages >= 3 ? 0.5 : 0.0);
-          if (score > best_score) {
-            best_score = score;
-            best = a;
-            best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
-            best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
-            best.n_cig = n_cig; best.n_rg = n_rg; best.n_cot = n_cot;
-            best_smem = (size_t)stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
+  //   load cycles = TMA bytes (halo rows and halo columns included) / (L2->SM share of one SM ~ 23 B/cycle)
+  //   + a fixed hand-off cost per band.
+  // Column split w: the band covers TW = ceil(Wo / w) output columns; x is fetched as a (TW + kw - 1)-wide halo box and dz
+  // row by row at the same pitch.  Wide images (W >= 128) would otherwise be limited to TH = 1 (3x halo re-read).
+  for (int wsplit = 1; wsplit <= 16; ++wsplit) {
+    const int TW = (g.Wo + wsplit - 1) / wsplit;
+    if (wsplit > 1 && (TW < 16 || (g.Wo + TW - 1) / TW != wsplit)) continue;
+    const int bands_w = (g.Wo + TW - 1) / TW;
+    // row-wise dz loads land at t * BW * 128 B: keep every row on the 512-B period of the 32B-atom swizzle
+    const int BW = bands_w > 1 ? round_up_i(TW + g.kw - 1, 4) : g.Wo + g.kw - 1;
+    if (BW > 256) continue;
+    for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
+      if (co_pad % NT) continue;
+      for (int CIB = cblocks; CIB >= 1; --CIB) {
+        if (cblocks % CIB) continue;
+        for (int RG = g.kh; RG >= 1; --RG) {
+          int acc = RG * a.SG * CIB;
+          if (acc * NT > 512 || acc > kMaxAcc) continue;
+          for (int TH = 16; TH >= 1; --TH) {
+            if (TH > g.Ho && TH > 1) continue;
+            int BH = TH + RG - 1;
+            if (BH > 256) continue;
+            int x_slots = round_up_i(BH * BW + 4 * a.SG + 8, 8);
+            int dz_slots = round_up_i(TH * BW, 8);
+            size_t stage = (size_t)CIB * x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
+            int stages = (int)((kMaxSmemBytes - 4096) / stage);
+            if (stages < 2) continue;
+            if (stages > 4) stages = 4;
+            int n_rg = (g.kh + RG - 1) / RG, n_cig = cblocks / CIB, n_cot = co_pad / NT;
+            double costN = (32.0 + NT / 4.0) > NT / 2.0 ? (32.0 + NT / 4.0) : NT / 2.0;
+            double mma = (double)n_cig * n_rg * n_cot * acc * costN * (bands_w * BW / 8.0);
+            double bytes = ((double)n_cot * n_rg * cblocks * BH / TH * BW + (double)n_cig * n_rg * (co_pad / 32) * TW) * 128.0 * bands_w;
+            double t = mma > bytes / 23.0 ? mma : bytes / 23.0;
+            t += 500.0 * bands_w / TH * (n_cig * n_rg * n_cot);  // per-band hand-off (barrier round trips, TMA issue)
+            if (stages == 2) t *= 1.08;                            // less slack for the TMA latency
+            double score = 1e9 / t + TH * 1e-3;
+            if (score > best_score) {
+              best_score = score;
+              best = a;
+              best.TW = TW; best.bands_w = bands_w; best.BW = BW; best.dz_rowwise = bands_w > 1 ? 1 : 0;
+              best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
+              best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
+              best.n_cig = n_cig; best.n_rg = n_rg; best.n_cot = n_cot;
+              best_smem = (size_t)stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
+            }
           }
         }
       }
@@ -471,7 +494,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
   }
   if (best_score < 0) return false;
   a = best;
-  a.bands_per_img = (g.Ho + a.TH - 1) / a.TH;
+  a.bands_per_img = ((g.Ho + a.TH - 1) / a.TH) * a.bands_w;
   a.num_bands = g.N * a.bands_per_img;
   a.ksteps = (a.TH * a.BW + 7) / 8;
   int gy = a.n_cig * a.n_rg * a.n_cot;
@@ -513,9 +536,9 @@ int tc_wgrad_describe(const Geom &g, char *buf, size_t n) {
   if (g.st != 1 || g.ps != 1 || (g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl)) return snprintf(buf, n, "tc_wgrad: no plan");
   const WgArgs &a = pl.a;
   return snprintf(buf, n,
-                  "tc_wgrad: band TH %d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
+                  "tc_wgrad: band TH %d TW %d x%d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
                   "stages %d, smem %zu B, tmem %d cols, grid %d x %d, ksteps %d",
-                  a.TH, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
+                  a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
                   pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
 }
 
@@ -563,7 +586,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)small.sw * 4, (cuuint64_t)small.sh * 4, (cuuint64_t)small.sn * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.TH, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(a.dz_rowwise ? a.TW : a.BW), (cuuint32_t)(a.dz_rowwise ? 1 : a.TH), 1};
     int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
