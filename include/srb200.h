@@ -119,9 +119,12 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
  * Data gradient.  Replaces cudnn_convolution_backward_input (and, for transposed == 1, the
  * backward of ConvTranspose2d).  dz is the gradient w.r.t. PixelShuffle(z), i.e. in y's layout;
  * the un-shuffle is folded into the load addressing.   dx (N,Cin,H,W).
+ *   relu_mask  optional (NULL = none), same shape as dx: dx = relu_mask > 0 ? dx : 0 is applied in the epilogue.
+ *              Passing the layer's own input x when x = ReLU(.) of the previous layer folds that layer's
+ *              threshold_backward into this kernel (base_networks.py:69 backward), saving one pass over dx.
  */
-int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *dx,
-                   void *ws, size_t ws_bytes, void *stream);
+int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
+                   const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * Weight + bias gradient.  Replaces cudnn_convolution_backward_weight + the bias aten::sum.

@@ -228,6 +228,7 @@ Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, co
   e.slope = p->slope;
   e.residual = to_t4(residual);
   e.preact = to_t4(preact);
+  e.mask = to_t4(nullptr);
   e.round_tf32 = round_out;
   return e;
 }
@@ -371,8 +372,8 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
   return SRB_OK;
 }
 
-int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *dx, void *ws,
-                   size_t ws_bytes, void *stream) {
+int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
+                   const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream) {
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
@@ -383,6 +384,7 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   Epi e;
   memset(&e, 0, sizeof(e));
   e.act = SRB_ACT_NONE;
+  e.mask = to_t4(relu_mask);
   e.round_tf32 = want_round(p, tdx, p->Cin);
   if (!p->transposed) {
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {

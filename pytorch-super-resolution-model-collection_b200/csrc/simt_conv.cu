@@ -133,6 +133,7 @@ k_gather(Geom g, T4 in, const float *__restrict__ w, T4 out, Epi epi) {
       if (epi.preact.p) epi.preact.p[ps_offset(epi.preact, g.ps, n, co, oy, ox)] = z;
       float y = apply_act(z, epi.act, slope);
       if (epi.residual.p) y += __ldg(epi.residual.p + ps_offset(epi.residual, g.ps, n, co, oy, ox));
+      if (epi.mask.p && !(__ldg(epi.mask.p + ps_offset(epi.mask, g.ps, n, co, oy, ox)) > 0.f)) y = 0.f;
       if (epi.round_tf32) y = round_tf32(y);
       out.p[off] = y;
     }
@@ -245,6 +246,7 @@ k_scatter(Geom g, T4 in, const float *__restrict__ w, T4 out, Epi epi) {
       float y = apply_act(z, epi.act, slope);
       if (epi.residual.p)
         y += __ldg(epi.residual.p + n * epi.residual.sn + ci * epi.residual.sc + iy * epi.residual.sh + ix * epi.residual.sw);
+      if (epi.mask.p && !(__ldg(epi.mask.p + n * epi.mask.sn + ci * epi.mask.sc + iy * epi.mask.sh + ix * epi.mask.sw) > 0.f)) y = 0.f;
       if (epi.round_tf32) y = round_tf32(y);
       out.p[off] = y;
     }

@@ -60,6 +60,7 @@ struct Epi {
   float slope;
   T4 residual;  // p == null -> none
   T4 preact;    // p == null -> none
+  T4 mask;      // p == null -> none; else y = mask > 0 ? y : 0 applied last (ReLU backward of the producer of the written tensor)
   int round_tf32;  // store y RN-rounded to tf32 (feeds a tensor-core consumer)
 };
 

@@ -94,11 +94,12 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   const bool has_bias = a.epi.bias != nullptr;
   const bool rnd = a.epi.round_tf32 != 0;
   const bool has_res = EXTRA && a.epi.residual.p != nullptr, has_pre = EXTRA && a.epi.preact.p != nullptr;
+  const bool has_mask = EXTRA && a.epi.mask.p != nullptr;  // MODE 0 / 3 only (dgrad never shuffles)
   const int ngroups = a.NT >> 4;
   int t_cur = -1, oy = 0, ox = 0;
   bool pix_ok = false;
   float *po = nullptr, *pp = nullptr;
-  const float *pr = nullptr;
+  const float *pr = nullptr, *pm = nullptr;
 #pragma unroll 1
   for (int item = half; item < mtb * ngroups; item += 2) {
     const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
@@ -114,6 +115,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
         if (EXTRA) {
           pr = a.epi.residual.p + (n * a.epi.residual.sn + yy * a.epi.residual.sh + xx * a.epi.residual.sw);
           pp = a.epi.preact.p + (n * a.epi.preact.sn + yy * a.epi.preact.sh + xx * a.epi.preact.sw);
+          pm = a.epi.mask.p + (n * a.epi.mask.sn + yy * a.epi.mask.sh + xx * a.epi.mask.sw);
         }
       }
     }
@@ -140,6 +142,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
           if (a.epi.preact.p) a.epi.preact.p[ps_offset(a.epi.preact, a.ps, n, co, oy, ox)] = z[j];
           float y = act == SRB_ACT_NONE ? z[j] : (act == SRB_ACT_RELU ? fmaxf(z[j], 0.f) : (z[j] > 0.f ? z[j] : z[j] * slope));
           if (a.epi.residual.p) y += __ldg(a.epi.residual.p + ps_offset(a.epi.residual, a.ps, n, co, oy, ox));
+          if (a.epi.mask.p && !(__ldg(a.epi.mask.p + ps_offset(a.epi.mask, a.ps, n, co, oy, ox)) > 0.f)) y = 0.f;
           if (rnd) y = round_tf32_fast(y);
           a.out.p[ps_offset(a.out, a.ps, n, co, oy, ox)] = y;
         }
@@ -183,6 +186,14 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
         const float4 rr = __ldg((const float4 *)(prg + (MODE == 2 ? (q4 >> 1) * qs_r2 + (q4 & 1) * qs_r : q4 * qs_r)));
         if (MODE == 2) { z[q4] += rr.x; z[4 + q4] += rr.y; z[8 + q4] += rr.z; z[12 + q4] += rr.w; }
         else { z[4 * q4] += rr.x; z[4 * q4 + 1] += rr.y; z[4 * q4 + 2] += rr.z; z[4 * q4 + 3] += rr.w; }
+      }
+    }
+    if (MODE == 0 && has_mask) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 mm = __ldg((const float4 *)(pm + cbase + 4 * q4));
+        z[4 * q4] = mm.x > 0.f ? z[4 * q4] : 0.f; z[4 * q4 + 1] = mm.y > 0.f ? z[4 * q4 + 1] : 0.f;
+        z[4 * q4 + 2] = mm.z > 0.f ? z[4 * q4 + 2] : 0.f; z[4 * q4 + 3] = mm.w > 0.f ? z[4 * q4 + 3] : 0.f;
       }
     }
     if (rnd) {
@@ -456,16 +467,17 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       bias_s[j] = (a.epi.bias && co < a.Co) ? __ldg(a.epi.bias + co) : 0.f;
     }
     const bool lay0 = a.out.sc == 1 && (!a.epi.residual.p || a.epi.residual.sc == 1) &&
-                      (!a.epi.preact.p || a.epi.preact.sc == 1);
+                      (!a.epi.preact.p || a.epi.preact.sc == 1) && (!a.epi.mask.p || a.epi.mask.sc == 1);
     const bool lay1 = a.out.sw == 1 && (!a.epi.residual.p || a.epi.residual.sw == 1) &&
                       (!a.epi.preact.p || a.epi.preact.sw == 1);
     int fmode = 3;  // see epilogue_items
     if ((a.Co & 15) == 0) {
       if (a.ps == 1 && lay0) fmode = 0;
+      else if (a.epi.mask.p) fmode = 3;  // masks only exist on the vector path of mode 0
       else if (a.ps == 4 && lay1 && (a.out.sh & 3) == 0) fmode = 1;
       else if (a.ps == 2 && lay0 && ((a.Co >> 2) & 3) == 0) fmode = 2;
     }
-    const bool extra = a.epi.residual.p != nullptr || a.epi.preact.p != nullptr;
+    const bool extra = a.epi.residual.p != nullptr || a.epi.preact.p != nullptr || a.epi.mask.p != nullptr;
     asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");  // bias_s visible to all epilogue warps
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;

@@ -39,6 +39,7 @@ struct WgArgs {
   int c4;                 // Cin <= 4: x is the zero-padded NHWC4 image seen through an overlapping-stride TMA view whose
                           // 32 "channels" are the 8-pixel x 4-channel window starting at the slot; an accumulator's four
                           // 32-lane M-blocks are four consecutive FILTER ROWS (LBO = one slot row); RG = ceil(kh/4) accumulators
+  int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
   float *db_part;         // bias gradient partials [gridDim.x][4 warps][n_cot * NT], or null
 };
@@ -53,6 +54,50 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t l
   d |= (uint64_t)1 << 46;  // descriptor version
   d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
   return d;
+}
+
+// tcgen05.mma with the descriptors given as (low, high) word pairs: the running low words are bumped by plain 32-bit adds
+// in uniform registers, no 64-bit OR per MMA.
+template <bool ACCUM>
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %5, 0; mov.b64 da, {%1, %3}; mov.b64 db, {%2, %3};\n"
+      "  tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p; }" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(ACCUM ? 1u : 0u)
+      : "memory");
+}
+
+// All MMAs of one band (one pipeline stage) for NACC accumulators: straight-line issue code per K-step -- one add and one
+// MMA per accumulator.  (The previous runtime-predicated loop spent ~24 instructions per MMA and was issue bound.)
+template <int NACC>
+__device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, uint32_t z_lo, uint32_t hi, uint32_t idesc,
+                                              uint32_t tmem_base, bool first) {
+  uint32_t al[NACC], tc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) {
+    al[j] = x_lo + (uint32_t)a.acc_off[j];
+    tc[j] = tmem_base + (uint32_t)(j * a.NT);
+  }
+  uint32_t bl = z_lo;
+  int ks = 0;
+  if (first) {  // very first K-step of this CTA: overwrite the accumulators
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) {
+      umma_tf32_lohi<false>(tc[j], al[j], bl, hi, idesc);
+      al[j] += 64u;
+    }
+    bl += 64u;
+    ks = 1;
+  }
+#pragma unroll 2
+  for (; ks < a.ksteps; ++ks) {
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) {
+      umma_tf32_lohi<true>(tc[j], al[j], bl, hi, idesc);
+      al[j] += 64u;  // 8 pixel rows x 128 B
+    }
+    bl += 64u;
+  }
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -155,7 +200,6 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
       const uint32_t a_hi = (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
       const uint32_t a_lbo = a.c4 ? ((((uint32_t)a.BW * 128u) >> 4) & 0x3FFF) << 16 : (128u >> 4) << 16;
       const uint32_t b_lbo = (((uint32_t)dz_bytes >> 4) & 0x3FFF) << 16;
-      const uint32_t x_step = (uint32_t)x_bytes >> 4, row_step = (uint32_t)a.BW * 8u;  // 128 B per slot >> 4
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
@@ -166,41 +210,17 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const uint32_t x_lo = ((sx >> 4) & 0x3FFF) | a_lbo;
         const uint32_t z_lo = (((sx + a.CIB * x_bytes) >> 4) & 0x3FFF) | b_lbo;
         if (elect_one()) {
-          // per-accumulator A start (low descriptor word) for this stage; fully unrolled, branch-uniform issue
-          uint32_t lo[kMaxAcc];
-          if (a.c4) {
-#pragma unroll
-            for (int j = 0; j < kMaxAcc; ++j) {  // accumulator j = (row group, 8-pixel window group)
-              const int rg = j / a.SG, sg = j - rg * a.SG;
-              lo[j] = x_lo + (j < a.RG * a.SG ? (uint32_t)(4 * rg) * row_step + (uint32_t)sg * 64u : 0u);
-            }
-          } else {
-            int i = 0;
-            uint32_t lo_r = x_lo;
-            for (int rl = 0; rl < rg_valid; ++rl, lo_r += row_step) {
-              uint32_t lo_s = lo_r;
-              for (int sg = 0; sg < a.SG; ++sg, lo_s += 32u) {
-                uint32_t l = lo_s;
-                for (int cb = 0; cb < a.CIB; ++cb, l += x_step, ++i)
-#pragma unroll
-                  for (int j = 0; j < kMaxAcc; ++j)
-                    if (j == i) lo[j] = l;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < kMaxAcc; ++j)
-              if (j >= i) lo[j] = x_lo;
-          }
-          const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;
-          uint32_t ko = 0;
-          for (int ks = 0; ks < a.ksteps; ++ks, ko += 64u) {
-            const uint64_t bdesc = ((uint64_t)a_hi << 32) | (uint64_t)(z_lo + ko);
-            const uint32_t accflag = (it | ks) ? 1u : 0u;
-#pragma unroll
-            for (int j = 0; j < kMaxAcc; ++j)
-              if (j < nacc)
-                umma_tf32_ss(tmem_base + (uint32_t)(j * a.NT), ((uint64_t)a_hi << 32) | (uint64_t)(lo[j] + ko), bdesc, idesc,
-                             accflag);
+          const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;  // a prefix of acc_off (filter-row major)
+          const bool first = it == 0;
+          switch (nacc) {
+            case 1: wg_issue_band<1>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 2: wg_issue_band<2>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 3: wg_issue_band<3>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 4: wg_issue_band<4>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 5: wg_issue_band<5>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 6: wg_issue_band<6>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 7: wg_issue_band<7>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            default: wg_issue_band<8>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
           }
           umma_commit_arrive(&empty_bar[st]);
         }
@@ -557,6 +577,18 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_wgrad workspace: need %zu bytes, have %zu",
               need, ws_bytes);
   WgArgs &a = pl.a;
+  {  // A-descriptor offsets of the accumulators, in 16-byte units (one pixel slot = 128 B = 8 units)
+    const int row_step = a.BW * 8, x_step = a.x_slots * 8;
+    for (int j = 0; j < kMaxAcc; ++j) a.acc_off[j] = 0;
+    if (a.c4) {
+      for (int rg = 0; rg < a.RG; ++rg)
+        for (int sg = 0; sg < a.SG; ++sg) a.acc_off[rg * a.SG + sg] = 4 * rg * row_step + sg * 64;
+    } else {
+      for (int rl = 0; rl < a.RG; ++rl)
+        for (int sg = 0; sg < a.SG; ++sg)
+          for (int cb = 0; cb < a.CIB; ++cb) a.acc_off[(rl * a.SG + sg) * a.CIB + cb] = rl * row_step + sg * 32 + cb * x_step;
+    }
+  }
   a.partial = (float *)wsp;
   float *db_part = a.partial + pl.partial_floats;
   a.db_part = db_small ? db_part : nullptr;

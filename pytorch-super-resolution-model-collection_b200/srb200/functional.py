@@ -31,6 +31,28 @@ def set_grad_scale(s):
     _state["grad_scale"] = float(s)
 
 
+_state["fuse_relu_bwd"] = True
+
+
+def set_fuse_relu_backward(on):
+    """Fold a ReLU layer's threshold_backward into the dgrad epilogue of its consumer conv (default on)."""
+    _state["fuse_relu_bwd"] = bool(on)
+
+
+class _ReluToken:
+    """Handshake between a conv whose output is y = ReLU(z) and the conv that consumes y.
+
+    The consumer's dgrad can apply the producer's ReLU mask (y > 0, y being its own saved input) in its epilogue, so
+    the producer's backward may skip srb_act_bwd.  Safe by construction: ReLU masking is idempotent, so whenever the
+    gradient that reaches the producer is not exactly the tensor the consumer wrote (several consumers, autograd
+    accumulation, hooks), the producer simply masks again.  `premasked` identifies that tensor."""
+    __slots__ = ("consumers", "premasked")
+
+    def __init__(self):
+        self.consumers = 0
+        self.premasked = None
+
+
 _workspaces = {}
 
 
@@ -92,7 +114,8 @@ class _FusedConv(torch.autograd.Function):
     """y = PixelShuffle_ps(act(conv(x, w) + b)) + residual   (one kernel forward; act_bwd + wgrad + dgrad backward)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope):
+    def forward(ctx, x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
+                out_token):
         _require_cuda(x, weight, bias, alpha, residual)
         x = _dense(x)
         weight = weight.contiguous()
@@ -121,6 +144,7 @@ class _FusedConv(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.params = (weight, bias)  # GradBucket direct-write targets (ddp.py)
+        ctx.in_token, ctx.out_token = in_token, out_token
         ctx.save_for_backward(x, weight, alpha, preact if need_preact else (y if act is not None else None))
         return y
 
@@ -130,10 +154,16 @@ class _FusedConv(torch.autograd.Function):
         p = ctx.p
         dev = x.device
         st = _stream(dev)
+        tok = ctx.out_token
+        premasked = tok is not None and tok.premasked == (dy.data_ptr(), dy._version, tuple(dy.shape), tuple(dy.stride()))
+        if tok is not None:
+            tok.premasked = None
         dy = _dense(dy)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
         dalpha = None
-        if ctx.act is not None:
+        if premasked:
+            dz = dy  # the consumer's dgrad epilogue already applied this layer's ReLU mask (and the tf32 rounding)
+        elif ctx.act is not None:
             dz = torch.empty(dy.shape, dtype=torch.float32, device=dev, memory_format=_out_format(p.Cout))
             if ctx.act == "prelu":
                 dalpha = torch.zeros_like(alpha)
@@ -174,10 +204,29 @@ class _FusedConv(torch.autograd.Function):
             dx = torch.empty(x.shape, dtype=torch.float32, device=dev,
                              memory_format=torch.channels_last if _is_cl(x) else torch.contiguous_format)
             tdx = t4(dx)
+            itok = ctx.in_token
+            fuse = itok is not None and itok.consumers == 1 and _state["fuse_relu_bwd"]
+            tmask = t4(x) if fuse else None  # x = ReLU(z_prev): its sign pattern is the producer's mask
             ws = _workspace(dev, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_DGRAD))
-            check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight), ctypes.byref(tdx),
-                                     _ptr(ws), ws.numel(), st))
-        return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None
+            check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
+                                     ctypes.byref(tmask) if fuse else None, ctypes.byref(tdx), _ptr(ws), ws.numel(), st))
+            if fuse:
+                itok.premasked = (dx.data_ptr(), dx._version, tuple(dx.shape), tuple(dx.stride()))
+        return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None, None, None
+
+
+def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope):
+    """_FusedConv.apply plus the ReLU-backward handshake (see _ReluToken)."""
+    in_token = getattr(x, "_srb_relu", None) if x.requires_grad else None
+    if in_token is not None:
+        in_token.consumers += 1
+    # y = ReLU(z) exactly (no residual on top); only worth it when a gradient will flow back into this layer
+    out_token = _ReluToken() if (act == "relu" and residual is None and torch.is_grad_enabled()) else None
+    y = _FusedConv.apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
+                         out_token)
+    if out_token is not None and y.requires_grad:
+        y._srb_relu = out_token
+    return y
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, activation=None, alpha=None, slope=0.2, residual=None,
@@ -188,15 +237,15 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, activation=None, alpha=Non
     """
     if activation == "prelu":
         assert alpha is not None and alpha.numel() == 1, "base_networks.py uses nn.PReLU() with one shared slope"
-    return _FusedConv.apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
-                            int(stride), int(padding), 0, False, int(pixel_shuffle), activation, slope)
+    return _apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
+                  int(stride), int(padding), 0, False, int(pixel_shuffle), activation, slope)
 
 
 def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, activation=None, alpha=None,
                      slope=0.2, residual=None):
     """Fused ConvTranspose2d -> +bias -> act -> +residual (weight is (Cin, Cout, kh, kw) like torch)."""
-    return _FusedConv.apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
-                            int(stride), int(padding), int(output_padding), True, 1, activation, slope)
+    return _apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
+                  int(stride), int(padding), int(output_padding), True, 1, activation, slope)
 
 
 class _PReLU(torch.autograd.Function):

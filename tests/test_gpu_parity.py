@@ -265,6 +265,52 @@ def test_pixel_shuffle_permutation_bit_exact(r, C, H, W, math):
         assert torch.equal(xg.grad.cpu(), TF.pixel_unshuffle(gy, r))
 
 
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+@pytest.mark.parametrize("topology", ["chain", "two_convs", "conv_and_torch"])
+def test_relu_backward_folded_into_consumer_dgrad(math, topology):
+    """The consumer's dgrad epilogue applies the producer's ReLU mask (srb_conv_dgrad relu_mask).  Folding must not change
+    a single bit of any gradient, and must stay correct when the ReLU output has more than one consumer."""
+    _need_gpu()
+    srb200.set_math(math)
+    gen = torch.Generator().manual_seed(5)
+    x0 = torch.randn(2, 32, 12, 14, generator=gen)
+    ws = [torch.randn(32, 32, 3, 3, generator=gen) / 17 for _ in range(3)]
+    bs = [torch.randn(32, generator=gen) * 0.1 for _ in range(3)]
+
+    def run(fuse, use_srb=True):
+        srb200.set_fuse_relu_backward(fuse)
+        dev = DEV if use_srb else "cpu"
+        x = x0.to(dev)
+        if use_srb:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x.requires_grad_(True)
+        w = [t.to(dev).requires_grad_(True) for t in ws]
+        b = [t.to(dev).requires_grad_(True) for t in bs]
+        if use_srb:
+            conv = lambda t, i, act: srb200.conv2d(t, w[i], b[i], 1, 1, activation=act)
+        else:
+            conv = lambda t, i, act: (TF.relu(TF.conv2d(t, w[i], b[i], 1, 1)) if act else TF.conv2d(t, w[i], b[i], 1, 1))
+        h = conv(x, 0, "relu")
+        if topology == "chain":
+            out = conv(conv(h, 1, "relu"), 2, None)
+        elif topology == "two_convs":
+            out = conv(h, 1, None) + conv(h, 2, None)
+        else:
+            out = conv(h, 1, None) + 0.5 * h
+        out.square().sum().backward()
+        return [x.grad] + [t.grad for t in w + b]
+
+    try:
+        fused, plain = run(True), run(False)
+    finally:
+        srb200.set_fuse_relu_backward(True)
+    for a, c in zip(fused, plain):
+        assert torch.equal(a, c)
+    if math == "fp32":
+        for a, c in zip(fused, run(True, use_srb=False)):
+            assert rel_l2(a, c) < 1e-4
+
+
 def test_act_corner_cases_at_zero():
     """z == 0: ReLU grad is 0, PReLU/LeakyReLU take the slope branch (ATen semantics)."""
     _need_gpu()
