@@ -103,6 +103,7 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
                    void *ws, size_t ws_bytes, cudaStream_t st);
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
+int tc_conv_get_dbg();
 int tc_conv_describe(const Geom &g, char *buf, size_t n);
 int tc_wgrad_describe(const Geom &g, char *buf, size_t n);
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);

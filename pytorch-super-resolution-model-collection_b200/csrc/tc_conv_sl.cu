@@ -710,6 +710,7 @@ int g_sl_dbg = 0;
 
 void tc_conv_set_trace(long long *buf, long long max_ctas) { g_sl_trace = buf; g_sl_trace_ctas = max_ctas; }
 void tc_conv_set_dbg(int flags) { g_sl_dbg = flags; }
+int tc_conv_get_dbg() { return g_sl_dbg; }
 
 bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/) {
   if (g.st != 1 || g.N <= 0) return false;

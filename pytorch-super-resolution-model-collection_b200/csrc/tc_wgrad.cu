@@ -39,6 +39,7 @@ struct WgArgs {
   int c4;                 // Cin <= 4: x is the zero-padded NHWC4 image seen through an overlapping-stride TMA view whose
                           // 32 "channels" are the 8-pixel x 4-channel window starting at the slot; an accumulator's four
                           // 32-lane M-blocks are four consecutive FILTER ROWS (LBO = one slot row); RG = ceil(kh/4) accumulators
+  int dbg;                // debug knobs (srb_debug_set_flags): 2 = stages are TMA-loaded only once, 4 = no MMAs are issued
   int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
   float *db_part;         // bias gradient partials [gridDim.x][4 warps][n_cot * NT], or null
@@ -65,6 +66,21 @@ __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "  tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p; }" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(ACCUM ? 1u : 0u)
       : "memory");
+}
+
+// db partial sums of one dz stage: NB 32-channel blocks, 4 rows per LDS.128 (see the caller for the lane mapping)
+template <int NB>
+__device__ __forceinline__ void db_rows(float4 (&dbs)[8], uint32_t sz, int dz_bytes, int rows, int lane_grp, int lrow, int lchunk) {
+  for (int q0 = lane_grp * 4; q0 < rows; q0 += 16) {
+    const int q = q0 + lrow;
+    const uint32_t off = sz + (uint32_t)q * 128u + ((uint32_t)(lchunk ^ ((q & 3) << 1)) << 4);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(off + (uint32_t)(j * dz_bytes)));
+      dbs[j].x += v.x; dbs[j].y += v.y; dbs[j].z += v.z; dbs[j].w += v.w;
+    }
+  }
 }
 
 // All MMAs of one band (one pipeline stage) for NACC accumulators: straight-line issue code per K-step -- one add and one
@@ -131,7 +147,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *p = (uint4 *)smem;
     const int n16 = a.stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += kWgThreads) p[i] = z;
+    for (int i = threadIdx.x; i < ((a.dbg & 16) ? 0 : n16); i += kWgThreads) p[i] = z;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -170,6 +186,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int oh0 = bh * a.TH, ox0 = (rem - bh * a.bands_w) * a.TW;
         uint8_t *sx = smem + (size_t)st * stage_bytes;
         uint8_t *sz = sx + a.CIB * x_bytes;
+        if ((a.dbg & 2) && it >= a.stages) {
+          if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
+          __syncwarp();
+          continue;
+        }
         if (elect_one()) {
           mbar_expect_tx(&full_bar[st], tx_bytes);
           if (a.c4) {
@@ -212,7 +233,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         if (elect_one()) {
           const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;  // a prefix of acc_off (filter-row major)
           const bool first = it == 0;
-          switch (nacc) {
+          switch ((a.dbg & 4) ? 0 : nacc) {
+            case 0: break;
             case 1: wg_issue_band<1>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
             case 2: wg_issue_band<2>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
             case 3: wg_issue_band<3>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
@@ -233,48 +255,60 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     // ===================== epilogue: dump the partial dW tile =====================
     const int lane_grp = warp & 3;
     if (do_db) {
-      // While the MMAs run, these warps walk the same stages and sum the dz tiles over pixels (rows of 128 B holding
-      // 32 channels; 128B_ATOM_32B swizzle: 32-byte atom index XOR (row & 3)).  Warp w takes rows w, w+4, ...
-      float dbs[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dbs[j] = 0.f;
+      // While the MMAs run, these warps walk the same stages and sum the dz tiles over pixels (db).  A warp reads four
+      // 128-B rows per LDS.128: lane l takes row q0 + l/8 and the 16-B chunk holding channels 4*(l%8)..+3 of every
+      // 32-channel block (128B_ATOM_32B swizzle: 32-byte atom index XOR (row & 3), i.e. 16-B chunk index XOR ((row & 3) << 1)).
       const int rows = a.TH * a.BW;
-      // this lane's byte offset inside a 128-B row, for rows q with q % 4 == i (swizzle: 32-byte atom index XOR (q & 3))
-      uint32_t lane_off[4];
+      float4 dbs[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) lane_off[i] = ((uint32_t)lane * 4u) ^ ((uint32_t)i << 5);
+      for (int j = 0; j < 8; ++j) dbs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int lrow = lane >> 3, lchunk = lane & 7;
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
         mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
         const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)a.CIB * x_bytes);
-        // four consecutive rows per warp and step; rows .. round_up(rows, 4) lie in the tile's zero tail (dz_slots % 8 == 0)
-        for (int q0 = lane_grp * 4; q0 < rows; q0 += 16) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t off = sz + (uint32_t)(q0 + i) * 128u + lane_off[i];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nb) {
-                float v;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(off + (uint32_t)j * (uint32_t)dz_bytes));
-                dbs[j] += v;
-              }
+        if (!(a.dbg & 8)) {
+          // rows .. round_up(rows, 8) lie in the tile's zero tail (dz_slots % 8 == 0); warp w takes rows 4w.., 4w+16..
+          switch (nb) {
+            case 1: db_rows<1>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 2: db_rows<2>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 3: db_rows<3>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 4: db_rows<4>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 5: db_rows<5>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 6: db_rows<6>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 7: db_rows<7>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            default: db_rows<8>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
           }
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[st])) : "memory");
       }
-      float *dp = a.db_part + ((size_t)blockIdx.x * 4 + lane_grp) * (size_t)(a.n_cot * a.NT) + (size_t)cot * a.NT;
+      // fold the four row-lanes (lanes l, l^8, l^16 hold the same channels), then lanes 0..7 store 4 channels each
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nb) dp[j * 32 + lane] = dbs[j];
+      for (int j = 0; j < 8; ++j) {
+        if (j < nb) {
+          float4 v = dbs[j];
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+          }
+          dbs[j] = v;
+        }
+      }
+      float *dp = a.db_part + ((size_t)blockIdx.x * 4 + lane_grp) * (size_t)(a.n_cot * a.NT) + (size_t)cot * a.NT;
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nb) *(float4 *)(dp + j * 32 + lane * 4) = dbs[j];
+      }
     }
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = lane_grp * 32 + lane;
     float *dst = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * ACC * 128 * a.NT;
-    for (int acc = 0; acc < ACC; ++acc) {
+    for (int acc = 0; acc < ((a.dbg & 32) ? 0 : ACC); ++acc) {
       const int rl = acc / (a.SG * a.CIB);
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.NT);
       float *row = dst + ((size_t)acc * 128 + m) * a.NT;
@@ -589,6 +623,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
           for (int cb = 0; cb < a.CIB; ++cb) a.acc_off[(rl * a.SG + sg) * a.CIB + cb] = rl * row_step + sg * 32 + cb * x_step;
     }
   }
+  a.dbg = tc_conv_get_dbg();
   a.partial = (float *)wsp;
   float *db_part = a.partial + pl.partial_floats;
   a.db_part = db_small ? db_part : nullptr;

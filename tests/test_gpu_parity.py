@@ -305,10 +305,10 @@ def test_relu_backward_folded_into_consumer_dgrad(math, topology):
     finally:
         srb200.set_fuse_relu_backward(True)
     for a, c in zip(fused, plain):
-        assert torch.equal(a, c)
+        assert (a is None and c is None) or torch.equal(a, c)  # unused layers (conv_and_torch) have no gradient
     if math == "fp32":
         for a, c in zip(fused, run(True, use_srb=False)):
-            assert rel_l2(a, c) < 1e-4
+            assert (a is None and c is None) or rel_l2(a, c) < 1e-4
 
 
 def test_act_corner_cases_at_zero():

@@ -42,8 +42,10 @@ if has launches; then
   echo "ncu launches exit $?"
 fi
 if has full; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_conv_sl|k_tc_wgrad" \
-      --launch-skip 16 -c 10 -f -o "$OUT/espcn_full" python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/full_run.log" 2>&1
+  # FULL_WL / FULL_K / FULL_SKIP / FULL_COUNT select the workload, kernel regex and launch window of the --set full capture
+  WL=${FULL_WL:-espcn_x4_b128_lr64}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${FULL_K:-k_conv_sl|k_tc_wgrad}" \
+      --launch-skip ${FULL_SKIP:-16} -c ${FULL_COUNT:-10} -f -o "$OUT/full_$WL" python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/full_run.log" 2>&1
   echo "ncu full exit $?"
   ls -la "$OUT"
 fi
