@@ -101,10 +101,13 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass);
  *   residual same shape as y, or NULL
  *   y        (N,Cout,Ho*ps,Wo*ps)
  *   preact   optional, same shape as y: receives PixelShuffle(z) (needed by PReLU backward), or NULL
+ *   relu_bits optional (NULL = none): receives the packed sign pattern of z, 16 channels per uint16 --
+ *            word ((n*Ho+oy)*Wo+ox)*(Cout/16) + c/16, bit c%16 set iff z[n,c,oy,ox] > 0 -- i.e. the ReLU mask of y in
+ *            1/32 of y's bytes.  Tensor path only (srb_conv_uses_tensor_path), ps == 1, Cout % 16 == 0; else SRB_EUNSUPPORTED.
  */
 int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
                    const float *alpha, const srb_tensor4 *residual, const srb_tensor4 *y,
-                   const srb_tensor4 *preact, void *ws, size_t ws_bytes, void *stream);
+                   const srb_tensor4 *preact, uint16_t *relu_bits, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * Activation backward (threshold_backward / _prelu_kernel_backward / leaky_relu_backward):
@@ -122,9 +125,12 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
  *   relu_mask  optional (NULL = none), same shape as dx: dx = relu_mask > 0 ? dx : 0 is applied in the epilogue.
  *              Passing the layer's own input x when x = ReLU(.) of the previous layer folds that layer's
  *              threshold_backward into this kernel (base_networks.py:69 backward), saving one pass over dx.
+ *   relu_bits  optional (NULL = none): the same mask in the packed form srb_conv_fprop's relu_bits wrote for the layer
+ *              that produced x (geometry of dx: word ((n*H+iy)*W+ix)*(Cin/16) + c/16).  Costs 1/32 of the float mask's
+ *              traffic.  Tensor-path dgrad with Cin % 16 == 0 only; else SRB_EUNSUPPORTED (pass relu_mask instead).
  */
 int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
-                   const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream);
+                   const uint16_t *relu_bits, const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * Weight + bias gradient.  Replaces cudnn_convolution_backward_weight + the bias aten::sum.

@@ -229,6 +229,8 @@ Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, co
   e.residual = to_t4(residual);
   e.preact = to_t4(preact);
   e.mask = to_t4(nullptr);
+  e.bits_out = nullptr;
+  e.bits_in = nullptr;
   e.round_tf32 = round_out;
   return e;
 }
@@ -311,7 +313,7 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
 
 int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
                    const float *alpha, const srb_tensor4 *residual, const srb_tensor4 *y, const srb_tensor4 *preact,
-                   void *ws, size_t ws_bytes, void *stream) {
+                   uint16_t *relu_bits, void *ws, size_t ws_bytes, void *stream) {
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
@@ -322,10 +324,14 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   T4 tx = to_t4(x), ty = to_t4(y);
   if (!p->transposed) {
     Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
-    if (p->math != SRB_MATH_FP32 && tc_conv_supported(g, tx, ty, false))
-      return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
+    e.bits_out = relu_bits;
+    const bool tc = p->math != SRB_MATH_FP32 && tc_conv_supported(g, tx, ty, false);
+    SRB_REQUIRE(!relu_bits || (tc && p->ps == 1 && (p->Cout & 15) == 0), SRB_EUNSUPPORTED,
+                "relu_bits needs the tensor path, no PixelShuffle and Cout %% 16 == 0");
+    if (tc) return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
     return simt_conv_gather(g, tx, w, ty, e, st);
   }
+  SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits with a transposed convolution");
   Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
   return simt_conv_scatter(g, tx, w, ty, e, st);
 }
@@ -373,7 +379,7 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
 }
 
 int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
-                   const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream) {
+                   const uint16_t *relu_bits, const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream) {
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
@@ -384,17 +390,23 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   Epi e;
   memset(&e, 0, sizeof(e));
   e.act = SRB_ACT_NONE;
-  e.mask = to_t4(relu_mask);
+  e.mask = to_t4(relu_bits ? nullptr : relu_mask);  // the packed pattern wins when both are given
+  e.bits_out = nullptr;
+  e.bits_in = relu_bits;
   e.round_tf32 = want_round(p, tdx, p->Cin);
   if (!p->transposed) {
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
       // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
       Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
-      if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true))
+      if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true)) {
+        SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
         return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
+      }
     }
+    SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits needs the tensor-path dgrad (use relu_mask)");
     return simt_conv_scatter(g, tdz, w, tdx, e, st);
   }
+  SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits with a transposed convolution (use relu_mask)");
   // ConvTranspose2d backward-data is a plain gather conv of dz (big side) producing dx (small side)
   return simt_conv_gather(g, tdz, w, tdx, e, st);
 }

@@ -61,6 +61,11 @@ struct Epi {
   T4 residual;  // p == null -> none
   T4 preact;    // p == null -> none
   T4 mask;      // p == null -> none; else y = mask > 0 ? y : 0 applied last (ReLU backward of the producer of the written tensor)
+  // Packed ReLU sign pattern of the WRITTEN tensor, 16 channels per uint16: word ((n*Ho+oy)*Wo+ox)*(Co/16) + c/16, bit c%16
+  // (tensor path only, Co % 16 == 0, no PixelShuffle).  bits_out: set where the pre-activation is > 0 (fprop of a ReLU
+  // layer); bits_in: the written value is zeroed where the bit is clear (dgrad of the layer that consumes that ReLU output).
+  unsigned short *bits_out;
+  const unsigned short *bits_in;
   int round_tf32;  // store y RN-rounded to tf32 (feeds a tensor-core consumer)
 };
 

@@ -100,6 +100,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   bool pix_ok = false;
   float *po = nullptr, *pp = nullptr;
   const float *pr = nullptr, *pm = nullptr;
+  long long pixw = 0;  // first bit word of this thread's pixel
 #pragma unroll 1
   for (int item = half; item < mtb * ngroups; item += 2) {
     const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
@@ -109,6 +110,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
       const int ty = q / a.BW, tx = q - ty * a.BW;
       oy = oy0 + ty; ox = ox0 + tx;
       pix_ok = (ty < rows_valid) && (tx < cols_valid);
+      pixw = (((long long)n * a.Ho + oy) * a.Wo + ox) * (a.Co >> 4);
       if (MODE != 3) {
         const long long yy = (long long)oy * a.ps, xx = (long long)ox * a.ps;
         po = a.out.p + (n * a.out.sn + yy * a.out.sh + xx * a.out.sw);
@@ -133,6 +135,12 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
         const float4 b = lds128(bias_saddr + (uint32_t)(j0 + j) * 4u);
         z[j] += b.x; z[j + 1] += b.y; z[j + 2] += b.z; z[j + 3] += b.w;
       }
+    }
+    if (MODE != 3 && a.epi.bits_out) {
+      uint32_t mbits = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mbits |= (z[j] > 0.f ? 1u : 0u) << j;
+      a.epi.bits_out[pixw + (cbase >> 4)] = (unsigned short)mbits;
     }
     if (MODE == 3) {
 #pragma unroll
@@ -187,6 +195,11 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
         if (MODE == 2) { z[q4] += rr.x; z[4 + q4] += rr.y; z[8 + q4] += rr.z; z[12 + q4] += rr.w; }
         else { z[4 * q4] += rr.x; z[4 * q4 + 1] += rr.y; z[4 * q4 + 2] += rr.z; z[4 * q4 + 3] += rr.w; }
       }
+    }
+    if (a.epi.bits_in) {
+      const uint32_t mbits = __ldg(a.epi.bits_in + pixw + (cbase >> 4));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = ((mbits >> j) & 1u) ? z[j] : 0.f;
     }
     if (MODE == 0 && has_mask) {
 #pragma unroll

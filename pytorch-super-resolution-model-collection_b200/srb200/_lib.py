@@ -39,9 +39,10 @@ SYMBOLS = {
     "srb_conv_workspace_bytes": (ctypes.c_size_t, [_P(ConvParams), ctypes.c_int]),
     "srb_conv_describe_plan": (ctypes.c_int, [_P(ConvParams), ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
     "srb_conv_fprop": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _vp, _vp, _P(Tensor4), _P(Tensor4),
-                                      _P(Tensor4), _vp, ctypes.c_size_t, _vp]),
+                                      _P(Tensor4), _vp, _vp, ctypes.c_size_t, _vp]),
     "srb_act_bwd": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _P(Tensor4), _vp, _vp]),
-    "srb_conv_dgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _P(Tensor4), _vp, ctypes.c_size_t, _vp]),
+    "srb_conv_dgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _vp, _P(Tensor4), _vp, ctypes.c_size_t,
+                                      _vp]),
     "srb_conv_wgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _vp, ctypes.c_float,
                                       ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
     "srb_pixel_unshuffle": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp]),

@@ -46,11 +46,26 @@ class _ReluToken:
     the producer's backward may skip srb_act_bwd.  Safe by construction: ReLU masking is idempotent, so whenever the
     gradient that reaches the producer is not exactly the tensor the consumer wrote (several consumers, autograd
     accumulation, hooks), the producer simply masks again.  `premasked` identifies that tensor."""
-    __slots__ = ("consumers", "premasked")
+    __slots__ = ("consumers", "premasked", "bits")
 
     def __init__(self):
         self.consumers = 0
         self.premasked = None
+        self.bits = None  # packed sign pattern of y written by the producer's fprop epilogue (int16, 16 channels per word)
+
+
+_tc_cache = {}
+
+
+def _uses_tensor_path(p, pas, x_cl, y_cl):
+    """Cached srb_conv_uses_tensor_path (host-only planner query)."""
+    key = (p.N, p.Cin, p.H, p.W, p.Cout, p.kh, p.kw, p.stride, p.pad, p.out_pad, p.transposed, p.ps, p.math, pas,
+           bool(x_cl), bool(y_cl))
+    r = _tc_cache.get(key)
+    if r is None:
+        r = bool(lib.srb_conv_uses_tensor_path(ctypes.byref(p), pas, 1 if x_cl else 0, 1 if y_cl else 0))
+        _tc_cache[key] = r
+    return r
 
 
 _workspaces = {}
@@ -64,6 +79,19 @@ def _workspace(device, nbytes):
         ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+_ws_cache = {}
+
+
+def _ws_bytes(p, pas):
+    """Cached srb_conv_workspace_bytes (the planner enumeration costs ~10 us of host time per query)."""
+    key = (p.N, p.Cin, p.H, p.W, p.Cout, p.kh, p.kw, p.stride, p.pad, p.out_pad, p.transposed, p.ps, p.math, pas)
+    r = _ws_cache.get(key)
+    if r is None:
+        r = int(lib.srb_conv_workspace_bytes(ctypes.byref(p), pas))
+        _ws_cache[key] = r
+    return r
 
 
 def _stream(device):
@@ -131,13 +159,18 @@ class _FusedConv(torch.autograd.Function):
         if residual is not None:
             assert tuple(residual.shape) == oshape, "residual must match the block output"
             residual = _dense(residual)
-        ws = _workspace(x.device, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_FPROP))
+        bits = None
+        if out_token is not None and ps == 1 and p.Cout % 16 == 0 and _is_cl(y) and \
+                _uses_tensor_path(p, _lib.PASS_FPROP, _is_cl(x), True):
+            bits = torch.empty((p.N, ho.value, wo.value, p.Cout // 16), dtype=torch.int16, device=x.device)
+            out_token.bits = bits
+        ws = _workspace(x.device, _ws_bytes(p, _lib.PASS_FPROP))
         tx, ty = t4(x), t4(y)
         tr = t4(residual) if residual is not None else None
         tp = t4(preact) if preact is not None else None
         check(lib.srb_conv_fprop(ctypes.byref(p), ctypes.byref(tx), _ptr(weight), _ptr(bias), _ptr(alpha),
                                  ctypes.byref(tr) if tr is not None else None, ctypes.byref(ty),
-                                 ctypes.byref(tp) if tp is not None else None,
+                                 ctypes.byref(tp) if tp is not None else None, _ptr(bits),
                                  _ptr(ws), ws.numel(), _stream(x.device)))
         ctx.p = p
         ctx.act = act
@@ -197,7 +230,7 @@ class _FusedConv(torch.autograd.Function):
                 db_t = db = torch.empty(weight.shape[1] if p.transposed else weight.shape[0], dtype=torch.float32,
                                         device=dev) if ctx.has_bias else None
                 scale = 1.0
-            ws = _workspace(dev, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_WGRAD))
+            ws = _workspace(dev, _ws_bytes(p, _lib.PASS_WGRAD))
             check(lib.srb_conv_wgrad(ctypes.byref(p), ctypes.byref(tx), ctypes.byref(tdz), _ptr(dw_t), _ptr(db_t),
                                      ctypes.c_float(scale), 0, _ptr(ws), ws.numel(), st))
         if ctx.needs_input_grad[0]:
@@ -206,10 +239,17 @@ class _FusedConv(torch.autograd.Function):
             tdx = t4(dx)
             itok = ctx.in_token
             fuse = itok is not None and itok.consumers == 1 and _state["fuse_relu_bwd"]
-            tmask = t4(x) if fuse else None  # x = ReLU(z_prev): its sign pattern is the producer's mask
-            ws = _workspace(dev, lib.srb_conv_workspace_bytes(ctypes.byref(p), _lib.PASS_DGRAD))
+            # x = ReLU(z_prev): its sign pattern is the producer's mask -- in packed form when the producer's fprop wrote
+            # it and this dgrad runs on the tensor path, else read from x itself
+            bits = None
+            if fuse and itok.bits is not None and p.Cin % 16 == 0 and \
+                    _uses_tensor_path(p, _lib.PASS_DGRAD, _is_cl(dx), _is_cl(dz)):
+                bits = itok.bits
+            tmask = t4(x) if (fuse and bits is None) else None
+            ws = _workspace(dev, _ws_bytes(p, _lib.PASS_DGRAD))
             check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
-                                     ctypes.byref(tmask) if fuse else None, ctypes.byref(tdx), _ptr(ws), ws.numel(), st))
+                                     ctypes.byref(tmask) if tmask is not None else None, _ptr(bits), ctypes.byref(tdx),
+                                     _ptr(ws), ws.numel(), st))
             if fuse:
                 itok.premasked = (dx.data_ptr(), dx._version, tuple(dx.shape), tuple(dx.stride()))
         return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None, None, None

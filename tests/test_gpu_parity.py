@@ -311,6 +311,26 @@ def test_relu_backward_folded_into_consumer_dgrad(math, topology):
             assert (a is None and c is None) or rel_l2(a, c) < 1e-4
 
 
+@pytest.mark.parametrize("Cin,Cout,k,p,H,W", [(32, 64, 3, 1, 9, 13), (3, 64, 5, 0, 18, 17), (64, 32, 3, 0, 16, 16)])
+def test_packed_relu_sign_bits_match_output(Cin, Cout, k, p, H, W):
+    """srb_conv_fprop's relu_bits: bit c%16 of word [n, oy, ox, c/16] is set exactly where y > 0 (bit-exact)."""
+    _need_gpu()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, Cin, H, W, generator=gen).to(DEV)
+    if Cin >= 8:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(DEV).requires_grad_(True)
+    b = (torch.randn(Cout, generator=gen) * 0.1).to(DEV).requires_grad_(True)
+    y = srb200.conv2d(x, w, b, 1, p, activation="relu")
+    tok = getattr(y, "_srb_relu", None)
+    assert tok is not None and tok.bits is not None, "tensor-path ReLU layers must emit the packed mask"
+    bits = tok.bits.cpu().numpy().view(np.uint16)                      # (N, Ho, Wo, Cout/16)
+    pos = (y.detach().permute(0, 2, 3, 1) > 0).cpu().numpy()            # (N, Ho, Wo, Cout)
+    unpacked = ((bits[..., None] >> np.arange(16, dtype=np.uint16)) & 1).reshape(pos.shape).astype(bool)
+    assert np.array_equal(unpacked, pos)
+
+
 def test_act_corner_cases_at_zero():
     """z == 0: ReLU grad is 0, PReLU/LeakyReLU take the slope branch (ATen semantics)."""
     _need_gpu()
