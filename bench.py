@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="auto", choices=["auto", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -209,7 +210,8 @@ def main():
     model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[a.workload]
     config = {"workload": a.workload, "model": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
               "lr_hw": [h, w], "loss": loss_kind, "optimizer": opt_key, "parallelism": "dp%d" % world,
-              "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches"}
+              "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches",
+              "launch": "eager" if a.no_graph else "cuda-graph replay (fwd+loss+bwd graph per input slot, optimizer graph)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -242,7 +244,7 @@ def main():
     net = srb200.models.MODELS[model_key](*margs)
     host.init_model(model_key, net)
     net.to(dev).train()
-    opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5)
+    opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5, capturable=not a.no_graph)
     bucket = srb200.GradBucket(net, world_size=world)
     lossf = host.loss_for(model_key)
     oshape = out_shape(model_key, margs, batch, h, w)
@@ -265,6 +267,50 @@ def main():
         opt.step()
         return loss
 
+    # ---- whole-step CUDA graphs --------------------------------------------------------------------------------
+    # The small nets are host-launch bound when every kernel is launched from Python (ESPCN: ~30 launches per 0.8 ms
+    # step), so the step is captured once per input slot: graph A[i] = zero non-direct grads + forward + loss + backward on
+    # the resident batch i, graph B = gradient clipping + optimizer.  The NCCL all-reduce of the flat gradient buffer
+    # stays an eager call between the two.  libsrb200 never allocates or synchronises, so its launches (and the tensor
+    # maps encoded at capture time) are captured as they are.
+    graphs = {}
+
+    def capture_graphs():
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.stream(side):
+            ga, losses, per_graph = [], [], []
+            for i in range(3):
+                g = torch.cuda.CUDAGraph()
+                out = torch.zeros((), device=dev)
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    bucket.begin_step()
+                    loss = lossf(net(dev_x[i]), dev_t[i])
+                    loss.backward()
+                    out.copy_(loss.detach())
+                per_graph.append(_lib.launch_count() - c0)
+                ga.append(g)
+                losses.append(out)
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, pool=pool, stream=side):
+                if model_key == "vdsr":
+                    torch.nn.utils.clip_grad_norm_(net.parameters(), host.VDSR_CLIP)
+                opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs.update(a=ga, b=gb, loss=losses, launches=per_graph[0])
+
+    def step_slot(i):
+        """One training step on resident batch slot i (graph replay when captured, eager otherwise)."""
+        if not graphs:
+            return step(dev_x[i], dev_t[i])
+        graphs["a"][i].replay()
+        bucket.all_reduce()
+        graphs["b"].replay()
+        return graphs["loss"][i]
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -275,11 +321,12 @@ def main():
     def prefetch(i):
         """H2D copy of step i's batch from pinned host memory on the copy stream (overlaps the previous step's kernels)."""
         with torch.cuda.stream(copy_stream):
-            x = host_x[i % 3].to(dev, non_blocking=True)
-            t = host_t[i % 3].to(dev, non_blocking=True)
+            # into the resident slot (the graphs read fixed addresses); slot i%3 was last read by step i-3, long finished
+            dev_x[i % 3].copy_(host_x[i % 3], non_blocking=True)
+            dev_t[i % 3].copy_(host_t[i % 3], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return x, t, ev
+        return ev
 
     def timed(nsteps, e2e):
         barrier()
@@ -293,17 +340,15 @@ def main():
             nxt = prefetch(0)
         for i in range(nsteps):
             if e2e:
-                x, t, ev = nxt
+                ev = nxt
                 if i + 1 < nsteps:
                     nxt = prefetch(i + 1)
                 main.wait_event(ev)
-                x.record_stream(main)
-                t.record_stream(main)
-                loss = step(x, t)
+                loss = step_slot(i % 3)
                 loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
                 main.synchronize()
             else:
-                step(dev_x[i % 3], dev_t[i % 3])
+                step_slot(i % 3)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -315,12 +360,14 @@ def main():
 
     for i in range(a.warmup):
         step(dev_x[i % 3], dev_t[i % 3])
+    if not a.no_graph:
+        capture_graphs()
+        for i in range(3):
+            step_slot(i)
     l0 = _lib.launch_count()
     with Clocks(local_rank) as ck:
         ms = timed(a.steps, e2e=False)
-        launches = _lib.launch_count() - l0
-        for i in range(3):
-            step(host_x[i % 3].to(dev), host_t[i % 3].to(dev))
+        launches = graphs["launches"] * a.steps if graphs else _lib.launch_count() - l0
         ms_e2e = timed(a.steps, e2e=True)
     clocks = ck.summary()
 

@@ -46,6 +46,7 @@ struct SlArgs {
   int t_bufs, tmem_cols;  // accumulator buffers in TMEM (2: epilogue of band i overlaps the MMAs of band i+1)
   int ps;
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
+  int v8;              // out / residual / preact / mask rows are 32-byte aligned: mode-0 epilogue uses 256-bit global accesses
   int dbg;             // debug knobs (srb_debug_set_flags): 1 = epilogue does nothing, 2 = A tiles are loaded only once per buffer
   long long *trace;    // debug (srb_debug_set_trace): 8 timestamps per CTA, null in production
   T4 out;
@@ -79,6 +80,18 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return r;
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction -- half the LSU wavefronts of float4.
+// Macros on purpose: the operands are elements of register-resident arrays (taking their address would demote them to local memory).
+#define STG256(ptr, v, o)                                                                                                  \
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(v[(o)]), "f"(v[(o) + 1]),       \
+               "f"(v[(o) + 2]), "f"(v[(o) + 3]), "f"(v[(o) + 4]), "f"(v[(o) + 5]), "f"(v[(o) + 6]), "f"(v[(o) + 7])         \
+               : "memory")
+#define LDG256(ptr, v, o)                                                                                                  \
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                              \
+               : "=f"(v[(o)]), "=f"(v[(o) + 1]), "=f"(v[(o) + 2]), "=f"(v[(o) + 3]), "=f"(v[(o) + 4]), "=f"(v[(o) + 5]),  \
+                 "=f"(v[(o) + 6]), "=f"(v[(o) + 7])                                                                        \
+               : "l"(ptr))
+
 // One epilogue warp's share of the band: work items (M-tile, 16-column group), item = half, half+2, ...
 //   MODE 0: NHWC, no shuffle           -> 4 x float4 at channel cbase + 4q
 //   MODE 1: PixelShuffle(4) into NCHW  -> one output channel c = cbase/16; quad q = sub-row i: 4 contiguous j
@@ -100,7 +113,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   bool pix_ok = false;
   float *po = nullptr, *pp = nullptr;
   const float *pr = nullptr, *pm = nullptr;
-  long long pixw = 0;  // first bit word of this thread's pixel
+  int pixw = 0;  // first bit word of this thread's pixel (host guarantees N*Ho*Wo*Co/16 < 2^31)
 #pragma unroll 1
   for (int item = half; item < mtb * ngroups; item += 2) {
     const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
@@ -110,7 +123,7 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
       const int ty = q / a.BW, tx = q - ty * a.BW;
       oy = oy0 + ty; ox = ox0 + tx;
       pix_ok = (ty < rows_valid) && (tx < cols_valid);
-      pixw = (((long long)n * a.Ho + oy) * a.Wo + ox) * (a.Co >> 4);
+      pixw = ((n * a.Ho + oy) * a.Wo + ox) * (a.Co >> 4);
       if (MODE != 3) {
         const long long yy = (long long)oy * a.ps, xx = (long long)ox * a.ps;
         po = a.out.p + (n * a.out.sn + yy * a.out.sh + xx * a.out.sw);
@@ -173,7 +186,10 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
       pg = po + c; qs_o = a.out.sw; qs_o2 = a.out.sh;
       if (EXTRA) { prg = pr + c; ppg = pp + c; qs_r = a.epi.residual.sw; qs_r2 = a.epi.residual.sh; qs_p = a.epi.preact.sw; qs_p2 = a.epi.preact.sh; }
     }
-    if (has_pre) {
+    if (MODE == 0 && has_pre && a.v8) {
+      STG256(ppg, z, 0);
+      STG256(ppg + 8, z, 8);
+    } else if (has_pre) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const float4 zq = MODE == 2 ? make_float4(z[q4], z[4 + q4], z[8 + q4], z[12 + q4])
@@ -188,7 +204,13 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
 #pragma unroll
       for (int j = 0; j < 16; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
     }
-    if (has_res) {
+    if (MODE == 0 && has_res && a.v8) {
+      float rr[16];
+      LDG256(prg, rr, 0);
+      LDG256(prg + 8, rr, 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] += rr[j];
+    } else if (has_res) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const float4 rr = __ldg((const float4 *)(prg + (MODE == 2 ? (q4 >> 1) * qs_r2 + (q4 & 1) * qs_r : q4 * qs_r)));
@@ -212,6 +234,11 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
     if (rnd) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) z[j] = round_tf32_fast(z[j]);
+    }
+    if (MODE == 0 && a.v8) {
+      STG256(pg, z, 0);
+      STG256(pg + 8, z, 8);
+      continue;
     }
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
@@ -829,6 +856,12 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   }
   a.out = out;
   a.epi = epi;
+  {
+    auto ok32 = [](const T4 &t) {
+      return !t.p || ((((uintptr_t)t.p) & 31) == 0 && (t.sn & 7) == 0 && (t.sh & 7) == 0 && (t.sw & 7) == 0);
+    };
+    a.v8 = (ok32(out) && ok32(epi.residual) && ok32(epi.preact)) ? 1 : 0;
+  }
   a.dbg = g_sl_dbg;
   a.trace = ((long long)pl.grid_x * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;
 

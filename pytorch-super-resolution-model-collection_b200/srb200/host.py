@@ -52,21 +52,22 @@ def init_model(name, net):
     return net
 
 
-def make_optimizer(name, params, lr=1e-5):
+def make_optimizer(name, params, lr=1e-5, capturable=False):
     """Same optimizers and hyper-parameters as the reference drivers (srcnn.py:79, espcn.py:79, fsrcnn.py:106,
     vdsr.py:89-90, edsr.py:93).  On CUDA parameters torch's single-kernel multi-tensor implementation is selected
     (`fused=True`): identical update rule, one launch instead of ~7 per step -- it matters for the tiny nets."""
     params = list(params)
     fused = {"fused": True} if (params and params[0].is_cuda) else {}
+    adam = dict(fused, capturable=True) if (capturable and fused) else fused  # step counter on the device: CUDA-graph safe
     if name == "srcnn":
         return torch.optim.SGD(params, lr=lr, **fused)
     if name == "espcn":
-        return torch.optim.Adam(params, lr=lr, **fused)
+        return torch.optim.Adam(params, lr=lr, **adam)
     if name == "fsrcnn":
         return torch.optim.SGD(params, lr=lr, momentum=0.9, **fused)
     if name == "vdsr":
         return torch.optim.SGD(params, lr=lr, momentum=0.9, weight_decay=1e-4, **fused)
-    return torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-8, **fused)
+    return torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-8, **adam)
 
 
 def loss_for(name):
