@@ -703,8 +703,15 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
           t += 600.0 / ((double)TH * TW);  // per-band hand-offs (accumulator swap, first-MMA latency)
           if (t_bufs == 1) t *= (ctas == 2 ? 1.1 : 1.3);  // the epilogue is only hidden by a co-resident CTA, if any
           if (a_bufs == 1) t *= 1.15;                       // operand loads serialise with the MMAs
+          // wave quantisation of the persistent grid: the slowest CTA walks ceil(work / slots) bands
           const long long work = (long long)g.N * bands_h * bands_w * (Npad / NT);
-          if (work < 148) t *= 148.0 / (double)(work > 0 ? work : 1);  // do not starve the SMs on tiny problems
+          const long long slots_sm = 148LL * ctas;
+          const long long waves = (work + slots_sm - 1) / slots_sm;
+          if (waves < 4) t *= (double)(waves * slots_sm) / (double)(work > 0 ? work : 1);  // many waves: tail effects are small
+          // fixed cost per CTA (TMEM alloc, barrier init, first operand + resident weight fetch, drain of the last
+          // epilogue), amortised over the pixels one CTA produces
+          const long long waves_sm = (work + 147) / 148;  // bands per SM, however many CTAs share it
+          t += (2500.0 + (b_res ? 0.02 * b_stage * b_stages : 0.0)) / ((double)waves_sm * TH * TW);
           if (best_t < 0 || t < best_t) {
             best_t = t;
             a.TH = TH; a.TW = TW; a.BW = BW; a.BH = BH; a.bands_h = bands_h; a.bands_w = bands_w;
@@ -727,15 +734,13 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   a.ps = g.ps;
   pl->Npad = Npad;
   pl->n_tiles_n = Npad / NT;
-  {  // persistent grid: as many CTAs as fit on the chip, bands split evenly
+  {  // persistent grid: as many CTAs as fit on the chip; CTA x walks bands x, x + grid, ...
     const long long num_bands = (long long)g.N * a.bands_h * a.bands_w;
     long long slots = (long long)pl->ctas_per_sm * 148 / pl->n_tiles_n;
     if (slots < 1) slots = 1;
     long long P = num_bands < slots ? num_bands : slots;
     if (P < 1) P = 1;
-    const long long per = (num_bands + P - 1) / P;
-    pl->grid_x = (int)(per > 0 ? (num_bands + per - 1) / per : 1);
-    if (pl->grid_x < 1) pl->grid_x = 1;
+    pl->grid_x = (int)P;
   }
   pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
   pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;

@@ -338,8 +338,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
 // dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order => deterministic)
 // blockDim = (32 elements, 8 split lanes): lane y sums splits y, y+8, ... ; the 8 lane sums are folded in shared memory
 // in a fixed order.  Element index runs co-fastest so that the partial reads (n contiguous) coalesce.
-__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
-  __shared__ float red[8][33];
+__global__ void __launch_bounds__(512) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
+  __shared__ float red[16][33];
   const long long total = (long long)a.Co * a.Ci * a.kh * a.kw;
   const int ACC = a.RG * a.SG * a.CIB;
   const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
   if (is_db) {  // bias gradient: splits x 4 warp partials per channel
     const int co = (int)(i - total);
     const size_t pitch = (size_t)(a.n_cot * a.NT);
-    for (int z = threadIdx.y; z < splits * 4; z += 8) sum += a.db_part[(size_t)z * pitch + co];
+    for (int z = threadIdx.y; z < splits * 4; z += 16) sum += a.db_part[(size_t)z * pitch + co];
   }
   if (i < total) {
     const int co = (int)(i % a.Co);
@@ -374,14 +374,22 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
     }
     const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
     const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
-    for (int z = threadIdx.y; z < splits; z += 8) sum += p[(size_t)z * split_stride];
+    // 16 split lanes; four independent loads in flight per thread
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = threadIdx.y;
+    for (; z + 48 < splits; z += 64) {
+      s0 += p[(size_t)z * split_stride]; s1 += p[(size_t)(z + 16) * split_stride];
+      s2 += p[(size_t)(z + 32) * split_stride]; s3 += p[(size_t)(z + 48) * split_stride];
+    }
+    for (; z < splits; z += 16) s0 += p[(size_t)z * split_stride];
+    sum = (s0 + s1) + (s2 + s3);
   }
   red[threadIdx.y][threadIdx.x] = sum;
   __syncthreads();
   if (threadIdx.y == 0 && (i < total || is_db)) {
     float t = red[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
+    for (int y = 1; y < 16; ++y) t += red[y][threadIdx.x];
     t *= scale;
     float *d = is_db ? db + (i - total) : dw + dst;
     *d = accumulate ? *d + t : t;
@@ -668,7 +676,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   {
     long long total = (long long)g.Co * g.Ci * g.kh * g.kw;
     if (db_small) total += g.Co;
-    k_wgrad_finish<<<(unsigned)((total + 31) / 32), dim3(32, 8), 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, db_small, scale, accumulate);
+    k_wgrad_finish<<<(unsigned)((total + 31) / 32), dim3(32, 16), 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
