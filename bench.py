@@ -246,7 +246,7 @@ def main():
     net.to(dev).train()
     opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5, capturable=not a.no_graph)
     bucket = srb200.GradBucket(net, world_size=world)
-    lossf = host.loss_for(model_key)
+    lossf = host.loss_for(model_key, fused=True)
     oshape = out_shape(model_key, margs, batch, h, w)
 
     gen = torch.Generator().manual_seed(1 + rank)

@@ -154,6 +154,16 @@ int srb_prelu_fwd(const float *x, const float *alpha, float *y, int64_t n, void 
 int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx, float *dalpha, int64_t n,
                   void *stream);
 
+/*
+ * Regression losses with mean reduction over n contiguous floats: kind 0 = MSE (nn.MSELoss, srcnn.py:84, espcn.py:84,
+ * vdsr.py:96), kind 1 = L1 (nn.L1Loss, edsr.py:98).  y and t must share one dense layout.
+ *   fwd: *loss = mean((y-t)^2) or mean(|y-t|); deterministic two-stage sum; ws >= srb_loss_workspace_bytes().
+ *   bwd: dy = *grad_loss * d loss / d y in one pass (mse_backward / l1_loss backward: sign(y-t), 0 at equality).
+ */
+size_t srb_loss_workspace_bytes(void);
+int srb_loss_fwd(int kind, const float *y, const float *t, int64_t n, float *loss, void *ws, size_t ws_bytes, void *stream);
+int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const float *grad_loss, float *dy, void *stream);
+
 /* Round n contiguous floats to tf32 (round-to-nearest, ties away) in place or out of place. */
 int srb_round_tf32(const float *x, float *y, int64_t n, void *stream);
 

@@ -178,6 +178,70 @@ __global__ void k_round_tf32(const float *__restrict__ x, float *y, long long n)
     y[i] = round_tf32(x[i]);
 }
 
+// ---- fused regression losses (srcnn.py:84 / edsr.py:98: nn.MSELoss / nn.L1Loss with mean reduction) -------------------
+// forward: per-block partial sums of (y-t)^2 or |y-t| in a fixed order, a second tiny kernel folds them (deterministic);
+// backward: dy = g * 2 (y - t) / n   or   g * sign(y - t) / n   in one pass (g = upstream gradient, a device scalar).
+__global__ void __launch_bounds__(256) k_loss_partial(const float4 *__restrict__ y, const float4 *__restrict__ t, long long n4,
+                                                      const float *__restrict__ ytail, const float *__restrict__ ttail, int ntail,
+                                                      int l1, float *__restrict__ partial) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(y + i), b = __ldg(t + i);
+    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+    s += l1 ? (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3)) : (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) {
+    const float d = __ldg(ytail + threadIdx.x) - __ldg(ttail + threadIdx.x);
+    s += l1 ? fabsf(d) : d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int w = 1; w < 8; ++w) v += red[w];
+    partial[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_loss_finish(const float *__restrict__ partial, int nblocks, float inv_n, float *loss) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0] * inv_n;
+}
+
+__global__ void __launch_bounds__(256) k_loss_bwd(const float *__restrict__ y, const float *__restrict__ t, long long n, int l1,
+                                                  float inv_n, const float *__restrict__ g, float *__restrict__ dy) {
+  const float c = __ldg(g) * inv_n * (l1 ? 1.f : 2.f);
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg((const float4 *)y + i), b = __ldg((const float4 *)t + i);
+    float4 o;
+    if (l1) {  // ATen l1_loss backward: sign(y - t), 0 at equality
+      o.x = a.x > b.x ? c : (a.x < b.x ? -c : 0.f); o.y = a.y > b.y ? c : (a.y < b.y ? -c : 0.f);
+      o.z = a.z > b.z ? c : (a.z < b.z ? -c : 0.f); o.w = a.w > b.w ? c : (a.w < b.w ? -c : 0.f);
+    } else {
+      o.x = c * (a.x - b.x); o.y = c * (a.y - b.y); o.z = c * (a.z - b.z); o.w = c * (a.w - b.w);
+    }
+    ((float4 *)dy)[i] = o;
+  }
+  if (blockIdx.x == 0) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    if (i < n) {
+      const float a = __ldg(y + i), b = __ldg(t + i);
+      dy[i] = l1 ? (a > b ? c : (a < b ? -c : 0.f)) : c * (a - b);
+    }
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -478,6 +542,32 @@ int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx
   SRB_REQUIRE(x && dy && alpha && dx && n >= 0, SRB_EINVAL, "bad prelu args");
   if (n == 0) return SRB_OK;
   k_prelu_bwd<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, alpha, dx, dalpha, n);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+size_t srb_loss_workspace_bytes(void) { return 148 * 16 * sizeof(float); }
+
+int srb_loss_fwd(int kind, const float *y, const float *t, int64_t n, float *loss, void *ws, size_t ws_bytes, void *stream) {
+  SRB_REQUIRE(y && t && loss && n > 0 && (kind == 0 || kind == 1), SRB_EINVAL, "bad loss args");
+  SRB_REQUIRE(ws && ws_bytes >= srb_loss_workspace_bytes(), SRB_EWORKSPACE, "loss workspace too small");
+  SRB_REQUIRE(((((uintptr_t)y) | ((uintptr_t)t)) & 15) == 0, SRB_EUNSUPPORTED, "loss tensors must be 16-byte aligned");
+  const long long n4 = n >> 2;
+  const unsigned blocks = ew_blocks(n4 > 0 ? n4 : 1);
+  k_loss_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)y, (const float4 *)t, n4, y + (n4 << 2), t + (n4 << 2),
+                                                           (int)(n & 3), kind, (float *)ws);
+  k_loss_finish<<<1, 256, 0, (cudaStream_t)stream>>>((const float *)ws, (int)blocks, 1.0f / (float)n, loss);
+  count_launch(2);
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const float *grad_loss, float *dy, void *stream) {
+  SRB_REQUIRE(y && t && grad_loss && dy && n > 0 && (kind == 0 || kind == 1), SRB_EINVAL, "bad loss args");
+  SRB_REQUIRE(((((uintptr_t)y) | ((uintptr_t)t) | ((uintptr_t)dy)) & 15) == 0, SRB_EUNSUPPORTED,
+              "loss tensors must be 16-byte aligned");
+  k_loss_bwd<<<ew_blocks((n >> 2) > 0 ? (n >> 2) : 1), 256, 0, (cudaStream_t)stream>>>(y, t, n, kind, 1.0f / (float)n, grad_loss, dy);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

@@ -49,6 +49,9 @@ SYMBOLS = {
     "srb_prelu_fwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_prelu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_round_tf32": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
+    "srb_loss_workspace_bytes": (ctypes.c_size_t, []),
+    "srb_loss_fwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_size_t, _vp]),
+    "srb_loss_bwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
     "srb_launch_count": (ctypes.c_int64, []),
 }
 

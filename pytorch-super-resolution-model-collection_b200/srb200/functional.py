@@ -316,3 +316,42 @@ def prelu(x, alpha):
     """Stand-alone PReLU with one shared slope (fsrcnn.py:26)."""
     assert alpha.numel() == 1
     return _PReLU.apply(x, alpha)
+
+
+class _Loss(torch.autograd.Function):
+    """mean((y-t)^2) / mean(|y-t|) with a one-pass backward (srb_loss_fwd / srb_loss_bwd)."""
+
+    @staticmethod
+    def forward(ctx, y, t, kind):
+        _require_cuda(y, t)
+        assert y.shape == t.shape, "loss operands must have the same shape"
+        y = _dense(y)
+        if t.stride() != y.stride():  # same dense layout on both sides (layout plumbing, not arithmetic)
+            t = t.contiguous(memory_format=torch.channels_last) if (y.dim() == 4 and _is_cl(y)) else t.contiguous()
+            if t.stride() != y.stride():
+                y = y.contiguous()
+                t = t.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=y.device)
+        ws = _workspace(y.device, int(lib.srb_loss_workspace_bytes()))
+        check(lib.srb_loss_fwd(kind, _ptr(y), _ptr(t), y.numel(), _ptr(loss), _ptr(ws), ws.numel(), _stream(y.device)))
+        ctx.kind = kind
+        ctx.save_for_backward(y, t)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        y, t = ctx.saved_tensors
+        g = g.contiguous()
+        dy = torch.empty_like(y)
+        check(lib.srb_loss_bwd(ctx.kind, _ptr(y), _ptr(t), y.numel(), _ptr(g), _ptr(dy), _stream(y.device)))
+        return dy, None, None
+
+
+def mse_loss(y, t):
+    """nn.MSELoss() (mean) as two fused kernels forward and one backward (srcnn.py:84, espcn.py:84, vdsr.py:96)."""
+    return _Loss.apply(y, t, 0)
+
+
+def l1_loss(y, t):
+    """nn.L1Loss() (mean) (edsr.py:98)."""
+    return _Loss.apply(y, t, 1)

@@ -70,7 +70,11 @@ def make_optimizer(name, params, lr=1e-5, capturable=False):
     return torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-8, **adam)
 
 
-def loss_for(name):
+def loss_for(name, fused=False):
+    """nn.L1Loss for EDSR (edsr.py:98), nn.MSELoss for the others; fused=True selects libsrb200's one-pass kernels."""
+    if fused:
+        from . import functional as F
+        return F.l1_loss if name == "edsr" else F.mse_loss
     return TF.l1_loss if name == "edsr" else TF.mse_loss
 
 

@@ -331,6 +331,25 @@ def test_packed_relu_sign_bits_match_output(Cin, Cout, k, p, H, W):
     assert np.array_equal(unpacked, pos)
 
 
+@pytest.mark.parametrize("kind", ["mse", "l1"])
+@pytest.mark.parametrize("shape", [(2, 3, 17, 19), (4, 3, 64, 64), (1, 1, 1, 3)])
+def test_fused_losses_match_torch(kind, shape):
+    """srb_loss_fwd / srb_loss_bwd vs nn.MSELoss / nn.L1Loss (mean), including the n % 4 tail and an upstream factor."""
+    _need_gpu()
+    gen = torch.Generator().manual_seed(9)
+    y0, t0 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    t0.view(-1)[0] = y0.view(-1)[0]  # an exact tie: l1 gradient must be 0 there
+    yr = y0.clone().requires_grad_(True)
+    ref = (TF.l1_loss if kind == "l1" else TF.mse_loss)(yr, t0)
+    (3.0 * ref).backward()
+    yg = y0.to(DEV).requires_grad_(True)
+    out = (srb200.l1_loss if kind == "l1" else srb200.mse_loss)(yg, t0.to(DEV))
+    (3.0 * out).backward()
+    assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert rel_l2(yg.grad, yr.grad) < 1e-6
+    assert yg.grad.view(-1)[0].item() == 0.0 if kind == "l1" else True
+
+
 def test_act_corner_cases_at_zero():
     """z == 0: ReLU grad is 0, PReLU/LeakyReLU take the slope branch (ATen semantics)."""
     _need_gpu()
