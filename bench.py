@@ -245,7 +245,7 @@ def main():
     config = {"workload": a.workload, "model": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
               "lr_hw": [h, w], "loss": loss_kind, "optimizer": opt_key, "parallelism": "dp%d" % world,
               "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches",
-              "launch": "eager" if a.no_graph else "cuda-graph replay (fwd+loss+bwd graph per input slot, optimizer graph)"}
+              "launch": "eager" if a.no_graph else "cuda-graph replay (srb200.TrainStepGraphs: fwd+loss+bwd[+allreduce] graph per input slot, optimizer graph)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -301,49 +301,22 @@ def main():
         opt.step()
         return loss
 
-    # ---- whole-step CUDA graphs --------------------------------------------------------------------------------
-    # The small nets are host-launch bound when every kernel is launched from Python (ESPCN: ~30 launches per 0.8 ms
-    # step), so the step is captured once per input slot: graph A[i] = zero non-direct grads + forward + loss + backward on
-    # the resident batch i, graph B = gradient clipping + optimizer.  The NCCL all-reduce of the flat gradient buffer
-    # stays an eager call between the two.  libsrb200 never allocates or synchronises, so its launches (and the tensor
-    # maps encoded at capture time) are captured as they are.
+    # ---- whole-step CUDA graphs (srb200.TrainStepGraphs) -----------------------------------------------------------------
+    # The small nets are host-launch bound when every kernel is launched from Python, so the step is captured once per
+    # resident input slot: backward graph (zero non-direct grads + forward + loss + backward [+ NCCL all-reduce]) and an
+    # optimizer graph (clipping + step).
     graphs = {}
 
     def capture_graphs():
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        pool = torch.cuda.graph_pool_handle()
-        with torch.cuda.stream(side):
-            ga, losses, per_graph = [], [], []
-            for i in range(3):
-                g = torch.cuda.CUDAGraph()
-                out = torch.zeros((), device=dev)
-                c0 = _lib.launch_count()
-                with torch.cuda.graph(g, pool=pool, stream=side):
-                    bucket.begin_step()
-                    loss = lossf(net(dev_x[i]), dev_t[i])
-                    loss.backward()
-                    out.copy_(loss.detach())
-                per_graph.append(_lib.launch_count() - c0)
-                ga.append(g)
-                losses.append(out)
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, pool=pool, stream=side):
-                if model_key == "vdsr":
-                    torch.nn.utils.clip_grad_norm_(net.parameters(), host.VDSR_CLIP)
-                opt.step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graphs.update(a=ga, b=gb, loss=losses, launches=per_graph[0])
+        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)),
+                                    clip_norm=host.VDSR_CLIP if model_key == "vdsr" else None)
+        graphs.update(stepper=st, launches=st.launches_per_step)
 
     def step_slot(i):
         """One training step on resident batch slot i (graph replay when captured, eager otherwise)."""
         if not graphs:
             return step(dev_x[i], dev_t[i])
-        graphs["a"][i].replay()
-        bucket.all_reduce()
-        graphs["b"].replay()
-        return graphs["loss"][i]
+        return graphs["stepper"].step(i)
 
     def barrier():
         if world > 1:

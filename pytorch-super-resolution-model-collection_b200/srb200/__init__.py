@@ -11,6 +11,7 @@ from . import base_networks
 from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBlock, Upsample2xBlock
 from .convert import convert, PReLU, ConvTranspose2d, Conv2d
 from .ddp import GradBucket
+from .graphs import TrainStepGraphs
 from . import models, host
 
 __version__ = "0.1.0"

@@ -1,0 +1,88 @@
+"""Whole-step CUDA-graph replay for the training loop body (espcn.py:126-131 and its siblings).
+
+The small SR nets are host-launch bound when every kernel is launched from Python (ESPCN cfg2: ~35 launches per 0.65 ms
+step).  libsrb200 never allocates, synchronises or reads device data on the host, so the whole step -- zeroing of the
+non-conv gradients, forward, loss, backward (autograd), gradient clipping, optimizer -- can be captured once per input
+slot and replayed.  Tensor maps are encoded at capture time against the graph's private memory pool, which is why the
+inputs live in fixed "slots" that the caller refills (device-to-device or pinned-host-to-device copies).
+
+    stepper = srb200.TrainStepGraphs(net, loss_fn, optimizer, bucket, slots=[(x0, t0), (x1, t1)], clip_norm=None)
+    loss = stepper.step(i)         # replays slot i; returns the 0-dim loss tensor of that slot (device)
+
+Data parallel: the NCCL all-reduce of the flat gradient buffer sits between the backward graph and the optimizer graph.
+With `capture_allreduce=True` it is captured into the backward graph (NCCL supports stream capture); if that capture
+fails the class falls back to an eager all-reduce between two graphs.
+"""
+import torch
+
+from . import _lib
+
+
+class TrainStepGraphs:
+    def __init__(self, net, loss_fn, optimizer, bucket, slots, clip_norm=None, capture_allreduce=True):
+        self.net, self.loss_fn, self.opt, self.bucket = net, loss_fn, optimizer, bucket
+        self.slots = list(slots)
+        self.clip_norm = clip_norm
+        self.dev = self.slots[0][0].device
+        self.fused_comm = False
+        self.launches_per_step = 0
+        self._capture(capture_allreduce and bucket.world > 1)
+
+    # -- eager version of the same step (warm-up, debugging, instrumentation) ---------------------------------------
+    def eager_step(self, x, t):
+        self.bucket.begin_step()
+        loss = self.loss_fn(self.net(x), t)
+        loss.backward()
+        self.bucket.all_reduce()
+        if self.clip_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.clip_norm)
+        self.opt.step()
+        return loss
+
+    def _capture_once(self, with_comm):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        pool = torch.cuda.graph_pool_handle()
+        fwd_bwd, losses, counts = [], [], []
+        with torch.cuda.stream(side):
+            for x, t in self.slots:
+                g = torch.cuda.CUDAGraph()
+                out = torch.zeros((), device=self.dev)
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    self.bucket.begin_step()
+                    loss = self.loss_fn(self.net(x), t)
+                    loss.backward()
+                    out.copy_(loss.detach())
+                    if with_comm:
+                        self.bucket.all_reduce()
+                counts.append(_lib.launch_count() - c0)
+                fwd_bwd.append(g)
+                losses.append(out)
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail, pool=pool, stream=side):
+                if self.clip_norm is not None:
+                    torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.clip_norm)
+                self.opt.step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.fwd_bwd, self.tail, self.losses = fwd_bwd, tail, losses
+        self.launches_per_step = counts[0]
+        self.fused_comm = with_comm
+
+    def _capture(self, want_comm):
+        if want_comm:
+            try:
+                self._capture_once(True)
+                return
+            except Exception:  # NCCL capture unavailable in this setup: keep the collective eager
+                torch.cuda.synchronize(self.dev)
+        self._capture_once(False)
+
+    def step(self, i):
+        """Replay the step on slot i (the caller has already put that step's batch into the slot tensors)."""
+        self.fwd_bwd[i].replay()
+        if not self.fused_comm:
+            self.bucket.all_reduce()
+        self.tail.replay()
+        return self.losses[i]

@@ -350,6 +350,52 @@ def test_fused_losses_match_torch(kind, shape):
     assert yg.grad.view(-1)[0].item() == 0.0 if kind == "l1" else True
 
 
+@pytest.mark.parametrize("name,args,shape", [("espcn", (3, 64, 4), (4, 3, 24, 24)), ("vdsr", (3, 64, 3), (2, 3, 32, 32))])
+def test_cuda_graph_replay_equals_eager_training(name, args, shape):
+    """srb200.TrainStepGraphs: three replayed steps must leave exactly the parameters that three eager steps leave
+    (the library neither allocates nor synchronises, and every tensor map is encoded at capture time)."""
+    _need_gpu()
+    from srb200 import host
+
+    def make():
+        torch.manual_seed(0)
+        net = M.MODELS[name](*args)
+        host.init_model(name, net)
+        net.to(DEV).train()
+        opt = host.make_optimizer(name, net.parameters(), lr=1e-3, capturable=True)
+        return net, opt, srb200.GradBucket(net, world_size=1)
+
+    gen = torch.Generator().manual_seed(4)
+    xs = [torch.rand(shape, generator=gen).to(DEV) for _ in range(2)]
+    net_e, opt_e, bk_e = make()
+    with torch.no_grad():
+        oshape = net_e(xs[0]).shape
+    ts = [torch.rand(oshape, generator=gen).to(DEV) for _ in range(2)]
+    lossf = host.loss_for(name, fused=True)
+    clip = host.VDSR_CLIP if name == "vdsr" else None
+
+    def eager(net, opt, bk, i):
+        bk.begin_step()
+        l = lossf(net(xs[i % 2]), ts[i % 2])
+        l.backward()
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
+        opt.step()
+        return l.item()
+
+    losses_e = [eager(net_e, opt_e, bk_e, i) for i in range(4)]
+    bk_e.detach()
+    net_g, opt_g, bk_g = make()
+    first = eager(net_g, opt_g, bk_g, 0)  # one eager step creates the optimizer state (not capturable: host-side init)
+    st = srb200.TrainStepGraphs(net_g, lossf, opt_g, bk_g, slots=list(zip(xs, ts)), clip_norm=clip)
+    assert st.launches_per_step >= 8
+    losses_g = [first] + [st.step(i % 2).item() for i in range(1, 4)]
+    assert losses_g == losses_e
+    for (k, p), (_, q) in zip(net_g.named_parameters(), net_e.named_parameters()):
+        assert torch.equal(p, q), k
+    bk_g.detach()
+
+
 def test_act_corner_cases_at_zero():
     """z == 0: ReLU grad is 0, PReLU/LeakyReLU take the slope branch (ATen semantics)."""
     _need_gpu()
