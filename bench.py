@@ -441,8 +441,18 @@ def main():
             r = cpu_reference_run(a.workload, 1000, 1, budget_s=15.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Teardown order matters: CUDA graphs that captured NCCL kernels must be gone before the communicator is, and a
+        # communicator abort can block in this torch/NCCL build.  All ranks rendezvous, then leave without running the
+        # interpreter's (and NCCL's) destructors -- every result has been printed and flushed by now.
+        graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
