@@ -34,6 +34,7 @@ WORKLOADS = {
     "espcn_x4_b128_lr64": ("espcn", (3, 64, 4), 128, (64, 64), "mse", "espcn"),
     "vdsr_b64_128": ("vdsr", (3, 64, 18), 64, (128, 128), "mse", "vdsr"),
     "edsr64_x4_b32_lr32": ("edsr", (3, 64, 16), 32, (32, 32), "l1", "edsr"),
+    "edsr256_x4_b32_lr32": ("edsr", (3, 256, 32), 32, (32, 32), "l1", "edsr"),  # cfg4 shapes, TF32 on fp32 storage (bf16: next round)
     "srcnn_x2_b16": ("srcnn", (3, 64), 16, (64, 64), "mse", "srcnn"),
 }
 DEFAULT_WORKLOAD = "espcn_x4_b128_lr64"
@@ -271,6 +272,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     srb200.set_math(a.math)
 

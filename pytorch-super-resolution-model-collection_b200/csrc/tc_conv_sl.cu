@@ -698,6 +698,11 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
           }
           const double a_bytes = (double)chunks * BH * BW * sb / ((double)TH * TW);
           const double b_bytes = (c4 || b_res) ? 0.0 : (double)kblocks * NT * 128 / (eff * MTB * 128.0);
+          {  // TMA writes share the SMEM port with the MMAs' operand reads (measured: 50 -> 55..61 cycles per MMA in-kernel,
+             // profiles/r1_trace_conv_sl.txt): stretch the MMA time by written / read bytes per pixel
+            const double mma_smem_per_px = (c4 ? kblocks : kblocks * 4) * (4096.0 + NT * 32.0) / 128.0 / eff;
+            t_mma *= 1.0 + (a_bytes + b_bytes) / mma_smem_per_px;
+          }
           const double t_mem = (a_bytes + b_bytes + 4.0 * NT) / 48.0;  // ~48 B/clk/SM of L2->SM + store bandwidth
           double t = t_mma > t_mem ? t_mma : t_mem;
           t += 600.0 / ((double)TH * TW);  // per-band hand-offs (accumulator swap, first-MMA latency)

@@ -338,18 +338,21 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
 // dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order => deterministic)
 // blockDim = (32 elements, 8 split lanes): lane y sums splits y, y+8, ... ; the 8 lane sums are folded in shared memory
 // in a fixed order.  Element index runs co-fastest so that the partial reads (n contiguous) coalesce.
-__global__ void __launch_bounds__(512) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
-  __shared__ float red[16][33];
+// blockDim = (32 outputs, L split lanes, G output groups), 32*L*G = 256: few splits -> many outputs per block.
+template <int L>
+__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
+  constexpr int G = 8 / L;
+  __shared__ float red[G][L][33];
   const long long total = (long long)a.Co * a.Ci * a.kh * a.kw;
   const int ACC = a.RG * a.SG * a.CIB;
-  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * G + threadIdx.z) * 32 + threadIdx.x;
   float sum = 0.f;
   long long dst = 0;
   const bool is_db = db != nullptr && i >= total && i < total + a.Co;
   if (is_db) {  // bias gradient: splits x 4 warp partials per channel
     const int co = (int)(i - total);
     const size_t pitch = (size_t)(a.n_cot * a.NT);
-    for (int z = threadIdx.y; z < splits * 4; z += 16) sum += a.db_part[(size_t)z * pitch + co];
+    for (int z = threadIdx.y; z < splits * 4; z += L) sum += a.db_part[(size_t)z * pitch + co];
   }
   if (i < total) {
     const int co = (int)(i % a.Co);
@@ -374,23 +377,27 @@ __global__ void __launch_bounds__(512) k_wgrad_finish(WgArgs a, int splits, int 
     }
     const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
     const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
-    // 16 split lanes; four independent loads in flight per thread
+    // four independent loads in flight per thread; lane y takes splits y, y + L, ...
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int z = threadIdx.y;
-    for (; z + 48 < splits; z += 64) {
-      s0 += p[(size_t)z * split_stride]; s1 += p[(size_t)(z + 16) * split_stride];
-      s2 += p[(size_t)(z + 32) * split_stride]; s3 += p[(size_t)(z + 48) * split_stride];
+    for (; z + 3 * L < splits; z += 4 * L) {
+      s0 += p[(size_t)z * split_stride]; s1 += p[(size_t)(z + L) * split_stride];
+      s2 += p[(size_t)(z + 2 * L) * split_stride]; s3 += p[(size_t)(z + 3 * L) * split_stride];
     }
-    for (; z < splits; z += 16) s0 += p[(size_t)z * split_stride];
+    for (; z < splits; z += L) s0 += p[(size_t)z * split_stride];
     sum = (s0 + s1) + (s2 + s3);
   }
-  red[threadIdx.y][threadIdx.x] = sum;
-  __syncthreads();
-  if (threadIdx.y == 0 && (i < total || is_db)) {
-    float t = red[0][threadIdx.x];
+  if (L > 1) {
+    red[threadIdx.z][threadIdx.y][threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      sum = red[threadIdx.z][0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 16; ++y) t += red[y][threadIdx.x];
-    t *= scale;
+      for (int y = 1; y < L; ++y) sum += red[threadIdx.z][y][threadIdx.x];
+    }
+  }
+  if (threadIdx.y == 0 && (i < total || is_db)) {
+    const float t = sum * scale;
     float *d = is_db ? db + (i - total) : dw + dst;
     *d = accumulate ? *d + t : t;
   }
@@ -676,7 +683,14 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   {
     long long total = (long long)g.Co * g.Ci * g.kh * g.kw;
     if (db_small) total += g.Co;
-    k_wgrad_finish<<<(unsigned)((total + 31) / 32), dim3(32, 16), 0, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, dw, db_small, scale, accumulate);
+    const int splits = (int)pl.grid.x, gyy = (int)pl.grid.y;
+    const long long groups = (total + 31) / 32;
+    if (splits <= 3)
+      k_wgrad_finish<1><<<(unsigned)((groups + 7) / 8), dim3(32, 1, 8), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
+    else if (splits <= 24)
+      k_wgrad_finish<4><<<(unsigned)((groups + 1) / 2), dim3(32, 4, 2), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
+    else
+      k_wgrad_finish<8><<<(unsigned)groups, dim3(32, 8, 1), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }

@@ -95,10 +95,17 @@ def run(name, variant, steps, warmup):
     else:
         opt = torch.optim.SGD(net.parameters(), lr=1e-5, **fused)
     lf = F.l1_loss if loss == "l1" else F.mse_loss
+    bf16 = "bf16" in variant  # autocast: what "the reference's cuDNN build in bf16" means for cfg4
+
+    def fwd_loss(i):
+        if bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return lf(net(x[i % 3]).float(), t[i % 3])
+        return lf(net(x[i % 3]), t[i % 3])
 
     def step(i):
         opt.zero_grad(set_to_none=True)
-        l = lf(net(x[i % 3]), t[i % 3])
+        l = fwd_loss(i)
         l.backward()
         if optk == "vdsr":
             torch.nn.utils.clip_grad_norm_(net.parameters(), 0.4)
@@ -117,7 +124,7 @@ def run(name, variant, steps, warmup):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool, stream=side):
                     opt.zero_grad(set_to_none=False)
-                    lf(net(x[i]), t[i]).backward()
+                    fwd_loss(i).backward()
                     if optk == "vdsr":
                         torch.nn.utils.clip_grad_norm_(net.parameters(), 0.4)
                     opt.step()
@@ -148,9 +155,10 @@ if __name__ == "__main__":
     ap.add_argument("--workloads", default="espcn_x4_b128_lr64,vdsr_b64_128,edsr64_x4_b32_lr32")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--variants", default="as-is,tuned,tuned-cl,tuned-cl-graph")
     a = ap.parse_args()
     for wl in a.workloads.split(","):
-        for v in ("as-is", "tuned", "tuned-cl", "tuned-cl-graph"):
+        for v in a.variants.split(","):
             try:
                 run(wl, v, a.steps, a.warmup)
             except Exception as e:  # report, keep going

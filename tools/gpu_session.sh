@@ -23,7 +23,7 @@ if has bench; then
   echo "bench exit $?"; cat "$OUT/bench_espcn.json"
 fi
 if has bench_more; then
-  for wl in vdsr_b64_128 edsr64_x4_b32_lr32 srcnn_x2_b16; do
+  for wl in vdsr_b64_128 edsr64_x4_b32_lr32 srcnn_x2_b16 edsr256_x4_b32_lr32; do
     timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
     echo "bench $wl exit $?"; cut -c1-600 "$OUT/bench_$wl.json"
   done

@@ -36,18 +36,22 @@ def run(name, N, Ci, H, W, Co, k, p, bias=True):
     torch.cuda.synchronize()
     buf = ctypes.create_string_buffer(512)
     lib.srb_conv_describe_plan(ctypes.byref(prm), 2, buf, 512)
-    print("%-12s %7.1f us/call   %s" % (name, e0.elapsed_time(e1) * 100, buf.value.decode()[:150]))
+    print("%-12s %7.1f us/call   %s" % (name, e0.elapsed_time(e1) * 100, buf.value.decode()[:230]))
 
 if __name__ == "__main__":
     dbg = lib.srb_debug_set_flags
     dbg.argtypes = [ctypes.c_int]
     dbg.restype = None
-    for flags in (0, 8, 10, 12, 14):
+    for flags in (0, 2, 4, 6, 8, 32):
         dbg(flags)
         print("#### debug flags %d (2: TMA once, 4: no MMA, 8: no db sums, 16: no smem zeroing, 32: no partial dump)" % flags)
-        run("espcn L1", 128, 3, 64, 64, 64, 5, 0)
-        run("espcn L2", 128, 64, 60, 60, 32, 3, 0)
-        run("espcn L3", 128, 32, 58, 58, 48, 3, 0)
-        run("vdsr body", 64, 64, 128, 128, 64, 3, 1, bias=False)
-        run("edsr64 body", 32, 64, 32, 32, 64, 3, 1)
+        only = sys.argv[1] if len(sys.argv) > 1 else ""
+        if not only:
+            run("espcn L1", 128, 3, 64, 64, 64, 5, 0)
+            run("espcn L2", 128, 64, 60, 60, 32, 3, 0)
+            run("espcn L3", 128, 32, 58, 58, 48, 3, 0)
+            run("vdsr body", 64, 64, 128, 128, 64, 3, 1, bias=False)
+            run("edsr64 body", 32, 64, 32, 32, 64, 3, 1)
+        run("edsr256 body", 32, 256, 32, 32, 256, 3, 1)
+        run("edsr256 up2", 32, 256, 64, 64, 1024, 3, 1)
     dbg(0)
