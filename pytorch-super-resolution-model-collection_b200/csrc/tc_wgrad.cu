@@ -545,6 +545,10 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
             double bytes = ((double)n_cot * n_rg * cblocks * BH / TH * BW + (double)n_cig * n_rg * (co_pad / 32) * TW) * 128.0 * bands_w;
             double t = mma > bytes / 23.0 ? mma : bytes / 23.0;
             t += 500.0 * bands_w / TH * (n_cig * n_rg * n_cot);  // per-band hand-off (barrier round trips, TMA issue)
+            // every TMA instruction costs issue slots and a request round trip; row-wise dz loads issue NT/32 * TH small
+            // boxes per band (edsr256: 32 x 2 KB), which measurably starves the pipeline
+            const double n_tma = CIB + (bands_w > 1 ? (double)(NT / 32) * TH : (double)(NT / 32));
+            t += 40.0 * n_tma * bands_w / TH * (n_cig * n_rg * n_cot);
             if (stages == 2) t *= 1.08;                            // less slack for the TMA latency
             double score = 1e9 / t + TH * 1e-3;
             if (score > best_score) {
