@@ -641,17 +641,24 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   const bool c4 = g.Ci <= 4;
   const int sb = c4 ? 16 : 128;
   const int Npad = round_up_i(g.Co, 16);
-  int NT = Npad;
-  if (NT > 256) {
-    NT = 256;
-    while (Npad % NT) NT -= 16;
+  int NT0 = Npad;
+  if (NT0 > 256) {
+    NT0 = 256;
+    while (Npad % NT0) NT0 -= 16;
   }
   const int spairs = (g.kw + 1) / 2;
   const int kextra = c4 ? 2 * spairs - 1 : g.kw - 1;
   const int chunks = c4 ? 1 : (g.Ci + 31) / 32;
   const int kblocks = c4 ? g.kh * spairs : g.kh * g.kw * chunks;
-  const double mma_per_tile = (c4 ? kblocks : kblocks * 4) * mma_cost(NT);
   double best_t = -1.0;
+  // N tile: the widest that fits.  Half-width tiles (two N tiles, more M tiles per band, half the streamed-weight traffic
+  // per pixel) were measured SLOWER on the 256 -> 256 layers (101 vs 95 us, profiles/README.md), so kMaxNSplit stays 1.
+  constexpr int kMaxNSplit = 1;
+  for (int nsplit = 1; nsplit <= kMaxNSplit; ++nsplit) {
+  if (nsplit == 2 && (c4 || NT0 < 128 || (NT0 / 2) % 16 != 0)) break;
+  const int NT = NT0 / nsplit;
+  const int n_tiles = Npad / NT;
+  const double mma_per_tile = (c4 ? kblocks : kblocks * 4) * mma_cost(NT);
   for (int ctas = 2; ctas >= 1; --ctas) {
     const int smem_cap = ctas == 2 ? 111 * 1024 : 226 * 1024;
     const int col_cap = ctas == 2 ? 256 : 512;
@@ -717,6 +724,7 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
           // epilogue), amortised over the pixels one CTA produces
           const long long waves_sm = (work + 147) / 148;  // bands per SM, however many CTAs share it
           t += (2500.0 + (b_res ? 0.02 * b_stage * b_stages : 0.0)) / ((double)waves_sm * TH * TW);
+          t *= (double)n_tiles;  // every pixel is visited once per N tile
           if (best_t < 0 || t < best_t) {
             best_t = t;
             a.TH = TH; a.TW = TW; a.BW = BW; a.BH = BH; a.bands_h = bands_h; a.bands_w = bands_w;
@@ -734,7 +742,9 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
       }
     }
   }
+  }  // nsplit
   if (best_t < 0) return false;
+  const int NT = a.NT;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Co = g.Co; a.kh = g.kh; a.kw = g.kw; a.pad = g.pad; a.c4 = c4 ? 1 : 0;
   a.ps = g.ps;
   pl->Npad = Npad;
