@@ -66,3 +66,53 @@ def test_workspace_query_is_host_only():
     p = _lib.ConvParams(16, 64, 32, 32, 64, 3, 3, 1, 1, 0, 0, 1, 1, 0.2, 2)
     for ps in (0, 1, 2):
         assert _lib.lib.srb_conv_workspace_bytes(ctypes.byref(p), ps) >= 256
+
+
+# ---- planner invariants (host only: srb_conv_describe_plan never touches the GPU) ------------------------------------
+import re  # noqa: E402
+lib = _lib.lib
+
+_PLAN_SHAPES = [(n, c, h, w, co, k, p) for (n, h, w) in [(1, 7, 5), (2, 24, 24), (16, 32, 32), (128, 64, 64), (64, 128, 128), (4, 200, 300)]
+                for (c, co) in [(3, 64), (64, 64), (64, 32), (32, 48), (64, 3), (256, 256), (96, 160), (64, 256), (12, 12)]
+                for (k, p) in [(1, 0), (3, 1), (3, 0), (5, 0), (9, 4)]]
+
+
+def test_tile_plans_respect_hardware_limits():
+    """Every plan the library reports must fit one SM: <= 227 KB dynamic shared memory, <= 512 TMEM columns,
+    a non-empty grid no larger than the chip can hold resident (persistent kernels), and >= 2 TMA stages when streaming."""
+    buf = ctypes.create_string_buffer(1024)
+    seen = 0
+    for (n, c, h, w, co, k, p) in _PLAN_SHAPES:
+        if h + 2 * p < k or w + 2 * p < k:
+            continue
+        prm = _lib.ConvParams(n, c, h, w, co, k, k, 1, p, 0, 0, 1, _lib.ACT_RELU, 0.2, _lib.MATH_AUTO)
+        for pas in (0, 1, 2):
+            assert lib.srb_conv_describe_plan(ctypes.byref(prm), pas, buf, 1024) == 0
+            txt = buf.value.decode()
+            if "no plan" in txt or "CUDA-core" in txt:
+                continue
+            seen += 1
+            smem = int(re.search(r"smem (\d+) B", txt).group(1))
+            tmem = int(re.search(r"tmem (\d+) cols", txt).group(1))
+            gx, gy = (int(v) for v in re.search(r"grid (\d+) x (\d+)", txt).groups())
+            assert smem <= 227 * 1024, txt
+            assert tmem in (32, 64, 128, 256, 512), txt
+            assert gx >= 1 and gy >= 1, txt
+            if pas < 2:
+                ctas = int(re.search(r"\((\d) CTA/SM\)", txt).group(1))
+                assert gx * gy <= 148 * ctas, txt  # persistent grid: every CTA resident at once
+                assert ctas == 1 or (smem <= 111 * 1024 and tmem <= 256), txt
+            else:
+                assert gx * gy <= 148, txt
+                assert int(re.search(r"stages (\d+)", txt).group(1)) >= 1, txt
+    assert seen > 200
+
+
+def test_planner_queries_are_deterministic_and_cheap():
+    prm = _lib.ConvParams(64, 64, 128, 128, 64, 3, 3, 1, 1, 0, 0, 1, _lib.ACT_RELU, 0.2, _lib.MATH_AUTO)
+    b1, b2 = ctypes.create_string_buffer(512), ctypes.create_string_buffer(512)
+    for pas in (0, 1, 2):
+        lib.srb_conv_describe_plan(ctypes.byref(prm), pas, b1, 512)
+        lib.srb_conv_describe_plan(ctypes.byref(prm), pas, b2, 512)
+        assert b1.value == b2.value
+        assert lib.srb_conv_workspace_bytes(ctypes.byref(prm), pas) == lib.srb_conv_workspace_bytes(ctypes.byref(prm), pas)
