@@ -8,6 +8,8 @@ hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
 for r in rows[1:]:
+    if "spin_kernel" in r[ki]:
+        continue  # bench.py parks the GPU on torch.cuda._sleep in its instrumented pass; not part of a training step
     k = r[ki][:90]
     v = float(r[vi].replace(",", ""))
     a = agg.setdefault(k, [0, 0.0])
