@@ -11,6 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, tag = sys.argv[1], sys.argv[2]
+GENERIC = len(sys.argv) > 3  # third argument = workload name: no layer mapping, table only (profiles/<tag>_ncu_full_<workload>.md)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, data = rows[0], rows[2:]
@@ -39,9 +40,9 @@ def unit(k):
 out, md = {}, ["| call | layer | kernel | grid | time us | DRAM read MB | DRAM write MB | DRAM GB/s | tensor pipe % | mem->tensor % | L1/TEX % | regs | dyn smem KB |",
                "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for pos, r in enumerate(data):
-    if pos >= len(ORDER):
+    if not GENERIC and pos >= len(ORDER):
         break
-    call, layer = ORDER[pos]
+    call, layer = (("-", "launch %d" % pos) if GENERIC else ORDER[pos])
     name = r[ix["Kernel Name"]]
     kern = "k_conv_sl" if "k_conv_sl" in name else ("k_tc_wgrad" if "k_tc_wgrad" in name else name[:30])
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -58,6 +59,12 @@ for pos, r in enumerate(data):
     out[call + "|" + layer] = rec
     md.append("| %s | %s | %s | %s | %.1f | %.1f | %.1f | %.0f | %.1f | %.1f | %.1f | %d | %.0f |" % (
         call, layer, kern, rec["grid"], tus, rd / 1e6, wr / 1e6, rec["dram_gbs"] or 0, tens, memt, l1, rec["regs"], rec["dyn_smem_kb"]))
+if GENERIC:
+    open(os.path.join(ROOT, "profiles", "%s_ncu_full_%s.md" % (tag, sys.argv[3])), "w").write(
+        "# ncu --set full, %s: consecutive tensor-core kernel launches of one training step\n\n"
+        "Captured with `--clock-control none`, kernels replayed and serialised (cold caches).\n\n" % sys.argv[3] + "\n".join(md) + "\n")
+    print("\n".join(md))
+    sys.exit(0)
 json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "%s_ncu_full_espcn.md" % tag), "w").write(
     "# ncu --set full, one ESPCN cfg2 training step (tensor-core kernels in launch order)\n\n"
