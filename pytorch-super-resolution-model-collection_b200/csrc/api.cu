@@ -242,6 +242,24 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const float *__restrict__ y, c
   }
 }
 
+// dz (N, C<=3, H, W; any strides) -> NHWC4 (16 B per pixel, missing channels zero), tf32-rounded: lets the skinny output layers
+// (64->3, 32->3) use the tensor-core wgrad with Co = 4
+__global__ void k_pack_dz4(T4 dz, float4 *__restrict__ out, int N, int C, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long q = i / W;
+    const int h = (int)(q % H);
+    const int n = (int)(q / H);
+    const float *p = dz.p + n * dz.sn + (long long)h * dz.sh + (long long)w * dz.sw;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) v[c] = round_tf32(__ldg(p + c * dz.sc));
+    out[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -304,6 +322,25 @@ inline bool is_cl(const T4 &t, int C) { return t.sc == 1 && t.sw == C; }
 // Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 4 == 0, C >= 8)
 inline int want_round(const srb_conv_params *p, const T4 &t, int C) {
   return (p->math != SRB_MATH_FP32 && is_cl(t, C) && (C % 4) == 0 && C >= 8) ? 1 : 0;
+}
+
+// Skinny-output wgrad on the tensor path: geometry with Co padded to 4 and the NHWC4 view of the packed dz.
+// Workspace layout: [packed dz][dw for 4 output channels][db for 4][tensor-core wgrad workspace].
+struct SkinnyWg {
+  Geom g4;
+  T4 dz4;
+  size_t pack_bytes, dw_bytes, total;
+};
+inline bool skinny_wgrad_plan(const srb_conv_params *p, const Geom &g, const T4 &big, SkinnyWg *sk) {
+  if (p->transposed || p->math == SRB_MATH_FP32 || g.ps != 1 || g.st != 1 || g.Co >= 4) return false;
+  sk->g4 = g;
+  sk->g4.Co = 4;
+  sk->dz4 = T4{(float *)256, (long long)g.Ho * g.Wo * 4, 1, (long long)g.Wo * 4, 4};  // pointer patched by the caller
+  if (!tc_wgrad_supported(sk->g4, sk->dz4, big)) return false;
+  sk->pack_bytes = (((size_t)g.N * g.Ho * g.Wo * 4 * sizeof(float)) + 255) & ~(size_t)255;
+  sk->dw_bytes = (((size_t)4 * g.Ci * g.kh * g.kw + 4) * sizeof(float) + 255) & ~(size_t)255;
+  sk->total = sk->pack_bytes + sk->dw_bytes + tc_wgrad_ws_bytes(sk->g4) + 512;
+  return true;
 }
 
 }  // namespace
@@ -370,8 +407,15 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
   Geom g;
   if (make_geom(p, &g)) return 0;
   size_t a = 0, b = 0;
-  if (pass == 2) { a = simt_wgrad_ws_bytes(g); b = tc_wgrad_ws_bytes(g); }
-  else           { b = tc_conv_ws_bytes(g); }
+  if (pass == 2) {
+    a = simt_wgrad_ws_bytes(g);
+    b = tc_wgrad_ws_bytes(g);
+    SkinnyWg sk;
+    T4 cl{(float *)256, (long long)g.Hi * g.Wi * g.Ci, 1, (long long)g.Wi * g.Ci, g.Ci};  // would-be channels_last x
+    if (skinny_wgrad_plan(p, g, cl, &sk) && sk.total > b) b = sk.total;
+  } else {
+    b = tc_conv_ws_bytes(g);
+  }
   return (a > b ? a : b) + 256;
 }
 
@@ -495,6 +539,26 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   if (!p->transposed) {
     if (p->math != SRB_MATH_FP32 && tc_wgrad_supported(g, tdz, tx))
       return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    SkinnyWg sk;
+    uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+    if (!accumulate && ws && skinny_wgrad_plan(p, g, tx, &sk) && wsp + sk.total <= (uintptr_t)ws + ws_bytes) {
+      // 64->3 / 32->3 tails: pad dz to NHWC4, run the tensor-core wgrad for 4 output channels, keep the first Co
+      float *pack = (float *)wsp;
+      float *dw4 = (float *)(wsp + sk.pack_bytes);
+      float *db4 = dw4 + (size_t)4 * g.Ci * g.kh * g.kw;
+      void *ws_tc = (void *)(wsp + sk.pack_bytes + sk.dw_bytes);
+      const long long px = (long long)g.N * g.Ho * g.Wo;
+      k_pack_dz4<<<ew_blocks(px), 256, 0, st>>>(tdz, (float4 *)pack, g.N, g.Co, g.Ho, g.Wo);
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+      sk.dz4.p = pack;
+      rc = tc_conv_wgrad(sk.g4, sk.dz4, tx, dw4, db ? db4 : nullptr, scale, 0, ws_tc,
+                         (size_t)((uintptr_t)ws + ws_bytes - (uintptr_t)ws_tc), st);
+      if (rc) return rc;
+      SRB_CHECK_CUDA(cudaMemcpyAsync(dw, dw4, (size_t)g.Co * g.Ci * g.kh * g.kw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (db) SRB_CHECK_CUDA(cudaMemcpyAsync(db, db4, (size_t)g.Co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return SRB_OK;
+    }
     return simt_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
   }
   // transposed: small = x (Co := Cin), big = dz (Ci := Cout); db is a channel sum over the big side
