@@ -116,3 +116,53 @@ def test_planner_queries_are_deterministic_and_cheap():
         lib.srb_conv_describe_plan(ctypes.byref(prm), pas, b2, 512)
         assert b1.value == b2.value
         assert lib.srb_conv_workspace_bytes(ctypes.byref(prm), pas) == lib.srb_conv_workspace_bytes(ctypes.byref(prm), pas)
+
+
+def test_band_plans_cover_every_output_pixel():
+    """fprop/dgrad bands tile the output exactly: bands_h x TH and bands_w x TW cover Ho x Wo with no empty band, the halo
+    box is (TH+k-1) x (TW+k-1 [+1 for the Cin<=4 tap pairs]) and an M-tile group holds every slot of the band."""
+    buf = ctypes.create_string_buffer(1024)
+    checked = 0
+    for (n, c, h, w, co, k, p) in _PLAN_SHAPES:
+        if h + 2 * p < k or w + 2 * p < k:
+            continue
+        ho, wo = h + 2 * p - k + 1, w + 2 * p - k + 1
+        prm = _lib.ConvParams(n, c, h, w, co, k, k, 1, p, 0, 0, 1, _lib.ACT_NONE, 0.2, _lib.MATH_AUTO)
+        lib.srb_conv_describe_plan(ctypes.byref(prm), 0, buf, 1024)
+        txt = buf.value.decode()
+        m = re.search(r"band (\d+)x(\d+) \(halo (\d+)x(\d+)\), (\d+)x(\d+) bands/img, MTB (\d+)", txt)
+        if not m:
+            continue
+        th, tw, bh, bw, nh, nw, mtb = (int(v) for v in m.groups())
+        assert nh * th >= ho and (nh - 1) * th < ho, txt
+        assert nw * tw >= wo and (nw - 1) * tw < wo, txt
+        assert bh == th + k - 1, txt
+        assert bw in (tw + k - 1, tw + k), txt
+        assert (th - 1) * bw + tw <= 128 * mtb, txt  # last real slot of the band lies inside its M tiles
+        assert int(re.search(r"(\d+) bands on grid", txt).group(1)) == n * nh * nw, txt
+        checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_out_hw_matches_torch_shapes(seed):
+    """srb_conv_out_hw vs the shapes ATen produces for Conv2d / ConvTranspose2d (random small cases, CPU)."""
+    import random
+    import torch
+    import torch.nn.functional as TF
+    rnd = random.Random(seed)
+    for _ in range(40):
+        k, s = rnd.randint(1, 5), rnd.randint(1, 3)
+        p = rnd.randint(0, k - 1)
+        h, w = rnd.randint(k, 12), rnd.randint(k, 12)
+        tr = rnd.random() < 0.5
+        op = rnd.randint(0, s - 1) if tr else 0
+        x = torch.zeros(1, 2, h, w)
+        if tr:
+            y = TF.conv_transpose2d(x, torch.zeros(2, 3, k, k), None, s, p, op)
+        else:
+            y = TF.conv2d(x, torch.zeros(3, 2, k, k), None, s, p)
+        prm = _lib.ConvParams(1, 2, h, w, 3, k, k, s, p, op, 1 if tr else 0, 1, _lib.ACT_NONE, 0.2, _lib.MATH_AUTO)
+        ho, wo = ctypes.c_int32(), ctypes.c_int32()
+        assert lib.srb_conv_out_hw(ctypes.byref(prm), ctypes.byref(ho), ctypes.byref(wo)) == 0
+        assert (ho.value, wo.value) == tuple(y.shape[2:]), (k, s, p, op, h, w, tr)
