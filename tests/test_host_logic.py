@@ -86,3 +86,35 @@ def test_convert_on_live_reference_and_module_shim():
     from srb200 import base_networks as B
     for n in ("torch", "ConvBlock", "PSBlock", "ResnetBlock", "DeconvBlock", "Upsample2xBlock", "DenseBlock"):
         assert n in B.__all__ and hasattr(B, n)
+
+
+def test_host_optimizers_match_reference_hyperparameters():
+    """srb200.host.make_optimizer restates srcnn.py:79, espcn.py:79, fsrcnn.py:106, vdsr.py:89-90, edsr.py:93; on CPU
+    parameters it must not ask for the CUDA-only fused/capturable implementations."""
+    from srb200 import host
+    for name in ("srcnn", "espcn", "fsrcnn", "vdsr", "edsr"):
+        p1 = [torch.nn.Parameter(torch.zeros(3))]
+        p2 = [torch.nn.Parameter(torch.zeros(3))]
+        ours = host.make_optimizer(name, p1, lr=1e-4, capturable=True)
+        ref = R.make_optimizer(name, p2, lr=1e-4)
+        assert type(ours) is type(ref), name
+        a, b = ours.param_groups[0], ref.param_groups[0]
+        for k in ("lr", "momentum", "weight_decay", "betas", "eps", "nesterov"):
+            assert a.get(k) == b.get(k), (name, k)
+        assert not a.get("fused") and not a.get("capturable"), name
+
+
+def test_loss_selection_and_cpu_rejection():
+    from srb200 import host
+    import torch.nn.functional as TF
+    assert host.loss_for("edsr") is TF.l1_loss and host.loss_for("espcn") is TF.mse_loss
+    assert host.loss_for("edsr", fused=True) is srb200.l1_loss and host.loss_for("vdsr", fused=True) is srb200.mse_loss
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        srb200.mse_loss(torch.zeros(4), torch.zeros(4))
+
+
+def test_public_api_surface():
+    for name in ("conv2d", "conv_transpose2d", "prelu", "mse_loss", "l1_loss", "convert", "GradBucket", "TrainStepGraphs",
+                 "ConvBlock", "PSBlock", "ResnetBlock", "DeconvBlock", "Upsample2xBlock", "DenseBlock", "set_math",
+                 "set_fuse_relu_backward", "launch_count"):
+        assert hasattr(srb200, name), name
