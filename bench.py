@@ -243,7 +243,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[a.workload]
-    config = {"workload": a.workload, "model": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
+    config = {"workload": a.workload, "net": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
               "lr_hw": [h, w], "loss": loss_kind, "optimizer": opt_key, "parallelism": "dp%d" % world,
               "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches",
               "launch": "eager" if a.no_graph else "cuda-graph replay (srb200.TrainStepGraphs: fwd+loss+bwd[+allreduce] graph per input slot, optimizer graph)"}
@@ -252,7 +252,7 @@ def main():
         if rank != 0:
             return 0
         r = cpu_reference_run(a.workload, a.steps, a.warmup, budget_s=120.0)
-        line = {"impl": "reference", "metric": "SR training images/sec", "value": r["value"], "unit": "images/s",
+        line = {"impl": "reference", "metric": "SR training images/sec (device-timed)", "value": r["value"], "unit": "images/s",
                 "n_gpus": a.gpus, "steps": r["steps"], "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
@@ -430,7 +430,7 @@ def main():
                       for (n, k), v in tab.items()), key=lambda r: -r[3])
 
     imgs = batch * world * a.steps
-    line = {"metric": "SR training images/sec", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+    line = {"metric": "SR training images/sec (device-timed)", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if a.math == "auto" else "f32",
             "data": "synthetic", "config": config, "clocks": clocks,
