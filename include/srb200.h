@@ -15,7 +15,8 @@
  *
  * Tensors are fp32, logical NCHW with explicit element strides, so NCHW-contiguous and
  * channels_last (NHWC) memory are both accepted.  The tensor-core kernels (math = SRB_MATH_TF32)
- * require channels_last activations (sc == 1) with C % 32 == 0; everything else runs on the
+ * require channels_last activations (sc == 1) with C % 4 == 0 and C >= 8 (16-byte TMA pixel rows; wgrad: C % 32 == 0),
+ * or C <= 4 (packed to NHWC4 internally); everything else runs on the
  * generic fp32 CUDA-core kernels of the same library.
  *
  * Threading: re-entrant, no global mutable state besides a thread-local error string.  All work
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SRB200_VERSION 100
+#define SRB200_VERSION 200
 
 typedef enum srb_status {
   SRB_OK = 0,
@@ -47,7 +48,11 @@ typedef enum srb_act { SRB_ACT_NONE = 0, SRB_ACT_RELU = 1, SRB_ACT_PRELU = 2, SR
 typedef enum srb_math {
   SRB_MATH_FP32 = 0, /* CUDA-core fp32 FMA, fp32 accumulate (exact-order independent reference quality) */
   SRB_MATH_TF32 = 1, /* tcgen05 kind::tf32, operands RN-rounded to tf32, fp32 accumulate in TMEM */
-  SRB_MATH_AUTO = 2  /* TF32 tensor path when the layer qualifies, FP32 otherwise */
+  SRB_MATH_AUTO = 2, /* TF32 tensor path when the layer qualifies, FP32 otherwise */
+  SRB_MATH_EXACT = 3 /* fp32-accurate on the tensor cores: operands split hi+lo into tf32 pairs, three partial products
+                        (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) accumulated in fp32 ("3xTF32"); activations stay full fp32.
+                        Layers the tensor path cannot run fall to the FP32 CUDA-core kernels.  For the 1e-3 end-to-end
+                        contract at the BASELINE depths (VDSR-20, EDSR-256x32), where single-pass TF32 reaches ~1.5e-3. */
 } srb_math;
 
 /* Logical NCHW view with element strides (like torch.Tensor.stride()). */

@@ -31,11 +31,37 @@ NET_CASES = {
 }
 
 
+# Full BASELINE depths/widths (BASELINE.json configs 3-5).  Spatial sizes are small -- depth and width are
+# what matter for error accumulation.  These nets have up to 43 M parameters, so the fixture stores DIGESTS: the input,
+# target, output and loss in full, and per parameter / per gradient its L2 norm, its sum and 64 sampled entries
+# (indices drawn by a seeded generator).  The parameters themselves are regenerated at test time by the seeded init.
+DEEP_CASES = {
+    "vdsr18": ("vdsr", "Net", (3, 64, 18), (2, 3, 24, 20), "mse"),                 # vdsr.py:13-32, cfg3
+    "edsr256x32": ("edsr", "Net", (3, 256, 32), (1, 3, 12, 10), "l1"),             # edsr.py:13-45, cfg4
+    "srgan_g16": ("srgan", "Generator", (3, 64, 16), (2, 3, 16, 12), "mse"),       # srgan.py:14-42, cfg5
+    "srgan_d": ("srgan", "Discriminator", (3, 64, 128), (2, 3, 128, 128), "bce"),  # srgan.py:49-77, cfg5
+}
+DIGEST_SAMPLES = 64
+
+
+def digest(t, tag):
+    """{tag:norm, tag:sum, tag:sample} of a tensor (sample indices: generator seeded by the element count)."""
+    flat = t.detach().reshape(-1).double()
+    n = flat.numel()
+    idx = torch.randint(0, n, (DIGEST_SAMPLES,), generator=torch.Generator().manual_seed(n % 2147483647))
+    return {tag + ":norm": np.float64(flat.norm().item()), tag + ":sum": np.float64(flat.sum().item()),
+            tag + ":sample": flat[idx].numpy().astype(np.float64)}
+
+
 def _run(model, x, loss_kind):
     model.train()
     y = model(x)
     tgt = torch.rand(y.shape, generator=torch.Generator().manual_seed(2))
-    loss = torch.nn.functional.l1_loss(y, tgt) if loss_kind == "l1" else torch.nn.functional.mse_loss(y, tgt)
+    if loss_kind == "bce":  # srgan.py:157,276: BCELoss of the decision against the "real" label
+        tgt = torch.ones_like(y)
+        loss = torch.nn.functional.binary_cross_entropy(y, tgt)
+    else:
+        loss = torch.nn.functional.l1_loss(y, tgt) if loss_kind == "l1" else torch.nn.functional.mse_loss(y, tgt)
     loss.backward()
     return y, tgt, loss
 
@@ -62,6 +88,24 @@ def main():
             blob["grad:" + k] = p.grad.numpy()
         np.savez_compressed(os.path.join(OUT, "net_%s.npz" % name), **blob)
         print(name, "y", tuple(y.shape), "loss", loss.item(), "params", sum(p.numel() for p in net.parameters()))
+
+    for name, (mod, cls, args, xshape, loss_kind) in DEEP_CASES.items():
+        torch.manual_seed(0)
+        net = getattr(mods[mod], cls)(*args)
+        net.weight_init()
+        x = torch.rand(xshape, generator=torch.Generator().manual_seed(1))
+        blob = {"x": x.numpy(), "args": np.array(args, dtype=np.int64)}
+        for k, v in net.state_dict().items():
+            if v.dtype.is_floating_point:
+                blob.update(digest(v, "param:" + k))
+        torch.set_num_threads(8)
+        y, tgt, loss = _run(net, x, loss_kind)
+        torch.set_num_threads(1)
+        blob.update({"target": tgt.numpy(), "y": y.detach().numpy(), "loss": np.float64(loss.item())})
+        for k, p in net.named_parameters():
+            blob.update(digest(p.grad, "grad:" + k))
+        np.savez_compressed(os.path.join(OUT, "deep_%s.npz" % name), **blob)
+        print("deep", name, "y", tuple(y.shape), "loss", loss.item(), "params", sum(p.numel() for p in net.parameters()))
 
     # block-level cases straight from base_networks.py
     B = mods["base_networks"]

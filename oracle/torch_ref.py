@@ -411,3 +411,49 @@ def pixel_shuffle_law(t, r):
     n, crr, h, w = t.shape
     c = crr // (r * r)
     return t.reshape(n, c, r, r, h, w).permute(0, 1, 4, 2, 5, 3).reshape(n, c, h * r, w * r)
+
+
+# --------------------------------------------------------------------------------------------
+# mask-conditioned replay (test tool): the derivative of ReLU / PReLU / LeakyReLU is discontinuous in the
+# pre-activation, so a 1e-3 comparison of GRADIENTS is only meaningful on a common activation pattern.
+# --------------------------------------------------------------------------------------------
+class _ForcedAct(nn.Module):
+    """Stands in for one nn.ReLU / nn.LeakyReLU / nn.PReLU of an oracle net: y = z where the recorded pattern says
+    'positive', slope*z elsewhere -- the pattern comes from the implementation under test, not from sign(z)."""
+
+    def __init__(self, orig, feed):
+        super().__init__()
+        self.feed = feed
+        if isinstance(orig, nn.PReLU):
+            self.weight = orig.weight  # the same Parameter object: d(alpha) lands where the tests look for it
+            self.kind = "prelu"
+        elif isinstance(orig, nn.LeakyReLU):
+            self.kind, self.slope = "lrelu", orig.negative_slope
+        else:
+            self.kind, self.slope = "relu", 0.0
+
+    def forward(self, z):
+        m = self.feed.pop(0).to(z.dtype)
+        assert m.shape == z.shape, (m.shape, z.shape)
+        slope = self.weight if self.kind == "prelu" else self.slope
+        return z * m + (z * slope) * (1.0 - m)
+
+
+def with_forced_activations(net, masks):
+    """Swap every ReLU/LeakyReLU/PReLU module of `net` (in place; parameters untouched) for a _ForcedAct that consumes
+    `masks` (list of bool tensors in execution order).  Returns net."""
+    feed = list(masks)
+
+    def swap(mod):
+        for name, child in list(mod.named_children()):
+            if isinstance(child, (nn.ReLU, nn.LeakyReLU, nn.PReLU)):
+                setattr(mod, name, _ForcedAct(child, feed))
+            else:
+                swap(child)
+    swap(net)
+    net._forced_feed = feed
+    return net
+
+
+def count_convs(net):
+    return sum(1 for m in net.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)))

@@ -56,7 +56,7 @@ __global__ void k_act_bwd(T4 dy, T4 ref, T4 dz, int N, int C, int H, int W, int 
 }
 
 // out[n, k, h, w] (NHWC) = dz[n, c, h*r+i, w*r+j] with k = c*r*r + i*r + j, rounded to tf32
-__global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int r) {
+__global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int r, int rnd) {
   const long long total = (long long)N * H * W * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -66,7 +66,7 @@ __global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int
     int h = (int)(t % H);
     int n = (int)(t / H);
     float v = __ldg(dz.p + ps_offset(dz, r, n, k, h, w));
-    out.p[n * out.sn + (long long)h * out.sh + (long long)w * out.sw + k] = round_tf32(v);
+    out.p[n * out.sn + (long long)h * out.sh + (long long)w * out.sw + k] = rnd ? round_tf32(v) : v;
   }
 }
 
@@ -74,7 +74,7 @@ __global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int
 // (W*r floats each, fully coalesced reads) are staged in shared memory, then written as the W*K contiguous floats of the
 // NHWC output row (fully coalesced stores).  Row pitch W*r + 4 keeps the (i, j) gather off a single bank.
 __global__ void __launch_bounds__(256)
-k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r) {
+k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r, int rnd) {
   extern __shared__ float srow[];
   const int n = blockIdx.x / H, h = blockIdx.x - n * H;
   const int Wr = W * r, pitch = Wr + 4, rows = C * r, K = C * r * r;
@@ -102,7 +102,7 @@ k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r) {
     for (int e = threadIdx.x; e < W * q; e += blockDim.x) {
       const int w = e / q, ci = e - w * q;  // ci = c*4 + i
       float4 v = *(const float4 *)(srow + ci * pitch + 4 * w);
-      v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+      if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
       *(float4 *)(orow + (long long)w * K + 4 * ci) = v;
     }
   } else {
@@ -110,7 +110,8 @@ k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r) {
     for (int e = threadIdx.x; e < W * K; e += blockDim.x) {
       const int w = e / K, k = e - w * K;
       const int c = k / rr, ij = k - c * rr, i = ij / r, j = ij - i * r;
-      orow[(long long)w * out.sw + k] = round_tf32(srow[(c * r + i) * pitch + w * r + j]);
+      const float v = srow[(c * r + i) * pitch + w * r + j];
+      orow[(long long)w * out.sw + k] = rnd ? round_tf32(v) : v;
     }
   }
 }
@@ -274,7 +275,7 @@ int check_params(const srb_conv_params *p) {
               "bad kernel/stride/pad");
   SRB_REQUIRE(p->ps >= 1, SRB_EINVAL, "ps must be >= 1");
   SRB_REQUIRE(p->act >= SRB_ACT_NONE && p->act <= SRB_ACT_LRELU, SRB_EINVAL, "bad activation %d", p->act);
-  SRB_REQUIRE(p->math >= SRB_MATH_FP32 && p->math <= SRB_MATH_AUTO, SRB_EINVAL, "bad math mode %d", p->math);
+  SRB_REQUIRE(p->math >= SRB_MATH_FP32 && p->math <= SRB_MATH_EXACT, SRB_EINVAL, "bad math mode %d", p->math);
   SRB_REQUIRE(!(p->transposed && p->ps != 1), SRB_EUNSUPPORTED, "PixelShuffle fused with ConvTranspose2d");
   SRB_REQUIRE(p->transposed || p->out_pad == 0, SRB_EINVAL, "out_pad only for transposed");
   SRB_REQUIRE(!p->transposed || p->out_pad < p->stride, SRB_EINVAL, "out_pad must be < stride");
@@ -319,9 +320,12 @@ Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, co
 
 inline bool is_cl(const T4 &t, int C) { return t.sc == 1 && t.sw == C; }
 
+// single-pass tf32 operands (activations are stored tf32-rounded between layers)?  EXACT keeps full fp32 activations.
+inline bool is_tf32_math(int math) { return math == SRB_MATH_TF32 || math == SRB_MATH_AUTO; }
+
 // Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 4 == 0, C >= 8)
 inline int want_round(const srb_conv_params *p, const T4 &t, int C) {
-  return (p->math != SRB_MATH_FP32 && is_cl(t, C) && (C % 4) == 0 && C >= 8) ? 1 : 0;
+  return (is_tf32_math(p->math) && is_cl(t, C) && (C % 4) == 0 && C >= 8) ? 1 : 0;
 }
 
 // Skinny-output wgrad on the tensor path: geometry with Co padded to 4 and the NHWC4 view of the packed dz.
@@ -332,7 +336,7 @@ struct SkinnyWg {
   size_t pack_bytes, dw_bytes, total;
 };
 inline bool skinny_wgrad_plan(const srb_conv_params *p, const Geom &g, const T4 &big, SkinnyWg *sk) {
-  if (p->transposed || p->math == SRB_MATH_FP32 || g.ps != 1 || g.st != 1 || g.Co >= 4) return false;
+  if (p->transposed || !is_tf32_math(p->math) || g.ps != 1 || g.st != 1 || g.Co >= 4) return false;
   sk->g4 = g;
   sk->g4.Co = 4;
   sk->dz4 = T4{(float *)256, (long long)g.Ho * g.Wo * 4, 1, (long long)g.Wo * 4, 4};  // pointer patched by the caller
@@ -375,13 +379,15 @@ int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int 
   if (y_cl) { y.sc = 1; y.sw = Cy; y.sh = (long long)Wy * Cy; y.sn = y.sh * Hy; }
   else      { y.sw = 1; y.sh = Wy; y.sc = (long long)Hy * Wy; y.sn = y.sc * Cy; }
   x.p = y.p = (float *)16;
-  if (pass == 0) return tc_conv_supported(g, x, y, false) ? 1 : 0;
+  const bool exact = p->math == SRB_MATH_EXACT;
+  if (pass == 0) return (exact ? exact_conv_supported(g, y) : tc_conv_supported(g, x, y, false)) ? 1 : 0;
   if (pass == 1) {
     if (g.ps != 1 || g.st != 1 || g.kh != g.kw) return 0;
     Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
-    return tc_conv_supported(gd, y, x, true) ? 1 : 0;
+    if (gd.pad < 0) return 0;  // pad > k-1: srb_conv_dgrad takes the CUDA-core scatter kernel
+    return (exact ? exact_conv_supported(gd, x) : tc_conv_supported(gd, y, x, true)) ? 1 : 0;
   }
-  return tc_wgrad_supported(g, y, x) ? 1 : 0;
+  return (exact ? exact_wgrad_supported(g) : tc_wgrad_supported(g, y, x)) ? 1 : 0;
 }
 
 /* Debug only (not in the public header): per-CTA phase timestamps of the next k_conv_sl launches go to buf (8 x int64 per CTA). */
@@ -395,6 +401,7 @@ int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t
   int rc = make_geom(p, &g);
   if (rc) return rc;
   if (p->transposed || p->math == SRB_MATH_FP32) { snprintf(buf, n, "fp32 CUDA-core kernels"); return SRB_OK; }
+  if (p->math == SRB_MATH_EXACT && pass != 2) g.Ci = (3 * g.Ci + 3) / 4 * 4;  // the channel-tripled launch (exact.cu)
   if (pass == 0) tc_conv_describe(g, buf, n);
   else if (pass == 1) {
     Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
@@ -416,6 +423,16 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
   } else {
     b = tc_conv_ws_bytes(g);
   }
+  if (p->math == SRB_MATH_EXACT && !p->transposed && g.st == 1) {
+    size_t c = 0;
+    if (pass == 2) c = exact_wgrad_ws_bytes(g);
+    else if (pass == 0) c = exact_conv_ws_bytes(g);
+    else {
+      Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+      if (gd.pad >= 0) c = exact_conv_ws_bytes(gd);
+    }
+    if (c > b) b = c;
+  }
   return (a > b ? a : b) + 256;
 }
 
@@ -433,9 +450,11 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   if (!p->transposed) {
     Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
     e.bits_out = relu_bits;
-    const bool tc = p->math != SRB_MATH_FP32 && tc_conv_supported(g, tx, ty, false);
+    const bool ex = p->math == SRB_MATH_EXACT && exact_conv_supported(g, ty);
+    const bool tc = ex || (is_tf32_math(p->math) && tc_conv_supported(g, tx, ty, false));
     SRB_REQUIRE(!relu_bits || (tc && p->ps == 1 && (p->Cout & 15) == 0), SRB_EUNSUPPORTED,
                 "relu_bits needs the tensor path, no PixelShuffle and Cout %% 16 == 0");
+    if (ex) return exact_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
     if (tc) return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
     return simt_conv_gather(g, tx, w, ty, e, st);
   }
@@ -506,7 +525,12 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
       // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
       Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
-      if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true)) {
+      if (p->math == SRB_MATH_EXACT) {
+        if (gd.pad >= 0 && exact_conv_supported(gd, tdx)) {
+          SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
+          return exact_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
+        }
+      } else if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true)) {
         SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
         return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
       }
@@ -537,7 +561,9 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
   T4 tx = to_t4(x), tdz = to_t4(dz);
   if (!p->transposed) {
-    if (p->math != SRB_MATH_FP32 && tc_wgrad_supported(g, tdz, tx))
+    if (p->math == SRB_MATH_EXACT && exact_wgrad_supported(g))
+      return exact_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    if (is_tf32_math(p->math) && tc_wgrad_supported(g, tdz, tx))
       return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
     SkinnyWg sk;
     uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
@@ -577,16 +603,17 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
   SRB_REQUIRE(dz && dz->data && out && out->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(out->sc == 1, SRB_EINVAL, "pixel_unshuffle writes channels_last");
   long long total = (long long)g.N * g.Ho * g.Wo * g.Co;
+  const int rnd = is_tf32_math(p->math) ? 1 : 0;  // EXACT / FP32 keep the full fp32 gradient
   const size_t row_smem = (size_t)p->Cout * g.ps * ((size_t)g.Wo * g.ps + 4) * sizeof(float);
   if (dz->sw == 1 && row_smem <= 48 * 1024 && (long long)g.N * g.Ho < (1LL << 31)) {
     k_pixel_unshuffle_rows<<<(unsigned)(g.N * g.Ho), 256, row_smem, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, p->Cout,
-                                                                                            g.Ho, g.Wo, g.ps);
+                                                                                            g.Ho, g.Wo, g.ps, rnd);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     return SRB_OK;
   }
   k_pixel_unshuffle<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, g.Co, g.Ho, g.Wo,
-                                                                         g.ps);
+                                                                         g.ps, rnd);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

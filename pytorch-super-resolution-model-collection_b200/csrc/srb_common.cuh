@@ -116,4 +116,15 @@ size_t tc_wgrad_ws_bytes(const Geom &g);
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
 
+
+// 3xTF32 split-operand mode (exact.cu): fp32-accurate results from the same tensor-core kernels.
+bool exact_conv_supported(const Geom &g, const T4 &out);
+size_t exact_conv_ws_bytes(const Geom &g);
+int exact_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
+                      void *ws, size_t ws_bytes, cudaStream_t st);
+bool exact_wgrad_supported(const Geom &g);
+size_t exact_wgrad_ws_bytes(const Geom &g);
+int exact_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
+                     int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace srb

@@ -2,6 +2,7 @@
 #pragma once
 #include "srb_common.cuh"
 #include <cuda.h>
+#include <atomic>
 
 namespace srb {
 
@@ -115,5 +116,20 @@ inline int encode_tiled(CUtensorMap *map, void *base, int rank, const cuuint64_t
 
 
 inline int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
+
+// cudaFuncSetAttribute is PER DEVICE: remember which devices of this process already carry the attributes of a kernel.
+// Two threads racing on the same device both set the (idempotent) attribute; the bit is published afterwards.
+template <typename Kernel>
+inline int ensure_kernel_attrs(Kernel kernel, std::atomic<unsigned long long> &done_mask, int smem_bytes, bool carveout) {
+  int dev = 0;
+  SRB_CHECK_CUDA(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return SRB_OK;
+  SRB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (carveout)
+    SRB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (tracked) done_mask.fetch_or(1ull << dev, std::memory_order_release);
+  return SRB_OK;
+}
 
 }  // namespace srb

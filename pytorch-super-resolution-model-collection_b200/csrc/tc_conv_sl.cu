@@ -885,11 +885,10 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   a.dbg = g_sl_dbg;
   a.trace = ((long long)pl.grid_x * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_sl, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_sl, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+  {
+    static std::atomic<unsigned long long> attr_done{0};
+    int rc = ensure_kernel_attrs(k_conv_sl, attr_done, kMaxSmemBytes, true);
+    if (rc) return rc;
   }
   dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles_n);
   k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);

@@ -675,10 +675,10 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SRB_CHECK_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-    attr_set = true;
+  {
+    static std::atomic<unsigned long long> attr_done{0};
+    int rc = ensure_kernel_attrs(k_tc_wgrad, attr_done, kMaxSmemBytes, false);
+    if (rc) return rc;
   }
   k_tc_wgrad<<<pl.grid, kWgThreads, pl.smem, st>>>(mapX, mapZ, a);
   count_launch();

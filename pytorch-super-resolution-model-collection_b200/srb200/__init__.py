@@ -8,7 +8,7 @@ from ._lib import launch_count, SrbError, LIB_PATH
 from . import functional
 from .functional import conv2d, conv_transpose2d, prelu, set_math, get_math, set_grad_scale, set_fuse_relu_backward, mse_loss, l1_loss
 from . import base_networks
-from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBlock, Upsample2xBlock
+from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBlock, Upsample2xBlock, prepare
 from .convert import convert, PReLU, ConvTranspose2d, Conv2d
 from .ddp import GradBucket
 from .graphs import TrainStepGraphs

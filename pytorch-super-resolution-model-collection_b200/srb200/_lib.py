@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LRELU = 0, 1, 2, 3
-MATH_FP32, MATH_TF32, MATH_AUTO = 0, 1, 2
+MATH_FP32, MATH_TF32, MATH_AUTO, MATH_EXACT = 0, 1, 2, 3
 PASS_FPROP, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 
 

@@ -16,7 +16,7 @@ import torch  # re-exported on purpose: the model files get `torch` through the 
 
 from . import functional as F
 
-__all__ = ["torch", "DenseBlock", "ConvBlock", "DeconvBlock", "ResnetBlock", "PSBlock", "Upsample2xBlock"]
+__all__ = ["torch", "DenseBlock", "ConvBlock", "DeconvBlock", "ResnetBlock", "PSBlock", "Upsample2xBlock"]  # (prepare() is not star-exported: the model files never call it)
 
 _FUSABLE = (None, "relu", "prelu", "lrelu")
 
@@ -45,6 +45,13 @@ def _make_act(activation):
 
 
 class _ActMixin:
+    # Set by srb200.prepare()/convert() on the last conv block in front of a flatten (srgan.py:75 does
+    # `out.view(N, -1)`, which needs NCHW-contiguous memory): the block then returns NCHW instead of channels_last.
+    nchw_out = False
+
+    def _layout(self, out):
+        return out.contiguous() if self.nchw_out else out
+
     def _fused_act(self):
         """(activation code, alpha) if the block's activation can be fused into the conv epilogue."""
         if self.activation in _FUSABLE:
@@ -56,7 +63,10 @@ class _ActMixin:
         if self.activation is not None and not fused:
             if self.activation == "prelu":
                 return F.prelu(out, self.act.weight)
-            return self.act(out)
+            out = self.act(out)
+            if self.activation in ("relu", "lrelu"):
+                F._record(out)
+            return out
         return out
 
 
@@ -101,10 +111,10 @@ class ConvBlock(torch.nn.Module, _ActMixin):
         c = self.conv
         if self.norm is not None:
             out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0]))
-            return self._post(out, fused=False)
+            return self._layout(self._post(out, fused=False))
         a, alpha = self._fused_act()
         out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha)
-        return self._post(out, fused=self.activation in _FUSABLE)
+        return self._layout(self._post(out, fused=self.activation in _FUSABLE))
 
 
 class DeconvBlock(torch.nn.Module, _ActMixin):
@@ -127,11 +137,11 @@ class DeconvBlock(torch.nn.Module, _ActMixin):
         d = self.deconv
         if self.norm is not None:
             out = self.bn(F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0]))
-            return self._post(out, fused=False)
+            return self._layout(self._post(out, fused=False))
         a, alpha = self._fused_act()
         out = F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0],
                                  activation=a, alpha=alpha)
-        return self._post(out, fused=self.activation in _FUSABLE)
+        return self._layout(self._post(out, fused=self.activation in _FUSABLE))
 
 
 class ResnetBlock(torch.nn.Module, _ActMixin):
@@ -158,11 +168,11 @@ class ResnetBlock(torch.nn.Module, _ActMixin):
             out = self.bn(F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0]))
             out = self._post(out, fused=False)
             out = self.bn(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0]))
-            return torch.add(out, x)
+            return self._layout(torch.add(out, x))
         a, alpha = self._fused_act()
         out = F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0], activation=a, alpha=alpha)
         out = self._post(out, fused=self.activation in _FUSABLE)
-        return F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0], residual=x)
+        return self._layout(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0], residual=x))
 
 
 class PSBlock(torch.nn.Module, _ActMixin):
@@ -190,10 +200,10 @@ class PSBlock(torch.nn.Module, _ActMixin):
         r = self.ps.upscale_factor
         if self.norm is not None:
             out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], pixel_shuffle=r))
-            return self._post(out, fused=False)
+            return self._layout(self._post(out, fused=False))
         a, alpha = self._fused_act()
         out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha, pixel_shuffle=r)
-        return self._post(out, fused=self.activation in _FUSABLE)
+        return self._layout(self._post(out, fused=self.activation in _FUSABLE))
 
 
 class Upsample2xBlock(torch.nn.Module):
@@ -216,3 +226,24 @@ class Upsample2xBlock(torch.nn.Module):
 
     def forward(self, x):
         return self.upsample(x)
+
+
+_CONV_BLOCK_NAMES = ("ConvBlock", "DeconvBlock", "ResnetBlock", "PSBlock")
+
+
+def prepare(net):
+    """Layout fix-up for models that flatten a conv activation with `.view` (srgan.Discriminator, srgan.py:75): our
+    blocks hand channels_last memory to each other, which `.view(N, -1)` rejects (and whose element order would not
+    match the Linear weights anyway).  The last conv block registered before the first DenseBlock is told to return
+    NCHW-contiguous memory.  Called by srb200.convert(); call it yourself after building a model through the
+    `sys.modules['base_networks']` swap.  Returns net."""
+    last_conv = None
+    for m in net.modules():
+        name = type(m).__name__
+        if name == "DenseBlock":
+            if last_conv is not None:
+                last_conv.nchw_out = True
+            break
+        if name in _CONV_BLOCK_NAMES and type(m).__module__ == __name__:
+            last_conv = m
+    return net

@@ -50,12 +50,17 @@ def _swap_block(m):
 
 
 def convert(net):
-    """In-place conversion; returns net."""
+    """In-place conversion; returns net.  Ends with base_networks.prepare(net) (NCHW output in front of a `.view` flatten)."""
+    _convert(net)
+    return B.prepare(net)
+
+
+def _convert(net):
     for name, child in list(net.named_children()):
         tname = type(child).__name__
         if tname in _BLOCKS and not _is_ours(child):
             new = _swap_block(child)
-            convert(new)  # Upsample2xBlock holds nested blocks
+            _convert(new)  # Upsample2xBlock holds nested blocks
             setattr(net, name, new)
         elif type(child) is torch.nn.PReLU:
             child.__class__ = PReLU
@@ -64,5 +69,5 @@ def convert(net):
         elif type(child) is torch.nn.Conv2d and type(net).__name__ not in _BLOCKS:
             child.__class__ = Conv2d
         else:
-            convert(child)
+            _convert(child)
     return net

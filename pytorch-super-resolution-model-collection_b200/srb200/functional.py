@@ -17,12 +17,14 @@ _state = {"math": _lib.MATH_AUTO, "grad_scale": 1.0}
 
 
 def set_math(mode):
-    """'auto' (default): tcgen05 TF32 tensor path where a layer qualifies; 'fp32': CUDA-core fp32 everywhere."""
-    _state["math"] = {"auto": _lib.MATH_AUTO, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}[mode]
+    """'auto' (default): tcgen05 TF32 tensor path where a layer qualifies; 'fp32': CUDA-core fp32 everywhere;
+    'exact': fp32-accurate on the tensor cores by hi/lo operand splitting (3xTF32), full-fp32 activations."""
+    _state["math"] = {"auto": _lib.MATH_AUTO, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32,
+                      "exact": _lib.MATH_EXACT}[mode]
 
 
 def get_math():
-    return {_lib.MATH_AUTO: "auto", _lib.MATH_TF32: "tf32", _lib.MATH_FP32: "fp32"}[_state["math"]]
+    return {_lib.MATH_AUTO: "auto", _lib.MATH_TF32: "tf32", _lib.MATH_FP32: "fp32", _lib.MATH_EXACT: "exact"}[_state["math"]]
 
 
 def set_grad_scale(s):
@@ -32,10 +34,30 @@ def set_grad_scale(s):
 
 
 _state["fuse_relu_bwd"] = True
+_state["act_recorder"] = None
+
+
+def record_activation_masks(recorder):
+    """Test instrumentation: while `recorder` is a list, every ReLU / PReLU / LeakyReLU evaluated by the engine appends
+    the boolean pattern (pre-activation > 0) of its output, in execution order (None switches it off).  The parity tests
+    replay the CPU oracle's backward on exactly these patterns (activation gradients are discontinuous in z)."""
+    _state["act_recorder"] = recorder
+
+
+def _record(y, residual=None):
+    rec = _state["act_recorder"]
+    if rec is not None:
+        with torch.no_grad():
+            rec.append(((y - residual) if residual is not None else y) > 0)
 
 
 def set_fuse_relu_backward(on):
-    """Fold a ReLU layer's threshold_backward into the dgrad epilogue of its consumer conv (default on)."""
+    """Fold a ReLU layer's threshold_backward into the dgrad epilogue of its consumer conv (default on).
+
+    With the fusion on, the tensor autograd carries between the two layers is dL/dz (masked), not dL/dy.  Parameter and
+    input gradients are bit-identical either way; only an observer of the intermediate activation's gradient could tell.
+    `retain_grad()` / `register_hook()` on the activation (called before the consumer runs) switch the fusion off for
+    that tensor; `torch.autograd.grad(loss, activation)` cannot be detected -- call set_fuse_relu_backward(False) first."""
     _state["fuse_relu_bwd"] = bool(on)
 
 
@@ -46,10 +68,11 @@ class _ReluToken:
     the producer's backward may skip srb_act_bwd.  Safe by construction: ReLU masking is idempotent, so whenever the
     gradient that reaches the producer is not exactly the tensor the consumer wrote (several consumers, autograd
     accumulation, hooks), the producer simply masks again.  `premasked` identifies that tensor."""
-    __slots__ = ("consumers", "premasked", "bits")
+    __slots__ = ("consumers", "premasked", "bits", "observed")
 
     def __init__(self):
         self.consumers = 0
+        self.observed = False  # x.grad is watched (retain_grad / hooks): the consumer must not pre-mask it
         self.premasked = None
         self.bits = None  # packed sign pattern of y written by the producer's fprop epilogue (int16, 16 channels per word)
 
@@ -222,9 +245,16 @@ class _FusedConv(torch.autograd.Function):
             wparam, bparam = ctx.params
             direct = getattr(wparam, "_srb_direct", False) and wparam.grad is not None and \
                 (bparam is None or (getattr(bparam, "_srb_direct", False) and bparam.grad is not None))
+            accumulate = 0
             if direct:
-                # the wgrad kernel overwrites the parameter's slot of the flat gradient bucket, pre-scaled
+                # the wgrad kernel writes the parameter's slot of the flat gradient bucket, pre-scaled: the first write of a
+                # step overwrites (no zero_grad pass), later ones (a module applied twice before one backward, e.g.
+                # srgan.py:275-286, or micro-batch accumulation without begin_step) add -- GradBucket tracks `_srb_written`
                 dw_t, db_t, scale = wparam.grad, (bparam.grad if bparam is not None else None), _state["grad_scale"]
+                accumulate = 1 if getattr(wparam, "_srb_written", False) else 0
+                wparam._srb_written = True
+                if bparam is not None:
+                    bparam._srb_written = True
             else:
                 dw_t = dw = torch.empty_like(weight)
                 db_t = db = torch.empty(weight.shape[1] if p.transposed else weight.shape[0], dtype=torch.float32,
@@ -232,13 +262,13 @@ class _FusedConv(torch.autograd.Function):
                 scale = 1.0
             ws = _workspace(dev, _ws_bytes(p, _lib.PASS_WGRAD))
             check(lib.srb_conv_wgrad(ctypes.byref(p), ctypes.byref(tx), ctypes.byref(tdz), _ptr(dw_t), _ptr(db_t),
-                                     ctypes.c_float(scale), 0, _ptr(ws), ws.numel(), st))
+                                     ctypes.c_float(scale), accumulate, _ptr(ws), ws.numel(), st))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape, dtype=torch.float32, device=dev,
                              memory_format=torch.channels_last if _is_cl(x) else torch.contiguous_format)
             tdx = t4(dx)
             itok = ctx.in_token
-            fuse = itok is not None and itok.consumers == 1 and _state["fuse_relu_bwd"]
+            fuse = itok is not None and itok.consumers == 1 and not itok.observed and _state["fuse_relu_bwd"]
             # x = ReLU(z_prev): its sign pattern is the producer's mask -- in packed form when the producer's fprop wrote
             # it and this dgrad runs on the tensor path, else read from x itself
             bits = None
@@ -260,12 +290,18 @@ def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, p
     in_token = getattr(x, "_srb_relu", None) if x.requires_grad else None
     if in_token is not None:
         in_token.consumers += 1
+        # the fused dgrad hands the producer dL/dz (already masked) in place of dL/dy: anything that observes x.grad
+        # (retain_grad, tensor hooks registered before this call) must see the un-masked gradient, so do not fuse
+        if x.retains_grad or getattr(x, "_backward_hooks", None):
+            in_token.observed = True
     # y = ReLU(z) exactly (no residual on top); only worth it when a gradient will flow back into this layer
     out_token = _ReluToken() if (act == "relu" and residual is None and torch.is_grad_enabled()) else None
     y = _FusedConv.apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
                          out_token)
     if out_token is not None and y.requires_grad:
         y._srb_relu = out_token
+    if act is not None and _state["act_recorder"] is not None:
+        _record(y, residual)
     return y
 
 
@@ -315,7 +351,10 @@ class _PReLU(torch.autograd.Function):
 def prelu(x, alpha):
     """Stand-alone PReLU with one shared slope (fsrcnn.py:26)."""
     assert alpha.numel() == 1
-    return _PReLU.apply(x, alpha)
+    y = _PReLU.apply(x, alpha)
+    if _state["act_recorder"] is not None:
+        _record(y)
+    return y
 
 
 class _Loss(torch.autograd.Function):

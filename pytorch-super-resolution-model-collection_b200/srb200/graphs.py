@@ -11,9 +11,14 @@ inputs live in fixed "slots" that the caller refills (device-to-device or pinned
 
 Data parallel: the NCCL all-reduce of the flat gradient buffer sits between the backward graph and the optimizer graph.
 With `capture_allreduce=True` it is captured into the backward graph (NCCL supports stream capture); if that capture
-fails the class falls back to an eager all-reduce between two graphs.
+raises, the error is kept in `comm_capture_error`, a warning is issued and the all-reduce runs eagerly between two graphs.
+
+Requirements (checked): the optimizer state must already exist (one eager step first).  Limitation: a Python-float `lr` is
+baked into the captured optimizer kernel, so `param_group['lr'] = ...` decay (vdsr.py:108-112) has no effect on replays --
+construct the optimizer with a tensor lr (`lr=torch.tensor(1e-5, device=...)`) and update it in place.
 """
 import torch
+import torch.distributed  # noqa: F401  (DistBackendError)
 
 from . import _lib
 
@@ -25,8 +30,28 @@ class TrainStepGraphs:
         self.clip_norm = clip_norm
         self.dev = self.slots[0][0].device
         self.fused_comm = False
+        self.comm_capture_error = None  # why the NCCL all-reduce could not be captured (None: captured or not requested)
         self.launches_per_step = 0
+        self._check_optimizer_state()
         self._capture(capture_allreduce and bucket.world > 1)
+
+    def _check_optimizer_state(self):
+        """Adam's exp_avg / step and SGD's momentum buffers are created lazily by the first optimizer.step(); captured into
+        the tail graph that initialisation would be replayed (and reset the moments) on every step.  Require it to exist."""
+        opt = self.opt
+        needs_state = any(g.get("momentum", 0) for g in opt.param_groups) or isinstance(opt, (torch.optim.Adam, torch.optim.AdamW))
+        if not needs_state:
+            return
+        for g in opt.param_groups:
+            for p in g["params"]:
+                if p.requires_grad and len(opt.state.get(p, {})) == 0:
+                    raise RuntimeError(
+                        "TrainStepGraphs: optimizer state is missing for a parameter -- run one eager step "
+                        "(stepper-less: bucket.begin_step(); loss.backward(); optimizer.step()) before capturing, "
+                        "otherwise the lazy state initialisation is captured and replayed every step")
+            lr = g.get("lr")
+            if not torch.is_tensor(lr):
+                self.lr_baked = True  # scalar lr is baked into the captured optimizer kernel; see the class docstring
 
     # -- eager version of the same step (warm-up, debugging, instrumentation) ---------------------------------------
     def eager_step(self, x, t):
@@ -75,7 +100,12 @@ class TrainStepGraphs:
             try:
                 self._capture_once(True)
                 return
-            except Exception:  # NCCL capture unavailable in this setup: keep the collective eager
+            except (RuntimeError, torch.distributed.DistBackendError) as e:
+                # NCCL refused stream capture in this setup: report it, keep the collective eager between the two graphs
+                import warnings
+                self.comm_capture_error = "%s: %s" % (type(e).__name__, e)
+                warnings.warn("TrainStepGraphs: all-reduce not captured (%s); running it eagerly between the graphs"
+                              % self.comm_capture_error)
                 torch.cuda.synchronize(self.dev)
         self._capture_once(False)
 

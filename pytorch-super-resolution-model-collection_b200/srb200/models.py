@@ -10,7 +10,7 @@ utils.py and is restated only in the test oracle.
 import torch
 import torch.nn as nn
 
-from .base_networks import ConvBlock, PSBlock, ResnetBlock, Upsample2xBlock, DenseBlock
+from .base_networks import ConvBlock, PSBlock, ResnetBlock, Upsample2xBlock, DenseBlock, prepare
 from .convert import PReLU, ConvTranspose2d
 
 
@@ -147,11 +147,12 @@ class SRGANDiscriminator(nn.Module):
         self.dense_layers = _seq([
             DenseBlock(f * 8 * image_size // 16 * image_size // 16, f * 16, activation='lrelu', norm=None),
             DenseBlock(f * 16, 1, activation='sigmoid', norm=None)])
+        prepare(self)  # the last conv block returns NCHW so the reference's `.view` flatten (srgan.py:75) works unchanged
 
     def forward(self, x):
         out = self.input_conv(x)
         out = self.conv_blocks(out)
-        out = out.reshape(out.size()[0], -1)  # reference: .view (srgan.py:75); our activations are NHWC-strided
+        out = out.view(out.size()[0], -1)  # srgan.py:75
         return self.dense_layers(out)
 
 

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
 
 
 def test_version_and_error_string():
-    assert _lib.lib.srb_version() == 100
+    assert _lib.lib.srb_version() == 200
     p = _lib.ConvParams(1, 3, 8, 8, 4, 3, 3, 0, 1, 0, 0, 1, 0, 0.2, 0)  # stride 0
     ho, wo = ctypes.c_int32(), ctypes.c_int32()
     rc = _lib.lib.srb_conv_out_hw(ctypes.byref(p), ctypes.byref(ho), ctypes.byref(wo))

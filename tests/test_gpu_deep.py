@@ -1,0 +1,186 @@
+"""GPU suite (-m gpu), net level at the BASELINE depths: vdsr.Net(3,64,18) (cfg3), edsr.Net(3,256,32) (cfg4),
+srgan.Generator(3,64,16) and srgan.Discriminator(3,64,128) (cfg5) against the CPU oracle, whose parameters, outputs and
+gradients are pinned to the unmodified reference by tests/golden/deep_*.npz (tests/test_oracle.py).
+
+Gates (north_star: 1e-3 relative fp32):
+  math='exact' (3xTF32 split operands on tcgen05, fp32 activations)   outputs AND every gradient <= 1e-3
+  math='auto'  (single-pass TF32)                                     outputs <= max(1e-3, 4e-4*sqrt(#convs)) -- the
+               depth-aware bound SURVEY.md Appendix B measured (3-6e-4 per layer, 1.5e-3 through 20..69 layers) --
+               gradients <= 2x that (forward error in the saved activations + backward error)
+Gradients are compared on a COMMON activation pattern: ReLU/PReLU/LeakyReLU derivatives are discontinuous in the
+pre-activation, so the oracle's backward is replayed with the sign pattern the GPU forward produced
+(oracle.with_forced_activations) and with the same dL/dy -- the derivative kernels themselves must be 1e-3 exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import srb200
+from srb200 import models as M
+from srb200 import functional as F
+from oracle import torch_ref as R
+from util import DEEP, digest_close, load_golden, rel_l2
+from netcheck import run_against_oracle, tolerances
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    srb200.set_math("auto")
+    srb200.set_grad_scale(1.0)
+    yield
+    srb200.set_math("auto")
+    F.record_activation_masks(None)
+
+
+@pytest.mark.parametrize("case", sorted(DEEP))
+@pytest.mark.parametrize("math", ["exact", "auto"])
+def test_deep_net_matches_oracle(case, math):
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    name, loss_kind = DEEP[case]
+    g = load_golden("deep_" + case)
+    args = tuple(int(v) for v in g["args"])
+    x, tgt = torch.from_numpy(g["x"]), torch.from_numpy(g["target"])
+    r = run_against_oracle(name, args, loss_kind, x, tgt, math)
+    ty, tg = tolerances(math, r["n_convs"])
+    worst = max(r["grad_errs"].items(), key=lambda kv: kv[1])
+    print("\n%s math=%s: y rel-L2 %.3e (tol %.1e), worst grad %s %.3e (tol %.1e), %d convs"
+          % (case, math, r["y_err"], ty, worst[0], worst[1], tg, r["n_convs"]))
+    assert r["y_err"] < ty
+    assert r["y_forced_err"] < ty
+    for k, e in r["grad_errs"].items():
+        assert e < tg, (k, e)
+    # the reference's own output for this input (fixture), when this machine's seeded init reproduces the reference's
+    # parameters bit for bit (same torch build; checked, not assumed)
+    same_init = all(digest_close(v, g, "param:" + k, 1e-12) for k, v in r["ref"].state_dict().items()
+                    if v.dtype.is_floating_point)
+    if same_init:
+        assert rel_l2(r["y"], g["y"]) < ty
+    else:
+        print("note: seeded init differs from the fixture on this host; compared against the live oracle only")
+
+
+def test_srgan_discriminator_view_flatten_and_decision():
+    """srgan.Discriminator (srgan.py:49-77) through the block API: `.view` flatten works (prepare()), decisions match."""
+    assert torch.cuda.is_available()
+    srb200.set_math("fp32")
+    ref = R.build("srgan_d", (3, 16, 32), seed=0)
+    net = M.SRGANDiscriminator(3, 16, 32)
+    net.load_state_dict(ref.state_dict())
+    net.to(DEV).train()
+    ref.train()
+    x = torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    y = net(x.to(DEV))
+    assert tuple(y.shape) == (3, 1)
+    assert rel_l2(y.detach(), ref(x).detach()) < 1e-4
+    assert net.conv_blocks[-1].nchw_out and not net.conv_blocks[0].nchw_out
+
+
+def test_module_applied_twice_accumulates_under_grad_bucket():
+    """a conv used twice before one backward (srgan.py:275-286 runs D on real and fake) must
+    accumulate into its GradBucket slot, and a conv not reached in a step must read as zero gradient."""
+    assert torch.cuda.is_available()
+    srb200.set_math("fp32")
+    torch.manual_seed(0)
+    blk = srb200.ConvBlock(8, 8, 3, 1, 1, activation="relu", norm=None).to(DEV)
+    other = srb200.ConvBlock(8, 8, 3, 1, 1, activation=None, norm=None).to(DEV)
+    holder = torch.nn.ModuleList([blk, other])
+    x1 = torch.randn(2, 8, 9, 9, device=DEV)
+    x2 = torch.randn(2, 8, 9, 9, device=DEV)
+    # plain autograd accumulation (no bucket): the truth
+    (blk(x1).sum() + blk(x2).square().sum()).backward()
+    want_w, want_b = blk.conv.weight.grad.clone(), blk.conv.bias.grad.clone()
+    for p in holder.parameters():
+        p.grad = None
+    bucket = srb200.GradBucket(holder, world_size=1)
+    for _ in range(2):  # second pass: stale values from the first step must not leak
+        bucket.begin_step()
+        (blk(x1).sum() + blk(x2).square().sum()).backward()
+        bucket.all_reduce()
+        assert rel_l2(blk.conv.weight.grad, want_w) < 1e-5
+        assert rel_l2(blk.conv.bias.grad, want_b) < 1e-5
+        assert torch.count_nonzero(other.conv.weight.grad).item() == 0
+    # a step that only reaches `other`: blk's slot must be zero, not the previous step's gradient
+    bucket.begin_step()
+    other(x1).sum().backward()
+    bucket.all_reduce()
+    assert torch.count_nonzero(blk.conv.weight.grad).item() == 0
+    assert torch.count_nonzero(other.conv.weight.grad).item() > 0
+    bucket.detach()
+
+
+def test_retain_grad_disables_fused_relu_backward():
+    """with retain_grad() on a ReLU activation the consumer must not pre-mask its gradient."""
+    assert torch.cuda.is_available()
+    srb200.set_math("fp32")
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 8, 6, 6, generator=gen).to(DEV).requires_grad_(True)
+    w1 = (torch.randn(8, 8, 3, 3, generator=gen) / 8).to(DEV).requires_grad_(True)
+    w2 = (torch.randn(8, 8, 3, 3, generator=gen) / 8).to(DEV).requires_grad_(True)
+    h = srb200.conv2d(x, w1, None, 1, 1, activation="relu")
+    h.retain_grad()
+    srb200.conv2d(h, w2, None, 1, 1).sum().backward()
+    xr, w1r, w2r = (t.detach().cpu().requires_grad_(True) for t in (x, w1, w2))
+    hr = torch.relu(torch.nn.functional.conv2d(xr, w1r, None, 1, 1))
+    hr.retain_grad()
+    torch.nn.functional.conv2d(hr, w2r, None, 1, 1).sum().backward()
+    assert rel_l2(h.grad, hr.grad) < 1e-5          # dL/dy, NOT dL/dz: entries where y == 0 are not zeroed
+    assert rel_l2(x.grad, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("case", [
+    # Cin Cout k  p  act      res   ps  H   W   N
+    (64, 64, 3, 1, "relu", False, 1, 16, 16, 2),
+    (3, 64, 5, 0, "relu", False, 1, 18, 17, 2),
+    (64, 32, 3, 0, "relu", False, 1, 16, 16, 3),
+    (32, 3, 3, 0, None, False, 4, 13, 14, 2),
+    (64, 64, 3, 1, None, True, 1, 12, 20, 2),
+    (64, 3, 3, 1, None, True, 1, 16, 16, 2),
+    (64, 64, 3, 1, "prelu", False, 2, 8, 8, 2),
+    (256, 256, 3, 1, "relu", False, 1, 8, 8, 1),
+    (12, 12, 3, 1, None, False, 1, 10, 10, 2),
+    (1, 8, 3, 1, "lrelu", False, 1, 9, 9, 2),
+])
+def test_exact_mode_op_is_fp32_accurate(case):
+    """math='exact': one fused conv (fwd, dX, dW, db) within 2e-5 of the fp64-accumulated truth -- i.e. fp32 accuracy from
+    the tf32 tensor cores (single-pass TF32 measures 3e-4 on the same cases)."""
+    assert torch.cuda.is_available()
+    import torch.nn.functional as TF
+    srb200.set_math("exact")
+    Cin, Cout, k, p, act, res, ps, H, W, N = case
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(N, Cin, H, W, generator=gen)
+    w = torch.randn(Cout * ps * ps, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout * ps * ps, generator=gen) * 0.1
+    alpha = torch.tensor([0.25])
+    z0 = TF.conv2d(x, w, b, 1, p)
+    oshape = (N, Cout, z0.shape[2] * ps, z0.shape[3] * ps)
+    r = torch.randn(oshape, generator=gen) if res else None
+    gy = torch.randn(oshape, generator=gen)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wg, bg, ag = (t.to(DEV).requires_grad_(True) for t in (w, b, alpha))
+    rg = r.to(DEV) if res else None
+    y = srb200.conv2d(xg, wg, bg, 1, p, activation=act, alpha=ag if act == "prelu" else None, residual=rg, pixel_shuffle=ps)
+    y.backward(gy.to(DEV))
+    # truth in fp64 on the activation pattern of the GPU forward
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    zr = TF.conv2d(xr, wr, br, 1, p)
+    if ps > 1:
+        zr = TF.pixel_shuffle(zr, ps)
+    if act is not None:
+        yg = y.detach().cpu().double() - (r.double() if res else 0)
+        m = (yg > 0).double()
+        slope = {"relu": 0.0, "lrelu": 0.2, "prelu": 0.25}[act]
+        yr = zr * m + zr * (1 - m) * slope
+    else:
+        yr = zr
+    if res:
+        yr = yr + r.double()
+    yr.backward(gy.double())
+    assert rel_l2(y.detach(), yr.detach()) < 2e-5
+    assert rel_l2(xg.grad, xr.grad) < 2e-5
+    assert rel_l2(wg.grad, wr.grad) < 2e-5
+    assert rel_l2(bg.grad, br.grad) < 2e-5

@@ -83,39 +83,27 @@ NETS = {"srcnn": "l2", "espcn": "l2", "fsrcnn": "l2", "vdsr": "l2", "edsr": "l1"
 
 
 @pytest.mark.parametrize("name", sorted(NETS))
-@pytest.mark.parametrize("math", ["fp32", "auto"])
+@pytest.mark.parametrize("math", ["fp32", "auto", "exact"])
 def test_net_matches_reference_golden(name, math):
+    """Reduced-width nets whose fixtures hold the reference's parameters, output, loss and gradients in full.
+    Outputs/loss against the fixture; gradients against the oracle replayed on the GPU's activation pattern at the same
+    tolerance class (netcheck.run_against_oracle) -- fp32 also straight against the fixture's gradients."""
     _need_gpu()
-    srb200.set_math(math)
+    from netcheck import run_against_oracle, tolerances
     g = load_golden("net_" + name)
-    net = M.MODELS[name](*[int(v) for v in g["args"]])
-    load_state(net, g)
-    net.to(DEV).train()
-    x = torch.from_numpy(g["x"]).to(DEV)
-    tgt = torch.from_numpy(g["target"]).to(DEV)
-    y = net(x)
-    loss = TF.l1_loss(y, tgt) if NETS[name] == "l1" else TF.mse_loss(y, tgt)
-    loss.backward()
-    tol = 1e-4 if math == "fp32" else 1e-3
-    assert rel_l2(y.detach(), g["y"]) < tol
-    assert abs(loss.item() - float(g["loss"])) < tol * abs(float(g["loss"]))
-    gscale = max(np.abs(v).max() for k, v in g.items() if k.startswith("grad:"))
-    for k, p in net.named_parameters():
-        ref = g["grad:" + k]
-        if np.abs(ref).max() < 1e-5 * gscale:
-            continue  # mathematically-zero gradients (conv bias in front of BatchNorm): pure rounding noise
-        if math == "fp32":
-            gtol = tol * (3 if name == "edsr" else 1)  # L1 loss: sign(y - t) flips on a few pixels
-            assert rel_l2(p.grad, ref) < gtol, k
-        elif ref.size == 1:
-            # one shared PReLU slope: d(alpha) = sum(dy*z*[z<=0]) cancels to ~1e-4 of its terms; gate it
-            # against the gradient scale of the net instead of against itself
-            assert abs(p.grad.item() - float(ref.reshape(-1)[0])) < 2e-3 * gscale, k
-        else:
-            a = p.grad.detach().double().cpu().flatten()
-            b = torch.from_numpy(ref).double().flatten()
-            cos = (a @ b / (a.norm() * b.norm())).item()
-            assert cos > 0.999 and rel_l2(p.grad, ref) < 5e-2, (k, cos)  # see module docstring (mask flips)
+    args = tuple(int(v) for v in g["args"])
+    ref = R.build(name, args, init=False)
+    load_state(ref, g)
+    kind = "l1" if NETS[name] == "l1" else "mse"
+    r = run_against_oracle(name, args, kind, torch.from_numpy(g["x"]), torch.from_numpy(g["target"]), math, ref=ref)
+    ty, tg = tolerances(math, r["n_convs"])
+    if math == "fp32":
+        ty = tg = 1e-4
+    assert rel_l2(r["y"], g["y"]) < ty
+    loss = (TF.l1_loss if kind == "l1" else TF.mse_loss)(r["y"], torch.from_numpy(g["target"]))
+    assert abs(loss.item() - float(g["loss"])) < ty * abs(float(g["loss"]))
+    for k, e in r["grad_errs"].items():
+        assert e < tg, (k, e)
 
 
 # ---- op-level sweep against the CPU oracle ---------------------------------------------------------

@@ -118,3 +118,44 @@ def test_public_api_surface():
                  "ConvBlock", "PSBlock", "ResnetBlock", "DeconvBlock", "Upsample2xBlock", "DenseBlock", "set_math",
                  "set_fuse_relu_backward", "launch_count"):
         assert hasattr(srb200, name), name
+
+
+def test_prepare_marks_last_conv_block_before_a_dense_block():
+    """srgan.Discriminator flattens with `.view` (srgan.py:75); prepare()/convert() make the last conv
+    block hand back NCHW memory so the reference forward runs unchanged."""
+    import srb200
+    net = srb200.models.SRGANDiscriminator(3, 8, 32)
+    flags = [b.nchw_out for b in net.conv_blocks]
+    assert flags == [False] * 6 + [True] and not net.input_conv.nchw_out
+    g = srb200.models.SRGANGenerator(3, 8, 1)
+    assert not any(getattr(m, "nchw_out", False) for m in g.modules())  # no DenseBlock: nothing to mark
+
+
+def test_convert_prepares_the_live_reference_discriminator():
+    from oracle import ref_import
+    if not ref_import.available():
+        import pytest
+        pytest.skip("reference tree not present")
+    import srb200
+    mods = ref_import.load()
+    d = mods["srgan"].Discriminator(3, 8, 32)
+    srb200.convert(d)
+    assert type(d.conv_blocks[-1]).__module__ == "srb200.base_networks" and d.conv_blocks[-1].nchw_out
+    assert not d.conv_blocks[0].nchw_out
+
+
+def test_grad_bucket_written_flags_cpu():
+    """begin_step() resets the per-step 'written' flags of direct parameters; all_reduce() zeroes direct slots nobody wrote."""
+    import torch
+    import srb200
+    m = torch.nn.Sequential(torch.nn.Conv2d(2, 2, 3), torch.nn.PReLU())
+    b = srb200.GradBucket(m, world_size=1)
+    w = m[0].weight
+    b.direct_ids.add(id(w))  # CPU tensors are never 'direct'; emulate a CUDA conv parameter
+    w._srb_written = True
+    b.begin_step()
+    assert w._srb_written is False
+    w.grad.fill_(3.0)
+    b.all_reduce()  # nobody wrote w in this step
+    assert float(w.grad.abs().sum()) == 0.0 and w._srb_written is True
+    b.detach()

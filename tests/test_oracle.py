@@ -167,3 +167,51 @@ def test_oracle_equals_live_reference(name, mod, cls, args, xs):
     yb.square().mean().backward()
     for (k, pa), (_, pb) in zip(ref.named_parameters(), ours.named_parameters()):
         assert torch.equal(pa.grad, pb.grad), k
+
+
+# ---- the BASELINE depths (VDSR-18, EDSR 256x32, SRGAN G-16 / D): digest fixtures ------------------------------------
+from util import DEEP, digest_close, loss_of  # noqa: E402
+
+
+@pytest.mark.parametrize("case", sorted(DEEP))
+def test_oracle_deep_net_matches_reference_digest(case):
+    """Full-depth/width nets of BASELINE configs 3-5: the seeded oracle init reproduces the reference's parameters, and
+    its forward/backward reproduces the reference's output, loss and every gradient (digests: norm + 64 samples)."""
+    name, loss_kind = DEEP[case]
+    g = load_golden("deep_" + case)
+    net = R.build(name, tuple(int(v) for v in g["args"]), seed=0)
+    for k, v in net.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert digest_close(v, g, "param:" + k, 1e-12), k
+    net.train()
+    y = net(torch.from_numpy(g["x"]))
+    loss = loss_of(loss_kind, y, torch.from_numpy(g["target"]))
+    loss.backward()
+    assert rel_l2(y.detach(), g["y"]) < 1e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    gscale = max(float(g[k]) for k in g if k.startswith("grad:") and k.endswith(":norm"))
+    for k, p in net.named_parameters():
+        if float(g["grad:" + k + ":norm"]) < 1e-5 * gscale:
+            continue  # mathematically-zero gradients (bias in front of BatchNorm)
+        assert digest_close(p.grad, g, "grad:" + k, 2e-4), k
+
+
+def test_forced_activation_replay_is_identity_on_own_pattern():
+    """oracle.with_forced_activations fed with the net's own sign pattern changes nothing (the tool the GPU gradient gates use)."""
+    net = R.build("srgan_g", (3, 16, 2), seed=0)
+    x = torch.rand(2, 3, 8, 8, generator=torch.Generator().manual_seed(1))
+    masks = []
+    hooks = [m.register_forward_hook(lambda mod, i, o: masks.append(o.detach() > 0)) for m in net.modules()
+             if isinstance(m, (torch.nn.ReLU, torch.nn.PReLU, torch.nn.LeakyReLU))]
+    y = net(x)
+    for h in hooks:
+        h.remove()
+    y.square().mean().backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    R.with_forced_activations(net, masks)
+    y2 = net(x)
+    y2.square().mean().backward()
+    assert rel_l2(y2.detach(), y.detach()) < 1e-6
+    for k, p in net.named_parameters():
+        assert rel_l2(p.grad, ref[k]) < 1e-5, k
