@@ -3,13 +3,17 @@
 
     python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                   (the reference's CPU PyTorch path, host cores)
+    python bench.py --impl cudnn ...                       (the same nets on stock torch.nn -> cuDNN: the GPU baseline
+                                                            the north_star names; as-is and tuned variants)
 
 Workload at N=1 (and per rank, weak scaling, at N>1): BASELINE.json configs[1] -- ESPCN x4, 64x64 LR,
 batch 128, fwd + MSE + bwd + Adam (espcn.py:126-131), synthetic uniform inputs, weights from the
 net's own N(0, 0.02) init under seed 0.  One "step" = one such optimizer step.
 
 Prints ONE JSON line (rank 0).  value = images/s with inputs resident in HBM (CUDA events, max over ranks);
-e2e = same metric with the step's inputs copied from pinned host memory and the loss read back every step;
+e2e = same metric through the public API with HOST buffers: every step's LR/HR batches are copied from pinned host
+memory as the uint8 HWC pixels an image decoder produces (dataset.py:90 applies ToTensor on the host; here
+srb200.image_to_tensor does it on the device) and the loss is read back every step;
 roofline = the dominant kernel of the step, algorithmic bytes (or flops) per launch / its mean duration,
 timed live with CUDA events in a second instrumented pass of the same region;
 cpu_baseline = the CPU oracle port of the reference nets (oracle/torch_ref.py) on this box's host cores.
@@ -34,7 +38,7 @@ WORKLOADS = {
     "espcn_x4_b128_lr64": ("espcn", (3, 64, 4), 128, (64, 64), "mse", "espcn"),
     "vdsr_b64_128": ("vdsr", (3, 64, 18), 64, (128, 128), "mse", "vdsr"),
     "edsr64_x4_b32_lr32": ("edsr", (3, 64, 16), 32, (32, 32), "l1", "edsr"),
-    "edsr256_x4_b32_lr32": ("edsr", (3, 256, 32), 32, (32, 32), "l1", "edsr"),  # cfg4 shapes, TF32 on fp32 storage (bf16: next round)
+    "edsr256_x4_b32_lr32": ("edsr", (3, 256, 32), 32, (32, 32), "l1", "edsr"),  # cfg4 (--math bf16 = its dtype; auto = TF32 on fp32 storage)
     "srcnn_x2_b16": ("srcnn", (3, 64), 16, (64, 64), "mse", "srcnn"),
 }
 DEFAULT_WORKLOAD = "espcn_x4_b128_lr64"
@@ -44,9 +48,22 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+        pk = {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+              "source": "measured"}
+    else:
+        pk = {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+    # TF32 peak: measured with the MEASURED_PEAKS method (cuBLAS 8192^3, burst + sustained) by tools/measure_tf32_peak.py;
+    # bf16/2 only when that file is missing
+    pk["tf32_burst"], pk["tf32_sustained"], pk["tf32_source"] = pk["bf16_burst"] / 2, pk["bf16_sustained"] / 2, "bf16/2 (assumed)"
+    tpath = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.isfile(tpath):
+        try:
+            t = json.load(open(tpath))
+            pk["tf32_burst"], pk["tf32_sustained"] = t["tf32_tflops"], t["tf32_tflops_sustained"]
+            pk["tf32_source"] = "measured (profiles/tf32_peak.json: cuBLAS TF32 8192^3)"
+        except Exception:
+            pass
+    return pk
 
 
 def out_shape(model_key, args, n, h, w):
@@ -226,57 +243,66 @@ def algorithmic(name, key):
     return 4 * 3 * yb, 0  # act_bwd: dy, ref, dz
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="srb200", choices=["srb200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default="auto", choices=["auto", "fp32"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
-    a = ap.parse_args()
-    a.warmup = max(a.warmup, 3)
+METRIC = "SR training images/sec (device-timed)"
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[a.workload]
-    config = {"workload": a.workload, "net": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
-              "lr_hw": [h, w], "loss": loss_kind, "optimizer": opt_key, "parallelism": "dp%d" % world,
-              "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches",
-              "launch": "eager" if a.no_graph else "cuda-graph replay (srb200.TrainStepGraphs: fwd+loss+bwd[+allreduce] graph per input slot, optimizer graph)"}
 
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        r = cpu_reference_run(a.workload, a.steps, a.warmup, budget_s=120.0)
-        line = {"impl": "reference", "metric": "SR training images/sec (device-timed)", "value": r["value"], "unit": "images/s",
-                "n_gpus": a.gpus, "steps": r["steps"], "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
+def make_config(workload, world, no_graph, math):
+    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[workload]
+    return {"workload": workload, "net": model_key, "per_gpu_batch": batch, "global_batch": batch * world,
+            "lr_hw": [h, w], "loss": loss_kind, "optimizer": opt_key, "parallelism": "dp%d" % world, "math": math,
+            "l2": "per-step working set (activations+grads ~1 GB) exceeds the 126 MB L2; inputs rotate over 3 batches",
+            "launch": "eager" if no_graph else "cuda-graph replay (srb200.TrainStepGraphs: fwd+loss+bwd[+allreduce] graph per input slot, optimizer graph)"}
 
+
+class Ctx:
+    """Process-wide state shared by the measured workloads: rank / world / device / barrier."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dev = None
+        self.dist = None
+
+    def init_cuda(self, need_dist=True):
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device for this --impl: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1 and need_dist:
+            import torch.distributed as dist
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.dist is None:
+            return ms
+        t = torch.tensor([ms], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+
+def synth_images(batch, h, w, gen):
+    """Synthetic uint8 HWC image batch (what a decoder hands to dataset.py:90's ToTensor), pinned."""
+    return torch.randint(0, 256, (batch, h, w, 3), generator=gen, dtype=torch.uint8).pin_memory()
+
+
+def measure_srb(ctx, a, workload, steps, warmup, full):
+    """Our arm on one workload.  full: also the e2e leg, the instrumented roofline pass and the kernel table."""
+    import ctypes
     import srb200
     from srb200 import _lib
     from srb200 import host
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl srb200) needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[workload]
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     srb200.set_math(a.math)
-
     torch.manual_seed(0)
     net = srb200.models.MODELS[model_key](*margs)
     host.init_model(model_key, net)
@@ -286,66 +312,55 @@ def main():
     lossf = host.loss_for(model_key, fused=True)
     oshape = out_shape(model_key, margs, batch, h, w)
 
+    # host side: uint8 HWC pixels (pinned); device side: fp32 NCHW slots the step reads (filled by srb200.image_to_tensor)
     gen = torch.Generator().manual_seed(1 + rank)
-    host_x = [torch.rand((batch, 3, h, w), generator=gen).pin_memory() for _ in range(3)]
-    host_t = [torch.rand(oshape, generator=gen).pin_memory() for _ in range(3)]
-    dev_x = [t.to(dev) for t in host_x]
-    dev_t = [t.to(dev) for t in host_t]
+    host_x = [synth_images(batch, h, w, gen) for _ in range(3)]
+    host_t = [synth_images(batch, oshape[2], oshape[3], gen) for _ in range(3)]
+    stage_x = [torch.empty(t.shape, dtype=torch.uint8, device=dev) for t in host_x]
+    stage_t = [torch.empty(t.shape, dtype=torch.uint8, device=dev) for t in host_t]
+    dev_x = [srb200.image_to_tensor(t.to(dev)) for t in host_x]
+    dev_t = [srb200.image_to_tensor(t.to(dev)) for t in host_t]
     loss_host = torch.zeros(1).pin_memory()
+    clip = host.VDSR_CLIP if model_key == "vdsr" else None
 
     def step(x, t):
         bucket.begin_step()
-        y = net(x)
-        loss = lossf(y, t)
+        loss = lossf(net(x), t)
         loss.backward()
         bucket.all_reduce()
-        if model_key == "vdsr":
-            torch.nn.utils.clip_grad_norm_(net.parameters(), host.VDSR_CLIP)
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
         opt.step()
         return loss
 
-    # ---- whole-step CUDA graphs (srb200.TrainStepGraphs) -----------------------------------------------------------------
-    # The small nets are host-launch bound when every kernel is launched from Python, so the step is captured once per
-    # resident input slot: backward graph (zero non-direct grads + forward + loss + backward [+ NCCL all-reduce]) and an
-    # optimizer graph (clipping + step).
     graphs = {}
 
-    def capture_graphs():
-        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)),
-                                    clip_norm=host.VDSR_CLIP if model_key == "vdsr" else None)
-        graphs.update(stepper=st, launches=st.launches_per_step)
-
     def step_slot(i):
-        """One training step on resident batch slot i (graph replay when captured, eager otherwise)."""
         if not graphs:
             return step(dev_x[i], dev_t[i])
         return graphs["stepper"].step(i)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
-        """H2D copy of step i's batch from pinned host memory on the copy stream (overlaps the previous step's kernels)."""
+        """Step i's batch: pinned uint8 -> device staging (PCIe) -> fp32 NCHW slot (ToTensor on the device), all on the copy
+        stream, overlapping the previous step's kernels.  Slot i%3 was last read by step i-3 (host-synchronised since)."""
+        s = i % 3
         with torch.cuda.stream(copy_stream):
-            # into the resident slot (the graphs read fixed addresses); slot i%3 was last read by step i-3, long finished
-            dev_x[i % 3].copy_(host_x[i % 3], non_blocking=True)
-            dev_t[i % 3].copy_(host_t[i % 3], non_blocking=True)
+            stage_x[s].copy_(host_x[s], non_blocking=True)
+            stage_t[s].copy_(host_t[s], non_blocking=True)
+            srb200.image_to_tensor(stage_x[s], out=dev_x[s])
+            srb200.image_to_tensor(stage_t[s], out=dev_t[s])
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return ev
 
     def timed(nsteps, e2e):
-        barrier()
+        ctx.barrier()
         main = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if e2e:
-            # every step's inputs cross PCIe inside the timed region (double buffered: batch i+1 is in flight while
-            # step i computes) and every step's loss is read back by the host, like `loss.data[0]` in srcnn.py:134
             copy_stream.wait_event(e0)
             nxt = prefetch(0)
         for i in range(nsteps):
@@ -355,108 +370,335 @@ def main():
                     nxt = prefetch(i + 1)
                 main.wait_event(ev)
                 loss = step_slot(i % 3)
-                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # like `loss.data[0]`, srcnn.py:134
                 main.synchronize()
             else:
                 step_slot(i % 3)
         e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tms = torch.tensor([ms], device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = tms.item()
-        return ms
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
 
-    for i in range(a.warmup):
+    for i in range(warmup):
         step(dev_x[i % 3], dev_t[i % 3])
     if not a.no_graph:
-        capture_graphs()
+        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)), clip_norm=clip)
+        graphs.update(stepper=st, launches=st.launches_per_step)
         for i in range(3):
             step_slot(i)
     l0 = _lib.launch_count()
-    with Clocks(local_rank) as ck:
-        ms = timed(a.steps, e2e=False)
-        launches = graphs["launches"] * a.steps if graphs else _lib.launch_count() - l0
-        ms_e2e = timed(a.steps, e2e=True)
+    with Clocks(ctx.local_rank) as ck:
+        ms = timed(steps, e2e=False)
+        launches = graphs["launches"] * steps if graphs else _lib.launch_count() - l0
+        ms_e2e = timed(steps, e2e=True) if full else None
     clocks = ck.summary()
+    imgs = batch * world * steps
+    res = {"workload": workload, "value": imgs / (ms * 1e-3), "ms_per_step": ms / steps, "clocks": clocks,
+           "gpu_launches": int(launches), "steps": steps,
+           "comm": None if world == 1 else ("captured in the backward graph" if graphs and graphs["stepper"].fused_comm
+                                            else "eager between graphs")}
+    if graphs and getattr(graphs["stepper"], "comm_capture_error", None):
+        res["comm_capture_error"] = graphs["stepper"].comm_capture_error
+    if not full:
+        graphs.clear()
+        bucket.detach()
+        return res
+    res["e2e"] = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
+                  "h2d_bytes_per_step": int(host_x[0].numel() + host_t[0].numel()), "d2h_bytes_per_step": 4,
+                  "ms_per_step": ms_e2e / steps,
+                  "host_format": "uint8 HWC pixels, pinned; ToTensor (x/255, HWC->CHW) runs on the device"}
 
-    # instrumented pass for the roofline of the dominant kernel
+    # ---- instrumented pass: CUDA events around every C-ABI call on the launching stream --------------------------------
+    # The host is slower than the GPU on the small nets, so each instrumented step first parks the GPU on a spin kernel long
+    # enough for the host to enqueue the whole step: the spans then measure kernel execution, not launch latency.
     pk = peaks()
-    # The events bracket each C-ABI call on the launching stream.  The host is slower than the GPU on the small nets, so each
-    # instrumented step first parks the GPU on a spin kernel long enough for the host to enqueue the whole step: the spans then
-    # measure kernel execution, not launch latency.
     t0 = time.perf_counter()
     step(dev_x[0], dev_t[0])
     host_s = time.perf_counter() - t0
     torch.cuda.synchronize()
-    spin_cycles = int(1.5 * min(host_s, 0.02) * (clocks.get("sm_mhz") or 1900) * 1e6) + 200000  # <= 30 ms even under a profiler
+    spin_cycles = int(1.5 * min(host_s, 0.02) * (clocks.get("sm_mhz") or 1900) * 1e6) + 200000
     with KernelTimer(_lib) as kt:
-        barrier()
-        for i in range(min(a.steps, 20)):
+        ctx.barrier()
+        for i in range(min(steps, 20)):
             torch.cuda._sleep(spin_cycles)
             step(dev_x[i % 3], dev_t[i % 3])
         tab = kt.table()
     total_ms = sum(v[0] for v in tab.values())
     (dname, dkey), (dms, dcnt) = max(tab.items(), key=lambda kv: kv[1][0])
+    esize = 2 if a.math == "bf16" else 4
     by, fl = algorithmic(dname, dkey)
+    by = by * esize // 4
     dur_s = dms / dcnt * 1e-3
-    tf32_peak = pk["bf16_sustained"] / 2.0
-    t_hbm, t_tc = by / (pk["hbm_gbs"] * 1e9), fl / (tf32_peak * 1e12)
+    # kernels timed alone behind a spin kernel: the burst peak applies (B200_PROFILING.md)
+    tc_peak = pk["bf16_burst"] if a.math == "bf16" else pk["tf32_burst"]
+    t_hbm, t_tc = by / (pk["hbm_gbs"] * 1e9), fl / (tc_peak * 1e12)
     if t_hbm >= t_tc:
         roof = {"bound": "hbm", "achieved": by / dur_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
     else:
-        roof = {"bound": "tensor", "achieved": fl / dur_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s"}
+        roof = {"bound": "tensor", "achieved": fl / dur_s / 1e12, "peak": tc_peak, "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None  # DRAM read+write bytes of this kernel from the committed `ncu --set full` capture, if it is in there
+    roof["traffic"] = None
+    layer = "N%d Cin%d %dx%d Cout%d k%d s%d p%d ps%d" % dkey[:9]
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        rec = tr.get(dname + "|" + "N%d Cin%d %dx%d Cout%d k%d s%d p%d ps%d" % dkey[:9])
+        rec = tr.get(dname + "|" + layer)
         if rec:
             roof["traffic"] = rec["traffic"]
             roof["traffic_source"] = "profiles/ncu_traffic.json (%s, %.1f us under ncu)" % (rec["kernel"], rec["time_us"])
     except Exception:
         pass
     p_ = _lib.ConvParams(dkey[0], dkey[1], dkey[2], dkey[3], dkey[4], dkey[5], dkey[5], dkey[6], dkey[7], 0, dkey[9],
-                         dkey[8], 0, 0.2, _lib.MATH_AUTO if a.math == "auto" else _lib.MATH_FP32)
-    import ctypes
-    roof.update({"kernel": dname, "layer": "N%d Cin%d %dx%d Cout%d k%d s%d p%d ps%d" % dkey[:9],
+                         dkey[8], 0, 0.2, srb200.functional._state["math"])
+    roof.update({"kernel": dname, "layer": layer,
                  "tensor_path": bool(_lib.lib.srb_conv_uses_tensor_path(
                      ctypes.byref(p_), {"srb_conv_fprop": 0, "srb_conv_dgrad": 1, "srb_conv_wgrad": 2}.get(dname, 0), 1, 1)),
                  "us_per_launch": dur_s * 1e6, "share_of_kernel_time": dms / total_ms,
-                 "peak_source": pk["source"] + (" (tf32 = bf16_sustained/2)" if roof["bound"] == "tensor" else ""),
+                 "peak_source": pk["source"] + ("" if roof["bound"] == "hbm" else
+                                                " burst; " + ("bf16" if a.math == "bf16" else "tf32: " + pk["tf32_source"])),
                  "algorithmic_bytes": by, "algorithmic_flops": fl})
-    kernels = sorted(((n, "N%d Cin%d %dx%d Cout%d k%d s%d p%d ps%d" % k[:9], v[0] / v[1] * 1e3, v[0] / total_ms)
-                      for (n, k), v in tab.items()), key=lambda r: -r[3])
+    res["roofline"] = roof
+    res["kernels"] = [{"call": n, "layer": "N%d Cin%d %dx%d Cout%d k%d s%d p%d ps%d" % k[:9], "us": round(v[0] / v[1] * 1e3, 2),
+                       "share": round(v[0] / total_ms, 4)}
+                      for (n, k), v in sorted(tab.items(), key=lambda kv: -kv[1][0])]
+    graphs.clear()
+    bucket.detach()
+    return res
 
-    imgs = batch * world * a.steps
-    line = {"metric": "SR training images/sec (device-timed)", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if a.math == "auto" else "f32",
-            "data": "synthetic", "config": config, "clocks": clocks,
+
+# ------------------------------------------------------------------------------------------------
+# --impl cudnn: the same nets on stock torch.nn (ATen -> cuDNN), the GPU baseline the north_star names
+# ------------------------------------------------------------------------------------------------
+def reference_net(model_key, margs):
+    """The imported, unmodified reference class when /root/reference is present, else its line-by-line restatement
+    (oracle/torch_ref.py, bit-identical: tests/test_oracle.py::test_oracle_equals_live_reference)."""
+    from oracle import ref_import
+    torch.manual_seed(0)
+    if ref_import.available():
+        mods = ref_import.load()
+        cls = {"srcnn": ("srcnn", "Net"), "espcn": ("espcn", "Net"), "vdsr": ("vdsr", "Net"), "edsr": ("edsr", "Net")}[model_key]
+        net = getattr(mods[cls[0]], cls[1])(*margs)
+        net.weight_init()
+        return net, "reference classes (/root/reference)"
+    from oracle import torch_ref as R
+    return R.build(model_key, margs, seed=0), "restated reference nets (oracle/torch_ref.py)"
+
+
+def measure_cudnn(ctx, a, workload, variant, steps, warmup):
+    import torch.nn.functional as TF
+    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[workload]
+    dev, world = ctx.dev, ctx.world
+    torch.backends.cudnn.benchmark = variant != "as-is"
+    net, src = reference_net(model_key, margs)
+    net = net.to(dev).train()
+    cl = "cl" in variant
+    gen = torch.Generator().manual_seed(1 + ctx.rank)
+    oshape = out_shape(model_key, margs, batch, h, w)
+    host_x = [torch.rand((batch, 3, h, w), generator=gen).pin_memory() for _ in range(3)]
+    host_t = [torch.rand(oshape, generator=gen).pin_memory() for _ in range(3)]
+    x = [t.to(dev) for t in host_x]
+    t = [v.to(dev) for v in host_t]
+    if cl:
+        net = net.to(memory_format=torch.channels_last)
+        x = [v.contiguous(memory_format=torch.channels_last) for v in x]
+    graph = variant.endswith("-graph") and world == 1
+    fused = {"fused": variant != "as-is"}
+    if opt_key in ("espcn", "edsr"):
+        opt = torch.optim.Adam(net.parameters(), lr=1e-5, capturable=graph, **fused)
+    elif opt_key == "vdsr":
+        opt = torch.optim.SGD(net.parameters(), lr=1e-5, momentum=0.9, weight_decay=1e-4, **fused)
+    else:
+        opt = torch.optim.SGD(net.parameters(), lr=1e-5, **fused)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[ctx.local_rank])
+    lf = TF.l1_loss if loss_kind == "l1" else TF.mse_loss
+    bf16 = "bf16" in variant
+
+    def fwd_loss(xi, ti):
+        if bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return lf(model(xi).float(), ti)
+        return lf(model(xi), ti)
+
+    def step(i, set_none=True):
+        opt.zero_grad(set_to_none=set_none)
+        loss = fwd_loss(x[i % 3], t[i % 3])
+        loss.backward()
+        if opt_key == "vdsr":
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 0.4)
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    losses = [None] * 3
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        pool = torch.cuda.graph_pool_handle()
+        gs = []
+        with torch.cuda.stream(side):
+            for i in range(3):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    losses[i] = step(i, set_none=False).detach()
+                gs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        def run(i):
+            gs[i % 3].replay()
+            return losses[i % 3]
+        for i in range(3):
+            run(i)
+    else:
+        def run(i):
+            return step(i)
+    loss_host = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(i):
+        s = i % 3
+        with torch.cuda.stream(copy_stream):
+            x[s].copy_(host_x[s], non_blocking=True)
+            t[s].copy_(host_t[s], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def timed(n, e2e):
+        ctx.barrier()
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if e2e:
+            copy_stream.wait_event(e0)
+            nxt = prefetch(0)
+        for i in range(n):
+            if e2e:
+                ev = nxt
+                if i + 1 < n:
+                    nxt = prefetch(i + 1)
+                main.wait_event(ev)
+                loss = run(i)
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+                main.synchronize()
+            else:
+                run(i)
+        e1.record()
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
+
+    with Clocks(ctx.local_rank) as ck:
+        ms = timed(steps, False)
+        ms_e2e = timed(steps, True)
+    imgs = batch * world * steps
+    return {"variant": variant, "value": imgs / (ms * 1e-3), "ms_per_step": ms / steps,
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": int(host_x[0].numel() + host_t[0].numel()) * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": int(launches), "roofline": roof,
-            "kernels": [{"call": n, "layer": l, "us": round(us, 2), "share": round(sh, 4)} for n, l, us, sh in kernels]}
+                    "ms_per_step": ms_e2e / steps, "host_format": "fp32 CHW tensors, pinned (ToTensor on the host, as dataset.py:90)"},
+            "clocks": ck.summary(), "net_source": src, "allow_tf32": torch.backends.cudnn.allow_tf32,
+            "cudnn": torch.backends.cudnn.version()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="srb200", choices=["srb200", "reference", "cudnn"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default="auto", choices=["auto", "fp32", "exact", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
+    ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    ctx = Ctx()
+    rank, world = ctx.rank, ctx.world
+    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[a.workload]
+    config = make_config(a.workload, world, a.no_graph, a.math)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(a.workload, a.steps, a.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s",
+                "n_gpus": a.gpus, "steps": r["steps"], "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    ctx.init_cuda()
+    if a.impl == "cudnn":
+        variants = (a.variants.split(",") if a.variants else
+                    ["as-is", "tuned-cl-graph"] + (["tuned-cl-bf16-graph"] if a.workload.startswith("edsr256") else []))
+        runs = []
+        for v in variants:
+            try:
+                runs.append(measure_cudnn(ctx, a, a.workload, v, a.steps, a.warmup))
+            except Exception as e:  # report, keep going
+                runs.append({"variant": v, "error": repr(e)[:300]})
+        ok = [r for r in runs if "value" in r]
+        best = max(ok, key=lambda r: r["value"])
+        config.update({"launch": "stock torch.nn eager / cuda-graph per variant", "math": "cudnn (allow_tf32=%s)" % best["allow_tf32"]})
+        line = {"impl": "cudnn", "metric": METRIC, "value": best["value"], "unit": "images/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if "bf16" in best["variant"] else "tf32",
+                "data": "synthetic", "config": config, "clocks": best["clocks"], "e2e": best["e2e"], "gpu_launches": 0,
+                "best_variant": best["variant"], "variants": runs}
+        if rank == 0:
+            print(json.dumps(line))
+            sys.stdout.flush()
+        finish(ctx)
+        return 0
+
+    res = measure_srb(ctx, a, a.workload, a.steps, a.warmup, full=True)
+    line = {"metric": METRIC, "value": res["value"], "unit": "images/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"auto": "tf32", "fp32": "f32", "exact": "3xtf32", "bf16": "bf16"}[a.math],
+            "data": "synthetic", "config": config, "clocks": res["clocks"], "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "kernels": res["kernels"]}
+    if res.get("comm"):
+        line["comm"] = res["comm"]
+    if res.get("comm_capture_error"):
+        line["comm_capture_error"] = res["comm_capture_error"]
+    if a.workload == DEFAULT_WORKLOAD and not a.no_sub and a.math == "auto":
+        # BASELINE.json names VDSR cfg3 for the 1->8 GPU curve: a short device-timed sub-result rides along in the same line
+        try:
+            sub = measure_srb(ctx, a, "vdsr_b64_128", 12, 3, full=False)
+            line["sub_results"] = [{"workload": sub["workload"], "value": sub["value"], "unit": "images/s",
+                                    "ms_per_step": sub["ms_per_step"], "steps": sub["steps"], "n_gpus": world,
+                                    "comm": sub.get("comm"), "clocks": sub["clocks"]}]
+        except Exception as e:
+            line["sub_results"] = [{"workload": "vdsr_b64_128", "error": repr(e)[:300]}]
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             r = cpu_reference_run(a.workload, 1000, 1, budget_s=15.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
         sys.stdout.flush()
-    if world > 1:
+    finish(ctx)
+    return 0
+
+
+def finish(ctx):
+    if ctx.dist is not None:
         # Teardown order matters: CUDA graphs that captured NCCL kernels must be gone before the communicator is, and a
         # communicator abort can block in this torch/NCCL build.  All ranks rendezvous, then leave without running the
         # interpreter's (and NCCL's) destructors -- every result has been printed and flushed by now.
-        graphs.clear()
         torch.cuda.synchronize()
-        dist.barrier()
+        ctx.dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
-    return 0
 
 
 if __name__ == "__main__":

@@ -261,6 +261,20 @@ __global__ void k_pack_dz4(T4 dz, float4 *__restrict__ out, int N, int C, int H,
   }
 }
 
+// torchvision ToTensor (dataset.py:90,94,98 of the reference): uint8 HWC image in [0,255] -> float CHW in [0,1]
+__global__ void k_image_to_tensor(const unsigned char *__restrict__ src, float *__restrict__ dst, int N, int H, int W, int C,
+                                  float scale) {
+  const long long total = (long long)N * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long q = i / W;
+    const int h = (int)(q % H); q /= H;
+    const int c = (int)(q % C);
+    const long long n = q / C;
+    dst[i] = (float)__ldg(src + ((n * H + h) * W + w) * C + c) * scale;
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -659,6 +673,16 @@ int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const floa
   SRB_REQUIRE(((((uintptr_t)y) | ((uintptr_t)t) | ((uintptr_t)dy)) & 15) == 0, SRB_EUNSUPPORTED,
               "loss tensors must be 16-byte aligned");
   k_loss_bwd<<<ew_blocks((n >> 2) > 0 ? (n >> 2) : 1), 256, 0, (cudaStream_t)stream>>>(y, t, n, kind, 1.0f / (float)n, grad_loss, dy);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int32_t H, int32_t W, int32_t C, float scale,
+                        void *stream) {
+  SRB_REQUIRE(src_nhwc && dst_nchw && N >= 0 && H > 0 && W > 0 && C > 0, SRB_EINVAL, "bad image_to_tensor args");
+  if (N == 0) return SRB_OK;
+  k_image_to_tensor<<<ew_blocks((long long)N * C * H * W), 256, 0, (cudaStream_t)stream>>>(src_nhwc, dst_nchw, N, H, W, C, scale);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

@@ -48,6 +48,8 @@ SYMBOLS = {
     "srb_pixel_unshuffle": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp]),
     "srb_prelu_fwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_prelu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
+    "srb_image_to_tensor": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_float, _vp]),
     "srb_round_tf32": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "srb_loss_workspace_bytes": (ctypes.c_size_t, []),
     "srb_loss_fwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_size_t, _vp]),

@@ -394,3 +394,17 @@ def mse_loss(y, t):
 def l1_loss(y, t):
     """nn.L1Loss() (mean) (edsr.py:98)."""
     return _Loss.apply(y, t, 1)
+
+
+def image_to_tensor(img_u8, out=None):
+    """torchvision ToTensor on the device (dataset.py:90): uint8 (N,H,W,C) image batch in [0,255] -> fp32 (N,C,H,W) in [0,1].
+    The host ships 1-byte pixels; `out` (a resident fp32 NCHW buffer, e.g. a CUDA-graph input slot) is filled in place."""
+    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4:
+        raise RuntimeError("image_to_tensor needs a CUDA uint8 (N,H,W,C) tensor")
+    img_u8 = img_u8.contiguous()
+    n, h, w, c = img_u8.shape
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=img_u8.device)
+    assert out.is_contiguous() and tuple(out.shape) == (n, c, h, w) and out.dtype == torch.float32
+    check(lib.srb_image_to_tensor(_ptr(img_u8), _ptr(out), n, h, w, c, ctypes.c_float(1.0 / 255.0), _stream(img_u8.device)))
+    return out

@@ -4,15 +4,15 @@
 #   parts: any of  tests smoke bench bench_more ref cudnn launches full   (default: all)
 set -u
 TAG=${1:-r1}
-PARTS=${2:-"tests smoke bench bench_more ref cudnn launches full"}
+PARTS=${2:-"tests smoke bench bench_more ref cudnn peak launches full"}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 has() { [[ " $PARTS " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
 
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
-  echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log"
+  timeout 1800 python -m pytest tests -m gpu -q -s ${PYTEST_ARGS:-} > "$OUT/pytest_gpu.log" 2>&1
+  echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; grep -E "math=|FAILED|passed|failed|Error" "$OUT/pytest_gpu.log" | tail -40
 fi
 if has smoke; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
@@ -33,8 +33,23 @@ if has ref; then
   cat "$OUT/bench_reference.json"
 fi
 if has cudnn; then
-  timeout 600 python tools/cudnn_baseline.py > "$OUT/cudnn_baseline.jsonl" 2> "$OUT/cudnn_baseline.err"
-  cat "$OUT/cudnn_baseline.jsonl"
+  for wl in ${CUDNN_WL:-espcn_x4_b128_lr64 vdsr_b64_128 edsr256_x4_b32_lr32}; do
+    timeout 600 python bench.py --impl cudnn --workload $wl --steps 30 --warmup 5 > "$OUT/bench_cudnn_$wl.json" 2> "$OUT/bench_cudnn_$wl.err"
+    echo "cudnn $wl exit $?"; cut -c1-400 "$OUT/bench_cudnn_$wl.json"
+  done
+fi
+if has peak; then
+  TF32_PEAK_OUT="$OUT/tf32_peak.json" timeout 120 python tools/measure_tf32_peak.py 2> "$OUT/tf32_peak.err"
+fi
+if has sanitize; then
+  # mbarrier / TMEM hand-shake protocols under racecheck + synccheck: a slice of the op sweep
+  SEL=${SAN_K:-"(test_fused_conv_vs_oracle and auto and True) or test_exact_mode_op"}
+  timeout 420 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests -m gpu -x -q -k "$SEL" > "$OUT/sanitizer_racecheck.log" 2>&1
+  echo "racecheck exit $?" >> "$OUT/sanitizer_racecheck.log"; tail -4 "$OUT/sanitizer_racecheck.log"
+  timeout 420 compute-sanitizer --tool synccheck --print-limit 20 python -m pytest tests -m gpu -x -q -k "$SEL" > "$OUT/sanitizer_synccheck.log" 2>&1
+  echo "synccheck exit $?" >> "$OUT/sanitizer_synccheck.log"; tail -4 "$OUT/sanitizer_synccheck.log"
+  timeout 420 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests -m gpu -x -q -k "$SEL" > "$OUT/sanitizer_memcheck.log" 2>&1
+  echo "memcheck exit $?" >> "$OUT/sanitizer_memcheck.log"; tail -4 "$OUT/sanitizer_memcheck.log"
 fi
 if has launches; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
