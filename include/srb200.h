@@ -49,16 +49,23 @@ typedef enum srb_math {
   SRB_MATH_FP32 = 0, /* CUDA-core fp32 FMA, fp32 accumulate (exact-order independent reference quality) */
   SRB_MATH_TF32 = 1, /* tcgen05 kind::tf32, operands RN-rounded to tf32, fp32 accumulate in TMEM */
   SRB_MATH_AUTO = 2, /* TF32 tensor path when the layer qualifies, FP32 otherwise */
+  SRB_MATH_BF16 = 4, /* bf16 STORAGE: activations and activation gradients are bf16 NHWC tensors, operands feed
+                        tcgen05 kind::f16 (bf16 x bf16 -> fp32 in TMEM), parameters / parameter gradients / biases stay fp32
+                        (weights are converted while being packed).  3-channel network edges stay fp32 and run TF32.
+                        BASELINE cfg4 (EDSR 256x32 "bf16"); parity contract: the reference under torch.autocast(bfloat16). */
   SRB_MATH_EXACT = 3 /* fp32-accurate on the tensor cores: operands split hi+lo into tf32 pairs, three partial products
                         (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) accumulated in fp32 ("3xTF32"); activations stay full fp32.
                         Layers the tensor path cannot run fall to the FP32 CUDA-core kernels.  For the 1e-3 end-to-end
                         contract at the BASELINE depths (VDSR-20, EDSR-256x32), where single-pass TF32 reaches ~1.5e-3. */
 } srb_math;
 
-/* Logical NCHW view with element strides (like torch.Tensor.stride()). */
+typedef enum srb_dtype { SRB_F32 = 0, SRB_BF16 = 1 } srb_dtype;
+
+/* Logical NCHW view with element strides (like torch.Tensor.stride()); dtype = srb_dtype of the elements. */
 typedef struct srb_tensor4 {
   void *data;
   int64_t sn, sc, sh, sw;
+  int32_t dtype;
 } srb_tensor4;
 
 /*

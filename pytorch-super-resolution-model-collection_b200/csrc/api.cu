@@ -275,6 +275,95 @@ __global__ void k_image_to_tensor(const unsigned char *__restrict__ src, float *
   }
 }
 
+// ---- bf16 storage mode helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float h2f(unsigned short h) { return __uint_as_float((uint32_t)h << 16); }
+__device__ __forceinline__ unsigned short f2h(float v) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+  return (unsigned short)(r & 0xffffu);
+}
+
+// dz = dy * act'(ref) over n contiguous bf16 elements (same dense layout on all three); PReLU: dalpha += sum(dy*z*[z<=0])
+__global__ void k_act_bwd_flat_h(const unsigned short *__restrict__ dy, const unsigned short *__restrict__ ref,
+                                 unsigned short *dz, long long n, int act, float slope_in, const float *__restrict__ alpha,
+                                 float *dalpha) {
+  const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : (act == SRB_ACT_RELU ? 0.f : slope_in);
+  float da = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = h2f(__ldg(dy + i)), r = h2f(__ldg(ref + i));
+    dz[i] = f2h(r > 0.f ? g : g * slope);
+    if (act == SRB_ACT_PRELU && !(r > 0.f)) da += g * r;
+  }
+  if (act == SRB_ACT_PRELU && dalpha) {
+    for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    __shared__ float red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      da = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+      if (threadIdx.x == 0) atomicAdd(dalpha, da);
+    }
+  }
+}
+
+// pixel_unshuffle, bf16 NHWC -> bf16 NHWC: out[n,h,w,k = c*r*r + i*r + j] = dz[n, h*r+i, w*r+j, c]; one thread per
+// (pixel, sub-pixel, 8-channel group): one 16-byte load, eight 2-byte stores
+__global__ void k_pixel_unshuffle_h(T4 dz, T4 out, int N, int C, int H, int W, int r) {
+  const int rr = r * r, cg = C >> 3;
+  const long long total = (long long)N * H * W * rr * cg;
+  const unsigned short *src = (const unsigned short *)dz.p;
+  unsigned short *dst = (unsigned short *)out.p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g8 = (int)(i % cg);
+    long long q = i / cg;
+    const int ij = (int)(q % rr); q /= rr;
+    const int w = (int)(q % W); q /= W;
+    const int h = (int)(q % H);
+    const int n = (int)(q / H);
+    const int ii = ij / r, jj = ij - ii * r;
+    const uint4 v = __ldg((const uint4 *)(src + n * dz.sn + (long long)(h * r + ii) * dz.sh + (long long)(w * r + jj) * dz.sw + g8 * 8));
+    unsigned short *o = dst + n * out.sn + (long long)h * out.sh + (long long)w * out.sw + (long long)(g8 * 8) * rr + ij;
+    o[0 * rr] = (unsigned short)(v.x & 0xffffu); o[1 * rr] = (unsigned short)(v.x >> 16);
+    o[2 * rr] = (unsigned short)(v.y & 0xffffu); o[3 * rr] = (unsigned short)(v.y >> 16);
+    o[4 * rr] = (unsigned short)(v.z & 0xffffu); o[5 * rr] = (unsigned short)(v.z >> 16);
+    o[6 * rr] = (unsigned short)(v.w & 0xffffu); o[7 * rr] = (unsigned short)(v.w >> 16);
+  }
+}
+
+// bf16 NHWC (N,C,H,W logical) -> dense fp32 NHWC (tf32-representable by construction: bf16 has 8 mantissa bits)
+__global__ void k_h2f_nhwc(T4 x, float *__restrict__ out, int N, int C, int H, int W) {
+  const long long total = (long long)N * H * W * C;
+  const unsigned short *src = (const unsigned short *)x.p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long q = i / C;
+    const int w = (int)(q % W); q /= W;
+    const int h = (int)(q % H);
+    const int n = (int)(q / H);
+    out[i] = h2f(__ldg(src + n * x.sn + c * x.sc + (long long)h * x.sh + (long long)w * x.sw));
+  }
+}
+
+// dz (N, C<=8, H, W; fp32, any strides) -> bf16 NHWC8 (16 B per pixel, missing channels zero)
+__global__ void k_pack_dz8_h(T4 dz, uint4 *__restrict__ out, int N, int C, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long q = i / W;
+    const int h = (int)(q % H);
+    const int n = (int)(q / H);
+    const float *p = dz.p + n * dz.sn + (long long)h * dz.sh + (long long)w * dz.sw;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? __ldg(p + c * dz.sc) : 0.f;
+    uint4 o;
+    o.x = (uint32_t)f2h(v[0]) | ((uint32_t)f2h(v[1]) << 16); o.y = (uint32_t)f2h(v[2]) | ((uint32_t)f2h(v[3]) << 16);
+    o.z = (uint32_t)f2h(v[4]) | ((uint32_t)f2h(v[5]) << 16); o.w = (uint32_t)f2h(v[6]) | ((uint32_t)f2h(v[7]) << 16);
+    out[i] = o;
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -289,7 +378,7 @@ int check_params(const srb_conv_params *p) {
               "bad kernel/stride/pad");
   SRB_REQUIRE(p->ps >= 1, SRB_EINVAL, "ps must be >= 1");
   SRB_REQUIRE(p->act >= SRB_ACT_NONE && p->act <= SRB_ACT_LRELU, SRB_EINVAL, "bad activation %d", p->act);
-  SRB_REQUIRE(p->math >= SRB_MATH_FP32 && p->math <= SRB_MATH_EXACT, SRB_EINVAL, "bad math mode %d", p->math);
+  SRB_REQUIRE(p->math >= SRB_MATH_FP32 && p->math <= SRB_MATH_BF16, SRB_EINVAL, "bad math mode %d", p->math);
   SRB_REQUIRE(!(p->transposed && p->ps != 1), SRB_EUNSUPPORTED, "PixelShuffle fused with ConvTranspose2d");
   SRB_REQUIRE(p->transposed || p->out_pad == 0, SRB_EINVAL, "out_pad only for transposed");
   SRB_REQUIRE(!p->transposed || p->out_pad < p->stride, SRB_EINVAL, "out_pad must be < stride");
@@ -336,6 +425,11 @@ inline bool is_cl(const T4 &t, int C) { return t.sc == 1 && t.sw == C; }
 
 // single-pass tf32 operands (activations are stored tf32-rounded between layers)?  EXACT keeps full fp32 activations.
 inline bool is_tf32_math(int math) { return math == SRB_MATH_TF32 || math == SRB_MATH_AUTO; }
+
+// bf16 storage mode: an activation with C channels is a bf16 tensor iff its pixel rows are 16-byte multiples (C % 8 == 0);
+// the 3-channel network edges stay fp32
+inline int bf16_act_dtype(int C) { return (C % 8 == 0 && C >= 8) ? SRB_BF16 : SRB_F32; }
+inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Does the *written* tensor feed tensor-core consumers?  (channels_last, C % 4 == 0, C >= 8)
 inline int want_round(const srb_conv_params *p, const T4 &t, int C) {
@@ -392,7 +486,20 @@ int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int 
   int Cy = p->Cout, Hy = g.Ho * g.ps, Wy = g.Wo * g.ps;
   if (y_cl) { y.sc = 1; y.sw = Cy; y.sh = (long long)Wy * Cy; y.sn = y.sh * Hy; }
   else      { y.sw = 1; y.sh = Wy; y.sc = (long long)Hy * Wy; y.sn = y.sc * Cy; }
-  x.p = y.p = (float *)16;
+  x.p = y.p = (float *)32;
+  if (p->math == SRB_MATH_BF16) {
+    x.dt = bf16_act_dtype(g.Ci);
+    y.dt = bf16_act_dtype(Cy);
+    if (pass == 0) return tc_conv_supported(g, x, y, false) ? 1 : 0;
+    T4 ysmall = y;  // dz in conv-output geometry (after the un-shuffle when ps > 1)
+    ysmall.dt = bf16_act_dtype(g.Co);
+    if (pass == 1) {
+      if (g.ps != 1 || g.st != 1 || g.kh != g.kw) return 0;
+      Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+      return (gd.pad >= 0 && tc_conv_supported(gd, ysmall, x, true)) ? 1 : 0;
+    }
+    return 1;  // wgrad: always a tensor-core plan in this mode (mixed edges are converted first)
+  }
   const bool exact = p->math == SRB_MATH_EXACT;
   if (pass == 0) return (exact ? exact_conv_supported(g, y) : tc_conv_supported(g, x, y, false)) ? 1 : 0;
   if (pass == 1) {
@@ -416,6 +523,14 @@ int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t
   if (rc) return rc;
   if (p->transposed || p->math == SRB_MATH_FP32) { snprintf(buf, n, "fp32 CUDA-core kernels"); return SRB_OK; }
   if (p->math == SRB_MATH_EXACT && pass != 2) g.Ci = (3 * g.Ci + 3) / 4 * 4;  // the channel-tripled launch (exact.cu)
+  if (p->math == SRB_MATH_BF16) {
+    if (pass == 0) tc_conv_describe(g, buf, n, g.Ci > 4);
+    else if (pass == 1) {
+      Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+      tc_conv_describe(gd, buf, n, gd.Ci > 4);
+    } else tc_wgrad_describe(g, buf, n, g.Ci > 4 && g.Co >= 8);
+    return SRB_OK;
+  }
   if (pass == 0) tc_conv_describe(g, buf, n);
   else if (pass == 1) {
     Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
@@ -436,6 +551,14 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
     if (skinny_wgrad_plan(p, g, cl, &sk) && sk.total > b) b = sk.total;
   } else {
     b = tc_conv_ws_bytes(g);
+  }
+  if (p->math == SRB_MATH_BF16 && !p->transposed && g.st == 1 && pass == 2) {
+    // bf16 wgrad + the two mixed-edge conversions (dz -> fp32 NHWC for Cin <= 4; dz -> bf16 NHWC8 for Cout < 8)
+    Geom g8 = g;
+    g8.Co = g.Co < 8 ? 8 : g.Co;
+    size_t c = tc_wgrad_ws_bytes(g8, true) + a256((size_t)g.N * g.Ho * g.Wo * 8 * 2) + a256((size_t)8 * g.Ci * g.kh * g.kw * 4 + 64) +
+               (g.Ci <= 4 ? a256((size_t)g.N * g.Ho * g.Wo * g.Co * 4) + tc_wgrad_ws_bytes(g, false) : 0) + 2048;
+    if (c > b) b = c;
   }
   if (p->math == SRB_MATH_EXACT && !p->transposed && g.st == 1) {
     size_t c = 0;
@@ -461,6 +584,16 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
   T4 tx = to_t4(x), ty = to_t4(y);
+  if (p->math == SRB_MATH_BF16) {
+    SRB_REQUIRE(!p->transposed && g.st == 1, SRB_EUNSUPPORTED, "bf16 storage mode: strided / transposed convolutions are not built");
+    Epi e = make_epi(p, bias, alpha, residual, preact, 0);
+    e.bits_out = relu_bits;
+    SRB_REQUIRE(tc_conv_supported(g, tx, ty, false), SRB_EUNSUPPORTED,
+                "bf16 storage mode: x must be a bf16 channels_last tensor with Cin %% 8 == 0 (or fp32 with Cin <= 4)");
+    SRB_REQUIRE(!relu_bits || (p->ps == 1 && (p->Cout & 15) == 0), SRB_EUNSUPPORTED, "relu_bits needs no PixelShuffle and Cout %% 16 == 0");
+    return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
+  }
+  SRB_REQUIRE(tx.dt == SRB_F32 && ty.dt == SRB_F32, SRB_EUNSUPPORTED, "bf16 tensors need math = SRB_MATH_BF16");
   if (!p->transposed) {
     Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
     e.bits_out = relu_bits;
@@ -492,6 +625,18 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
   T4 tdz = to_t4(dz);
   long long total = (long long)p->N * C * H * W;
   if (total == 0) return SRB_OK;
+  if (tdz.dt == SRB_BF16) {
+    T4 a = to_t4(dy), b = to_t4(ref);
+    auto same = [&](const T4 &t) { return t.dt == SRB_BF16 && t.sn == tdz.sn && t.sc == tdz.sc && t.sh == tdz.sh && t.sw == tdz.sw; };
+    const bool nhwc = tdz.sc == 1 && tdz.sw == C && tdz.sh == (long long)W * C && tdz.sn == (long long)H * W * C;
+    const bool nchw = tdz.sw == 1 && tdz.sh == W && tdz.sc == (long long)H * W && tdz.sn == (long long)C * H * W;
+    SRB_REQUIRE(same(a) && same(b) && (nhwc || nchw), SRB_EUNSUPPORTED, "bf16 act_bwd needs dy, ref, dz in one dense layout");
+    k_act_bwd_flat_h<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const unsigned short *)a.p, (const unsigned short *)b.p,
+                                                                         (unsigned short *)tdz.p, total, p->act, p->slope, alpha, dalpha);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    return SRB_OK;
+  }
   {
     T4 a = to_t4(dy), b = to_t4(ref);
     auto dense = [&](const T4 &t) {
@@ -535,6 +680,18 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   e.bits_out = nullptr;
   e.bits_in = relu_bits;
   e.round_tf32 = want_round(p, tdx, p->Cin);
+  if (p->math == SRB_MATH_BF16) {
+    SRB_REQUIRE(!p->transposed && g.st == 1 && g.ps == 1 && g.kh == g.kw, SRB_EUNSUPPORTED,
+                "bf16 storage mode: dgrad needs a stride-1 square-kernel Conv2d (PixelShuffle layers: un-shuffle dz first)");
+    Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+    SRB_REQUIRE(gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true), SRB_EUNSUPPORTED,
+                "bf16 storage mode: dz must be bf16 channels_last with Cout %% 8 == 0 (or fp32 with Cout <= 4)");
+    SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
+    SRB_REQUIRE(!e.mask.p, SRB_EUNSUPPORTED, "bf16 storage mode: pass relu_bits, not relu_mask");
+    e.round_tf32 = 0;
+    return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
+  }
+  SRB_REQUIRE(tdz.dt == SRB_F32 && tdx.dt == SRB_F32, SRB_EUNSUPPORTED, "bf16 tensors need math = SRB_MATH_BF16");
   if (!p->transposed) {
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
       // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
@@ -574,6 +731,52 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   }
   SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
   T4 tx = to_t4(x), tdz = to_t4(dz);
+  if (p->math == SRB_MATH_BF16) {
+    SRB_REQUIRE(!p->transposed && g.st == 1 && g.ps == 1, SRB_EUNSUPPORTED,
+                "bf16 storage mode: wgrad needs a stride-1 Conv2d (PixelShuffle layers: un-shuffle dz first)");
+    uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+    const uintptr_t ws_end = (uintptr_t)ws + ws_bytes;
+    if (tx.dt == SRB_BF16 && tdz.dt == SRB_BF16) {
+      SRB_REQUIRE(tc_wgrad_supported(g, tdz, tx), SRB_EUNSUPPORTED, "bf16 wgrad: no plan for this layer");
+      return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    }
+    if (tx.dt == SRB_F32 && tdz.dt == SRB_BF16) {
+      // network input layer (Cin <= 4): dz -> fp32 NHWC (exactly representable in tf32), then the tf32 c4 wgrad
+      SRB_REQUIRE(g.Ci <= 4, SRB_EUNSUPPORTED, "bf16 storage mode: fp32 x with Cin > 4");
+      const size_t zb = a256((size_t)g.N * g.Ho * g.Wo * g.Co * sizeof(float));
+      SRB_REQUIRE(ws && wsp + zb <= ws_end, SRB_EWORKSPACE, "bf16 wgrad workspace too small");
+      float *z32 = (float *)wsp;
+      k_h2f_nhwc<<<ew_blocks((long long)g.N * g.Ho * g.Wo * g.Co), 256, 0, st>>>(tdz, z32, g.N, g.Co, g.Ho, g.Wo);
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+      T4 tz32{z32, (long long)g.Ho * g.Wo * g.Co, 1, (long long)g.Wo * g.Co, g.Co, SRB_F32};
+      SRB_REQUIRE(tc_wgrad_supported(g, tz32, tx), SRB_EUNSUPPORTED, "bf16 storage mode: no tf32 plan for the input layer's wgrad");
+      return tc_conv_wgrad(g, tz32, tx, dw, db, scale, accumulate, (void *)(wsp + zb), (size_t)(ws_end - (wsp + zb)), st);
+    }
+    if (tx.dt == SRB_BF16 && tdz.dt == SRB_F32) {
+      // network output layer (Cout < 8): dz -> bf16 NHWC8, wgrad for 8 output channels, keep the first Cout filters
+      SRB_REQUIRE(g.Co < 8 && !accumulate, SRB_EUNSUPPORTED, "bf16 storage mode: fp32 dz needs Cout < 8 and accumulate == 0");
+      Geom g8 = g;
+      g8.Co = 8;
+      const size_t pb = a256((size_t)g.N * g.Ho * g.Wo * 8 * 2), db8 = a256((size_t)8 * g.Ci * g.kh * g.kw * 4 + 64);
+      SRB_REQUIRE(ws && wsp + pb + db8 <= ws_end, SRB_EWORKSPACE, "bf16 wgrad workspace too small");
+      unsigned short *pack = (unsigned short *)wsp;
+      float *dw8 = (float *)(wsp + pb);
+      float *dbias8 = dw8 + (size_t)8 * g.Ci * g.kh * g.kw;
+      k_pack_dz8_h<<<ew_blocks((long long)g.N * g.Ho * g.Wo), 256, 0, st>>>(tdz, (uint4 *)pack, g.N, g.Co, g.Ho, g.Wo);
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+      T4 tz8{(float *)pack, (long long)g.Ho * g.Wo * 8, 1, (long long)g.Wo * 8, 8, SRB_BF16};
+      SRB_REQUIRE(tc_wgrad_supported(g8, tz8, tx), SRB_EUNSUPPORTED, "bf16 storage mode: no plan for the output layer's wgrad");
+      rc = tc_conv_wgrad(g8, tz8, tx, dw8, db ? dbias8 : nullptr, scale, 0, (void *)(wsp + pb + db8), (size_t)(ws_end - (wsp + pb + db8)), st);
+      if (rc) return rc;
+      SRB_CHECK_CUDA(cudaMemcpyAsync(dw, dw8, (size_t)g.Co * g.Ci * g.kh * g.kw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (db) SRB_CHECK_CUDA(cudaMemcpyAsync(db, dbias8, (size_t)g.Co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return SRB_OK;
+    }
+    SRB_REQUIRE(false, SRB_EUNSUPPORTED, "bf16 storage mode: fp32 x and fp32 dz (use math = auto)");
+  }
+  SRB_REQUIRE(tx.dt == SRB_F32 && tdz.dt == SRB_F32, SRB_EUNSUPPORTED, "bf16 tensors need math = SRB_MATH_BF16");
   if (!p->transposed) {
     if (p->math == SRB_MATH_EXACT && exact_wgrad_supported(g))
       return exact_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
@@ -616,6 +819,16 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
   if (p->N == 0) return SRB_OK;
   SRB_REQUIRE(dz && dz->data && out && out->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(out->sc == 1, SRB_EINVAL, "pixel_unshuffle writes channels_last");
+  if (dz->dtype == SRB_BF16 || out->dtype == SRB_BF16) {
+    SRB_REQUIRE(dz->dtype == SRB_BF16 && out->dtype == SRB_BF16 && dz->sc == 1 && (p->Cout % 8) == 0 &&
+                    (dz->sw % 8) == 0 && (dz->sh % 8) == 0 && (dz->sn % 8) == 0 && (((uintptr_t)dz->data) & 15) == 0,
+                SRB_EUNSUPPORTED, "bf16 pixel_unshuffle: both tensors bf16 channels_last, C %% 8 == 0");
+    const long long tot = (long long)g.N * g.Ho * g.Wo * g.ps * g.ps * (p->Cout / 8);
+    k_pixel_unshuffle_h<<<ew_blocks(tot), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, p->Cout, g.Ho, g.Wo, g.ps);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+    return SRB_OK;
+  }
   long long total = (long long)g.N * g.Ho * g.Wo * g.Co;
   const int rnd = is_tf32_math(p->math) ? 1 : 0;  // EXACT / FP32 keep the full fp32 gradient
   const size_t row_smem = (size_t)p->Cout * g.ps * ((size_t)g.Wo * g.ps + 4) * sizeof(float);

@@ -29,17 +29,20 @@ void count_launch(int n = 1);
     }                                 \
   } while (0)
 
-// Device-side strided NCHW view.
+// Device-side strided NCHW view.  Strides are in ELEMENTS; `dt` is the element type (SRB_F32: p is what it says;
+// SRB_BF16: p really points at __nv_bfloat16 data -- only the kernels that declare bf16 support look at dt).
 struct T4 {
   float *p;
   long long sn, sc, sh, sw;
+  int dt;
 };
 static inline T4 to_t4(const srb_tensor4 *t) {
   T4 r;
-  if (t) { r.p = (float *)t->data; r.sn = t->sn; r.sc = t->sc; r.sh = t->sh; r.sw = t->sw; }
-  else   { r.p = nullptr; r.sn = r.sc = r.sh = r.sw = 0; }
+  if (t) { r.p = (float *)t->data; r.sn = t->sn; r.sc = t->sc; r.sh = t->sh; r.sw = t->sw; r.dt = t->dtype; }
+  else   { r.p = nullptr; r.sn = r.sc = r.sh = r.sw = 0; r.dt = SRB_F32; }
   return r;
 }
+static inline bool is_bf16(const T4 &t) { return t.p != nullptr && t.dt == SRB_BF16; }
 
 // Geometry of one "gather" convolution:  small[n,co,oy,ox] <-> big[n,ci,oy*st-pad+r,ox*st-pad+s].
 //   Conv2d:           big = x (Ci=Cin, Hi=H, Wi=W),  small = conv output (Co=Cout*ps*ps, Ho, Wo)
@@ -109,10 +112,10 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
 int tc_conv_get_dbg();
-int tc_conv_describe(const Geom &g, char *buf, size_t n);
-int tc_wgrad_describe(const Geom &g, char *buf, size_t n);
+int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
+int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);
-size_t tc_wgrad_ws_bytes(const Geom &g);
+size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16 = false);
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
 

@@ -62,6 +62,38 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, ui
       : "memory");
 }
 
+// bf16 x bf16 -> fp32 (kind::f16): M=128, K=16 per instruction
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// two floats -> packed bf16x2 (lo at the lower address), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float ld_bf16(const void *p) {
+  return __uint_as_float((uint32_t)__ldg((const unsigned short *)p) << 16);
+}
+__device__ __forceinline__ void st_bf16(void *p, float v) {
+  *(unsigned short *)p = (unsigned short)(pack_bf16x2(v, 0.f) & 0xffffu);
+}
+// element access of a T4 of either dtype (slow generic paths only)
+__device__ __forceinline__ float ld_any(const T4 &t, long long off) {
+  return t.dt == SRB_BF16 ? ld_bf16((const unsigned short *)t.p + off) : __ldg(t.p + off);
+}
+__device__ __forceinline__ void st_any(const T4 &t, long long off, float v) {
+  if (t.dt == SRB_BF16) st_bf16((unsigned short *)t.p + off, v);
+  else t.p[off] = v;
+}
+
 // One lane of a fully converged warp (keeps the surrounding loop warp-uniform so the compiler keeps
 // descriptors / addresses in uniform registers instead of per-thread "waterfall" loops).
 __device__ __forceinline__ bool elect_one() {
@@ -100,11 +132,14 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 inline int encode_tiled(CUtensorMap *map, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                 const cuuint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                 const cuuint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool bf16 = false,
+                 const cuuint32_t *elem_strides = nullptr) {
+  cuuint32_t estr1[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t *estr = elem_strides ? elem_strides : estr1;
   EncodeTiledFn enc = get_encode_fn();
   SRB_REQUIRE(enc != nullptr, SRB_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims,
+                   strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -45,6 +45,10 @@ struct SlArgs {
   int b_resident;               // generic: b_stages == K-blocks, every weight tile is loaded once per CTA and stays
   int t_bufs, tmem_cols;  // accumulator buffers in TMEM (2: epilogue of band i overlaps the MMAs of band i+1)
   int ps;
+  int in_bf16;       // operands are bf16 (slot = 128 B = 64 channels, kind::f16 MMAs of K = 16); generic flavour only
+  int out_bf16;      // out / residual / preact are bf16 tensors
+  int chunk_elems;   // channels per A chunk: 32 (tf32) or 64 (bf16)
+  int v8h;           // bf16 outputs: rows are 32-byte aligned (256-bit accesses of 16 bf16 channels)
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
   int v8;              // out / residual / preact / mask rows are 32-byte aligned: mode-0 epilogue uses 256-bit global accesses
   int dbg;             // debug knobs (srb_debug_set_flags): 1 = epilogue does nothing, 2 = A tiles are loaded only once per buffer
@@ -160,12 +164,12 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
       for (int j = 0; j < 16; ++j) {
         const int co = cbase + j;
         if (co < a.Co) {
-          if (a.epi.preact.p) a.epi.preact.p[ps_offset(a.epi.preact, a.ps, n, co, oy, ox)] = z[j];
+          if (a.epi.preact.p) st_any(a.epi.preact, ps_offset(a.epi.preact, a.ps, n, co, oy, ox), z[j]);
           float y = act == SRB_ACT_NONE ? z[j] : (act == SRB_ACT_RELU ? fmaxf(z[j], 0.f) : (z[j] > 0.f ? z[j] : z[j] * slope));
-          if (a.epi.residual.p) y += __ldg(a.epi.residual.p + ps_offset(a.epi.residual, a.ps, n, co, oy, ox));
-          if (a.epi.mask.p && !(__ldg(a.epi.mask.p + ps_offset(a.epi.mask, a.ps, n, co, oy, ox)) > 0.f)) y = 0.f;
+          if (a.epi.residual.p) y += ld_any(a.epi.residual, ps_offset(a.epi.residual, a.ps, n, co, oy, ox));
+          if (a.epi.mask.p && !(ld_any(a.epi.mask, ps_offset(a.epi.mask, a.ps, n, co, oy, ox)) > 0.f)) y = 0.f;
           if (rnd) y = round_tf32_fast(y);
-          a.out.p[ps_offset(a.out, a.ps, n, co, oy, ox)] = y;
+          st_any(a.out, ps_offset(a.out, a.ps, n, co, oy, ox), y);
         }
       }
       continue;
@@ -250,6 +254,141 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
 }
 
 
+// ---- bf16-output epilogue (out / residual / preact are bf16 NHWC tensors; accumulators, bias and the math stay fp32) ----
+//   MODE 0: NHWC, no shuffle: 16 channels = 32 B per thread and item -> one 256-bit store
+//   MODE 2: PixelShuffle(2) into NHWC: an item is 32 accumulator columns = 8 output channels x 4 sub-pixels -> four 16-B stores
+#define STG256U(ptr, v, o)                                                                                                 \
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[(o)]), "r"(v[(o) + 1]),       \
+               "r"(v[(o) + 2]), "r"(v[(o) + 3]), "r"(v[(o) + 4]), "r"(v[(o) + 5]), "r"(v[(o) + 6]), "r"(v[(o) + 7])         \
+               : "memory")
+#define LDG256U(ptr, v, o)                                                                                                 \
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                              \
+               : "=r"(v[(o)]), "=r"(v[(o) + 1]), "=r"(v[(o) + 2]), "=r"(v[(o) + 3]), "=r"(v[(o) + 4]), "=r"(v[(o) + 5]),  \
+                 "=r"(v[(o) + 6]), "=r"(v[(o) + 7])                                                                        \
+               : "l"(ptr))
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_items_h(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
+                                                 int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid) {
+  typedef unsigned short bf;
+  const int act = a.epi.act;
+  const float slope = (act == SRB_ACT_PRELU) ? __ldg(a.epi.alpha) : a.epi.slope;
+  const bool has_bias = a.epi.bias != nullptr;
+  const bool has_res = a.epi.residual.p != nullptr, has_pre = a.epi.preact.p != nullptr;
+  constexpr int COLS = MODE == 2 ? 32 : 16;
+  const int ngroups = a.NT / COLS;
+  int t_cur = -1, oy = 0, ox = 0;
+  bool pix_ok = false;
+  bf *po = nullptr, *pp = nullptr;
+  const bf *pr = nullptr;
+  int pixw = 0;
+#pragma unroll 1
+  for (int item = half; item < mtb * ngroups; item += 2) {
+    const int t = item / ngroups, j0 = (item - t * ngroups) * COLS;
+    if (t != t_cur) {
+      t_cur = t;
+      const int q = t * 128 + m;
+      const int ty = q / a.BW, tx = q - ty * a.BW;
+      oy = oy0 + ty; ox = ox0 + tx;
+      pix_ok = (ty < rows_valid) && (tx < cols_valid);
+      pixw = ((n * a.Ho + oy) * a.Wo + ox) * (a.Co >> 4);
+      const long long yy = (long long)oy * a.ps, xx = (long long)ox * a.ps;
+      po = (bf *)a.out.p + (n * a.out.sn + yy * a.out.sh + xx * a.out.sw);
+      pr = (const bf *)a.epi.residual.p + (n * a.epi.residual.sn + yy * a.epi.residual.sh + xx * a.epi.residual.sw);
+      pp = (bf *)a.epi.preact.p + (n * a.epi.preact.sn + yy * a.epi.preact.sh + xx * a.epi.preact.sw);
+    }
+    const int cbase = n0 + j0;
+    if (cbase >= a.Co) continue;  // warp-uniform
+    float z[COLS];
+    {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(t * a.NT + j0), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
+      if (MODE == 2) {
+        tmem_ld16(trow + (uint32_t)(t * a.NT + j0 + 16), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[16 + j] = __uint_as_float(v[j]);
+      }
+    }
+    if (!pix_ok) continue;
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < COLS; j += 4) {
+        const float4 b = lds128(bias_saddr + (uint32_t)(j0 + j) * 4u);
+        z[j] += b.x; z[j + 1] += b.y; z[j + 2] += b.z; z[j + 3] += b.w;
+      }
+    }
+    if (MODE == 0 && a.epi.bits_out) {
+      uint32_t mbits = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mbits |= (z[j] > 0.f ? 1u : 0u) << j;
+      a.epi.bits_out[pixw + (cbase >> 4)] = (unsigned short)mbits;
+    }
+    if (MODE == 0) {
+      bf *pg = po + cbase;
+      if (has_pre) {
+        uint32_t u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+        STG256U(pp + cbase, u, 0);
+      }
+      if (act == SRB_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = fmaxf(z[j], 0.f);
+      } else if (act != SRB_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
+      }
+      if (has_res) {
+        uint32_t u[8];
+        LDG256U(pr + cbase, u, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { z[2 * j] += bf16_lo(u[j]); z[2 * j + 1] += bf16_hi(u[j]); }
+      }
+      if (a.epi.bits_in) {
+        const uint32_t mbits = __ldg(a.epi.bits_in + pixw + (cbase >> 4));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = ((mbits >> j) & 1u) ? z[j] : 0.f;
+      }
+      uint32_t u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(z[2 * j], z[2 * j + 1]);
+      STG256U(pg, u, 0);
+    } else {
+      // conv channel cbase + 4*cc + ij -> output channel c0 + cc (c0 = cbase / 4), sub-pixel ij = 2*i + j
+      const int c0 = cbase >> 2;
+#pragma unroll
+      for (int ij = 0; ij < 4; ++ij) {
+        const long long off = (long long)(ij >> 1) * a.out.sh + (long long)(ij & 1) * a.out.sw + c0;
+        float y[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) y[cc] = z[4 * cc + ij];
+        if (has_pre) {
+          const long long offp = (long long)(ij >> 1) * a.epi.preact.sh + (long long)(ij & 1) * a.epi.preact.sw + c0;
+          *(uint4 *)(pp + offp) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                                             pack_bf16x2(y[6], y[7]));
+        }
+        if (act == SRB_ACT_RELU) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) y[cc] = fmaxf(y[cc], 0.f);
+        } else if (act != SRB_ACT_NONE) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) y[cc] = y[cc] > 0.f ? y[cc] : y[cc] * slope;
+        }
+        if (has_res) {
+          const long long offr = (long long)(ij >> 1) * a.epi.residual.sh + (long long)(ij & 1) * a.epi.residual.sw + c0;
+          const uint4 r4 = __ldg((const uint4 *)(pr + offr));
+          y[0] += bf16_lo(r4.x); y[1] += bf16_hi(r4.x); y[2] += bf16_lo(r4.y); y[3] += bf16_hi(r4.y);
+          y[4] += bf16_lo(r4.z); y[5] += bf16_hi(r4.z); y[6] += bf16_lo(r4.w); y[7] += bf16_hi(r4.w);
+        }
+        *(uint4 *)(po + off) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                                          pack_bf16x2(y[6], y[7]));
+      }
+    }
+  }
+}
+
 // Ring positions of the MMA warp (buffer index + phase bit each; no divisions in the issue loop).
 struct MmaState {
   uint32_t a_buf, a_phase, b_st, b_phase, t_buf, t_phase;
@@ -258,7 +397,7 @@ struct MmaState {
 // (Called by the ONE elected thread of the MMA warp: every wait, MMA and commit of the band is issued by it.)
 // All MMAs of one band, generic operands: for every 32-channel chunk and filter tap, K = 4 x 8 over MTB_ M-tiles.
 // K-step outer / M-tile inner so that consecutive MMAs write different accumulators.
-template <int MTB_>
+template <int MTB_, bool BF>
 __device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, uint64_t *a_full, uint64_t *a_empty,
                                                  uint64_t *b_full, uint64_t *b_empty, uint32_t a_base, uint32_t b_base,
                                                  uint32_t tacc, uint32_t idesc) {
@@ -290,9 +429,13 @@ __device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, 
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
 #pragma unroll
-          for (int j = 0; j < MTB_; ++j)
-            umma_tf32_ss(tcol[j], d_hi | (uint64_t)(a_tap + (uint32_t)(j * 1024 + 2 * k4)), d_hi | (uint64_t)(b_lo + 2u * k4), idesc,
-                         k4 ? 1u : first_kb);
+          for (int j = 0; j < MTB_; ++j) {
+            // one K step = 32 bytes of every slot: 8 tf32 or 16 bf16 channels -- the descriptor arithmetic is byte-identical
+            if (BF) umma_bf16_ss(tcol[j], d_hi | (uint64_t)(a_tap + (uint32_t)(j * 1024 + 2 * k4)), d_hi | (uint64_t)(b_lo + 2u * k4), idesc,
+                                 k4 ? 1u : first_kb);
+            else umma_tf32_ss(tcol[j], d_hi | (uint64_t)(a_tap + (uint32_t)(j * 1024 + 2 * k4)), d_hi | (uint64_t)(b_lo + 2u * k4), idesc,
+                              k4 ? 1u : first_kb);
+          }
         }
         if (!a.b_resident) umma_commit_arrive(&b_empty[ms.b_st]);  // frees this weight stage once its MMAs have read it
         first_kb = 1u;
@@ -440,7 +583,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             mbar_arrive(&a_full[buf]);
           } else {
             mbar_expect_tx(&a_full[buf], (uint32_t)a.a_tx_bytes);
-            tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * 32, ix0, iy0, img);
+            tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * a.chunk_elems, ix0, iy0, img);
           }
         }
         __syncwarp();
@@ -460,7 +603,9 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
+    // (kind::f16 with bf16 operands: a/b format 1 instead of 2)
+    const uint32_t fmt = a.in_bf16 ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
     const long long clk0 = clock64();
     const long long gt0 = gtime();
     MmaState ms;
@@ -483,11 +628,16 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         else if (mtb == 2) mma_band_c4<2>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
         else if (mtb == 3) mma_band_c4<3>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
         else mma_band_c4<4>(a, ms, a_full, a_empty, a_base, b_base, tacc, idesc);
+      } else if (a.in_bf16) {
+        if (mtb == 1) mma_band_generic<1, true>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 2) mma_band_generic<2, true>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 3) mma_band_generic<3, true>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else mma_band_generic<4, true>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
       } else {
-        if (mtb == 1) mma_band_generic<1>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
-        else if (mtb == 2) mma_band_generic<2>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
-        else if (mtb == 3) mma_band_generic<3>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
-        else mma_band_generic<4>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        if (mtb == 1) mma_band_generic<1, false>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 2) mma_band_generic<2, false>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else if (mtb == 3) mma_band_generic<3, false>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
+        else mma_band_generic<4, false>(a, ms, a_full, a_empty, b_full, b_empty, a_base, b_base, tacc, idesc);
       }
       umma_commit_arrive(&t_full[ms.t_buf]);  // this band's accumulators are complete
       if (++ms.t_buf == (uint32_t)a.t_bufs) { ms.t_buf = 0; ms.t_phase ^= 1u; }
@@ -511,7 +661,12 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const bool lay1 = a.out.sw == 1 && (!a.epi.residual.p || a.epi.residual.sw == 1) &&
                       (!a.epi.preact.p || a.epi.preact.sw == 1);
     int fmode = 3;  // see epilogue_items
-    if ((a.Co & 15) == 0) {
+    int hmode = 3;  // bf16 outputs: epilogue_items_h mode (0, 2) or the generic scalar path (3)
+    if (a.out_bf16 && (a.Co & 15) == 0 && lay0 && a.v8h && !a.epi.mask.p) {
+      if (a.ps == 1) hmode = 0;
+      else if (a.ps == 2 && (a.NT & 31) == 0 && (a.Co & 31) == 0 && !a.epi.bits_out && !a.epi.bits_in) hmode = 2;
+    }
+    if (!a.out_bf16 && (a.Co & 15) == 0) {
       if (a.ps == 1 && lay0) fmode = 0;
       else if (a.epi.mask.p) fmode = 3;  // masks only exist on the vector path of mode 0
       else if (a.ps == 4 && lay1 && (a.out.sh & 3) == 0) fmode = 1;
@@ -530,12 +685,16 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       if (wi == 0 && warp == 2 && lane == 0) SL_TRACE(4);
       const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + tb * (uint32_t)acc_cols;
 #define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
+#define SL_EPIH(MODE) epilogue_items_h<MODE>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
       if (a.dbg & 1) {}
+      else if (a.out_bf16 && hmode == 0) SL_EPIH(0);
+      else if (a.out_bf16 && hmode == 2) SL_EPIH(2);
       else if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
       else if (fmode == 1) { if (extra) SL_EPI(1, true); else SL_EPI(1, false); }
       else if (fmode == 2) { if (extra) SL_EPI(2, true); else SL_EPI(2, false); }
       else SL_EPI(3, true);
 #undef SL_EPI
+#undef SL_EPIH
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): hand the buffer back
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -582,6 +741,27 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
       v = round_tf32(wval(w, n, k, r, s, Nn, Kk, kh, kw, flip));
     }
     out[i] = v;
+  }
+}
+
+// generic B operand for bf16 operands: out[chunk][tap][Npad][64] (bf16 RN), zero for n >= Nn or k >= Kk
+__global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__restrict__ out, int Nn, int Kk, int kh, int kw,
+                              int Npad, int chunks, int flip) {
+  const int taps = kh * kw;
+  const long long total = (long long)chunks * taps * Npad * 64;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 63);
+    long long q = i >> 6;
+    const int n = (int)(q % Npad); q /= Npad;
+    const int tap = (int)(q % taps);
+    const int c = (int)(q / taps);
+    const int k = c * 64 + kk;
+    float v = 0.f;
+    if (n < Nn && k < Kk) {
+      const int r = tap / kw, s = tap - r * kw;
+      v = wval(w, n, k, r, s, Nn, Kk, kh, kw, flip);
+    }
+    out[i] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xffffu);
   }
 }
 
@@ -636,9 +816,10 @@ inline double mma_cost(int N) {  // cycles of one SS-mode tf32 MMA, M=128 K=8 (t
   return c1 > c2 ? c1 : c2;
 }
 
-bool make_sl_plan(const Geom &g, SlPlan *pl) {
+bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false) {
   SlArgs &a = pl->a;
-  const bool c4 = g.Ci <= 4;
+  const bool c4 = g.Ci <= 4 && !bf16;
+  const int celems = bf16 ? 64 : 32;  // channels per 128-byte slot
   const int sb = c4 ? 16 : 128;
   const int Npad = round_up_i(g.Co, 16);
   int NT0 = Npad;
@@ -648,7 +829,7 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   }
   const int spairs = (g.kw + 1) / 2;
   const int kextra = c4 ? 2 * spairs - 1 : g.kw - 1;
-  const int chunks = c4 ? 1 : (g.Ci + 31) / 32;
+  const int chunks = c4 ? 1 : (g.Ci + celems - 1) / celems;
   const int kblocks = c4 ? g.kh * spairs : g.kh * g.kw * chunks;
   double best_t = -1.0;
   // N tile: the widest that fits.  Half-width tiles (two N tiles, more M tiles per band, half the streamed-weight traffic
@@ -747,6 +928,10 @@ bool make_sl_plan(const Geom &g, SlPlan *pl) {
   const int NT = a.NT;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Co = g.Co; a.kh = g.kh; a.kw = g.kw; a.pad = g.pad; a.c4 = c4 ? 1 : 0;
   a.ps = g.ps;
+  a.in_bf16 = bf16 ? 1 : 0;
+  a.out_bf16 = 0;
+  a.chunk_elems = celems;
+  a.v8h = 0;
   pl->Npad = Npad;
   pl->n_tiles_n = Npad / NT;
   {  // persistent grid: as many CTAs as fit on the chip; CTA x walks bands x, x + grid, ...
@@ -777,6 +962,14 @@ bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*
   if (g.kh > 16 || g.kw > 16) return false;
   if ((long long)g.N * g.Hi * g.Wi * (g.Ci > 4 ? g.Ci : 4) >= (1LL << 40)) return false;
   if ((long long)g.N * ((g.Ho + 0) * (long long)g.Wo) >= (1LL << 31)) return false;
+  if (in.dt == SRB_BF16) {
+    if (g.Ci % 8 != 0 || g.Ci < 8) return false;                       // TMA: 16-byte pixel stride
+    if (in.sc != 1) return false;                                       // channels_last activations
+    if ((in.sw % 8) || (in.sh % 8) || (in.sn % 8)) return false;       // TMA strides: multiples of 16 B
+    if (((uintptr_t)in.p) & 15) return false;
+    SlPlan ph;
+    return make_sl_plan(g, &ph, true);
+  }
   if (g.Ci > 4) {
     if (g.Ci % 4 != 0 || g.Ci < 8) return false;                       // TMA: 16-byte pixel stride
     if (in.sc != 1) return false;                                       // channels_last activations
@@ -802,14 +995,14 @@ size_t tc_conv_ws_bytes(const Geom &g) {
   return a;
 }
 
-int tc_conv_describe(const Geom &g, char *buf, size_t n) {
+int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
   SlPlan pl;
-  if (!make_sl_plan(g, &pl)) return snprintf(buf, n, "conv_sl: no plan");
+  if (!make_sl_plan(g, &pl, bf16)) return snprintf(buf, n, "conv_sl: no plan");
   const SlArgs &a = pl.a;
   return snprintf(buf, n,
                   "conv_sl %s: band %dx%d (halo %dx%d), %dx%d bands/img, MTB %d, NT %d x%d, chunks %d, a_bufs %d x %d B, "
                   "b_stages %d%s x %d B, smem %zu B, tmem %d cols (%d acc bufs), %d bands on grid %d x %d (%d CTA/SM)",
-                  a.c4 ? "c4" : "generic", a.TH, a.TW, a.BH, a.BW, a.bands_h, a.bands_w, a.MTB, a.NT, pl.n_tiles_n, a.chunks,
+                  a.c4 ? "c4" : (a.in_bf16 ? "generic-bf16" : "generic"), a.TH, a.TW, a.BH, a.BW, a.bands_h, a.bands_w, a.MTB, a.NT, pl.n_tiles_n, a.chunks,
                   a.a_bufs, a.a_buf_bytes, a.b_stages, (a.c4 || a.b_resident) ? " (resident)" : "", a.b_stage_bytes, pl.smem, a.tmem_cols, a.t_bufs,
                   g.N * a.bands_h * a.bands_w, pl.grid_x, pl.n_tiles_n, pl.ctas_per_sm);
 }
@@ -817,7 +1010,11 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n) {
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
                    void *ws, size_t ws_bytes, cudaStream_t st) {
   SlPlan pl;
-  SRB_REQUIRE(make_sl_plan(g, &pl), SRB_EUNSUPPORTED, "tc_conv: no band plan");
+  const bool bf_in = in.dt == SRB_BF16, bf_out = out.dt == SRB_BF16;
+  SRB_REQUIRE(make_sl_plan(g, &pl, bf_in), SRB_EUNSUPPORTED, "tc_conv: no band plan");
+  SRB_REQUIRE((!epi.residual.p || epi.residual.dt == out.dt) && (!epi.preact.p || epi.preact.dt == out.dt), SRB_EINVAL,
+              "residual / preact must have the dtype of the output");
+  SRB_REQUIRE(!epi.mask.p || epi.mask.dt == SRB_F32 || !bf_out, SRB_EUNSUPPORTED, "float relu_mask with bf16 tensors (use relu_bits)");
   SlArgs &a = pl.a;
   const size_t need = (pl.wpack_floats + pl.xpack_floats) * sizeof(float) + 512;
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
@@ -833,6 +1030,8 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (a.c4)
       k_pack_w_c4<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
+    else if (bf_in)
+      k_pack_w_sl_h<<<blocks, 256, 0, st>>>(w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
     else
       k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
     count_launch();
@@ -860,16 +1059,17 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   } else {
     {
       cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
-      cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sh * 4, (cuuint64_t)in.sn * 4};
-      cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-      int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box);
+      const cuuint64_t es = bf_in ? 2 : 4;
+      cuuint64_t strides[3] = {(cuuint64_t)in.sw * es, (cuuint64_t)in.sh * es, (cuuint64_t)in.sn * es};
+      cuuint32_t box[4] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+      int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf_in);
       if (rc) return rc;
     }
     {
-      cuuint64_t dims[3] = {32, (cuuint64_t)pl.Npad, (cuuint64_t)(a.chunks * g.kh * g.kw)};
+      cuuint64_t dims[3] = {(cuuint64_t)a.chunk_elems, (cuuint64_t)pl.Npad, (cuuint64_t)(a.chunks * g.kh * g.kw)};
       cuuint64_t strides[2] = {128, (cuuint64_t)pl.Npad * 128};
-      cuuint32_t box[3] = {32, (cuuint32_t)a.NT, 1};
-      int rc = encode_tiled(&mapB, wp, 3, dims, strides, box);
+      cuuint32_t box[3] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)a.NT, 1};
+      int rc = encode_tiled(&mapB, wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf_in);
       if (rc) return rc;
     }
     a.wpack = nullptr;
@@ -881,6 +1081,11 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
       return !t.p || ((((uintptr_t)t.p) & 31) == 0 && (t.sn & 7) == 0 && (t.sh & 7) == 0 && (t.sw & 7) == 0);
     };
     a.v8 = (ok32(out) && ok32(epi.residual) && ok32(epi.preact)) ? 1 : 0;
+    auto ok32h = [](const T4 &t) {  // bf16: strides in 2-byte elements
+      return !t.p || ((((uintptr_t)t.p) & 31) == 0 && (t.sn & 15) == 0 && (t.sh & 15) == 0 && (t.sw & 15) == 0);
+    };
+    a.out_bf16 = bf_out ? 1 : 0;
+    a.v8h = (bf_out && ok32h(out) && ok32h(epi.residual) && ok32h(epi.preact)) ? 1 : 0;
   }
   a.dbg = g_sl_dbg;
   a.trace = ((long long)pl.grid_x * pl.n_tiles_n <= g_sl_trace_ctas) ? g_sl_trace : nullptr;

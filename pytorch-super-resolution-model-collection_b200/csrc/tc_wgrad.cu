@@ -39,6 +39,10 @@ struct WgArgs {
   int c4;                 // Cin <= 4: x is the zero-padded NHWC4 image seen through an overlapping-stride TMA view whose
                           // 32 "channels" are the 8-pixel x 4-channel window starting at the slot; an accumulator's four
                           // 32-lane M-blocks are four consecutive FILTER ROWS (LBO = one slot row); RG = ceil(kh/4) accumulators
+  int bf16;               // operands are bf16: 64-channel blocks (128 B slots), standard 128B swizzle, K = 16 pixels per MMA, and an
+                          // accumulator's two 64-lane M-blocks are two consecutive s-taps (c2 == 0) or two ci-blocks (c2 == 1)
+  int c2;                 // bf16 only: M = 2 ci-blocks x 1 tap (LBO = one x tile) instead of 1 ci-block x 2 taps (LBO = one slot);
+                          // CIB then counts ci-block PAIRS and SG = kw
   int dbg;                // debug knobs (srb_debug_set_flags): 2 = stages are TMA-loaded only once, 4 = no MMAs are issued
   int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
@@ -59,13 +63,37 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t l
 
 // tcgen05.mma with the descriptors given as (low, high) word pairs: the running low words are bumped by plain 32-bit adds
 // in uniform registers, no 64-bit OR per MMA.
-template <bool ACCUM>
+template <bool ACCUM, bool BF = false>
 __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
-  asm volatile(
-      "{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %5, 0; mov.b64 da, {%1, %3}; mov.b64 db, {%2, %3};\n"
-      "  tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p; }" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(ACCUM ? 1u : 0u)
-      : "memory");
+  if (BF)
+    asm volatile(
+        "{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %5, 0; mov.b64 da, {%1, %3}; mov.b64 db, {%2, %3};\n"
+        "  tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p; }" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(ACCUM ? 1u : 0u)
+        : "memory");
+  else
+    asm volatile(
+        "{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %5, 0; mov.b64 da, {%1, %3}; mov.b64 db, {%2, %3};\n"
+        "  tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p; }" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(ACCUM ? 1u : 0u)
+        : "memory");
+}
+
+// db partial sums of one bf16 dz stage: NB 64-channel blocks; lane l takes row q0 + l/8 and the 16-B chunk (8 channels) l%8
+// (standard 128B swizzle: 16-B chunk index XOR (row & 7))
+template <int NB>
+__device__ __forceinline__ void db_rows_h(float (&dbs)[4][8], uint32_t sz, int dz_bytes, int rows, int lane_grp, int lrow, int lchunk) {
+  for (int q0 = lane_grp * 4; q0 < rows; q0 += 16) {
+    const int q = q0 + lrow;
+    const uint32_t off = sz + (uint32_t)q * 128u + ((uint32_t)(lchunk ^ (q & 7)) << 4);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(off + (uint32_t)(j * dz_bytes)));
+      dbs[j][0] += bf16_lo(v.x); dbs[j][1] += bf16_hi(v.x); dbs[j][2] += bf16_lo(v.y); dbs[j][3] += bf16_hi(v.y);
+      dbs[j][4] += bf16_lo(v.z); dbs[j][5] += bf16_hi(v.z); dbs[j][6] += bf16_lo(v.w); dbs[j][7] += bf16_hi(v.w);
+    }
+  }
 }
 
 // db partial sums of one dz stage: NB 32-channel blocks, 4 rows per LDS.128 (see the caller for the lane mapping)
@@ -85,9 +113,10 @@ __device__ __forceinline__ void db_rows(float4 (&dbs)[8], uint32_t sz, int dz_by
 
 // All MMAs of one band (one pipeline stage) for NACC accumulators: straight-line issue code per K-step -- one add and one
 // MMA per accumulator.  (The previous runtime-predicated loop spent ~24 instructions per MMA and was issue bound.)
-template <int NACC>
+template <int NACC, bool BF>
 __device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, uint32_t z_lo, uint32_t hi, uint32_t idesc,
                                               uint32_t tmem_base, bool first) {
+  constexpr uint32_t KADV = BF ? 128u : 64u;  // one K step = 16 (bf16) / 8 (tf32) pixel rows x 128 B, in 16-byte units
   uint32_t al[NACC], tc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) {
@@ -99,20 +128,20 @@ __device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, ui
   if (first) {  // very first K-step of this CTA: overwrite the accumulators
 #pragma unroll
     for (int j = 0; j < NACC; ++j) {
-      umma_tf32_lohi<false>(tc[j], al[j], bl, hi, idesc);
-      al[j] += 64u;
+      umma_tf32_lohi<false, BF>(tc[j], al[j], bl, hi, idesc);
+      al[j] += KADV;
     }
-    bl += 64u;
+    bl += KADV;
     ks = 1;
   }
 #pragma unroll 2
   for (; ks < a.ksteps; ++ks) {
 #pragma unroll
     for (int j = 0; j < NACC; ++j) {
-      umma_tf32_lohi<true>(tc[j], al[j], bl, hi, idesc);
-      al[j] += 64u;  // 8 pixel rows x 128 B
+      umma_tf32_lohi<true, BF>(tc[j], al[j], bl, hi, idesc);
+      al[j] += KADV;
     }
-    bl += 64u;
+    bl += KADV;
   }
 }
 
@@ -120,9 +149,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ, WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int nb = a.NT / 32;
+  const int blk_ch = a.bf16 ? 64 : 32;              // channels per 128-byte slot
+  const int nb = (a.NT + blk_ch - 1) / blk_ch;      // dz blocks per stage
+  const int XT = a.CIB * (a.c2 ? 2 : 1);            // x tiles (channel blocks) per stage
   const int x_bytes = a.x_slots * 128, dz_bytes = a.dz_slots * 128;
-  const int stage_bytes = a.CIB * x_bytes + nb * dz_bytes;
+  const int stage_bytes = XT * x_bytes + nb * dz_bytes;
   uint64_t *full_bar = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
   uint64_t *empty_bar = full_bar + a.stages;
   uint64_t *accum_bar = empty_bar + a.stages;
@@ -174,7 +205,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer: one halo band per stage =====================
     {
-      const uint32_t tx_bytes = (uint32_t)(a.CIB * a.BH * a.BW * 128 + nb * a.TH * (a.dz_rowwise ? a.TW : a.BW) * 128);
+      const uint32_t tx_bytes = (uint32_t)(XT * a.BH * a.BW * 128 + nb * a.TH * (a.dz_rowwise ? a.TW : a.BW) * 128);
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
@@ -185,7 +216,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int bh = rem / a.bands_w;
         const int oh0 = bh * a.TH, ox0 = (rem - bh * a.bands_w) * a.TW;
         uint8_t *sx = smem + (size_t)st * stage_bytes;
-        uint8_t *sz = sx + a.CIB * x_bytes;
+        uint8_t *sz = sx + XT * x_bytes;
         if ((a.dbg & 2) && it >= a.stages) {
           if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
           __syncwarp();
@@ -196,16 +227,16 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
           if (a.c4) {
             tma_load_4d(&mapX, &full_bar[st], sx, 0, 0, oh0, n);  // padded image: no negative coordinates
           } else {
-            for (int cb = 0; cb < a.CIB; ++cb)
-              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * a.CIB + cb) * 32, ox0 - a.pad, oh0 - a.pad + r0, n);
+            for (int cb = 0; cb < XT; ++cb)
+              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * XT + cb) * blk_ch, ox0 - a.pad, oh0 - a.pad + r0, n);
           }
           if (a.dz_rowwise) {
             for (int t = 0; t < a.TH; ++t)  // rows past the image (and columns past Wo) arrive as zeros
               for (int j = 0; j < nb; ++j)
-                tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, cot * a.NT + j * 32, ox0, oh0 + t, n);
+                tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, cot * a.NT + j * blk_ch, ox0, oh0 + t, n);
           } else {
             for (int j = 0; j < nb; ++j)
-              tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * 32, 0, oh0, n);
+              tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * blk_ch, 0, oh0, n);
           }
         }
         __syncwarp();
@@ -215,11 +246,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
     {
       // D=f32, A=B=tf32, both MN-major (bits 15,16), N>>3 at bit 17, M=128>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+      const uint32_t fmt = a.bf16 ? 1u : 2u;  // kind::f16 bf16 operands / kind::tf32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
       // descriptor high words are loop invariant; low word = (addr >> 4) | LBO << 16
-      const uint32_t a_hi = (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
-      const uint32_t a_lbo = a.c4 ? ((((uint32_t)a.BW * 128u) >> 4) & 0x3FFF) << 16 : (128u >> 4) << 16;
+      // bf16: standard 128B swizzle (layout type 2), 8 K-rows x 128 B per atom -> SBO = 1024 B
+      const uint32_t a_hi = a.bf16 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29)) : (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
+      const uint32_t a_lbo = a.c4 ? ((((uint32_t)a.BW * 128u) >> 4) & 0x3FFF) << 16
+                                  : (a.c2 ? (((uint32_t)x_bytes >> 4) & 0x3FFF) << 16 : (128u >> 4) << 16);
       const uint32_t b_lbo = (((uint32_t)dz_bytes >> 4) & 0x3FFF) << 16;
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
@@ -229,21 +263,26 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sx = smem_u32(smem + (size_t)st * stage_bytes);
         const uint32_t x_lo = ((sx >> 4) & 0x3FFF) | a_lbo;
-        const uint32_t z_lo = (((sx + a.CIB * x_bytes) >> 4) & 0x3FFF) | b_lbo;
+        const uint32_t z_lo = (((sx + XT * x_bytes) >> 4) & 0x3FFF) | b_lbo;
         if (elect_one()) {
           const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;  // a prefix of acc_off (filter-row major)
           const bool first = it == 0;
+#define WG_ISSUE(NA)                                                                         \
+  if (a.bf16) wg_issue_band<NA, true>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first);       \
+  else wg_issue_band<NA, false>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first);             \
+  break
           switch ((a.dbg & 4) ? 0 : nacc) {
             case 0: break;
-            case 1: wg_issue_band<1>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 2: wg_issue_band<2>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 3: wg_issue_band<3>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 4: wg_issue_band<4>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 5: wg_issue_band<5>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 6: wg_issue_band<6>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            case 7: wg_issue_band<7>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
-            default: wg_issue_band<8>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); break;
+            case 1: WG_ISSUE(1);
+            case 2: WG_ISSUE(2);
+            case 3: WG_ISSUE(3);
+            case 4: WG_ISSUE(4);
+            case 5: WG_ISSUE(5);
+            case 6: WG_ISSUE(6);
+            case 7: WG_ISSUE(7);
+            default: WG_ISSUE(8);
           }
+#undef WG_ISSUE
           umma_commit_arrive(&empty_bar[st]);
         }
         __syncwarp();
@@ -254,7 +293,45 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   } else {
     // ===================== epilogue: dump the partial dW tile =====================
     const int lane_grp = warp & 3;
-    if (do_db) {
+    if (do_db && a.bf16) {
+      const int rows = a.TH * a.BW;
+      float dbs[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dbs[j][e] = 0.f;
+      const int lrow = lane >> 3, lchunk = lane & 7;
+      int it = 0;
+      for (int band = band0; band < band1; ++band, ++it) {
+        const int st = it % a.stages;
+        mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
+        const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)XT * x_bytes);
+        if (!(a.dbg & 8)) {
+          switch (nb) {
+            case 1: db_rows_h<1>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 2: db_rows_h<2>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 3: db_rows_h<3>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            default: db_rows_h<4>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[st])) : "memory");
+      }
+      float *dp = a.db_part + ((size_t)blockIdx.x * 4 + lane_grp) * (size_t)(a.n_cot * a.NT) + (size_t)cot * a.NT;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nb) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = dbs[j][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            const int ch = j * 64 + lchunk * 8 + e;
+            if (lane < 8 && ch < a.NT) dp[ch] = v;
+          }
+        }
+      }
+    } else if (do_db) {
       // While the MMAs run, these warps walk the same stages and sum the dz tiles over pixels (db).  A warp reads four
       // 128-B rows per LDS.128: lane l takes row q0 + l/8 and the 16-B chunk holding channels 4*(l%8)..+3 of every
       // 32-channel block (128B_ATOM_32B swizzle: 32-byte atom index XOR (row & 3), i.e. 16-B chunk index XOR ((row & 3) << 1)).
@@ -267,7 +344,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
         mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
-        const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)a.CIB * x_bytes);
+        const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)XT * x_bytes);
         if (!(a.dbg & 8)) {
           // rows .. round_up(rows, 8) lie in the tile's zero tail (dz_slots % 8 == 0); warp w takes rows 4w.., 4w+16..
           switch (nb) {
@@ -366,6 +443,14 @@ __global__ void __launch_bounds__(32 * L * G) k_wgrad_finish(WgArgs a, int split
       by = cot;
       acc = (r >> 2) * a.SG + (s >> 3);
       m = (r & 3) * 32 + (s & 7) * 4 + ci;
+    } else if (a.bf16) {
+      const int cblk = ci >> 6, rgi = r / a.RG, rl = r - rgi * a.RG;
+      int cig, cb, sg, half;
+      if (a.c2) { const int cp = cblk >> 1; cig = cp / a.CIB; cb = cp - cig * a.CIB; sg = s; half = cblk & 1; }
+      else      { cig = cblk / a.CIB; cb = cblk - cig * a.CIB; sg = s >> 1; half = s & 1; }
+      by = (cig * a.n_rg + rgi) * a.n_cot + cot;
+      acc = (rl * a.SG + sg) * a.CIB + cb;
+      m = half * 64 + (ci & 63);
     } else {
       int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
       int rgi = r / a.RG, rl = r - rgi * a.RG;
@@ -438,7 +523,7 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   WgArgs &a = pl->a;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
-  a.c4 = 1;
+  a.c4 = 1; a.bf16 = 0; a.c2 = 0;
   a.TW = g.Wo; a.bands_w = 1; a.dz_rowwise = 0;
   a.BW = g.Wo + g.kw - 1;  // == Wi + 2*pad at stride 1
   if (a.BW > 256 || g.kw > 16 || g.kh > 16) return false;
@@ -493,10 +578,107 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   return true;
 }
 
-bool make_wg_plan(const Geom &g, WgPlan *pl) {
+// bf16 operands: 64-channel blocks, K = 16 pixels per MMA, M = 128 as two 64-lane blocks (WgArgs::bf16 / c2).
+bool make_wg_plan_h(const Geom &g, WgPlan *pl) {
+  WgArgs &a = pl->a;
+  a.c4 = 0; a.bf16 = 1;
+  pl->Hp = pl->Wp = 0;
+  pl->xpack_floats = 0;
+  a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
+  a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
+  const int cblocks = (g.Ci + 63) / 64;
+  const int co_pad = round_up_i(g.Co, 16);
+  double best_score = -1.0;
+  WgArgs best = a;
+  size_t best_smem = 0;
+  for (int c2 = 0; c2 <= 1; ++c2) {
+    if (c2 && (cblocks & 1)) continue;
+    const int units = c2 ? cblocks / 2 : cblocks;      // ci units (blocks or pairs) to distribute
+    const int SG = c2 ? g.kw : (g.kw + 1) / 2;
+    const double tap_eff = c2 ? 1.0 : (double)g.kw / (2.0 * SG);
+    for (int wsplit = 1; wsplit <= 16; ++wsplit) {
+      const int TW = (g.Wo + wsplit - 1) / wsplit;
+      if (wsplit > 1 && (TW < 16 || (g.Wo + TW - 1) / TW != wsplit)) continue;
+      const int bands_w = (g.Wo + TW - 1) / TW;
+      // row-wise dz loads land at t * BW * 128 B: keep every row on the 1024-B period of the 128B swizzle
+      const int BW = bands_w > 1 ? round_up_i(TW + g.kw - 1, 8) : g.Wo + g.kw - 1;
+      if (BW > 256) continue;
+      for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 16; NT -= 16) {
+        if (co_pad % NT) continue;
+        const int nb = (NT + 63) / 64;
+        for (int CIB = units; CIB >= 1; --CIB) {
+          if (units % CIB) continue;
+          const int XT = CIB * (c2 ? 2 : 1);
+          for (int RG = g.kh; RG >= 1; --RG) {
+            const int acc = RG * SG * CIB;
+            if (acc * NT > 512 || acc > kMaxAcc) continue;
+            for (int TH = 16; TH >= 1; --TH) {
+              if (TH > g.Ho && TH > 1) continue;
+              const int BH = TH + RG - 1;
+              if (BH > 256) continue;
+              const int x_slots = round_up_i(BH * BW + g.kw + 16, 16);
+              const int dz_slots = round_up_i(TH * BW, 16);
+              const size_t stage = (size_t)XT * x_slots * 128 + (size_t)nb * dz_slots * 128;
+              int stages = (int)((kMaxSmemBytes - 4096) / stage);
+              if (stages < 2) continue;
+              if (stages > 4) stages = 4;
+              const int n_rg = (g.kh + RG - 1) / RG, n_cig = units / CIB, n_cot = co_pad / NT;
+              // per image row, summed over grid.y: MMA cycles (K = 16 slots per MMA) vs L2->SM bytes
+              const double costN = (32.0 + NT / 4.0) > NT / 2.0 ? (32.0 + NT / 4.0) : NT / 2.0;
+              const double mma = (double)n_cig * n_rg * n_cot * acc * costN * (bands_w * BW / 16.0);
+              const double bytes = ((double)n_cot * n_rg * cblocks * BH / TH * BW + (double)n_cig * n_rg * n_cot * nb * TW) * 128.0 * bands_w;
+              // TMA writes share the SMEM port with the MMA operand reads (4 KB + NT*32 B per MMA)
+              const double mma_c = mma * (1.0 + bytes / ((double)n_cig * n_rg * n_cot * acc * (bands_w * BW / 16.0) * (4096.0 + NT * 32.0)));
+              double t = mma_c > bytes / 36.0 ? mma_c : bytes / 36.0;
+              t += 500.0 * bands_w / TH * (n_cig * n_rg * n_cot);
+              const double n_tma = XT + (bands_w > 1 ? (double)nb * TH : (double)nb);
+              t += 40.0 * n_tma * bands_w / TH * (n_cig * n_rg * n_cot);
+              if (stages == 2) t *= 1.08;
+              (void)tap_eff;  // already in `mma`: the wasted half-accumulator of an odd tap count is issued like a useful one
+              const double score = 1e9 / t + TH * 1e-3;
+              if (score > best_score) {
+                best_score = score;
+                best = a;
+                best.c2 = c2; best.SG = SG;
+                best.TW = TW; best.bands_w = bands_w; best.BW = BW; best.dz_rowwise = bands_w > 1 ? 1 : 0;
+                best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
+                best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
+                best.n_cig = n_cig; best.n_rg = n_rg; best.n_cot = n_cot;
+                best_smem = (size_t)stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (best_score < 0) return false;
+  a = best;
+  a.bands_per_img = ((g.Ho + a.TH - 1) / a.TH) * a.bands_w;
+  a.num_bands = g.N * a.bands_per_img;
+  a.ksteps = (a.TH * a.BW + 15) / 16;
+  const int gy = a.n_cig * a.n_rg * a.n_cot;
+  int target = 148 / gy;
+  if (target < 1) target = 1;
+  a.bands_per_cta = (a.num_bands + target - 1) / target;
+  if (a.bands_per_cta < 1) a.bands_per_cta = 1;
+  const int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
+  int cols = a.RG * a.SG * a.CIB * a.NT, tc = 32;
+  while (tc < cols) tc <<= 1;
+  a.tmem_cols = tc;
+  pl->grid = dim3(gx, gy);
+  pl->smem = best_smem;
+  pl->partial_floats = (size_t)gx * gy * a.RG * a.SG * a.CIB * 128 * a.NT;
+  pl->db_blocks = 0;
+  pl->db_floats = (size_t)gx * 4 * a.n_cot * a.NT;
+  return true;
+}
+
+bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false) {
+  if (bf16) return make_wg_plan_h(g, pl);
   if (g.Ci <= 4) return make_wg_plan_c4(g, pl);
   WgArgs &a = pl->a;
-  a.c4 = 0;
+  a.c4 = 0; a.bf16 = 0; a.c2 = 0;
   pl->Hp = pl->Wp = 0;
   pl->xpack_floats = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
@@ -591,6 +773,16 @@ bool make_wg_plan(const Geom &g, WgPlan *pl) {
 // small = dz (N,Co,Ho,Wo) NHWC, big = x (N,Ci,Hi,Wi) NHWC
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
   if (g.st != 1 || g.ps != 1 || g.N <= 0) return false;
+  if (small.dt != big.dt) return false;  // mixed operand types: the caller converts one side first
+  if (big.dt == SRB_BF16) {
+    if (g.Ci % 8 != 0 || g.Ci < 8 || g.Co % 8 != 0 || g.Co > 1024) return false;   // 16-byte pixel rows on both tensors
+    if (small.sc != 1 || big.sc != 1) return false;
+    if ((small.sw % 8) || (small.sh % 8) || (small.sn % 8) || (big.sw % 8) || (big.sh % 8) || (big.sn % 8)) return false;
+    if ((((uintptr_t)small.p) | ((uintptr_t)big.p)) & 15) return false;
+    if (g.kh > 16 || g.kw > 16) return false;
+    WgPlan ph;
+    return make_wg_plan(g, &ph, true);
+  }
   const bool c4 = g.Ci <= 4;
   if ((!c4 && g.Ci % 32 != 0) || g.Co % 4 != 0 || g.Co > 1024) return false;
   if (small.sc != 1 || (!c4 && big.sc != 1)) return false;
@@ -603,27 +795,29 @@ bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
   return make_wg_plan(g, &pl);
 }
 
-int tc_wgrad_describe(const Geom &g, char *buf, size_t n) {
+int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16) {
   WgPlan pl;
-  if (g.st != 1 || g.ps != 1 || (g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl)) return snprintf(buf, n, "tc_wgrad: no plan");
+  if (g.st != 1 || g.ps != 1 || (!bf16 && g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl, bf16)) return snprintf(buf, n, "tc_wgrad: no plan");
   const WgArgs &a = pl.a;
   return snprintf(buf, n,
-                  "tc_wgrad: band TH %d TW %d x%d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
+                  "tc_wgrad%s: band TH %d TW %d x%d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
                   "stages %d, smem %zu B, tmem %d cols, grid %d x %d, ksteps %d",
-                  a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
+                  a.bf16 ? (a.c2 ? "-bf16(ci pairs)" : "-bf16(tap pairs)") : "", a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
                   pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
 }
 
-size_t tc_wgrad_ws_bytes(const Geom &g) {
+size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16) {
   WgPlan pl;
-  if (g.st != 1 || g.ps != 1 || (g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl)) return 0;
+  if (g.st != 1 || g.ps != 1 || (!bf16 && g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl, bf16)) return 0;
   return (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 1024;
 }
 
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
   WgPlan pl;
-  SRB_REQUIRE(make_wg_plan(g, &pl), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
+  const bool bf = big.dt == SRB_BF16;
+  SRB_REQUIRE(small.dt == big.dt, SRB_EINVAL, "tc_wgrad: x and dz must have one dtype");
+  SRB_REQUIRE(make_wg_plan(g, &pl, bf), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
   size_t need = (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 256;
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_wgrad workspace: need %zu bytes, have %zu",
@@ -635,6 +829,12 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     if (a.c4) {
       for (int rg = 0; rg < a.RG; ++rg)
         for (int sg = 0; sg < a.SG; ++sg) a.acc_off[rg * a.SG + sg] = 4 * rg * row_step + sg * 64;
+    } else if (a.bf16) {
+      // tap pairs: accumulator (rl, sg, cb) starts at tap s = 2*sg of ci-block cb; ci pairs: at tap s = sg of ci-block 2*cb
+      for (int rl = 0; rl < a.RG; ++rl)
+        for (int sg = 0; sg < a.SG; ++sg)
+          for (int cb = 0; cb < a.CIB; ++cb)
+            a.acc_off[(rl * a.SG + sg) * a.CIB + cb] = rl * row_step + (a.c2 ? sg * 8 + 2 * cb * x_step : sg * 16 + cb * x_step);
     } else {
       for (int rl = 0; rl < a.RG; ++rl)
         for (int sg = 0; sg < a.SG; ++sg)
@@ -662,17 +862,19 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     int rc = encode_tiled(&mapX, xp, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   } else {
+    const cuuint64_t es = bf ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
-    cuuint64_t strides[3] = {(cuuint64_t)big.sw * 4, (cuuint64_t)big.sh * 4, (cuuint64_t)big.sn * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-    int rc = encode_tiled(&mapX, big.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    cuuint64_t strides[3] = {(cuuint64_t)big.sw * es, (cuuint64_t)big.sh * es, (cuuint64_t)big.sn * es};
+    cuuint32_t box[4] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    int rc = encode_tiled(&mapX, big.p, 4, dims, strides, box, bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bf);
     if (rc) return rc;
   }
   {
+    const cuuint64_t es = bf ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
-    cuuint64_t strides[3] = {(cuuint64_t)small.sw * 4, (cuuint64_t)small.sh * 4, (cuuint64_t)small.sn * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)(a.dz_rowwise ? a.TW : a.BW), (cuuint32_t)(a.dz_rowwise ? 1 : a.TH), 1};
-    int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    cuuint64_t strides[3] = {(cuuint64_t)small.sw * es, (cuuint64_t)small.sh * es, (cuuint64_t)small.sn * es};
+    cuuint32_t box[4] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)(a.dz_rowwise ? a.TW : a.BW), (cuuint32_t)(a.dz_rowwise ? 1 : a.TH), 1};
+    int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bf);
     if (rc) return rc;
   }
   {

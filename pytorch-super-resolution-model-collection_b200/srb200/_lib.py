@@ -11,13 +11,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LRELU = 0, 1, 2, 3
-MATH_FP32, MATH_TF32, MATH_AUTO, MATH_EXACT = 0, 1, 2, 3
+MATH_FP32, MATH_TF32, MATH_AUTO, MATH_EXACT, MATH_BF16 = 0, 1, 2, 3, 4
+F32, BF16 = 0, 1
 PASS_FPROP, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 
 
 class Tensor4(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("sn", ctypes.c_int64), ("sc", ctypes.c_int64),
-                ("sh", ctypes.c_int64), ("sw", ctypes.c_int64)]
+                ("sh", ctypes.c_int64), ("sw", ctypes.c_int64), ("dtype", ctypes.c_int32)]
 
 
 class ConvParams(ctypes.Structure):
@@ -84,9 +85,14 @@ def check(rc):
 
 
 def t4(t):
-    """torch.Tensor (4-D, fp32, CUDA) -> Tensor4 (logical NCHW + element strides)."""
+    """torch.Tensor (4-D, fp32 or bf16, CUDA) -> Tensor4 (logical NCHW + element strides + dtype)."""
     s = t.stride()
-    return Tensor4(t.data_ptr(), s[0], s[1], s[2], s[3])
+    return Tensor4(t.data_ptr(), s[0], s[1], s[2], s[3], BF16 if t.dtype == _torch_bf16() else F32)
+
+
+def _torch_bf16():
+    import torch
+    return torch.bfloat16
 
 
 def launch_count():

@@ -88,7 +88,12 @@ class DenseBlock(torch.nn.Module):
 
     def forward(self, x):
         out = self.bn(self.fc(x)) if self.norm is not None else self.fc(x)
-        return self.act(out) if self.activation is not None else out
+        if self.activation is None:
+            return out
+        out = self.act(out)
+        if self.activation in ("relu", "lrelu", "prelu"):
+            F._record(out)
+        return out
 
 
 class ConvBlock(torch.nn.Module, _ActMixin):

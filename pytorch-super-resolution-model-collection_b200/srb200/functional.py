@@ -18,13 +18,16 @@ _state = {"math": _lib.MATH_AUTO, "grad_scale": 1.0}
 
 def set_math(mode):
     """'auto' (default): tcgen05 TF32 tensor path where a layer qualifies; 'fp32': CUDA-core fp32 everywhere;
-    'exact': fp32-accurate on the tensor cores by hi/lo operand splitting (3xTF32), full-fp32 activations."""
+    'exact': fp32-accurate on the tensor cores by hi/lo operand splitting (3xTF32), full-fp32 activations;
+    'bf16': bf16 STORAGE (BASELINE cfg4): activations and their gradients are bf16 channels_last tensors feeding
+    tcgen05 kind::f16, parameters and their gradients stay fp32, the 3-channel network edges stay fp32 / TF32."""
     _state["math"] = {"auto": _lib.MATH_AUTO, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32,
-                      "exact": _lib.MATH_EXACT}[mode]
+                      "exact": _lib.MATH_EXACT, "bf16": _lib.MATH_BF16}[mode]
 
 
 def get_math():
-    return {_lib.MATH_AUTO: "auto", _lib.MATH_TF32: "tf32", _lib.MATH_FP32: "fp32", _lib.MATH_EXACT: "exact"}[_state["math"]]
+    return {_lib.MATH_AUTO: "auto", _lib.MATH_TF32: "tf32", _lib.MATH_FP32: "fp32", _lib.MATH_EXACT: "exact",
+            _lib.MATH_BF16: "bf16"}[_state["math"]]
 
 
 def set_grad_scale(s):
@@ -144,6 +147,27 @@ def _require_cuda(*ts):
                                % (t.device, t.dtype))
 
 
+def _bf16_mode():
+    return _state["math"] == _lib.MATH_BF16
+
+
+def _act_dtype(channels):
+    """Storage type of an activation with `channels` channels: bf16 in bf16 mode when its pixel rows are 16-byte
+    multiples (C % 8 == 0), fp32 otherwise (all other modes; the 3-channel network edges)."""
+    return torch.bfloat16 if (_bf16_mode() and channels % 8 == 0 and channels >= 8) else torch.float32
+
+
+def _as_act(t):
+    """Layout/dtype plumbing at the engine boundary (no arithmetic): dense memory, and in bf16 mode the storage type."""
+    t = _dense(t)
+    want = _act_dtype(t.shape[1])
+    if t.dtype != want:
+        t = t.to(want)
+    if want == torch.bfloat16 and not _is_cl(t):
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -167,21 +191,23 @@ class _FusedConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
                 out_token):
-        _require_cuda(x, weight, bias, alpha, residual)
-        x = _dense(x)
+        _require_cuda(weight, bias, alpha)
+        if not x.is_cuda:
+            raise RuntimeError("srb200 kernels need CUDA tensors (got %s); there is no CPU path" % x.device)
+        x = _as_act(x)
         weight = weight.contiguous()
         p = _params(x, weight, stride, pad, out_pad, transposed, ps, act, slope)
         ho, wo = ctypes.c_int32(), ctypes.c_int32()
         check(lib.srb_conv_out_hw(ctypes.byref(p), ctypes.byref(ho), ctypes.byref(wo)))
         oshape = (p.N, p.Cout, ho.value * ps, wo.value * ps)
         fmt = _out_format(p.Cout)
-        y = torch.empty(oshape, dtype=torch.float32, device=x.device, memory_format=fmt)
+        y = torch.empty(oshape, dtype=_act_dtype(p.Cout), device=x.device, memory_format=fmt)
         # PReLU backward needs z itself; relu/lrelu can use sign(y) unless a residual was added on top
         need_preact = act == "prelu" or (act is not None and residual is not None)
         preact = torch.empty_like(y) if need_preact else None
         if residual is not None:
             assert tuple(residual.shape) == oshape, "residual must match the block output"
-            residual = _dense(residual)
+            residual = _as_act(residual)
         bits = None
         if out_token is not None and ps == 1 and p.Cout % 16 == 0 and _is_cl(y) and \
                 _uses_tensor_path(p, _lib.PASS_FPROP, _is_cl(x), True):
@@ -214,13 +240,13 @@ class _FusedConv(torch.autograd.Function):
         premasked = tok is not None and tok.premasked == (dy.data_ptr(), dy._version, tuple(dy.shape), tuple(dy.stride()))
         if tok is not None:
             tok.premasked = None
-        dy = _dense(dy)
+        dy = _as_act(dy)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
         dalpha = None
         if premasked:
             dz = dy  # the consumer's dgrad epilogue already applied this layer's ReLU mask (and the tf32 rounding)
         elif ctx.act is not None:
-            dz = torch.empty(dy.shape, dtype=torch.float32, device=dev, memory_format=_out_format(p.Cout))
+            dz = torch.empty(dy.shape, dtype=dy.dtype, device=dev, memory_format=_out_format(p.Cout))
             if ctx.act == "prelu":
                 dalpha = torch.zeros_like(alpha)
             tdy, tref, tdz = t4(dy), t4(ref), t4(dz)
@@ -232,10 +258,11 @@ class _FusedConv(torch.autograd.Function):
             # PixelShuffle layer on the tensor path: undo the shuffle once (NHWC, tf32) and run dgrad/wgrad as a
             # plain conv with Cout*r*r output channels
             r = p.ps
-            dzu = torch.empty((p.N, p.Cout * r * r, dz.shape[2] // r, dz.shape[3] // r), dtype=torch.float32,
+            dzu = torch.empty((p.N, p.Cout * r * r, dz.shape[2] // r, dz.shape[3] // r), dtype=dz.dtype,
                               device=dev, memory_format=torch.channels_last)
             tdz0, tdzu = t4(dz), t4(dzu)
             check(lib.srb_pixel_unshuffle(ctypes.byref(p), ctypes.byref(tdz0), ctypes.byref(tdzu), st))
+            dzu = _as_act(dzu)  # bf16 mode with an fp32 (3-channel) shuffled output: the un-shuffled gradient is stored bf16
             p = ConvParams(p.N, p.Cin, p.H, p.W, p.Cout * r * r, p.kh, p.kw, p.stride, p.pad, 0, 0, 1, p.act,
                            p.slope, p.math)
             dz = dzu
@@ -264,7 +291,7 @@ class _FusedConv(torch.autograd.Function):
             check(lib.srb_conv_wgrad(ctypes.byref(p), ctypes.byref(tx), ctypes.byref(tdz), _ptr(dw_t), _ptr(db_t),
                                      ctypes.c_float(scale), accumulate, _ptr(ws), ws.numel(), st))
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(x.shape, dtype=torch.float32, device=dev,
+            dx = torch.empty(x.shape, dtype=x.dtype, device=dev,
                              memory_format=torch.channels_last if _is_cl(x) else torch.contiguous_format)
             tdx = t4(dx)
             itok = ctx.in_token
@@ -275,6 +302,8 @@ class _FusedConv(torch.autograd.Function):
             if fuse and itok.bits is not None and p.Cin % 16 == 0 and \
                     _uses_tensor_path(p, _lib.PASS_DGRAD, _is_cl(dx), _is_cl(dz)):
                 bits = itok.bits
+            if fuse and bits is None and p.math == _lib.MATH_BF16:
+                fuse = False  # bf16 storage mode folds the mask only in its packed form
             tmask = t4(x) if (fuse and bits is None) else None
             ws = _workspace(dev, _ws_bytes(p, _lib.PASS_DGRAD))
             check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),

@@ -145,7 +145,7 @@ def test_retain_grad_disables_fused_relu_backward():
     (1, 8, 3, 1, "lrelu", False, 1, 9, 9, 2),
 ])
 def test_exact_mode_op_is_fp32_accurate(case):
-    """math='exact': one fused conv (fwd, dX, dW, db) within 2e-5 of the fp64-accumulated truth -- i.e. fp32 accuracy from
+    """math='exact': one fused conv (fwd, dX, dW, db) within 5e-5 of the fp64-accumulated truth -- i.e. fp32 accuracy from
     the tf32 tensor cores (single-pass TF32 measures 3e-4 on the same cases)."""
     assert torch.cuda.is_available()
     import torch.nn.functional as TF
@@ -180,7 +180,7 @@ def test_exact_mode_op_is_fp32_accurate(case):
     if res:
         yr = yr + r.double()
     yr.backward(gy.double())
-    assert rel_l2(y.detach(), yr.detach()) < 2e-5
-    assert rel_l2(xg.grad, xr.grad) < 2e-5
-    assert rel_l2(wg.grad, wr.grad) < 2e-5
-    assert rel_l2(bg.grad, br.grad) < 2e-5
+    assert rel_l2(y.detach(), yr.detach()) < 5e-5
+    assert rel_l2(xg.grad, xr.grad) < 5e-5
+    assert rel_l2(wg.grad, wr.grad) < 5e-5
+    assert rel_l2(bg.grad, br.grad) < 5e-5
