@@ -320,7 +320,6 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     stage_t = [torch.empty(t.shape, dtype=torch.uint8, device=dev) for t in host_t]
     dev_x = [srb200.image_to_tensor(t.to(dev)) for t in host_x]
     dev_t = [srb200.image_to_tensor(t.to(dev)) for t in host_t]
-    loss_host = torch.zeros(1).pin_memory()
     clip = host.VDSR_CLIP if model_key == "vdsr" else None
 
     def step(x, t):
@@ -355,25 +354,37 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
             ev.record(copy_stream)
         return ev
 
+    loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
+
     def timed(nsteps, e2e):
         ctx.barrier()
         main = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        seen = 0.0
         if e2e:
             copy_stream.wait_event(e0)
             nxt = prefetch(0)
         for i in range(nsteps):
             if e2e:
+                # every step: its batch crosses PCIe (prefetched one step ahead on the copy stream) and its loss is read by the
+                # host (like `loss.data[0]`, srcnn.py:134) -- the read of step i-1 happens while step i runs, so the GPU never idles
                 ev = nxt
                 if i + 1 < nsteps:
                     nxt = prefetch(i + 1)
                 main.wait_event(ev)
                 loss = step_slot(i % 3)
-                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # like `loss.data[0]`, srcnn.py:134
-                main.synchronize()
+                loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_evs[i % 2].record(main)
+                if i > 0:
+                    loss_evs[(i - 1) % 2].synchronize()
+                    seen += float(loss_hosts[(i - 1) % 2][0])
             else:
                 step_slot(i % 3)
+        if e2e:
+            loss_evs[(nsteps - 1) % 2].synchronize()
+            seen += float(loss_hosts[(nsteps - 1) % 2][0])
         e1.record()
         ctx.barrier()
         return ctx.max_over_ranks(e0.elapsed_time(e1))

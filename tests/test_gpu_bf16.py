@@ -102,7 +102,8 @@ def test_bf16_fused_conv_vs_bf16_operand_truth(case):
     assert rel_l2(y.detach().float(), yr.detach()) < (t_store if y_bf16 else t_f32)
     # backward truth uses dz as the kernels saw it: for bf16 y the activation backward / un-shuffle re-round dz to bf16 only
     # when an activation is applied (dz = dy * act'), which is exact for relu and one more rounding for prelu/lrelu
-    assert rel_l2(xg.grad.float(), xr.grad) < (t_store if x_in_bf16 else t_f32)
+    # (the dgrad of a bf16 dz multiplies bf16-rounded weights even when dx itself is an fp32 3-channel tensor)
+    assert rel_l2(xg.grad.float(), xr.grad) < t_store
     assert rel_l2(wg.grad, wr.grad) < (4e-3 if act in ("prelu", "lrelu") else t_f32 * 2)
     assert rel_l2(bg.grad, br.grad) < (4e-3 if act in ("prelu", "lrelu") else t_f32 * 2)
 

@@ -1,21 +1,30 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count / total / mean / share."""
-import collections
+#!/usr/bin/env python
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name (count, total, mean, share)."""
 import csv
 import sys
+from collections import OrderedDict
 
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
-hdr = rows[0]
-ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-agg = collections.OrderedDict()
-for r in rows[1:]:
-    if "spin_kernel" in r[ki]:
-        continue  # bench.py parks the GPU on torch.cuda._sleep in its instrumented pass; not part of a training step
-    k = r[ki][:90]
-    v = float(r[vi].replace(",", ""))
+path = sys.argv[1]
+skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rows = []
+with open(path) as f:
+    lines = [l for l in f if not l.startswith("==")]
+rd = csv.DictReader(lines)
+for r in rd:
+    if r.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    v = float(r["Metric Value"].replace(",", ""))
+    unit = r.get("Metric Unit", "ns")
+    us = v / 1000.0 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1000.0)
+    rows.append((r["Kernel Name"], us))
+rows = rows[skip:]
+agg = OrderedDict()
+for k, us in rows:
     a = agg.setdefault(k, [0, 0.0])
     a[0] += 1
-    a[1] += v
+    a[1] += us
 tot = sum(a[1] for a in agg.values())
-print("%-92s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share"))
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-    print("%-92s %6d %12.1f %10.1f %7.3f" % (k, a[0], a[1] / 1e3, a[1] / a[0] / 1e3, a[1] / tot))
+print("%-100s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share"))
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("%-100s %6d %12.1f %10.1f %7.3f" % (k[:100], n, t, t / n, t / tot))
+print("total %.1f us over %d launches" % (tot, len(rows)))
