@@ -98,6 +98,11 @@ int srb_conv_out_hw(const srb_conv_params *p, int32_t *Ho, int32_t *Wo);
  * 0 = fp32 CUDA-core path.  pass: 0 fprop, 1 dgrad, 2 wgrad.  x_cl / y_cl: channels_last flags. */
 int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int y_cl);
 
+/* PixelShuffle layers (p->ps > 1): 1 when srb_conv_dgrad and srb_conv_wgrad take dz in y's (shuffled) layout and fold the
+ * pixel-un-shuffle into their TMA load addressing (channels_last x and dz, Cout a multiple of the 128-byte channel block:
+ * 32 fp32 / 64 bf16 channels); 0 when the caller has to run srb_pixel_unshuffle first and pass ps = 1 geometry. */
+int srb_conv_backward_folds_ps(const srb_conv_params *p, int x_cl, int dz_cl);
+
 /* Diagnostic: human-readable tile plan the tensor path would use for this layer (host only, no GPU work). */
 int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t n);
 

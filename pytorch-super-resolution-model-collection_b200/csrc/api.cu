@@ -511,6 +511,21 @@ int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int 
   return (exact ? exact_wgrad_supported(g) : tc_wgrad_supported(g, y, x)) ? 1 : 0;
 }
 
+int srb_conv_backward_folds_ps(const srb_conv_params *p, int x_cl, int dz_cl) {
+  Geom g;
+  if (make_geom(p, &g) || p->transposed || g.ps <= 1 || g.st != 1 || g.kh != g.kw) return 0;
+  if (!(is_tf32_math(p->math) || p->math == SRB_MATH_BF16) || !x_cl || !dz_cl) return 0;
+  const int dt = p->math == SRB_MATH_BF16 ? SRB_BF16 : SRB_F32;
+  if (p->math == SRB_MATH_BF16 && (bf16_act_dtype(g.Ci) != SRB_BF16 || bf16_act_dtype(p->Cout) != SRB_BF16)) return 0;
+  // dense channels_last views: x (N,Ci,Hi,Wi); dz in y's layout (N,Cout,Ho*r,Wo*r)
+  T4 x{(float *)256, (long long)g.Hi * g.Wi * g.Ci, 1, (long long)g.Wi * g.Ci, g.Ci, dt};
+  T4 z{(float *)256, (long long)g.Ho * g.ps * g.Wo * g.ps * p->Cout, 1, (long long)g.Wo * g.ps * p->Cout, p->Cout, dt};
+  Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+  Geom g1 = g;
+  g1.ps = 1;
+  return (gd.pad >= 0 && tc_conv_supported(gd, z, x, true, g.ps) && tc_wgrad_supported(g1, z, x, g.ps)) ? 1 : 0;
+}
+
 /* Debug only (not in the public header): per-CTA phase timestamps of the next k_conv_sl launches go to buf (8 x int64 per CTA). */
 void srb_debug_set_trace(void *buf, long long max_ctas) { tc_conv_set_trace((long long *)buf, max_ctas); }
 void srb_debug_set_flags(int flags) { tc_conv_set_dbg(flags); }
@@ -681,18 +696,27 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   e.bits_in = relu_bits;
   e.round_tf32 = want_round(p, tdx, p->Cin);
   if (p->math == SRB_MATH_BF16) {
-    SRB_REQUIRE(!p->transposed && g.st == 1 && g.ps == 1 && g.kh == g.kw, SRB_EUNSUPPORTED,
-                "bf16 storage mode: dgrad needs a stride-1 square-kernel Conv2d (PixelShuffle layers: un-shuffle dz first)");
+    SRB_REQUIRE(!p->transposed && g.st == 1 && g.kh == g.kw, SRB_EUNSUPPORTED,
+                "bf16 storage mode: dgrad needs a stride-1 square-kernel Conv2d");
     Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
-    SRB_REQUIRE(gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true), SRB_EUNSUPPORTED,
-                "bf16 storage mode: dz must be bf16 channels_last with Cout %% 8 == 0 (or fp32 with Cout <= 4)");
+    SRB_REQUIRE(gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true, g.ps), SRB_EUNSUPPORTED,
+                "bf16 storage mode: dz must be bf16 channels_last with Cout %% 8 == 0 (PixelShuffle layers: Cout %% 64 == 0, "
+                "else un-shuffle first), or fp32 with Cout <= 4");
     SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
     SRB_REQUIRE(!e.mask.p, SRB_EUNSUPPORTED, "bf16 storage mode: pass relu_bits, not relu_mask");
     e.round_tf32 = 0;
-    return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st);
+    return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
   }
   SRB_REQUIRE(tdz.dt == SRB_F32 && tdx.dt == SRB_F32, SRB_EUNSUPPORTED, "bf16 tensors need math = SRB_MATH_BF16");
   if (!p->transposed) {
+    if (is_tf32_math(p->math) && g.ps > 1 && g.st == 1 && g.kh == g.kw) {
+      // PixelShuffle layer: dz arrives in y's (shuffled) layout; the un-shuffle is the TMA traversal of the A operand
+      Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+      SRB_REQUIRE(gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true, g.ps), SRB_EUNSUPPORTED,
+                  "dgrad of a PixelShuffle layer needs channels_last dz with Cout %% 32 == 0 (else srb_pixel_unshuffle first)");
+      SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
+      return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
+    }
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
       // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
       Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
@@ -732,14 +756,17 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   SRB_REQUIRE(x && x->data && dz && dz->data && dw, SRB_EINVAL, "null tensor");
   T4 tx = to_t4(x), tdz = to_t4(dz);
   if (p->math == SRB_MATH_BF16) {
-    SRB_REQUIRE(!p->transposed && g.st == 1 && g.ps == 1, SRB_EUNSUPPORTED,
-                "bf16 storage mode: wgrad needs a stride-1 Conv2d (PixelShuffle layers: un-shuffle dz first)");
+    SRB_REQUIRE(!p->transposed && g.st == 1, SRB_EUNSUPPORTED, "bf16 storage mode: wgrad needs a stride-1 Conv2d");
     uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
     const uintptr_t ws_end = (uintptr_t)ws + ws_bytes;
+    const int z_ps = g.ps;
+    g.ps = 1;  // from here on g is the plain conv; dz's shuffled layout is handled by the dz TMA traversal (z_ps)
     if (tx.dt == SRB_BF16 && tdz.dt == SRB_BF16) {
-      SRB_REQUIRE(tc_wgrad_supported(g, tdz, tx), SRB_EUNSUPPORTED, "bf16 wgrad: no plan for this layer");
-      return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+      SRB_REQUIRE(tc_wgrad_supported(g, tdz, tx, z_ps), SRB_EUNSUPPORTED,
+                  "bf16 wgrad: no plan for this layer (PixelShuffle layers need Cout %% 64 == 0, else un-shuffle dz first)");
+      return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st, z_ps);
     }
+    SRB_REQUIRE(z_ps == 1, SRB_EUNSUPPORTED, "bf16 storage mode: PixelShuffle layer with an fp32 side (un-shuffle dz first)");
     if (tx.dt == SRB_F32 && tdz.dt == SRB_BF16) {
       // network input layer (Cin <= 4): dz -> fp32 NHWC (exactly representable in tf32), then the tf32 c4 wgrad
       SRB_REQUIRE(g.Ci <= 4, SRB_EUNSUPPORTED, "bf16 storage mode: fp32 x with Cin > 4");
@@ -780,6 +807,13 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
   if (!p->transposed) {
     if (p->math == SRB_MATH_EXACT && exact_wgrad_supported(g))
       return exact_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    if (is_tf32_math(p->math) && g.ps > 1) {
+      Geom g1 = g;
+      g1.ps = 1;
+      SRB_REQUIRE(tc_wgrad_supported(g1, tdz, tx, g.ps), SRB_EUNSUPPORTED,
+                  "wgrad of a PixelShuffle layer needs channels_last x / dz with Cout %% 32 == 0 (else srb_pixel_unshuffle first)");
+      return tc_conv_wgrad(g1, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st, g.ps);
+    }
     if (is_tf32_math(p->math) && tc_wgrad_supported(g, tdz, tx))
       return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
     SkinnyWg sk;

@@ -105,19 +105,22 @@ int simt_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, fl
 int channel_sum(const T4 &t, int N, int C, int H, int W, float *out, float scale, int accumulate, cudaStream_t st);
 
 // Tensor-core (tcgen05) path, tc_conv.cu.
-bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_as_gather);
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_as_gather, int in_ps = 1);
 size_t tc_conv_ws_bytes(const Geom &g);
+// in_ps > 1: `in` holds PixelShuffle_r of the logical input (g.Ci = C * r * r logical channels, in has C); the un-shuffle
+// happens in the TMA traversal
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
-                   void *ws, size_t ws_bytes, cudaStream_t st);
+                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps = 1);
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
 int tc_conv_get_dbg();
 int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
 int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
-bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);
+bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big, int z_ps = 1);
 size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16 = false);
+// z_ps > 1: `small` holds PixelShuffle_r of dz (in y's layout); un-shuffled by the TMA traversal, dw/db come out in filter order
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
-                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st);
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps = 1);
 
 
 // 3xTF32 split-operand mode (exact.cu): fp32-accurate results from the same tensor-core kernels.

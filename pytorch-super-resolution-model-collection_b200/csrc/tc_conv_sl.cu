@@ -49,6 +49,8 @@ struct SlArgs {
   int out_bf16;      // out / residual / preact are bf16 tensors
   int chunk_elems;   // channels per A chunk: 32 (tf32) or 64 (bf16)
   int v8h;           // bf16 outputs: rows are 32-byte aligned (256-bit accesses of 16 bf16 channels)
+  int in_ps;         // > 1: the input tensor is PixelShuffle_r of the logical input (dgrad of a PSBlock conv): chunk c is
+  int in_cpb;        //      sub-pixel phase c / in_cpb, channel block c % in_cpb, fetched through a stride-r TMA traversal
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
   int v8;              // out / residual / preact / mask rows are 32-byte aligned: mode-0 epilogue uses 256-bit global accesses
   int dbg;             // debug knobs (srb_debug_set_flags): 1 = epilogue does nothing, 2 = A tiles are loaded only once per buffer
@@ -583,7 +585,14 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             mbar_arrive(&a_full[buf]);
           } else {
             mbar_expect_tx(&a_full[buf], (uint32_t)a.a_tx_bytes);
-            tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, c * a.chunk_elems, ix0, iy0, img);
+            int cc = c, ix = ix0, iy = iy0;
+            if (a.in_ps > 1) {  // pixel-un-shuffle folded into the load: phase (i, j) of the shuffled gradient
+              const int ij = c / a.in_cpb;
+              cc = c - ij * a.in_cpb;
+              iy = iy0 * a.in_ps + ij / a.in_ps;
+              ix = ix0 * a.in_ps + ij % a.in_ps;
+            }
+            tma_load_4d(&mapA, &a_full[buf], a_smem + (size_t)buf * a.a_buf_bytes, cc * a.chunk_elems, ix, iy, img);
           }
         }
         __syncwarp();
@@ -724,8 +733,15 @@ __device__ __forceinline__ float wval(const float *__restrict__ w, int n, int k,
 }
 
 // generic B operand: out[chunk][tap][Npad][32] (tf32 RN), zero for n >= Nn or k >= Kk
+// perm_C > 0 (input un-shuffle fold): launch K index k = ij * perm_C + c stands for the filter's channel c * perm_rr + ij
+__device__ __forceinline__ int perm_k(int k, int perm_C, int perm_rr) {
+  if (perm_C <= 0) return k;
+  const int ij = k / perm_C;
+  return (k - ij * perm_C) * perm_rr + ij;
+}
+
 __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad,
-                            int chunks, int flip) {
+                            int chunks, int flip, int perm_C, int perm_rr) {
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -738,7 +754,7 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
     float v = 0.f;
     if (n < Nn && k < Kk) {
       const int r = tap / kw, s = tap - r * kw;
-      v = round_tf32(wval(w, n, k, r, s, Nn, Kk, kh, kw, flip));
+      v = round_tf32(wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip));
     }
     out[i] = v;
   }
@@ -746,7 +762,7 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
 
 // generic B operand for bf16 operands: out[chunk][tap][Npad][64] (bf16 RN), zero for n >= Nn or k >= Kk
 __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__restrict__ out, int Nn, int Kk, int kh, int kw,
-                              int Npad, int chunks, int flip) {
+                              int Npad, int chunks, int flip, int perm_C, int perm_rr) {
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -759,7 +775,7 @@ __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__res
     float v = 0.f;
     if (n < Nn && k < Kk) {
       const int r = tap / kw, s = tap - r * kw;
-      v = wval(w, n, k, r, s, Nn, Kk, kh, kw, flip);
+      v = wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip);
     }
     out[i] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xffffu);
   }
@@ -816,7 +832,7 @@ inline double mma_cost(int N) {  // cycles of one SS-mode tf32 MMA, M=128 K=8 (t
   return c1 > c2 ? c1 : c2;
 }
 
-bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false) {
+bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
   SlArgs &a = pl->a;
   const bool c4 = g.Ci <= 4 && !bf16;
   const int celems = bf16 ? 64 : 32;  // channels per 128-byte slot
@@ -848,13 +864,13 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false) {
         for (int wsplit = 1; wsplit <= 16; ++wsplit) {
           const int TW = (g.Wo + wsplit - 1) / wsplit;
           const int BW = TW + kextra;
-          if (BW > 256 || TW > 128 * MTB) continue;
+          if (BW * in_ps > 256 || TW > 128 * MTB) continue;  // TMA box dims <= 256 (the un-shuffling traversal spans r x as many)
           int TH = (128 * MTB - TW) / BW + 1;
           if (TH > g.Ho) TH = g.Ho;
           const int bands_h = (g.Ho + TH - 1) / TH;
           TH = (g.Ho + bands_h - 1) / bands_h;
           const int BH = TH + g.kh - 1;
-          if (BH > 256) continue;
+          if (BH * in_ps > 256) continue;
           const int bands_w = (g.Wo + TW - 1) / TW;
           int slots = BH * BW;
           const int need = 128 * MTB + (g.kh - 1) * BW + kextra;
@@ -932,6 +948,8 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false) {
   a.out_bf16 = 0;
   a.chunk_elems = celems;
   a.v8h = 0;
+  a.in_ps = in_ps;
+  a.in_cpb = in_ps > 1 ? g.Ci / (in_ps * in_ps) / celems : 0;
   pl->Npad = Npad;
   pl->n_tiles_n = Npad / NT;
   {  // persistent grid: as many CTAs as fit on the chip; CTA x walks bands x, x + grid, ...
@@ -957,8 +975,12 @@ void tc_conv_set_trace(long long *buf, long long max_ctas) { g_sl_trace = buf; g
 void tc_conv_set_dbg(int flags) { g_sl_dbg = flags; }
 int tc_conv_get_dbg() { return g_sl_dbg; }
 
-bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/) {
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/, int in_ps) {
   if (g.st != 1 || g.N <= 0) return false;
+  if (in_ps > 1) {  // `in` is PixelShuffle_r of the logical input: needs whole channel chunks per sub-pixel phase
+    const int celems = in.dt == SRB_BF16 ? 64 : 32, rr = in_ps * in_ps;
+    if (in_ps > 8 || g.Ci % rr != 0 || (g.Ci / rr) % celems != 0) return false;
+  }
   if (g.kh > 16 || g.kw > 16) return false;
   if ((long long)g.N * g.Hi * g.Wi * (g.Ci > 4 ? g.Ci : 4) >= (1LL << 40)) return false;
   if ((long long)g.N * ((g.Ho + 0) * (long long)g.Wo) >= (1LL << 31)) return false;
@@ -968,7 +990,7 @@ bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*
     if ((in.sw % 8) || (in.sh % 8) || (in.sn % 8)) return false;       // TMA strides: multiples of 16 B
     if (((uintptr_t)in.p) & 15) return false;
     SlPlan ph;
-    return make_sl_plan(g, &ph, true);
+    return make_sl_plan(g, &ph, true, in_ps);
   }
   if (g.Ci > 4) {
     if (g.Ci % 4 != 0 || g.Ci < 8) return false;                       // TMA: 16-byte pixel stride
@@ -977,7 +999,7 @@ bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*
     if (((uintptr_t)in.p) & 15) return false;
   }
   SlPlan p;
-  return make_sl_plan(g, &p);
+  return make_sl_plan(g, &p, false, in_ps);
 }
 
 size_t tc_conv_ws_bytes(const Geom &g) {
@@ -1008,10 +1030,12 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
 }
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
-                   void *ws, size_t ws_bytes, cudaStream_t st) {
+                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps) {
   SlPlan pl;
   const bool bf_in = in.dt == SRB_BF16, bf_out = out.dt == SRB_BF16;
-  SRB_REQUIRE(make_sl_plan(g, &pl, bf_in), SRB_EUNSUPPORTED, "tc_conv: no band plan");
+  SRB_REQUIRE(make_sl_plan(g, &pl, bf_in, in_ps), SRB_EUNSUPPORTED, "tc_conv: no band plan");
+  SRB_REQUIRE(in_ps == 1 || !pl.a.c4, SRB_EUNSUPPORTED, "tc_conv: un-shuffled input needs the generic operand flavour");
+  const int perm_C = in_ps > 1 ? g.Ci / (in_ps * in_ps) : 0, perm_rr = in_ps * in_ps;
   SRB_REQUIRE((!epi.residual.p || epi.residual.dt == out.dt) && (!epi.preact.p || epi.preact.dt == out.dt), SRB_EINVAL,
               "residual / preact must have the dtype of the output");
   SRB_REQUIRE(!epi.mask.p || epi.mask.dt == SRB_F32 || !bf_out, SRB_EUNSUPPORTED, "float relu_mask with bf16 tensors (use relu_bits)");
@@ -1031,9 +1055,10 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     if (a.c4)
       k_pack_w_c4<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
     else if (bf_in)
-      k_pack_w_sl_h<<<blocks, 256, 0, st>>>(w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+      k_pack_w_sl_h<<<blocks, 256, 0, st>>>(w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0,
+                                            perm_C, perm_rr);
     else
-      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     if (a.c4) {
@@ -1058,11 +1083,15 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     a.wpack = wp;
   } else {
     {
-      cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+      // in_ps > 1: the map describes the SHUFFLED tensor (C, W*r, H*r, N) and is traversed with element strides (1, r, r, 1):
+      // a box of (BW*r) x (BH*r) delivers BW x BH pixels of one sub-pixel phase
+      const cuuint64_t r = (cuuint64_t)in_ps;
+      cuuint64_t dims[4] = {(cuuint64_t)(in_ps > 1 ? perm_C : g.Ci), (cuuint64_t)g.Wi * r, (cuuint64_t)g.Hi * r, (cuuint64_t)g.N};
       const cuuint64_t es = bf_in ? 2 : 4;
       cuuint64_t strides[3] = {(cuuint64_t)in.sw * es, (cuuint64_t)in.sh * es, (cuuint64_t)in.sn * es};
-      cuuint32_t box[4] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-      int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf_in);
+      cuuint32_t box[4] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)(a.BW * in_ps), (cuuint32_t)(a.BH * in_ps), 1};
+      cuuint32_t estr[4] = {1, (cuuint32_t)in_ps, (cuuint32_t)in_ps, 1};
+      int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf_in, in_ps > 1 ? estr : nullptr);
       if (rc) return rc;
     }
     {

@@ -43,6 +43,9 @@ struct WgArgs {
                           // accumulator's two 64-lane M-blocks are two consecutive s-taps (c2 == 0) or two ci-blocks (c2 == 1)
   int c2;                 // bf16 only: M = 2 ci-blocks x 1 tap (LBO = one x tile) instead of 1 ci-block x 2 taps (LBO = one slot);
                           // CIB then counts ci-block PAIRS and SG = kw
+  int z_ps, z_cpb;        // z_ps > 1: dz is given as PixelShuffle_r(dz) (y's layout, C = Co / r^2 channels): N-block q of the GEMM is
+                          // sub-pixel phase q / z_cpb, channel block q % z_cpb, fetched through a stride-r TMA traversal; the
+                          // GEMM's output channel co' = ij * C + c is filter co = c * r^2 + ij (k_wgrad_finish undoes it)
   int dbg;                // debug knobs (srb_debug_set_flags): 2 = stages are TMA-loaded only once, 4 = no MMAs are issued
   int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
@@ -230,13 +233,21 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int cb = 0; cb < XT; ++cb)
               tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * XT + cb) * blk_ch, ox0 - a.pad, oh0 - a.pad + r0, n);
           }
-          if (a.dz_rowwise) {
-            for (int t = 0; t < a.TH; ++t)  // rows past the image (and columns past Wo) arrive as zeros
-              for (int j = 0; j < nb; ++j)
-                tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, cot * a.NT + j * blk_ch, ox0, oh0 + t, n);
-          } else {
-            for (int j = 0; j < nb; ++j)
-              tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, cot * a.NT + j * blk_ch, 0, oh0, n);
+          for (int j = 0; j < nb; ++j) {
+            int zc = cot * a.NT + j * blk_ch, zx = a.dz_rowwise ? ox0 : 0, zy = oh0, zr = 1;
+            if (a.z_ps > 1) {  // pixel-un-shuffle folded into the load (host guarantees NT % blk_ch == 0)
+              const int q = zc / blk_ch, ij = q / a.z_cpb;
+              zr = a.z_ps;
+              zc = (q - ij * a.z_cpb) * blk_ch;
+              zx = zx * zr + ij % zr;
+              zy = zy * zr + ij / zr;
+            }
+            if (a.dz_rowwise) {
+              for (int t = 0; t < a.TH; ++t)  // rows past the image (and columns past Wo) arrive as zeros
+                tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, zc, zx, zy + t * zr, n);
+            } else {
+              tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, zc, zx, zy, n);
+            }
           }
         }
         __syncwarp();
@@ -412,78 +423,100 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   }
 }
 
-// dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]   (fixed summation order => deterministic)
-// blockDim = (32 elements, 8 split lanes): lane y sums splits y, y+8, ... ; the 8 lane sums are folded in shared memory
-// in a fixed order.  Element index runs co-fastest so that the partial reads (n contiguous) coalesce.
-// blockDim = (32 outputs, L split lanes, G output groups): few splits -> many outputs per block, many splits -> many lanes.
-template <int L, int G>
-__global__ void __launch_bounds__(32 * L * G) k_wgrad_finish(WgArgs a, int splits, int gy, float *dw, float *db, float scale, int accumulate) {
-  __shared__ float red[G][L][33];
-  const long long total = (long long)a.Co * a.Ci * a.kh * a.kw;
+// Where GEMM column co, filter tap (ci, r, s) lives in a CTA's partial dump: grid.y index, accumulator, TMEM lane m, column n.
+__device__ __forceinline__ void wg_locate(const WgArgs &a, int co, int ci, int r, int s, int &by, int &acc, int &m, int &n) {
+  const int cot = co / a.NT;
+  n = co - cot * a.NT;
+  if (a.c4) {
+    by = cot;
+    acc = (r >> 2) * a.SG + (s >> 3);
+    m = (r & 3) * 32 + (s & 7) * 4 + ci;
+  } else if (a.bf16) {
+    const int cblk = ci >> 6, rgi = r / a.RG, rl = r - rgi * a.RG;
+    int cig, cb, sg, half;
+    if (a.c2) { const int cp = cblk >> 1; cig = cp / a.CIB; cb = cp - cig * a.CIB; sg = s; half = cblk & 1; }
+    else      { cig = cblk / a.CIB; cb = cblk - cig * a.CIB; sg = s >> 1; half = s & 1; }
+    by = (cig * a.n_rg + rgi) * a.n_cot + cot;
+    acc = (rl * a.SG + sg) * a.CIB + cb;
+    m = half * 64 + (ci & 63);
+  } else {
+    const int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
+    const int rgi = r / a.RG, rl = r - rgi * a.RG;
+    const int sg = s >> 2, sl = s & 3;
+    by = (cig * a.n_rg + rgi) * a.n_cot + cot;
+    acc = (rl * a.SG + sg) * a.CIB + cb;
+    m = sl * 32 + (ci & 31);
+  }
+}
+
+// GEMM column co' -> filter index (identity unless dz was un-shuffled on the fly: co' = ij * C + c  ->  c * r^2 + ij)
+__device__ __forceinline__ int wg_filter_of(const WgArgs &a, int co) {
+  if (a.z_ps <= 1) return co;
+  const int rr = a.z_ps * a.z_ps, C = a.Co / rr, ij = co / C;
+  return (co - ij * C) * rr + ij;
+}
+
+// dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]      (fixed summation order => deterministic)
+// One block = 32 GEMM columns x CT input channels x all taps.  Reads: a warp walks 32 consecutive columns of one partial row
+// (128 B, coalesced) over the splits with 8 independent accumulators; the sums are transposed through shared memory so that
+// the OIHW stores are contiguous runs of CT*kh*kw floats per filter.  (The previous one-thread-per-output kernel spent
+// 47 us on EDSR-256's 28 MB of partials: 4-byte stores 9 KB apart and 3 loads in flight per thread.)
+__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, int CT, float *dw, float *db, float scale,
+                                                      int accumulate) {
+  extern __shared__ float tile[];  // [32][CT * taps + 1]
+  const int taps = a.kh * a.kw, items = CT * taps, pitch = items + 1;
+  const int co_tiles = (a.Co + 31) / 32, ci_tiles = (a.Ci + CT - 1) / CT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ACC = a.RG * a.SG * a.CIB;
-  const long long i = ((long long)blockIdx.x * G + threadIdx.z) * 32 + threadIdx.x;
-  float sum = 0.f;
-  long long dst = 0;
-  const bool is_db = db != nullptr && i >= total && i < total + a.Co;
-  if (is_db) {  // bias gradient: splits x 4 warp partials per channel
-    const int co = (int)(i - total);
-    const size_t pitch = (size_t)(a.n_cot * a.NT);
-    for (int z = threadIdx.y; z < splits * 4; z += L) sum += a.db_part[(size_t)z * pitch + co];
-  }
-  if (i < total) {
-    const int co = (int)(i % a.Co);
-    long long q = i / a.Co;
-    const int s = (int)(q % a.kw); q /= a.kw;
-    const int r = (int)(q % a.kh);
-    const int ci = (int)(q / a.kh);
-    dst = (((long long)co * a.Ci + ci) * a.kh + r) * a.kw + s;
-    const int cot = co / a.NT, n = co - cot * a.NT;
-    int by, acc, m;
-    if (a.c4) {
-      by = cot;
-      acc = (r >> 2) * a.SG + (s >> 3);
-      m = (r & 3) * 32 + (s & 7) * 4 + ci;
-    } else if (a.bf16) {
-      const int cblk = ci >> 6, rgi = r / a.RG, rl = r - rgi * a.RG;
-      int cig, cb, sg, half;
-      if (a.c2) { const int cp = cblk >> 1; cig = cp / a.CIB; cb = cp - cig * a.CIB; sg = s; half = cblk & 1; }
-      else      { cig = cblk / a.CIB; cb = cblk - cig * a.CIB; sg = s >> 1; half = s & 1; }
-      by = (cig * a.n_rg + rgi) * a.n_cot + cot;
-      acc = (rl * a.SG + sg) * a.CIB + cb;
-      m = half * 64 + (ci & 63);
-    } else {
-      int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
-      int rgi = r / a.RG, rl = r - rgi * a.RG;
-      int sg = s >> 2, sl = s & 3;
-      by = (cig * a.n_rg + rgi) * a.n_cot + cot;
-      acc = (rl * a.SG + sg) * a.CIB + cb;
-      m = sl * 32 + (ci & 31);
+  const size_t ss = (size_t)gy * ACC * 128 * a.NT;  // floats between consecutive splits
+  if ((int)blockIdx.x < co_tiles * ci_tiles) {
+    const int cot32 = blockIdx.x % co_tiles, ci0 = (blockIdx.x / co_tiles) * CT;
+    const int co = cot32 * 32 + tx;
+    for (int j = ty; j < items; j += 8) {
+      const int cl = j / taps, tap = j - cl * taps, r = tap / a.kw, s = tap - r * a.kw, ci = ci0 + cl;
+      float sum = 0.f;
+      if (co < a.Co && ci < a.Ci) {
+        int by, acc, m, n;
+        wg_locate(a, co, ci, r, s, by, acc, m, n);
+        const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+        int z = 0;
+        for (; z + 7 < splits; z += 8) {
+          s0 += p[(size_t)z * ss]; s1 += p[(size_t)(z + 1) * ss]; s2 += p[(size_t)(z + 2) * ss]; s3 += p[(size_t)(z + 3) * ss];
+          s4 += p[(size_t)(z + 4) * ss]; s5 += p[(size_t)(z + 5) * ss]; s6 += p[(size_t)(z + 6) * ss]; s7 += p[(size_t)(z + 7) * ss];
+        }
+        for (; z < splits; ++z) s0 += p[(size_t)z * ss];
+        sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+      }
+      tile[tx * pitch + j] = sum;
     }
-    const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
-    const size_t split_stride = (size_t)gy * ACC * 128 * a.NT;
-    // four independent loads in flight per thread; lane y takes splits y, y + L, ...
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int z = threadIdx.y;
-    for (; z + 3 * L < splits; z += 4 * L) {
-      s0 += p[(size_t)z * split_stride]; s1 += p[(size_t)(z + L) * split_stride];
-      s2 += p[(size_t)(z + 2 * L) * split_stride]; s3 += p[(size_t)(z + 3 * L) * split_stride];
-    }
-    for (; z < splits; z += L) s0 += p[(size_t)z * split_stride];
-    sum = (s0 + s1) + (s2 + s3);
-  }
-  if (L > 1) {
-    red[threadIdx.z][threadIdx.y][threadIdx.x] = sum;
     __syncthreads();
-    if (threadIdx.y == 0) {
-      sum = red[threadIdx.z][0][threadIdx.x];
-#pragma unroll
-      for (int y = 1; y < L; ++y) sum += red[threadIdx.z][y][threadIdx.x];
+    for (int e = threadIdx.x; e < 32 * items; e += 256) {
+      const int col = e / items, j = e - col * items;
+      const int co2 = cot32 * 32 + col, ci = ci0 + j / taps;
+      if (co2 < a.Co && ci < a.Ci) {
+        float *d = dw + ((size_t)wg_filter_of(a, co2) * a.Ci + ci0) * taps + j;
+        const float t = tile[col * pitch + j] * scale;
+        *d = accumulate ? *d + t : t;
+      }
     }
-  }
-  if (threadIdx.y == 0 && (i < total || is_db)) {
-    const float t = sum * scale;
-    float *d = is_db ? db + (i - total) : dw + dst;
-    *d = accumulate ? *d + t : t;
+  } else if (db != nullptr) {
+    // bias gradient: splits x 4 warp partials per channel; 32 channels per block, 8 z-lanes folded through shared memory
+    const int co = ((int)blockIdx.x - co_tiles * ci_tiles) * 32 + tx;
+    const size_t pitch_db = (size_t)(a.n_cot * a.NT);
+    float sum = 0.f;
+    if (co < a.Co)
+      for (int z = ty; z < splits * 4; z += 8) sum += a.db_part[(size_t)z * pitch_db + co];
+    tile[ty * 33 + tx] = sum;
+    __syncthreads();
+    if (ty == 0 && co < a.Co) {
+      float t = tile[tx];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) t += tile[y * 33 + tx];
+      t *= scale;
+      float *d = db + wg_filter_of(a, co);
+      *d = accumulate ? *d + t : t;
+    }
   }
 }
 
@@ -521,6 +554,7 @@ struct WgPlan {
 // Cin <= 4 (network inputs): see WgArgs::c4.
 bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   WgArgs &a = pl->a;
+  a.z_ps = 1; a.z_cpb = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
   a.c4 = 1; a.bf16 = 0; a.c2 = 0;
@@ -579,9 +613,10 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
 }
 
 // bf16 operands: 64-channel blocks, K = 16 pixels per MMA, M = 128 as two 64-lane blocks (WgArgs::bf16 / c2).
-bool make_wg_plan_h(const Geom &g, WgPlan *pl) {
+bool make_wg_plan_h(const Geom &g, WgPlan *pl, int z_ps) {
   WgArgs &a = pl->a;
   a.c4 = 0; a.bf16 = 1;
+  a.z_ps = z_ps; a.z_cpb = z_ps > 1 ? g.Co / (z_ps * z_ps) / 64 : 0;
   pl->Hp = pl->Wp = 0;
   pl->xpack_floats = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
@@ -602,9 +637,10 @@ bool make_wg_plan_h(const Geom &g, WgPlan *pl) {
       const int bands_w = (g.Wo + TW - 1) / TW;
       // row-wise dz loads land at t * BW * 128 B: keep every row on the 1024-B period of the 128B swizzle
       const int BW = bands_w > 1 ? round_up_i(TW + g.kw - 1, 8) : g.Wo + g.kw - 1;
-      if (BW > 256) continue;
+      if (BW * z_ps > 256) continue;
       for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 16; NT -= 16) {
         if (co_pad % NT) continue;
+        if (z_ps > 1 && NT % 64) continue;  // whole 64-channel blocks per sub-pixel phase
         const int nb = (NT + 63) / 64;
         for (int CIB = units; CIB >= 1; --CIB) {
           if (units % CIB) continue;
@@ -615,7 +651,7 @@ bool make_wg_plan_h(const Geom &g, WgPlan *pl) {
             for (int TH = 16; TH >= 1; --TH) {
               if (TH > g.Ho && TH > 1) continue;
               const int BH = TH + RG - 1;
-              if (BH > 256) continue;
+              if (BH > 256 || TH * z_ps > 256) continue;
               const int x_slots = round_up_i(BH * BW + g.kw + 16, 16);
               const int dz_slots = round_up_i(TH * BW, 16);
               const size_t stage = (size_t)XT * x_slots * 128 + (size_t)nb * dz_slots * 128;
@@ -674,11 +710,12 @@ bool make_wg_plan_h(const Geom &g, WgPlan *pl) {
   return true;
 }
 
-bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false) {
-  if (bf16) return make_wg_plan_h(g, pl);
-  if (g.Ci <= 4) return make_wg_plan_c4(g, pl);
+bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
+  if (bf16) return make_wg_plan_h(g, pl, z_ps);
+  if (g.Ci <= 4) return z_ps == 1 && make_wg_plan_c4(g, pl);
   WgArgs &a = pl->a;
   a.c4 = 0; a.bf16 = 0; a.c2 = 0;
+  a.z_ps = z_ps; a.z_cpb = z_ps > 1 ? g.Co / (z_ps * z_ps) / 32 : 0;
   pl->Hp = pl->Wp = 0;
   pl->xpack_floats = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
@@ -702,7 +739,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false) {
     const int bands_w = (g.Wo + TW - 1) / TW;
     // row-wise dz loads land at t * BW * 128 B: keep every row on the 512-B period of the 32B-atom swizzle
     const int BW = bands_w > 1 ? round_up_i(TW + g.kw - 1, 4) : g.Wo + g.kw - 1;
-    if (BW > 256) continue;
+    if (BW * z_ps > 256) continue;
     for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
       if (co_pad % NT) continue;
       for (int CIB = cblocks; CIB >= 1; --CIB) {
@@ -713,7 +750,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false) {
           for (int TH = 16; TH >= 1; --TH) {
             if (TH > g.Ho && TH > 1) continue;
             int BH = TH + RG - 1;
-            if (BH > 256) continue;
+            if (BH > 256 || TH * z_ps > 256) continue;
             int x_slots = round_up_i(BH * BW + 4 * a.SG + 8, 8);
             int dz_slots = round_up_i(TH * BW, 8);
             size_t stage = (size_t)CIB * x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
@@ -771,9 +808,13 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false) {
 }  // namespace
 
 // small = dz (N,Co,Ho,Wo) NHWC, big = x (N,Ci,Hi,Wi) NHWC
-bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
+bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big, int z_ps) {
   if (g.st != 1 || g.ps != 1 || g.N <= 0) return false;
   if (small.dt != big.dt) return false;  // mixed operand types: the caller converts one side first
+  if (z_ps > 1) {  // `small` is PixelShuffle_r(dz): whole channel blocks per sub-pixel phase
+    const int blk = big.dt == SRB_BF16 ? 64 : 32, rr = z_ps * z_ps;
+    if (z_ps > 8 || g.Co % rr != 0 || (g.Co / rr) % blk != 0 || g.Ci <= 4) return false;
+  }
   if (big.dt == SRB_BF16) {
     if (g.Ci % 8 != 0 || g.Ci < 8 || g.Co % 8 != 0 || g.Co > 1024) return false;   // 16-byte pixel rows on both tensors
     if (small.sc != 1 || big.sc != 1) return false;
@@ -781,7 +822,7 @@ bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
     if ((((uintptr_t)small.p) | ((uintptr_t)big.p)) & 15) return false;
     if (g.kh > 16 || g.kw > 16) return false;
     WgPlan ph;
-    return make_wg_plan(g, &ph, true);
+    return make_wg_plan(g, &ph, true, z_ps);
   }
   const bool c4 = g.Ci <= 4;
   if ((!c4 && g.Ci % 32 != 0) || g.Co % 4 != 0 || g.Co > 1024) return false;
@@ -792,7 +833,7 @@ bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
   if (!c4 && (((uintptr_t)big.p) & 15)) return false;
   if (g.kh > 16 || g.kw > 16) return false;
   WgPlan pl;
-  return make_wg_plan(g, &pl);
+  return make_wg_plan(g, &pl, false, z_ps);
 }
 
 int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16) {
@@ -813,11 +854,11 @@ size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16) {
 }
 
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
-                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps) {
   WgPlan pl;
   const bool bf = big.dt == SRB_BF16;
   SRB_REQUIRE(small.dt == big.dt, SRB_EINVAL, "tc_wgrad: x and dz must have one dtype");
-  SRB_REQUIRE(make_wg_plan(g, &pl, bf), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
+  SRB_REQUIRE(make_wg_plan(g, &pl, bf, z_ps), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
   size_t need = (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 256;
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_wgrad workspace: need %zu bytes, have %zu",
@@ -870,11 +911,15 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     if (rc) return rc;
   }
   {
-    const cuuint64_t es = bf ? 2 : 4;
-    cuuint64_t dims[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
+    // z_ps > 1: the map describes the SHUFFLED gradient (C, Wo*r, Ho*r, N), traversed with element strides (1, r, r, 1)
+    const cuuint64_t es = bf ? 2 : 4, r = (cuuint64_t)z_ps;
+    cuuint64_t dims[4] = {(cuuint64_t)(g.Co / (z_ps * z_ps)), (cuuint64_t)g.Wo * r, (cuuint64_t)g.Ho * r, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)small.sw * es, (cuuint64_t)small.sh * es, (cuuint64_t)small.sn * es};
-    cuuint32_t box[4] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)(a.dz_rowwise ? a.TW : a.BW), (cuuint32_t)(a.dz_rowwise ? 1 : a.TH), 1};
-    int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bf);
+    cuuint32_t box[4] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)((a.dz_rowwise ? a.TW : a.BW) * z_ps),
+                         (cuuint32_t)((a.dz_rowwise ? 1 : a.TH) * z_ps), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)z_ps, (cuuint32_t)z_ps, 1};
+    int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bf,
+                          z_ps > 1 ? estr : nullptr);
     if (rc) return rc;
   }
   {
@@ -886,16 +931,16 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   {
-    long long total = (long long)g.Co * g.Ci * g.kh * g.kw;
-    if (db_small) total += g.Co;
-    const int splits = (int)pl.grid.x, gyy = (int)pl.grid.y;
-    const long long groups = (total + 31) / 32;
-    if (splits <= 3)
-      k_wgrad_finish<1, 8><<<(unsigned)((groups + 7) / 8), dim3(32, 1, 8), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
-    else if (splits <= 24)
-      k_wgrad_finish<4, 2><<<(unsigned)((groups + 1) / 2), dim3(32, 4, 2), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
-    else  // 16 lanes measured 11 us vs 17 us with 8 lanes on the ESPCN layers (138-148 splits)
-      k_wgrad_finish<16, 1><<<(unsigned)groups, dim3(32, 16, 1), 0, st>>>(a, splits, gyy, dw, db_small, scale, accumulate);
+    const int taps = g.kh * g.kw;
+    int CT = 288 / taps;
+    CT = CT < 1 ? 1 : (CT > 4 ? 4 : CT);
+    if (CT > g.Ci) CT = g.Ci;
+    const int co_tiles = (g.Co + 31) / 32, ci_tiles = (g.Ci + CT - 1) / CT;
+    const unsigned blocks = (unsigned)(co_tiles * ci_tiles + (db_small ? co_tiles : 0));
+    size_t fsm = (size_t)32 * (CT * taps + 1) * sizeof(float);
+    if (fsm < 8 * 33 * sizeof(float)) fsm = 8 * 33 * sizeof(float);
+    SRB_REQUIRE(fsm <= 48 * 1024, SRB_EUNSUPPORTED, "tc_wgrad finish: filter too large");
+    k_wgrad_finish<<<blocks, 256, fsm, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, CT, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }

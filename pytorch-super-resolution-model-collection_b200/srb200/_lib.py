@@ -37,6 +37,7 @@ SYMBOLS = {
     "srb_last_error": (ctypes.c_char_p, []),
     "srb_conv_out_hw": (ctypes.c_int, [_P(ConvParams), _P(ctypes.c_int32), _P(ctypes.c_int32)]),
     "srb_conv_uses_tensor_path": (ctypes.c_int, [_P(ConvParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "srb_conv_backward_folds_ps": (ctypes.c_int, [_P(ConvParams), ctypes.c_int, ctypes.c_int]),
     "srb_conv_workspace_bytes": (ctypes.c_size_t, [_P(ConvParams), ctypes.c_int]),
     "srb_conv_describe_plan": (ctypes.c_int, [_P(ConvParams), ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
     "srb_conv_fprop": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _vp, _vp, _P(Tensor4), _P(Tensor4),

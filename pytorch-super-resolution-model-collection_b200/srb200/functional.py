@@ -94,6 +94,19 @@ def _uses_tensor_path(p, pas, x_cl, y_cl):
     return r
 
 
+_fold_cache = {}
+
+
+def _folds_ps(p, x_cl, dz_cl):
+    """Cached srb_conv_backward_folds_ps (host-only planner query)."""
+    key = (p.N, p.Cin, p.H, p.W, p.Cout, p.kh, p.kw, p.stride, p.pad, p.ps, p.math, bool(x_cl), bool(dz_cl))
+    r = _fold_cache.get(key)
+    if r is None:
+        r = bool(lib.srb_conv_backward_folds_ps(ctypes.byref(p), 1 if x_cl else 0, 1 if dz_cl else 0))
+        _fold_cache[key] = r
+    return r
+
+
 _workspaces = {}
 
 
@@ -254,7 +267,9 @@ class _FusedConv(torch.autograd.Function):
                                   ctypes.byref(tdz), _ptr(dalpha), st))
         else:
             dz = dy
-        if p.ps > 1 and p.math != _lib.MATH_FP32 and x.shape[1] % 4 == 0 and x.shape[1] >= 8 and _is_cl(x):
+        if p.ps > 1 and _folds_ps(p, _is_cl(x), _is_cl(dz)):
+            pass  # dgrad / wgrad read dz in y's layout: the un-shuffle is their TMA traversal (no extra pass over dz)
+        elif p.ps > 1 and p.math != _lib.MATH_FP32 and x.shape[1] % 4 == 0 and x.shape[1] >= 8 and _is_cl(x):
             # PixelShuffle layer on the tensor path: undo the shuffle once (NHWC, tf32) and run dgrad/wgrad as a
             # plain conv with Cout*r*r output channels
             r = p.ps
