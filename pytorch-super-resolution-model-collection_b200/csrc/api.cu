@@ -561,6 +561,13 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
   if (pass == 2) {
     a = simt_wgrad_ws_bytes(g);
     b = tc_wgrad_ws_bytes(g);
+    if (g.ps > 1 && !p->transposed) {  // PixelShuffle layer: dz may be un-shuffled by the kernel's own TMA traversal
+      Geom g1 = g;
+      g1.ps = 1;
+      const size_t c1 = tc_wgrad_ws_bytes(g1, false, g.ps), c2 = tc_wgrad_ws_bytes(g1, true, g.ps);
+      if (c1 > b) b = c1;
+      if (c2 > b) b = c2;
+    }
     SkinnyWg sk;
     T4 cl{(float *)256, (long long)g.Hi * g.Wi * g.Ci, 1, (long long)g.Wi * g.Ci, g.Ci};  // would-be channels_last x
     if (skinny_wgrad_plan(p, g, cl, &sk) && sk.total > b) b = sk.total;

@@ -117,7 +117,7 @@ int tc_conv_get_dbg();
 int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
 int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big, int z_ps = 1);
-size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16 = false);
+size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16 = false, int z_ps = 1);
 // z_ps > 1: `small` holds PixelShuffle_r of dz (in y's layout); un-shuffled by the TMA traversal, dw/db come out in filter order
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps = 1);

@@ -23,6 +23,7 @@
 // warps 2..5 = epilogue (tcgen05.ld -> bias -> act -> +residual -> tf32 round -> store at the pixel-shuffled address).
 // CTAs are sized for two per SM (<= 112 KB smem, <= 256 TMEM columns) so one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
+#include <string.h>
 
 namespace srb {
 
@@ -49,6 +50,9 @@ struct SlArgs {
   int out_bf16;      // out / residual / preact are bf16 tensors
   int chunk_elems;   // channels per A chunk: 32 (tf32) or 64 (bf16)
   int v8h;           // bf16 outputs: rows are 32-byte aligned (256-bit accesses of 16 bf16 channels)
+  int cl;            // thread-block cluster size along grid.x (1 or 2).  2: the streamed weight ring is SHARED by the CTA pair --
+                     // each CTA fetches half of every weight stage and TMA-multicasts it into both CTAs' shared memory, so the
+                     // L2 -> SM weight traffic per SM halves; the pair walks its bands in lock-step (same K-block sequence)
   int in_ps;         // > 1: the input tensor is PixelShuffle_r of the logical input (dgrad of a PSBlock conv): chunk c is
   int in_cpb;        //      sub-pixel phase c / in_cpb, channel block c % in_cpb, fetched through a stride-r TMA traversal
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
@@ -439,7 +443,10 @@ __device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, 
                               k4 ? 1u : first_kb);
           }
         }
-        if (!a.b_resident) umma_commit_arrive(&b_empty[ms.b_st]);  // frees this weight stage once its MMAs have read it
+        if (!a.b_resident) {  // frees this weight stage (in both CTAs of a sharing pair) once its MMAs have read it
+          if (a.cl > 1) umma_commit_arrive_mc(&b_empty[ms.b_st], 3);
+          else umma_commit_arrive(&b_empty[ms.b_st]);
+        }
         first_kb = 1u;
         a_tap += 8u;  // next tap in the row: one slot (128 B) later
         if (!a.b_resident && ++ms.b_st == (uint32_t)a.b_stages) { ms.b_st = 0; ms.b_phase ^= 1u; }
@@ -527,7 +534,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
       mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], (kThreads - 64) / 32);
     }
-    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], (uint32_t)a.cl); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -538,9 +545,13 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (a.cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast into them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) SL_TRACE(1);
+  // every CTA walks the same number of band slots; a slot past the last band only keeps a shared weight ring in lock-step
+  const int iters = (num_bands + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = a.cl > 1 ? cluster_ctarank() : 0u;
 
 // band index -> image, origin and number of M-tiles holding at least one real pixel
 #define SL_BAND_GEOM(band)                                                                 \
@@ -573,14 +584,18 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       __syncwarp();
     }
     uint32_t ac = 0, kb = 0;  // running A-chunk / K-block counters
-    for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
-      SL_BAND_GEOM(band)
+    const uint32_t half_rows = (uint32_t)(a.NT / a.cl), half_bytes = half_rows * 128u;
+    for (int it = 0; it < iters; ++it) {
+      const int band = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool valid = band < num_bands;
+      if (!valid && (a.cl == 1 || a.c4 || a.b_resident)) break;
+      SL_BAND_GEOM(valid ? band : 0)
       (void)mtb;
       const int ix0 = ox0 - a.pad, iy0 = oy0 - a.pad;
-      for (int c = 0; c < a.chunks; ++c, ++ac) {
+      for (int c = 0; c < a.chunks; ++c) {
         const uint32_t buf = ac % (uint32_t)a.a_bufs;
-        mbar_wait(&a_empty[buf], ((ac / (uint32_t)a.a_bufs) & 1u) ^ 1u);
-        if (elect_one()) {
+        if (valid) mbar_wait(&a_empty[buf], ((ac / (uint32_t)a.a_bufs) & 1u) ^ 1u);
+        if (valid && elect_one()) {
           if ((a.dbg & 2) && ac >= (uint32_t)a.a_bufs) {
             mbar_arrive(&a_full[buf]);
           } else {
@@ -596,13 +611,18 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           }
         }
         __syncwarp();
+        if (valid) ++ac;
         if (!a.c4 && !a.b_resident) {
           for (int tap = 0; tap < taps; ++tap, ++kb) {
             const uint32_t st = kb % (uint32_t)a.b_stages;
-            mbar_wait(&b_empty[st], ((kb / (uint32_t)a.b_stages) & 1u) ^ 1u);
+            mbar_wait(&b_empty[st], ((kb / (uint32_t)a.b_stages) & 1u) ^ 1u);  // released by every CTA that shares the ring
             if (elect_one()) {
               mbar_expect_tx(&b_full[st], (uint32_t)a.b_stage_bytes);
-              tma_load_3d(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes, 0, n0, c * taps + tap);
+              if (a.cl > 1)  // my half of the stage, into both CTAs
+                tma_load_3d_mc(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes + crank * half_bytes, 0,
+                               n0 + (int)(crank * half_rows), c * taps + tap, (uint16_t)3);
+              else
+                tma_load_3d(&mapB, &b_full[st], b_smem + (size_t)st * a.b_stage_bytes, 0, n0, c * taps + tap);
             }
             __syncwarp();
           }
@@ -622,7 +642,18 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (a.c4 || a.b_resident) mbar_wait(&b_full[0], 0);
     bool first = true;
     if (elect_one())
-    for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+    for (int it = 0; it < iters; ++it) {
+      const int band = (int)blockIdx.x + it * (int)gridDim.x;
+      if (band >= num_bands) {
+        if (a.cl == 1 || a.c4 || a.b_resident) break;
+        // idle slot of a sharing pair: consume the weight stages without issuing MMAs so that the peer's ring keeps moving
+        for (int q = 0; q < a.chunks * taps; ++q) {
+          mbar_wait(&b_full[ms.b_st], ms.b_phase);
+          umma_commit_arrive_mc(&b_empty[ms.b_st], 3);
+          if (++ms.b_st == (uint32_t)a.b_stages) { ms.b_st = 0; ms.b_phase ^= 1u; }
+        }
+        continue;
+      }
       SL_BAND_GEOM(band)
       (void)img;
       mbar_wait(&t_empty[ms.t_buf], ms.t_phase ^ 1u);  // epilogue has drained this accumulator buffer
@@ -715,6 +746,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (a.cl > 1) cluster_sync_all();  // no CTA of the pair may exit while the other can still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
@@ -819,6 +851,10 @@ __global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H,
     xp[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
+
+long long *g_sl_trace = nullptr;
+long long g_sl_trace_ctas = 0;
+int g_sl_dbg = 0;
 
 struct SlPlan {
   SlArgs a;
@@ -960,14 +996,13 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
     if (P < 1) P = 1;
     pl->grid_x = (int)P;
   }
+  // share the streamed weight ring between the two CTAs of a cluster (see SlArgs::cl)
+  a.cl = (!c4 && !a.b_resident && pl->ctas_per_sm == 1 && pl->grid_x >= 2 && !(g_sl_dbg & 64)) ? 2 : 1;
+  if (a.cl == 2) pl->grid_x &= ~1;
   pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
   pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;
   return true;
 }
-
-long long *g_sl_trace = nullptr;
-long long g_sl_trace_ctas = 0;
-int g_sl_dbg = 0;
 
 }  // namespace
 
@@ -1097,7 +1132,7 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     {
       cuuint64_t dims[3] = {(cuuint64_t)a.chunk_elems, (cuuint64_t)pl.Npad, (cuuint64_t)(a.chunks * g.kh * g.kw)};
       cuuint64_t strides[2] = {128, (cuuint64_t)pl.Npad * 128};
-      cuuint32_t box[3] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)a.NT, 1};
+      cuuint32_t box[3] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)(a.NT / a.cl), 1};
       int rc = encode_tiled(&mapB, wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf_in);
       if (rc) return rc;
     }
@@ -1125,7 +1160,24 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     if (rc) return rc;
   }
   dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles_n);
-  k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+  if (a.cl > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_sl, mapA, mapB, a));
+  } else {
+    k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+  }
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

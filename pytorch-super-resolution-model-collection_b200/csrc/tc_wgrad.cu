@@ -457,52 +457,78 @@ __device__ __forceinline__ int wg_filter_of(const WgArgs &a, int co) {
 }
 
 // dW[co][ci][r][s] (=|+=) scale * sum_over_splits partial[...]      (fixed summation order => deterministic)
-// One block = 32 GEMM columns x CT input channels x all taps.  Reads: a warp walks 32 consecutive columns of one partial row
-// (128 B, coalesced) over the splits with 8 independent accumulators; the sums are transposed through shared memory so that
-// the OIHW stores are contiguous runs of CT*kh*kw floats per filter.  (The previous one-thread-per-output kernel spent
-// 47 us on EDSR-256's 28 MB of partials: 4-byte stores 9 KB apart and 3 loads in flight per thread.)
-__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, int CT, float *dw, float *db, float scale,
-                                                      int accumulate) {
-  extern __shared__ float tile[];  // [32][CT * taps + 1]
-  const int taps = a.kh * a.kw, items = CT * taps, pitch = items + 1;
-  const int co_tiles = (a.Co + 31) / 32, ci_tiles = (a.Ci + CT - 1) / CT;
+// A work item is one (ci, tap) pair of a tile of 32 GEMM columns: a 128-byte partial row per split.  One block owns IPB
+// consecutive items j = ci * taps + tap, i.e. a contiguous run of IPB floats in each of its 32 filters.
+//   lanes8 == 0 (few splits):  the 8 warps take different items, each thread walks the splits with 8 independent accumulators
+//   lanes8 == 1 (many splits): the 8 warps share every item, warp y sums splits y, y+8, ...; folded in a fixed order in smem
+// The sums are staged in shared memory so that the OIHW stores are contiguous runs.  (The previous one-thread-per-output
+// kernel spent 47 us on EDSR-256's 28 MB of partials: 4-byte stores 9 KB apart and 3 loads in flight per thread.)
+__global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, int IPB, int lanes8, float *dw, float *db,
+                                                      float scale, int accumulate) {
+  extern __shared__ float tile[];  // [32][IPB + 1] (+ [8][33] fold buffer when lanes8)
+  const int taps = a.kh * a.kw, total_items = a.Ci * taps, pitch = IPB + 1;
+  const int co_tiles = (a.Co + 31) / 32, groups = (total_items + IPB - 1) / IPB;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ACC = a.RG * a.SG * a.CIB;
   const size_t ss = (size_t)gy * ACC * 128 * a.NT;  // floats between consecutive splits
-  if ((int)blockIdx.x < co_tiles * ci_tiles) {
-    const int cot32 = blockIdx.x % co_tiles, ci0 = (blockIdx.x / co_tiles) * CT;
+  if ((int)blockIdx.x < co_tiles * groups) {
+    const int cot32 = blockIdx.x % co_tiles, j0 = (blockIdx.x / co_tiles) * IPB;
     const int co = cot32 * 32 + tx;
-    for (int j = ty; j < items; j += 8) {
-      const int cl = j / taps, tap = j - cl * taps, r = tap / a.kw, s = tap - r * a.kw, ci = ci0 + cl;
+    const int nitems = min(IPB, total_items - j0);
+    float *fold = tile + 32 * pitch;
+    for (int jj = lanes8 ? 0 : ty; jj < nitems; jj += lanes8 ? 1 : 8) {
+      const int j = j0 + jj, ci = j / taps, tap = j - ci * taps, r = tap / a.kw, s = tap - r * a.kw;
       float sum = 0.f;
-      if (co < a.Co && ci < a.Ci) {
+      if (co < a.Co) {
         int by, acc, m, n;
         wg_locate(a, co, ci, r, s, by, acc, m, n);
         const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
-        int z = 0;
-        for (; z + 7 < splits; z += 8) {
-          s0 += p[(size_t)z * ss]; s1 += p[(size_t)(z + 1) * ss]; s2 += p[(size_t)(z + 2) * ss]; s3 += p[(size_t)(z + 3) * ss];
-          s4 += p[(size_t)(z + 4) * ss]; s5 += p[(size_t)(z + 5) * ss]; s6 += p[(size_t)(z + 6) * ss]; s7 += p[(size_t)(z + 7) * ss];
+        if (lanes8) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int z = ty;
+          for (; z + 24 < splits; z += 32) {
+            s0 += p[(size_t)z * ss]; s1 += p[(size_t)(z + 8) * ss]; s2 += p[(size_t)(z + 16) * ss]; s3 += p[(size_t)(z + 24) * ss];
+          }
+          for (; z < splits; z += 8) s0 += p[(size_t)z * ss];
+          sum = (s0 + s1) + (s2 + s3);
+        } else {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+          int z = 0;
+          for (; z + 7 < splits; z += 8) {
+            s0 += p[(size_t)z * ss]; s1 += p[(size_t)(z + 1) * ss]; s2 += p[(size_t)(z + 2) * ss]; s3 += p[(size_t)(z + 3) * ss];
+            s4 += p[(size_t)(z + 4) * ss]; s5 += p[(size_t)(z + 5) * ss]; s6 += p[(size_t)(z + 6) * ss]; s7 += p[(size_t)(z + 7) * ss];
+          }
+          for (; z < splits; ++z) s0 += p[(size_t)z * ss];
+          sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
         }
-        for (; z < splits; ++z) s0 += p[(size_t)z * ss];
-        sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
       }
-      tile[tx * pitch + j] = sum;
+      if (lanes8) {
+        fold[ty * 33 + tx] = sum;
+        __syncthreads();
+        if (ty == 0) {
+          float t = fold[tx];
+#pragma unroll
+          for (int y = 1; y < 8; ++y) t += fold[y * 33 + tx];
+          tile[tx * pitch + jj] = t;
+        }
+        __syncthreads();
+      } else {
+        tile[tx * pitch + jj] = sum;
+      }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * items; e += 256) {
-      const int col = e / items, j = e - col * items;
-      const int co2 = cot32 * 32 + col, ci = ci0 + j / taps;
-      if (co2 < a.Co && ci < a.Ci) {
-        float *d = dw + ((size_t)wg_filter_of(a, co2) * a.Ci + ci0) * taps + j;
-        const float t = tile[col * pitch + j] * scale;
+    for (int e = threadIdx.x; e < 32 * nitems; e += 256) {
+      const int col = e / nitems, jj = e - col * nitems;
+      const int co2 = cot32 * 32 + col;
+      if (co2 < a.Co) {
+        float *d = dw + (size_t)wg_filter_of(a, co2) * total_items + j0 + jj;
+        const float t = tile[col * pitch + jj] * scale;
         *d = accumulate ? *d + t : t;
       }
     }
   } else if (db != nullptr) {
     // bias gradient: splits x 4 warp partials per channel; 32 channels per block, 8 z-lanes folded through shared memory
-    const int co = ((int)blockIdx.x - co_tiles * ci_tiles) * 32 + tx;
+    const int co = ((int)blockIdx.x - co_tiles * groups) * 32 + tx;
     const size_t pitch_db = (size_t)(a.n_cot * a.NT);
     float sum = 0.f;
     if (co < a.Co)
@@ -847,9 +873,9 @@ int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16) {
                   pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
 }
 
-size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16) {
+size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16, int z_ps) {
   WgPlan pl;
-  if (g.st != 1 || g.ps != 1 || (!bf16 && g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl, bf16)) return 0;
+  if (g.st != 1 || g.ps != 1 || (!bf16 && g.Ci > 4 && g.Ci % 32 != 0) || !make_wg_plan(g, &pl, bf16, z_ps)) return 0;
   return (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 1024;
 }
 
@@ -931,16 +957,17 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   {
-    const int taps = g.kh * g.kw;
-    int CT = 288 / taps;
-    CT = CT < 1 ? 1 : (CT > 4 ? 4 : CT);
-    if (CT > g.Ci) CT = g.Ci;
-    const int co_tiles = (g.Co + 31) / 32, ci_tiles = (g.Ci + CT - 1) / CT;
-    const unsigned blocks = (unsigned)(co_tiles * ci_tiles + (db_small ? co_tiles : 0));
-    size_t fsm = (size_t)32 * (CT * taps + 1) * sizeof(float);
-    if (fsm < 8 * 33 * sizeof(float)) fsm = 8 * 33 * sizeof(float);
-    SRB_REQUIRE(fsm <= 48 * 1024, SRB_EUNSUPPORTED, "tc_wgrad finish: filter too large");
-    k_wgrad_finish<<<blocks, 256, fsm, st>>>(a, (int)pl.grid.x, (int)pl.grid.y, CT, dw, db_small, scale, accumulate);
+    const int taps = g.kh * g.kw, total_items = g.Ci * taps, splits = (int)pl.grid.x;
+    const int co_tiles = (g.Co + 31) / 32;
+    // many splits (small layers, one output tile): all 8 warps of a block share each item; else one item per warp
+    const int lanes8 = splits > 24 ? 1 : 0;
+    int IPB = lanes8 ? 4 : 36;
+    // keep at least ~2 blocks per SM when the layer is small
+    while (IPB > (lanes8 ? 1 : 8) && (long long)co_tiles * ((total_items + IPB - 1) / IPB) < 296) IPB = (IPB + 1) / 2;
+    const int groups = (total_items + IPB - 1) / IPB;
+    const unsigned blocks = (unsigned)(co_tiles * groups + (db_small ? co_tiles : 0));
+    const size_t fsm = ((size_t)32 * (IPB + 1) + 8 * 33) * sizeof(float);
+    k_wgrad_finish<<<blocks, 256, fsm, st>>>(a, splits, (int)pl.grid.y, IPB, lanes8, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
