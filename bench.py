@@ -310,6 +310,8 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5, capturable=not a.no_graph)
     bucket = srb200.GradBucket(net, world_size=world)
     lossf = host.loss_for(model_key, fused=True)
+    # criterion evaluated inside the last conv's epilogue where the net allows it (ESPCN, SRCNN, EDSR), plain fused kernels else
+    fwd_loss = srb200.FusedLoss(net, "l1" if loss_kind == "l1" else "mse") if not a.no_loss_fusion else (lambda x, t: lossf(net(x), t))
     oshape = out_shape(model_key, margs, batch, h, w)
 
     # host side: uint8 HWC pixels (pinned); device side: fp32 NCHW slots the step reads (filled by srb200.image_to_tensor)
@@ -324,7 +326,7 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
 
     def step(x, t):
         bucket.begin_step()
-        loss = lossf(net(x), t)
+        loss = fwd_loss(x, t)
         loss.backward()
         bucket.all_reduce()
         if clip is not None:
@@ -392,7 +394,7 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     for i in range(warmup):
         step(dev_x[i % 3], dev_t[i % 3])
     if not a.no_graph:
-        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)), clip_norm=clip)
+        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)), clip_norm=clip, forward_loss=fwd_loss)
         graphs.update(stepper=st, launches=st.launches_per_step)
         for i in range(3):
             step_slot(i)
@@ -622,6 +624,7 @@ def main():
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "exact", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-loss-fusion", action="store_true", help="evaluate the criterion with the stand-alone loss kernels")
     ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
     ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")
     a = ap.parse_args()

@@ -127,6 +127,24 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
                    const srb_tensor4 *preact, uint16_t *relu_bits, void *ws, size_t ws_bytes, void *stream);
 
 /*
+ * Forward of the network's LAST convolution fused with the regression loss that follows it in the training loop
+ * (`loss = MSELoss(model(x), target)`, espcn.py:128-129, srcnn.py:128-129; L1Loss in edsr.py:152-153):
+ *     y = PixelShuffle_ps(conv(x) + bias);   *loss = mean((y-t)^2) [kind 0] or mean(|y-t|) [kind 1];
+ *     dz = d loss / d y  (2 (y-t) / n or sign(y-t) / n), written by the same epilogue
+ * so the loss forward, the loss backward and (for PixelShuffle layers) the pixel-un-shuffle of the gradient never run as
+ * kernels.  y may be NULL (the loss is then the only product).  dz_unshuffled != 0 (requires ps == 4, NCHW y/target):
+ * dz is the conv's own dense NHWC tensor (N, Cout*ps*ps, Ho, Wo), ready for srb_conv_dgrad/wgrad with ps = 1 geometry;
+ * dz_unshuffled == 0 (requires ps == 1): dz has y's shape and strides of its own.  The loss sum is deterministic
+ * (per-warp partials folded in a fixed order).  Layers with an activation or a residual are SRB_EUNSUPPORTED.
+ */
+int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
+                        const srb_tensor4 *target, int loss_kind, const srb_tensor4 *y, const srb_tensor4 *dz, int dz_unshuffled,
+                        float *loss, void *ws, size_t ws_bytes, void *stream);
+
+/* x[i] *= *g for n contiguous floats unless *g == 1 (device scalar; the upstream gradient of a scalar loss). */
+int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream);
+
+/*
  * Activation backward (threshold_backward / _prelu_kernel_backward / leaky_relu_backward):
  *   dz = dy * act'(.)   elementwise over the (N,Cout,Ho*ps,Wo*ps) tensor; for PReLU also
  *   *dalpha += sum(dy * z * [z <= 0]).   `ref` is y for RELU/LRELU and the saved preact z for PRELU.

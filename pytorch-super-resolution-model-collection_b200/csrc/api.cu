@@ -364,6 +364,16 @@ __global__ void k_pack_dz8_h(T4 dz, uint4 *__restrict__ out, int N, int C, int H
   }
 }
 
+// x *= *g unless *g == 1 (the usual upstream gradient of a scalar loss): every block reads g and leaves early
+__global__ void k_scale_by_scalar(float *x, long long n, const float *__restrict__ g, int rnd) {
+  const float s = __ldg(g);
+  if (s == 1.0f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i] * s;
+    x[i] = rnd ? round_tf32(v) : v;
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -418,6 +428,12 @@ Epi make_epi(const srb_conv_params *p, const float *bias, const float *alpha, co
   e.bits_out = nullptr;
   e.bits_in = nullptr;
   e.round_tf32 = round_out;
+  e.loss_kind = 0;
+  e.loss_coef = 0.f;
+  e.target = to_t4(nullptr);
+  e.dz = to_t4(nullptr);
+  e.dz_unshuf = nullptr;
+  e.loss_part = nullptr;
   return e;
 }
 
@@ -573,6 +589,7 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
     if (skinny_wgrad_plan(p, g, cl, &sk) && sk.total > b) b = sk.total;
   } else {
     b = tc_conv_ws_bytes(g);
+    if (pass == 0) b += 40 * 1024;  // per-warp loss partials of srb_conv_fprop_loss
   }
   if (p->math == SRB_MATH_BF16 && !p->transposed && g.st == 1 && pass == 2) {
     // bf16 wgrad + the two mixed-edge conversions (dz -> fp32 NHWC for Cin <= 4; dz -> bf16 NHWC8 for Cout < 8)
@@ -630,6 +647,45 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits with a transposed convolution");
   Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
   return simt_conv_scatter(g, tx, w, ty, e, st);
+}
+
+int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
+                        const srb_tensor4 *target, int loss_kind, const srb_tensor4 *y, const srb_tensor4 *dz, int dz_unshuffled,
+                        float *loss, void *ws, size_t ws_bytes, void *stream) {
+  Geom g;
+  int rc = make_geom(p, &g);
+  if (rc) return rc;
+  SRB_REQUIRE(p->N > 0 && x && x->data && w && target && target->data && dz && dz->data && loss, SRB_EINVAL, "null tensor");
+  SRB_REQUIRE(loss_kind == 0 || loss_kind == 1, SRB_EINVAL, "loss kind: 0 = MSE, 1 = L1");
+  SRB_REQUIRE(!p->transposed && p->act == SRB_ACT_NONE && (is_tf32_math(p->math) || p->math == SRB_MATH_BF16), SRB_EUNSUPPORTED,
+              "fused loss: Conv2d without activation on the tensor path (math auto / tf32 / bf16)");
+  T4 tx = to_t4(x), ty = to_t4(y), tt = to_t4(target), tdz = to_t4(dz);
+  if (!ty.p) { ty = tt; ty.p = nullptr; }  // geometry of y (= target's) without storing it
+  T4 probe = ty;
+  probe.p = (float *)256;
+  SRB_REQUIRE(tc_conv_supported(g, tx, probe, false), SRB_EUNSUPPORTED, "fused loss: this layer does not run on the tensor path");
+  Epi e = make_epi(p, bias, nullptr, nullptr, nullptr, 0);
+  e.loss_kind = loss_kind + 1;
+  e.loss_coef = (float)(1.0 / ((double)g.N * g.Ho * g.Wo * g.Co));
+  e.target = tt;
+  e.round_tf32 = is_tf32_math(p->math) ? 1 : 0;  // rounds the emitted gradient (it feeds tf32 dgrad / wgrad)
+  if (dz_unshuffled) {
+    SRB_REQUIRE(tdz.dt == SRB_F32 && tdz.sc == 1 && tdz.sw == g.Co && tdz.sh == (long long)g.Wo * g.Co &&
+                    tdz.sn == (long long)g.Ho * g.Wo * g.Co, SRB_EINVAL, "un-shuffled dz must be a dense NHWC (N,Cout*r*r,Ho,Wo) tensor");
+    e.dz_unshuf = tdz.p;
+  } else {
+    e.dz = tdz;
+  }
+  return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, (cudaStream_t)stream, 1, loss);
+}
+
+int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream) {
+  SRB_REQUIRE(x && g && n >= 0, SRB_EINVAL, "bad scale args");
+  if (n == 0) return SRB_OK;
+  k_scale_by_scalar<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n, g, round_to_tf32);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
 }
 
 int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tensor4 *ref, const float *alpha,
@@ -719,10 +775,10 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
     if (is_tf32_math(p->math) && g.ps > 1 && g.st == 1 && g.kh == g.kw) {
       // PixelShuffle layer: dz arrives in y's (shuffled) layout; the un-shuffle is the TMA traversal of the A operand
       Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
-      SRB_REQUIRE(gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true, g.ps), SRB_EUNSUPPORTED,
-                  "dgrad of a PixelShuffle layer needs channels_last dz with Cout %% 32 == 0 (else srb_pixel_unshuffle first)");
-      SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
-      return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
+      if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true, g.ps)) {
+        SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
+        return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
+      }  // else: the CUDA-core scatter kernel below un-shuffles through its own addressing
     }
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
       // stride-1 dgrad == gather conv of dz with the flipped, transposed filter and pad' = k-1-pad
@@ -817,9 +873,9 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
     if (is_tf32_math(p->math) && g.ps > 1) {
       Geom g1 = g;
       g1.ps = 1;
-      SRB_REQUIRE(tc_wgrad_supported(g1, tdz, tx, g.ps), SRB_EUNSUPPORTED,
-                  "wgrad of a PixelShuffle layer needs channels_last x / dz with Cout %% 32 == 0 (else srb_pixel_unshuffle first)");
-      return tc_conv_wgrad(g1, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st, g.ps);
+      if (tc_wgrad_supported(g1, tdz, tx, g.ps))
+        return tc_conv_wgrad(g1, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st, g.ps);
+      // else: the CUDA-core wgrad below un-shuffles through its own addressing
     }
     if (is_tf32_math(p->math) && tc_wgrad_supported(g, tdz, tx))
       return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);

@@ -70,6 +70,18 @@ struct Epi {
   unsigned short *bits_out;
   const unsigned short *bits_in;
   int round_tf32;  // store y RN-rounded to tf32 (feeds a tensor-core consumer)
+  // Regression loss fused into the epilogue of the network's last conv (espcn.py:129, srcnn.py:129, edsr.py:153):
+  //   loss_kind 1 = MSE, 2 = L1 (mean over all elements); target has y's shape; every epilogue warp leaves the sum of its
+  //   (y-t)^2 / |y-t| terms in loss_part[cta * 8 + warp] (folded in a fixed order afterwards: deterministic);
+  //   the gradient g = loss_coef * 2 (y - t) or loss_coef * sign(y - t) goes either to dz_unshuf -- the conv's own
+  //   (N, Ho, Wo, Co) NHWC layout, i.e. PixelShuffle already undone (PS(4) -> NCHW layers) -- or to dz (y's layout, ps == 1).
+  //   out.p may be null: the loss is then the only product of the forward pass.
+  int loss_kind;
+  float loss_coef;
+  T4 target;
+  T4 dz;
+  float *dz_unshuf;
+  float *loss_part;
 };
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -110,7 +122,7 @@ size_t tc_conv_ws_bytes(const Geom &g);
 // in_ps > 1: `in` holds PixelShuffle_r of the logical input (g.Ci = C * r * r logical channels, in has C); the un-shuffle
 // happens in the TMA traversal
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
-                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps = 1);
+                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps = 1, float *loss_out = nullptr);
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
 int tc_conv_get_dbg();

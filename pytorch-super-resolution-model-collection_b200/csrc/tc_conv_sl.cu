@@ -30,6 +30,7 @@ namespace srb {
 namespace {
 
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kMaxLossCtas = 1024;  // fused loss: per-warp partial sums of at most this many CTAs
 constexpr int kMaxBStages = 8;
 
 struct SlArgs {
@@ -259,6 +260,86 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   }
 }
 
+
+// ---- loss-fused epilogue of the network's last conv (no activation, no residual; fp32 outputs) --------------------------------
+//   MODE 1: PixelShuffle(4) into NCHW (ESPCN): y/target addressed like epilogue_items MODE 1; the gradient is written
+//           un-shuffled -- 16 consecutive conv channels of this pixel = 64 contiguous bytes of the (N,Ho,Wo,Co) tensor
+//   MODE 3: anything with ps == 1: scalar accesses, gradient in y's layout
+template <int MODE>
+__device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
+                                                    int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid, float &lsum) {
+  const bool has_bias = a.epi.bias != nullptr;
+  const bool l1 = a.epi.loss_kind == 2;
+  const bool rnd = a.epi.round_tf32 != 0;  // here: round the GRADIENT (it feeds the tensor-core dgrad / wgrad)
+  const float coef = a.epi.loss_coef * (l1 ? 1.f : 2.f);
+  const int ngroups = a.NT >> 4;
+#pragma unroll 1
+  for (int item = half; item < mtb * ngroups; item += 2) {
+    const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
+    const int q = t * 128 + m;
+    const int ty = q / a.BW, tx = q - ty * a.BW;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    const bool pix_ok = (ty < rows_valid) && (tx < cols_valid);
+    const int cbase = n0 + j0;
+    if (cbase >= a.Co) continue;  // warp-uniform
+    uint32_t v[16];
+    tmem_ld16(trow + (uint32_t)(t * a.NT + j0), v);
+    if (!pix_ok) continue;
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = lds128(bias_saddr + (uint32_t)(j0 + j) * 4u);
+        z[j] += b.x; z[j + 1] += b.y; z[j + 2] += b.z; z[j + 3] += b.w;
+      }
+    }
+    if (MODE == 1) {
+      const int c = cbase >> 4;
+      const long long yy = (long long)oy * 4, xx = (long long)ox * 4;
+      const float *pt = a.epi.target.p + (n * a.epi.target.sn + c * a.epi.target.sc + yy * a.epi.target.sh + xx * a.epi.target.sw);
+      float *po = a.out.p ? a.out.p + (n * a.out.sn + c * a.out.sc + yy * a.out.sh + xx * a.out.sw) : nullptr;
+      float g[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 tt = __ldg((const float4 *)(pt + q4 * a.epi.target.sh));
+        const float d0 = z[4 * q4] - tt.x, d1 = z[4 * q4 + 1] - tt.y, d2 = z[4 * q4 + 2] - tt.z, d3 = z[4 * q4 + 3] - tt.w;
+        if (l1) {
+          lsum += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+          g[4 * q4] = d0 > 0.f ? coef : (d0 < 0.f ? -coef : 0.f); g[4 * q4 + 1] = d1 > 0.f ? coef : (d1 < 0.f ? -coef : 0.f);
+          g[4 * q4 + 2] = d2 > 0.f ? coef : (d2 < 0.f ? -coef : 0.f); g[4 * q4 + 3] = d3 > 0.f ? coef : (d3 < 0.f ? -coef : 0.f);
+        } else {
+          lsum += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          g[4 * q4] = coef * d0; g[4 * q4 + 1] = coef * d1; g[4 * q4 + 2] = coef * d2; g[4 * q4 + 3] = coef * d3;
+        }
+        if (po) *(float4 *)(po + q4 * a.out.sh) = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+      }
+      if (rnd) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = round_tf32_fast(g[j]);
+      }
+      float *pd = a.epi.dz_unshuf + ((long long)(n * a.Ho + oy) * a.Wo + ox) * a.Co + cbase;
+      STG256(pd, g, 0);
+      STG256(pd + 8, g, 8);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = cbase + j;
+        if (co < a.Co) {
+          const float tt = __ldg(a.epi.target.p + ps_offset(a.epi.target, 1, n, co, oy, ox));
+          const float d = z[j] - tt;
+          float g;
+          if (l1) { lsum += fabsf(d); g = d > 0.f ? coef : (d < 0.f ? -coef : 0.f); }
+          else    { lsum += d * d; g = coef * d; }
+          if (rnd) g = round_tf32_fast(g);
+          if (a.out.p) a.out.p[ps_offset(a.out, 1, n, co, oy, ox)] = z[j];
+          a.epi.dz.p[ps_offset(a.epi.dz, 1, n, co, oy, ox)] = g;
+        }
+      }
+    }
+  }
+}
 
 // ---- bf16-output epilogue (out / residual / preact are bf16 NHWC tensors; accumulators, bias and the math stay fp32) ----
 //   MODE 0: NHWC, no shuffle: 16 channels = 32 B per thread and item -> one 256-bit store
@@ -716,6 +797,8 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");  // bias_s visible to all epilogue warps
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;
+    float lsum = 0.f;  // this thread's share of the fused loss sum
+    const int lmode = a.epi.loss_kind ? ((a.ps == 4 && a.epi.dz_unshuf) ? 1 : 3) : 0;
     uint32_t wi = 0;
     for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++wi) {
       SL_BAND_GEOM(band)
@@ -727,6 +810,8 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 #define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
 #define SL_EPIH(MODE) epilogue_items_h<MODE>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
       if (a.dbg & 1) {}
+      else if (lmode == 1) epilogue_items_loss<1>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum);
+      else if (lmode == 3) epilogue_items_loss<3>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum);
       else if (a.out_bf16 && hmode == 0) SL_EPIH(0);
       else if (a.out_bf16 && hmode == 2) SL_EPIH(2);
       else if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
@@ -741,6 +826,11 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       if (lane == 0) mbar_arrive(&t_empty[tb]);
       if (wi == 0 && warp == 2 && lane == 0) SL_TRACE(5);
     }
+    if (lmode) {  // one partial per epilogue warp, summed over the lanes in a fixed (butterfly) order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      if (lane == 0) a.epi.loss_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (warp - 2)] = lsum;
+    }
   }
 #undef SL_BAND_GEOM
 
@@ -753,6 +843,20 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                  : "memory");
   }
   if (threadIdx.x == 0) SL_TRACE(6);
+}
+
+// loss = inv_n * sum of the per-warp partials, in a fixed order (one block)
+__global__ void __launch_bounds__(256) k_sl_loss_finish(const float *__restrict__ partial, int n, float inv_n, float *loss) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0] * inv_n;
 }
 
 // Filter element for GEMM row n (output channel of this launch), K index k (input channel of this launch), tap (r,s):
@@ -997,7 +1101,9 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
     pl->grid_x = (int)P;
   }
   // share the streamed weight ring between the two CTAs of a cluster (see SlArgs::cl)
-  a.cl = (!c4 && !a.b_resident && pl->ctas_per_sm == 1 && pl->grid_x >= 2 && !(g_sl_dbg & 64)) ? 2 : 1;
+  // MEASURED SLOWER (r2f: EDSR-256 bf16 fprop 60 -> 64 us, VDSR body 185 -> 203 us): the L2 slices run at 17 % and the limit
+  // is the SMEM operand path of the MMAs, which multicast does not relieve; kept behind debug flag 64 for experiments.
+  a.cl = (!c4 && !a.b_resident && pl->ctas_per_sm == 1 && pl->grid_x >= 2 && (g_sl_dbg & 64)) ? 2 : 1;
   if (a.cl == 2) pl->grid_x &= ~1;
   pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
   pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;
@@ -1064,9 +1170,10 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
                   g.N * a.bands_h * a.bands_w, pl.grid_x, pl.n_tiles_n, pl.ctas_per_sm);
 }
 
-int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
-                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps) {
+int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi_in,
+                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps, float *loss_out) {
   SlPlan pl;
+  Epi epi = epi_in;
   const bool bf_in = in.dt == SRB_BF16, bf_out = out.dt == SRB_BF16;
   SRB_REQUIRE(make_sl_plan(g, &pl, bf_in, in_ps), SRB_EUNSUPPORTED, "tc_conv: no band plan");
   SRB_REQUIRE(in_ps == 1 || !pl.a.c4, SRB_EUNSUPPORTED, "tc_conv: un-shuffled input needs the generic operand flavour");
@@ -1075,12 +1182,28 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
               "residual / preact must have the dtype of the output");
   SRB_REQUIRE(!epi.mask.p || epi.mask.dt == SRB_F32 || !bf_out, SRB_EUNSUPPORTED, "float relu_mask with bf16 tensors (use relu_bits)");
   SlArgs &a = pl.a;
-  const size_t need = (pl.wpack_floats + pl.xpack_floats) * sizeof(float) + 512;
+  const size_t loss_bytes = epi.loss_kind ? (size_t)kMaxLossCtas * 8 * sizeof(float) + 256 : 0;
+  const size_t need = (pl.wpack_floats + pl.xpack_floats) * sizeof(float) + 512 + loss_bytes;
   uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
   SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_conv workspace: need %zu bytes, have %zu",
               need + 256, ws_bytes);
   float *wp = (float *)wsp;
   float *xp = (float *)((wsp + pl.wpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
+  if (epi.loss_kind) {
+    SRB_REQUIRE(loss_out != nullptr && (long long)pl.grid_x * pl.n_tiles_n <= kMaxLossCtas, SRB_EINVAL, "fused loss: bad arguments");
+    SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
+                    out.dt == SRB_F32 && epi.target.p && epi.target.dt == SRB_F32,
+                SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
+    if (g.ps == 4 && epi.dz_unshuf) {
+      auto ok = [](const T4 &t) { return !t.p || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0); };
+      SRB_REQUIRE((g.Co & 15) == 0 && ok(out) && ok(epi.target) && (((uintptr_t)epi.dz_unshuf) & 31) == 0, SRB_EUNSUPPORTED,
+                  "fused loss with PixelShuffle(4): NCHW-contiguous y / target, Cout*16 channels");
+    } else {
+      SRB_REQUIRE(g.ps == 1 && epi.dz.p && epi.dz.dt == SRB_F32 && !epi.dz_unshuf, SRB_EUNSUPPORTED,
+                  "fused loss: PixelShuffle(4) with an un-shuffled gradient, or no PixelShuffle with the gradient in y's layout");
+    }
+    epi.loss_part = (float *)(((uintptr_t)xp + pl.xpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
+  }
 
   // 1. operands: weights (and, for c4, the NHWC4 image)
   {
@@ -1180,6 +1303,12 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   }
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
+  if (epi.loss_kind) {
+    const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
+    k_sl_loss_finish<<<1, 256, 0, st>>>(epi.loss_part, (int)(grid.x * grid.y * 8), (float)(1.0 / numel), loss_out);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+  }
   return SRB_OK;
 }
 

@@ -42,6 +42,9 @@ SYMBOLS = {
     "srb_conv_describe_plan": (ctypes.c_int, [_P(ConvParams), ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
     "srb_conv_fprop": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _vp, _vp, _P(Tensor4), _P(Tensor4),
                                       _P(Tensor4), _vp, _vp, ctypes.c_size_t, _vp]),
+    "srb_conv_fprop_loss": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _vp, _P(Tensor4), ctypes.c_int, _P(Tensor4),
+                                           _P(Tensor4), ctypes.c_int, _vp, _vp, ctypes.c_size_t, _vp]),
+    "srb_scale_by_scalar": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
     "srb_act_bwd": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _P(Tensor4), _vp, _vp]),
     "srb_conv_dgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _vp, _P(Tensor4), _vp, ctypes.c_size_t,
                                       _vp]),

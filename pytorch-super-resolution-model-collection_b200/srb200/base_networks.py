@@ -48,6 +48,17 @@ class _ActMixin:
     # Set by srb200.prepare()/convert() on the last conv block in front of a flatten (srgan.py:75 does
     # `out.view(N, -1)`, which needs NCHW-contiguous memory): the block then returns NCHW instead of channels_last.
     nchw_out = False
+    # Set by srb200.FusedLoss for one forward pass on the network's last block: (target, kind, holder).  The block then runs
+    # the conv with the loss fused into its epilogue (F.conv2d_loss) and leaves the loss in holder["loss"].
+    _loss_req = None
+
+    def _loss_forward(self, x, c, r):
+        target, kind, holder = self._loss_req
+        if not (x.is_cuda and F.loss_fusable(tuple(x.shape), F._is_cl(x), tuple(c.weight.shape), c.stride[0], c.padding[0], r)):
+            return None
+        loss, y = F.conv2d_loss(x, c.weight, c.bias, target, kind, c.stride[0], c.padding[0], r, need_output=True)
+        holder["loss"], holder["y"] = loss, y
+        return y
 
     def _layout(self, out):
         return out.contiguous() if self.nchw_out else out
@@ -114,6 +125,10 @@ class ConvBlock(torch.nn.Module, _ActMixin):
 
     def forward(self, x):
         c = self.conv
+        if self._loss_req is not None and self.norm is None and self.activation is None:
+            fused = self._loss_forward(x, c, 1)
+            if fused is not None:
+                return fused
         if self.norm is not None:
             out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0]))
             return self._layout(self._post(out, fused=False))
@@ -203,6 +218,10 @@ class PSBlock(torch.nn.Module, _ActMixin):
     def forward(self, x):
         c = self.conv
         r = self.ps.upscale_factor
+        if self._loss_req is not None and self.norm is None and self.activation is None:
+            fused = self._loss_forward(x, c, r)
+            if fused is not None:
+                return fused
         if self.norm is not None:
             out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], pixel_shuffle=r))
             return self._layout(self._post(out, fused=False))
@@ -252,3 +271,45 @@ def prepare(net):
         if name in _CONV_BLOCK_NAMES and type(m).__module__ == __name__:
             last_conv = m
     return net
+
+
+class FusedLoss(torch.nn.Module):
+    """`loss = FusedLoss(net, 'mse' | 'l1')(x, target)`  ==  `criterion(net(x), target)` of the reference loops
+    (espcn.py:128-129, srcnn.py:128-129, edsr.py:152-153) with the criterion evaluated inside the epilogue of the
+    network's last convolution: no loss-forward, loss-backward or pixel-un-shuffle kernels, and dL/dy never exists in
+    the shuffled layout.  Applies when the network's output IS the output of its last ConvBlock / PSBlock (no norm, no
+    activation) -- checked on the first call; otherwise (VDSR adds its global residual after the last conv, FSRCNN ends
+    in a transposed conv) the plain fused loss kernels are used."""
+
+    def __init__(self, net, kind="mse"):
+        super().__init__()
+        self.net = net
+        self.kind = {"l2": "mse"}.get(kind, kind)
+        self.last = None
+        for m in net.modules():
+            if type(m).__name__ in ("ConvBlock", "PSBlock") and type(m).__module__ == __name__:
+                self.last = m
+        self.mode = None  # decided on the first call: "fused" | "plain"
+
+    def _plain(self, x, target):
+        y = self.net(x)
+        return (F.l1_loss if self.kind == "l1" else F.mse_loss)(y, target)
+
+    def forward(self, x, target):
+        if self.mode == "plain" or self.last is None:
+            return self._plain(x, target)
+        holder = {}
+        self.last._loss_req = (target, self.kind, holder)
+        try:
+            y = self.net(x)
+        finally:
+            self.last._loss_req = None
+        if "loss" in holder and y is holder["y"]:
+            self.mode = "fused"
+            return holder["loss"]
+        if "loss" in holder:
+            # the network post-processes its last block's output: the fused loss would be wrong -- never use it here again
+            self.mode = "plain"
+            return (F.l1_loss if self.kind == "l1" else F.mse_loss)(y, target) if y.requires_grad else self._plain(x, target)
+        self.mode = "plain"
+        return (F.l1_loss if self.kind == "l1" else F.mse_loss)(y, target)

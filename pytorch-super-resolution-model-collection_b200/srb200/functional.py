@@ -452,3 +452,126 @@ def image_to_tensor(img_u8, out=None):
     assert out.is_contiguous() and tuple(out.shape) == (n, c, h, w) and out.dtype == torch.float32
     check(lib.srb_image_to_tensor(_ptr(img_u8), _ptr(out), n, h, w, c, ctypes.c_float(1.0 / 255.0), _stream(img_u8.device)))
     return out
+
+
+class _FusedConvLoss(torch.autograd.Function):
+    """loss = mean((y-t)^2) or mean(|y-t|) with y = PixelShuffle_ps(conv(x, w) + b), in ONE kernel (srb_conv_fprop_loss): the
+    epilogue of the last conv compares with the target, accumulates the loss and emits d loss / d y -- for PixelShuffle(4)
+    layers already un-shuffled into the conv's own NHWC layout.  Backward = wgrad + dgrad on that saved gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, kind, stride, pad, ps, need_output):
+        _require_cuda(weight, bias, target)
+        x = _as_act(x)
+        weight = weight.contiguous()
+        target = target.contiguous()
+        p = _params(x, weight, stride, pad, 0, False, ps, None, 0.2)
+        ho, wo = ctypes.c_int32(), ctypes.c_int32()
+        check(lib.srb_conv_out_hw(ctypes.byref(p), ctypes.byref(ho), ctypes.byref(wo)))
+        oshape = (p.N, p.Cout, ho.value * ps, wo.value * ps)
+        assert tuple(target.shape) == oshape, "target must have the shape of the network output"
+        dev = x.device
+        y = torch.empty(oshape, dtype=torch.float32, device=dev) if need_output else None
+        unshuf = ps > 1
+        if unshuf:
+            dz = torch.empty((p.N, p.Cout * ps * ps, ho.value, wo.value), dtype=torch.float32, device=dev,
+                             memory_format=torch.channels_last)
+        else:
+            dz = torch.empty(oshape, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = _workspace(dev, _ws_bytes(p, _lib.PASS_FPROP))
+        tx, tt, tdz = t4(x), t4(target), t4(dz)
+        ty = t4(y) if y is not None else None
+        check(lib.srb_conv_fprop_loss(ctypes.byref(p), ctypes.byref(tx), _ptr(weight), _ptr(bias), ctypes.byref(tt), kind,
+                                      ctypes.byref(ty) if ty is not None else None, ctypes.byref(tdz), 1 if unshuf else 0,
+                                      _ptr(loss), _ptr(ws), ws.numel(), _stream(dev)))
+        # geometry the backward kernels see: the plain conv with Cout*ps*ps output channels
+        ctx.pb = ConvParams(p.N, p.Cin, p.H, p.W, p.Cout * ps * ps, p.kh, p.kw, p.stride, p.pad, 0, 0, 1, _lib.ACT_NONE,
+                            p.slope, p.math) if unshuf else p
+        ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)
+        ctx.in_token = getattr(x, "_srb_relu", None) if x.requires_grad else None
+        if ctx.in_token is not None:
+            ctx.in_token.consumers += 1
+        ctx.save_for_backward(x, weight, dz)
+        ctx.set_materialize_grads(False)
+        if y is None:
+            return loss
+        ctx.mark_non_differentiable(y)
+        return loss, y
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        x, weight, dz = ctx.saved_tensors
+        p = ctx.pb
+        dev = x.device
+        st = _stream(dev)
+        if gloss is None:
+            return (None,) * 9
+        # d loss_total / d z = gloss * saved gradient (gloss == 1 for `loss.backward()`: the kernel then returns at once)
+        check(lib.srb_scale_by_scalar(_ptr(dz), dz.numel(), _ptr(gloss.contiguous().float()),
+                                      1 if p.math in (_lib.MATH_AUTO, _lib.MATH_TF32) else 0, st))
+        if p.math == _lib.MATH_BF16:
+            dz = _as_act(dz)
+        tdz, tx = t4(dz), t4(x)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            wparam, bparam = ctx.params
+            direct = getattr(wparam, "_srb_direct", False) and wparam.grad is not None and \
+                (bparam is None or (getattr(bparam, "_srb_direct", False) and bparam.grad is not None))
+            accumulate = 0
+            if direct:
+                dw_t, db_t, scale = wparam.grad, (bparam.grad if bparam is not None else None), _state["grad_scale"]
+                accumulate = 1 if getattr(wparam, "_srb_written", False) else 0
+                wparam._srb_written = True
+                if bparam is not None:
+                    bparam._srb_written = True
+            else:
+                dw_t = dw = torch.empty_like(weight)
+                db_t = db = torch.empty(weight.shape[0], dtype=torch.float32, device=dev) if ctx.has_bias else None
+                scale = 1.0
+            ws = _workspace(dev, _ws_bytes(p, _lib.PASS_WGRAD))
+            check(lib.srb_conv_wgrad(ctypes.byref(p), ctypes.byref(tx), ctypes.byref(tdz), _ptr(dw_t), _ptr(db_t),
+                                     ctypes.c_float(scale), accumulate, _ptr(ws), ws.numel(), st))
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=x.dtype, device=dev,
+                             memory_format=torch.channels_last if _is_cl(x) else torch.contiguous_format)
+            tdx = t4(dx)
+            itok = ctx.in_token
+            fuse = itok is not None and itok.consumers == 1 and not itok.observed and _state["fuse_relu_bwd"]
+            bits = None
+            if fuse and itok.bits is not None and p.Cin % 16 == 0 and \
+                    _uses_tensor_path(p, _lib.PASS_DGRAD, _is_cl(dx), _is_cl(dz)):
+                bits = itok.bits
+            if fuse and bits is None and p.math == _lib.MATH_BF16:
+                fuse = False
+            tmask = t4(x) if (fuse and bits is None) else None
+            ws = _workspace(dev, _ws_bytes(p, _lib.PASS_DGRAD))
+            check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
+                                     ctypes.byref(tmask) if tmask is not None else None, _ptr(bits), ctypes.byref(tdx),
+                                     _ptr(ws), ws.numel(), st))
+            if fuse:
+                itok.premasked = (dx.data_ptr(), dx._version, tuple(dx.shape), tuple(dx.stride()))
+        return dx, dw, db, None, None, None, None, None, None
+
+
+_LOSS_KINDS = {"mse": 0, "l2": 0, "l1": 1}
+
+
+def loss_fusable(x_shape, x_cl, weight_shape, stride, padding, pixel_shuffle):
+    """Can conv2d_loss run this last layer?  (Conv2d on the tensor path, stride 1; PixelShuffle 1 or 4.)"""
+    if stride != 1 or pixel_shuffle not in (1, 4) or _state["math"] in (_lib.MATH_FP32, _lib.MATH_EXACT):
+        return False
+    if pixel_shuffle == 4 and weight_shape[0] % 16 != 0:
+        return False
+    N, Cin, H, W = x_shape
+    p = ConvParams(N, Cin, H, W, weight_shape[0] // (pixel_shuffle ** 2), weight_shape[2], weight_shape[3], stride, padding, 0,
+                   0, pixel_shuffle, _lib.ACT_NONE, 0.2, _state["math"])
+    return _uses_tensor_path(p, _lib.PASS_FPROP, x_cl, False)
+
+
+def conv2d_loss(x, weight, bias, target, kind="mse", stride=1, padding=0, pixel_shuffle=1, need_output=False):
+    """Last conv of a network fused with nn.MSELoss / nn.L1Loss (mean): returns loss, or (loss, y) with need_output=True
+    (y is then a plain non-differentiable tensor: the gradient flows through the loss)."""
+    return _FusedConvLoss.apply(x, weight, bias, target, _LOSS_KINDS[kind], int(stride), int(padding), int(pixel_shuffle),
+                                bool(need_output))

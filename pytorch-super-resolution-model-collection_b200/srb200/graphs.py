@@ -24,8 +24,10 @@ from . import _lib
 
 
 class TrainStepGraphs:
-    def __init__(self, net, loss_fn, optimizer, bucket, slots, clip_norm=None, capture_allreduce=True):
+    def __init__(self, net, loss_fn, optimizer, bucket, slots, clip_norm=None, capture_allreduce=True, forward_loss=None):
         self.net, self.loss_fn, self.opt, self.bucket = net, loss_fn, optimizer, bucket
+        # forward_loss(x, t) -> loss replaces loss_fn(net(x), t) (e.g. srb200.FusedLoss: criterion inside the last conv's epilogue)
+        self.forward_loss = forward_loss if forward_loss is not None else (lambda x, t: loss_fn(net(x), t))
         self.slots = list(slots)
         self.clip_norm = clip_norm
         self.dev = self.slots[0][0].device
@@ -56,7 +58,7 @@ class TrainStepGraphs:
     # -- eager version of the same step (warm-up, debugging, instrumentation) ---------------------------------------
     def eager_step(self, x, t):
         self.bucket.begin_step()
-        loss = self.loss_fn(self.net(x), t)
+        loss = self.forward_loss(x, t)
         loss.backward()
         self.bucket.all_reduce()
         if self.clip_norm is not None:
@@ -76,7 +78,7 @@ class TrainStepGraphs:
                 c0 = _lib.launch_count()
                 with torch.cuda.graph(g, pool=pool, stream=side):
                     self.bucket.begin_step()
-                    loss = self.loss_fn(self.net(x), t)
+                    loss = self.forward_loss(x, t)
                     loss.backward()
                     out.copy_(loss.detach())
                     if with_comm:

@@ -184,3 +184,53 @@ def test_exact_mode_op_is_fp32_accurate(case):
     assert rel_l2(xg.grad, xr.grad) < 5e-5
     assert rel_l2(wg.grad, wr.grad) < 5e-5
     assert rel_l2(bg.grad, br.grad) < 5e-5
+
+
+@pytest.mark.parametrize("name,args,xshape,kind", [
+    ("espcn", (3, 64, 4), (3, 3, 20, 22), "mse"),      # PixelShuffle(4) -> NCHW: gradient emitted un-shuffled
+    ("espcn", (3, 64, 4), (2, 3, 16, 16), "l1"),
+    ("srcnn", (3, 64), (2, 3, 30, 28), "mse"),         # Cout = 3, no shuffle: gradient in y's layout
+    ("edsr", (3, 32, 2), (2, 3, 12, 12), "l1"),        # edsr.py:152-153
+    ("vdsr", (3, 64, 3), (2, 3, 16, 16), "mse"),       # global residual after the last conv: must fall back, same numbers
+])
+@pytest.mark.parametrize("math", ["auto", "bf16"])
+def test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, math):
+    """srb200.FusedLoss (criterion + its backward + the pixel-un-shuffle inside the last conv's epilogue) against the same
+    network with the stand-alone loss: loss value and every parameter gradient; and against the CPU oracle's loss."""
+    assert torch.cuda.is_available()
+    import torch.nn.functional as TF
+    if math == "bf16" and name in ("espcn", "srcnn"):
+        pytest.skip("bf16 storage is specified for the 64+-channel nets (cfg4); ESPCN/SRCNN keep fp32 storage")
+    srb200.set_math(math)
+    ref = R.build(name, args, seed=0)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.rand(xshape, generator=gen)
+    yref = ref(x).detach()
+    tgt = torch.rand(yref.shape, generator=gen)
+    lossf = TF.l1_loss if kind == "l1" else TF.mse_loss
+
+    def run(fused):
+        net = M.MODELS[name](*args)
+        net.load_state_dict(ref.state_dict())
+        net.to(DEV).train()
+        if fused:
+            fl = srb200.FusedLoss(net, kind)
+            for _ in range(2):  # the first call decides fused / plain; the second is the steady state
+                net.zero_grad()
+                loss = fl(x.to(DEV), tgt.to(DEV))
+                loss.backward()
+            mode = fl.mode
+        else:
+            loss = lossf(net(x.to(DEV)), tgt.to(DEV))
+            loss.backward()
+            mode = None
+        return loss.item(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}, mode
+
+    l_f, g_f, mode = run(True)
+    l_u, g_u, _ = run(False)
+    assert mode == ("plain" if name == "vdsr" else "fused")
+    assert abs(l_f - l_u) < 2e-6 * abs(l_u)
+    tol = 2e-3 if (kind == "l1" or math == "bf16") else 2e-4  # L1: sign(y - t) is taken before / after a rounding of y
+    for k in g_u:
+        assert rel_l2(g_f[k], g_u[k]) < tol, k
+    assert abs(l_f - lossf(yref, tgt).item()) < (3e-2 if math == "bf16" else 2e-3) * abs(l_u)
