@@ -407,8 +407,11 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     imgs = batch * world * steps
     res = {"workload": workload, "value": imgs / (ms * 1e-3), "ms_per_step": ms / steps, "clocks": clocks,
            "gpu_launches": int(launches), "steps": steps,
-           "comm": None if world == 1 else ("captured in the backward graph" if graphs and graphs["stepper"].fused_comm
-                                            else "eager between graphs")}
+           "comm": None if world == 1 else "%s all-reduce of the flat gradient buffer, %s" % (
+               {"peer": "libsrb200 one-kernel NVLink peer-memory", "nccl": "NCCL"}.get(bucket.comm, bucket.comm),
+               "captured in the backward graph" if graphs and graphs["stepper"].fused_comm else "eager between graphs")}
+    if getattr(bucket, "comm_fallback", None):
+        res["comm_fallback"] = bucket.comm_fallback
     if graphs and getattr(graphs["stepper"], "comm_capture_error", None):
         res["comm_capture_error"] = graphs["stepper"].comm_capture_error
     if not full:
@@ -683,6 +686,8 @@ def main():
         line["comm"] = res["comm"]
     if res.get("comm_capture_error"):
         line["comm_capture_error"] = res["comm_capture_error"]
+    if res.get("comm_fallback"):
+        line["comm_fallback"] = res["comm_fallback"]
     if a.workload == DEFAULT_WORKLOAD and not a.no_sub and a.math == "auto":
         # BASELINE.json names VDSR cfg3 for the 1->8 GPU curve: a short device-timed sub-result rides along in the same line
         try:

@@ -210,6 +210,18 @@ int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int
 /* Round n contiguous floats to tf32 (round-to-nearest, ties away) in place or out of place. */
 int srb_round_tf32(const float *x, float *y, int64_t n, void *stream);
 
+/*
+ * Data-parallel gradient exchange (the reference has none; BASELINE.json asks for it): in-place sum of
+ * the flat fp32 gradient buffer over `world` GPUs of one NVLink/NVSwitch box, ONE kernel per rank, no NCCL on this path.
+ *   bufs_dev  device array of `world` device pointers: every rank's flat buffer (peer-mapped symmetric memory, n floats each)
+ *   pads_dev  device array of `world` device pointers: every rank's signal pad (>= 32 zero-initialised uint32 words each)
+ *   state2    two zero-initialised uint32 words in LOCAL device memory (epoch, block counter) owned by this bucket
+ * Every rank of the group must enqueue the call the same number of times.  Rank r reduces slice r of all buffers in rank order
+ * and stores the result into slice r of all buffers, so all replicas end up bit-identical (deterministic).  world <= 16.
+ */
+int srb_allreduce_inplace(float *const *bufs_dev, uint32_t *const *pads_dev, int32_t rank, int32_t world, int64_t n,
+                          uint32_t *state2, void *stream);
+
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t srb_launch_count(void);
 

@@ -59,6 +59,7 @@ SYMBOLS = {
     "srb_loss_workspace_bytes": (ctypes.c_size_t, []),
     "srb_loss_fwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_size_t, _vp]),
     "srb_loss_bwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
+    "srb_allreduce_inplace": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _vp, _vp]),
     "srb_launch_count": (ctypes.c_int64, []),
 }
 

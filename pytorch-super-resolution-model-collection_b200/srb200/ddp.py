@@ -9,12 +9,19 @@ multi-device code at all; this is the exchange step BASELINE
   before one backward, srgan.py:275-286) accumulate, slots nobody wrote are zeroed before the reduction --
   no zero_grad pass, no autograd accumulation kernel, no flatten copy.
 * Everything else (PReLU slopes, BatchNorm, Linear) arrives through autograd and is copied into its slot.
-torch.distributed is plumbing only (process group + the all_reduce call).
+* The exchange itself is libsrb200's own kernel when the ranks share an NVLink/NVSwitch box: the flat buffer lives in
+  symmetric memory and srb_allreduce_inplace (csrc/comm.cu) reduces it in place over peer loads/stores, one launch per rank,
+  CUDA-graph capturable, deterministic.  torch.distributed is plumbing only (process group, handle exchange); NCCL's
+  all_reduce remains the fallback (SRB_ALLREDUCE=nccl forces it, CPU/gloo tests use it).
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import functional as F
+from ._lib import lib, check
 
 
 class GradBucket:
@@ -23,7 +30,13 @@ class GradBucket:
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.symm = None       # symmetric-memory handle when the one-kernel NVLink all-reduce is in use
+        self.comm = "none" if self.world == 1 else "nccl"
+        self.flat = None
+        if self.world > 1 and dev.type == "cuda" and os.environ.get("SRB_ALLREDUCE", "peer") != "nccl":
+            self._try_symmetric(total, dev)
+        if self.flat is None:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views = []
         self.direct_ids = set()
         off = 0
@@ -39,6 +52,36 @@ class GradBucket:
                             self.direct_ids.add(id(p))
         self._attach()
         F.set_grad_scale(1.0 / self.world)
+
+    def _try_symmetric(self, total, dev):
+        """Put the flat buffer into symmetric memory (peer-mapped over NVLink) so that libsrb200's own kernel can reduce it in
+        place (srb_allreduce_inplace).  torch only allocates and exchanges the handles; any failure leaves the NCCL path."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            n = (total + 3) // 4 * 4
+            buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if hdl.world_size != self.world or self.world > 16:
+                raise RuntimeError("unexpected symmetric-memory group size")
+            # device arrays of per-rank pointers to this tensor (allocation base + the tensor's offset) and to the signal pads
+            off = int(getattr(hdl, "offset", 0))
+            ptrs = [int(b) + off for b in hdl.buffer_ptrs]
+            if ptrs[hdl.rank] != buf.data_ptr():
+                raise RuntimeError("symmetric-memory pointer table does not match the local tensor")
+            buf.zero_()
+            self.flat = buf[:total]
+            self._symm_buf = buf
+            self.symm = hdl
+            self._peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+            self._peer_pads = torch.tensor([int(b) for b in hdl.signal_pad_ptrs], dtype=torch.int64, device=dev)
+            self._state2 = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.comm = "peer"
+            torch.cuda.synchronize(dev)
+            dist.barrier()  # every rank's buffer is zeroed and mapped before the first exchange
+        except Exception as e:  # no P2P / fabric support in this setup: NCCL
+            self.symm = None
+            self.flat = None
+            self.comm_fallback = "%s: %s" % (type(e).__name__, e)
 
     def _attach(self):
         for p, v in zip(self.params, self.views):
@@ -73,7 +116,13 @@ class GradBucket:
                 for p, v in zip(self.params, self.views):
                     if id(p) not in self.direct_ids:
                         v.mul_(1.0 / self.world)
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if self.symm is not None:
+                dev = self.flat.device
+                check(lib.srb_allreduce_inplace(ctypes.c_void_p(self._peer_bufs.data_ptr()), ctypes.c_void_p(self._peer_pads.data_ptr()),
+                                                self.symm.rank, self.world, self.flat.numel(), ctypes.c_void_p(self._state2.data_ptr()),
+                                                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         return self.flat
 
     def detach(self):
