@@ -590,6 +590,7 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
   } else {
     b = tc_conv_ws_bytes(g);
     if (pass == 0) b += 40 * 1024;  // per-warp loss partials of srb_conv_fprop_loss
+    if (g.st > 1) { const size_t c = tc_strided_ws_bytes(g); if (c > b) b = c; }
   }
   if (p->math == SRB_MATH_BF16 && !p->transposed && g.st == 1 && pass == 2) {
     // bf16 wgrad + the two mixed-edge conversions (dz -> fp32 NHWC for Cin <= 4; dz -> bf16 NHWC8 for Cout < 8)
@@ -642,10 +643,14 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
                 "relu_bits needs the tensor path, no PixelShuffle and Cout %% 16 == 0");
     if (ex) return exact_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
     if (tc) return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, st);
+    // strided Conv2d (SRGAN D, srgan.py:54-63): the input's st x st phase images as extra channels of a stride-1 tensor-core conv
+    if (is_tf32_math(p->math) && g.st > 1 && tc_strided_gather_supported(g, tx, ty)) return tc_strided_gather(g, tx, w, ty, e, ws, ws_bytes, st);
     return simt_conv_gather(g, tx, w, ty, e, st);
   }
   SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits with a transposed convolution");
   Epi e = make_epi(p, bias, alpha, residual, preact, want_round(p, ty, p->Cout));
+  // ConvTranspose2d (fsrcnn.py:33, DeconvBlock base_networks.py:77): st x st output phases, each a stride-1 tensor-core conv
+  if (is_tf32_math(p->math) && tc_strided_scatter_supported(g, tx, ty)) return tc_strided_scatter(g, tx, w, ty, e, ws, ws_bytes, st);
   return simt_conv_scatter(g, tx, w, ty, e, st);
 }
 
@@ -676,7 +681,9 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
   } else {
     e.dz = tdz;
   }
-  return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, (cudaStream_t)stream, 1, loss);
+  ConvOpt lo;
+  lo.loss_out = loss;
+  return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, (cudaStream_t)stream, lo);
 }
 
 int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream) {
@@ -768,7 +775,9 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
     SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
     SRB_REQUIRE(!e.mask.p, SRB_EUNSUPPORTED, "bf16 storage mode: pass relu_bits, not relu_mask");
     e.round_tf32 = 0;
-    return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
+    ConvOpt po;
+    po.in_ps = g.ps;
+    return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, po);
   }
   SRB_REQUIRE(tdz.dt == SRB_F32 && tdx.dt == SRB_F32, SRB_EUNSUPPORTED, "bf16 tensors need math = SRB_MATH_BF16");
   if (!p->transposed) {
@@ -777,7 +786,9 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
       Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
       if (gd.pad >= 0 && tc_conv_supported(gd, tdz, tdx, true, g.ps)) {
         SRB_REQUIRE(!relu_bits || (p->Cin & 15) == 0, SRB_EUNSUPPORTED, "relu_bits needs Cin %% 16 == 0");
-        return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, g.ps);
+        ConvOpt po;
+        po.in_ps = g.ps;
+        return tc_conv_gather(gd, tdz, w, true, tdx, e, ws, ws_bytes, st, po);
       }  // else: the CUDA-core scatter kernel below un-shuffles through its own addressing
     }
     if (p->math != SRB_MATH_FP32 && g.ps == 1 && g.st == 1 && g.kh == g.kw) {
@@ -794,10 +805,12 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
       }
     }
     SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits needs the tensor-path dgrad (use relu_mask)");
+    if (is_tf32_math(p->math) && g.st > 1 && tc_strided_scatter_supported(g, tdz, tdx)) return tc_strided_scatter(g, tdz, w, tdx, e, ws, ws_bytes, st);
     return simt_conv_scatter(g, tdz, w, tdx, e, st);
   }
   SRB_REQUIRE(!relu_bits, SRB_EUNSUPPORTED, "relu_bits with a transposed convolution (use relu_mask)");
   // ConvTranspose2d backward-data is a plain gather conv of dz (big side) producing dx (small side)
+  if (is_tf32_math(p->math) && g.st > 1 && tc_strided_gather_supported(g, tdz, tdx)) return tc_strided_gather(g, tdz, w, tdx, e, ws, ws_bytes, st);
   return simt_conv_gather(g, tdz, w, tdx, e, st);
 }
 

@@ -117,12 +117,39 @@ int simt_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, fl
 int channel_sum(const T4 &t, int N, int C, int H, int W, float *out, float scale, int accumulate, cudaStream_t st);
 
 // Tensor-core (tcgen05) path, tc_conv.cu.
-bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_as_gather, int in_ps = 1);
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool scatter_as_gather, int in_ps = 1, int pad_w = -1);
 size_t tc_conv_ws_bytes(const Geom &g);
-// in_ps > 1: `in` holds PixelShuffle_r of the logical input (g.Ci = C * r * r logical channels, in has C); the un-shuffle
-// happens in the TMA traversal
+// Options of the slot-linear conv beyond the plain stride-1 gather.
+struct ConvOpt {
+  // in_ps > 1: `in` holds the logical input in r x r INTERLEAVED form -- logical channel (ij, c), pixel (y, x) is
+  // in[c, y*r + ij/r, x*r + ij%r] (g.Ci = C * r * r logical channels, `in` has C) -- and is fetched through a stride-r TMA
+  // traversal.  Two uses: dz of a PixelShuffle layer (wmode 0: logical channel c*r*r + ij of the filter), and the r x r
+  // phase images of a STRIDED convolution's input (wmode 1).
+  int in_ps = 1;
+  int in_h = 0, in_w = 0;  // true spatial size of `in` when it is not g.Hi*in_ps x g.Wi*in_ps (strided convs with odd sizes)
+  int pad_w = -1;          // horizontal padding when it differs from g.pad (-1: same)
+  // How launch filter element (n, k, tap (tr, ts)) maps to the layer's filter w[(o * I + i) * kh0 * kw0 + r * kw0 + s]:
+  //   wmode 0: (r, s) = (tr, ts)                       [flip_transpose: (kh-1-tr, kw-1-ts) and o/i swapped]
+  //   wmode 1: strided-input phases: k = ph * C + c, ph = a * st + b: r = st * (tr + dmin_r) + a + pad0 (valid if 0 <= r < kh0),
+  //            same for s; invalid (phase, tap) pairs are skipped by the kernel (phase tap masks) -- o = n, i = c
+  //   wmode 2: one OUTPUT phase of a transposed / strided-backward conv: r = ra + st * (tmax_a - tr), s = rb + st * (tmax_b - ts);
+  //            o = k, i = n (the launch's output channel is the filter's second index)
+  int wmode = 0;
+  int st = 1, pad0 = 0, kh0 = 0, kw0 = 0;
+  int dmin_r = 0, dmin_s = 0;
+  int ra = 0, rb = 0, tmax_a = 0, tmax_b = 0;
+  float *loss_out = nullptr;  // fused loss (Epi::loss_kind): receives the mean loss
+};
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi,
-                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps = 1, float *loss_out = nullptr);
+                   void *ws, size_t ws_bytes, cudaStream_t st, const ConvOpt &opt = ConvOpt());
+// Strided Conv2d forward / ConvTranspose2d backward-data (input phases) and their adjoints (output phases) on the tensor path
+bool tc_strided_gather_supported(const Geom &g, const T4 &big, const T4 &small);
+int tc_strided_gather(const Geom &g, const T4 &big, const float *w, const T4 &small, const Epi &epi, void *ws, size_t ws_bytes,
+                      cudaStream_t st);
+bool tc_strided_scatter_supported(const Geom &g, const T4 &small, const T4 &big);
+int tc_strided_scatter(const Geom &g, const T4 &small, const float *w, const T4 &big, const Epi &epi, void *ws, size_t ws_bytes,
+                       cudaStream_t st);
+size_t tc_strided_ws_bytes(const Geom &g);
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
 int tc_conv_get_dbg();

@@ -56,6 +56,9 @@ struct SlArgs {
                      // L2 -> SM weight traffic per SM halves; the pair walks its bands in lock-step (same K-block sequence)
   int in_ps;         // > 1: the input tensor is PixelShuffle_r of the logical input (dgrad of a PSBlock conv): chunk c is
   int in_cpb;        //      sub-pixel phase c / in_cpb, channel block c % in_cpb, fetched through a stride-r TMA traversal
+  int kb_valid;      // K-blocks (chunk, tap) that exist: chunks * taps minus the taps the phase masks exclude
+  int pad_w;         // horizontal padding (== pad unless a phase launch of a strided / transposed conv says otherwise)
+  unsigned short phase_mask[16];  // in_ps > 1: bit (r*kw + s) set = tap (r, s) of that input phase exists (others are skipped)
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
   int v8;              // out / residual / preact / mask rows are 32-byte aligned: mode-0 epilogue uses 256-bit global accesses
   int dbg;             // debug knobs (srb_debug_set_flags): 1 = epilogue does nothing, 2 = A tiles are loaded only once per buffer
@@ -502,9 +505,15 @@ __device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, 
     mbar_wait(&a_full[ms.a_buf], ms.a_phase);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t a_tap = (((a_base + ms.a_buf * (uint32_t)a.a_buf_bytes) >> 4) & 0x3FFF) | lbo;
+    const uint32_t tmask = a.in_ps > 1 ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0xffffffffu;
     for (int r = 0; r < a.kh; ++r) {
       for (int s = 0; s < a.kw; ++s) {
         uint32_t b_lo;
+        if (!((tmask >> (r * a.kw + s)) & 1u)) {  // this tap does not exist for this input phase (strided conv)
+          if (a.b_resident) b_res += b_stage16;
+          a_tap += 8u;
+          continue;
+        }
         if (a.b_resident) {
           b_lo = b_res;
           b_res += b_stage16;
@@ -672,7 +681,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       if (!valid && (a.cl == 1 || a.c4 || a.b_resident)) break;
       SL_BAND_GEOM(valid ? band : 0)
       (void)mtb;
-      const int ix0 = ox0 - a.pad, iy0 = oy0 - a.pad;
+      const int ix0 = ox0 - a.pad_w, iy0 = oy0 - a.pad;
       for (int c = 0; c < a.chunks; ++c) {
         const uint32_t buf = ac % (uint32_t)a.a_bufs;
         if (valid) mbar_wait(&a_empty[buf], ((ac / (uint32_t)a.a_bufs) & 1u) ^ 1u);
@@ -694,9 +703,11 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         __syncwarp();
         if (valid) ++ac;
         if (!a.c4 && !a.b_resident) {
-          for (int tap = 0; tap < taps; ++tap, ++kb) {
-            const uint32_t st = kb % (uint32_t)a.b_stages;
-            mbar_wait(&b_empty[st], ((kb / (uint32_t)a.b_stages) & 1u) ^ 1u);  // released by every CTA that shares the ring
+          const uint32_t tmask = a.in_ps > 1 ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0xffffffffu;
+          for (int tap = 0; tap < taps; ++tap) {
+            if (!((tmask >> tap) & 1u)) continue;
+            const uint32_t st = kb++ % (uint32_t)a.b_stages;
+            mbar_wait(&b_empty[st], ((((kb - 1u) / (uint32_t)a.b_stages)) & 1u) ^ 1u);  // released by every CTA that shares the ring
             if (elect_one()) {
               mbar_expect_tx(&b_full[st], (uint32_t)a.b_stage_bytes);
               if (a.cl > 1)  // my half of the stage, into both CTAs
@@ -728,7 +739,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       if (band >= num_bands) {
         if (a.cl == 1 || a.c4 || a.b_resident) break;
         // idle slot of a sharing pair: consume the weight stages without issuing MMAs so that the peer's ring keeps moving
-        for (int q = 0; q < a.chunks * taps; ++q) {
+        for (int q = 0; q < a.kb_valid; ++q) {
           mbar_wait(&b_full[ms.b_st], ms.b_phase);
           umma_commit_arrive_mc(&b_empty[ms.b_st], 3);
           if (++ms.b_st == (uint32_t)a.b_stages) { ms.b_st = 0; ms.b_phase ^= 1u; }
@@ -876,8 +887,25 @@ __device__ __forceinline__ int perm_k(int k, int perm_C, int perm_rr) {
   return (k - ij * perm_C) * perm_rr + ij;
 }
 
+// Filter addressing of the phase launches of strided / transposed convolutions (ConvOpt::wmode 1 and 2, srb_common.cuh).
+struct WMap {
+  int wmode, st, pad0, kh0, kw0, dmin_r, dmin_s, ra, rb, tmax_a, tmax_b, C;  // C: channels per input phase (wmode 1)
+};
+// value of launch filter element (n, k, tap (tr, ts)); Nn / Kk: launch output / reduction channel counts
+__device__ __forceinline__ float wval_phase(const float *__restrict__ w, const WMap &m, int n, int k, int tr, int ts, int Nn, int Kk) {
+  if (m.wmode == 1) {
+    const int ph = k / m.C, c = k - ph * m.C, a = ph / m.st, b = ph - a * m.st;
+    const int r = m.st * (tr + m.dmin_r) + a + m.pad0, s = m.st * (ts + m.dmin_s) + b + m.pad0;
+    if (r < 0 || r >= m.kh0 || s < 0 || s >= m.kw0) return 0.f;
+    return __ldg(w + (((long long)n * m.C + c) * m.kh0 + r) * m.kw0 + s);
+  }
+  const int r = m.ra + m.st * (m.tmax_a - tr), s = m.rb + m.st * (m.tmax_b - ts);
+  if (r < 0 || r >= m.kh0 || s < 0 || s >= m.kw0) return 0.f;
+  return __ldg(w + (((long long)k * Nn + n) * m.kh0 + r) * m.kw0 + s);
+}
+
 __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad,
-                            int chunks, int flip, int perm_C, int perm_rr) {
+                            int chunks, int flip, int perm_C, int perm_rr, WMap wm) {
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -890,7 +918,8 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
     float v = 0.f;
     if (n < Nn && k < Kk) {
       const int r = tap / kw, s = tap - r * kw;
-      v = round_tf32(wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip));
+      v = wm.wmode ? round_tf32(wval_phase(w, wm, n, k, r, s, Nn, Kk))
+                   : round_tf32(wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip));
     }
     out[i] = v;
   }
@@ -898,7 +927,7 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
 
 // generic B operand for bf16 operands: out[chunk][tap][Npad][64] (bf16 RN), zero for n >= Nn or k >= Kk
 __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__restrict__ out, int Nn, int Kk, int kh, int kw,
-                              int Npad, int chunks, int flip, int perm_C, int perm_rr) {
+                              int Npad, int chunks, int flip, int perm_C, int perm_rr, WMap wm) {
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -911,7 +940,7 @@ __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__res
     float v = 0.f;
     if (n < Nn && k < Kk) {
       const int r = tap / kw, s = tap - r * kw;
-      v = wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip);
+      v = wm.wmode ? wval_phase(w, wm, n, k, r, s, Nn, Kk) : wval(w, n, perm_k(k, perm_C, perm_rr), r, s, Nn, Kk, kh, kw, flip);
     }
     out[i] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xffffu);
   }
@@ -1090,6 +1119,9 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
   a.v8h = 0;
   a.in_ps = in_ps;
   a.in_cpb = in_ps > 1 ? g.Ci / (in_ps * in_ps) / celems : 0;
+  a.pad_w = g.pad;
+  a.kb_valid = kblocks;
+  for (int i = 0; i < 16; ++i) a.phase_mask[i] = 0xffff;
   pl->Npad = Npad;
   pl->n_tiles_n = Npad / NT;
   {  // persistent grid: as many CTAs as fit on the chip; CTA x walks bands x, x + grid, ...
@@ -1116,7 +1148,7 @@ void tc_conv_set_trace(long long *buf, long long max_ctas) { g_sl_trace = buf; g
 void tc_conv_set_dbg(int flags) { g_sl_dbg = flags; }
 int tc_conv_get_dbg() { return g_sl_dbg; }
 
-bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/, int in_ps) {
+bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/, int in_ps, int /*pad_w*/) {
   if (g.st != 1 || g.N <= 0) return false;
   if (in_ps > 1) {  // `in` is PixelShuffle_r of the logical input: needs whole channel chunks per sub-pixel phase
     const int celems = in.dt == SRB_BF16 ? 64 : 32, rr = in_ps * in_ps;
@@ -1171,13 +1203,36 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
 }
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi_in,
-                   void *ws, size_t ws_bytes, cudaStream_t st, int in_ps, float *loss_out) {
+                   void *ws, size_t ws_bytes, cudaStream_t st, const ConvOpt &opt) {
   SlPlan pl;
   Epi epi = epi_in;
+  const int in_ps = opt.in_ps;
+  float *loss_out = opt.loss_out;
   const bool bf_in = in.dt == SRB_BF16, bf_out = out.dt == SRB_BF16;
   SRB_REQUIRE(make_sl_plan(g, &pl, bf_in, in_ps), SRB_EUNSUPPORTED, "tc_conv: no band plan");
   SRB_REQUIRE(in_ps == 1 || !pl.a.c4, SRB_EUNSUPPORTED, "tc_conv: un-shuffled input needs the generic operand flavour");
   const int perm_C = in_ps > 1 ? g.Ci / (in_ps * in_ps) : 0, perm_rr = in_ps * in_ps;
+  WMap wm;
+  wm.wmode = opt.wmode; wm.st = opt.st; wm.pad0 = opt.pad0; wm.kh0 = opt.kh0; wm.kw0 = opt.kw0;
+  wm.dmin_r = opt.dmin_r; wm.dmin_s = opt.dmin_s; wm.ra = opt.ra; wm.rb = opt.rb; wm.tmax_a = opt.tmax_a; wm.tmax_b = opt.tmax_b;
+  wm.C = perm_C > 0 ? perm_C : g.Ci;
+  if (opt.pad_w >= 0) pl.a.pad_w = opt.pad_w;
+  if (opt.wmode == 1) {  // which taps exist for which input phase
+    SRB_REQUIRE(in_ps > 1 && in_ps <= 4 && g.kh * g.kw <= 16 && !pl.a.c4, SRB_EUNSUPPORTED, "strided conv: unsupported phase geometry");
+    int valid = 0;
+    for (int ph = 0; ph < in_ps * in_ps; ++ph) {
+      const int pa = ph / in_ps, pb = ph % in_ps;
+      unsigned m = 0;
+      for (int tr = 0; tr < g.kh; ++tr)
+        for (int ts = 0; ts < g.kw; ++ts) {
+          const int r = opt.st * (tr + opt.dmin_r) + pa + opt.pad0, s2 = opt.st * (ts + opt.dmin_s) + pb + opt.pad0;
+          if (r >= 0 && r < opt.kh0 && s2 >= 0 && s2 < opt.kw0) m |= 1u << (tr * g.kw + ts);
+        }
+      pl.a.phase_mask[ph] = (unsigned short)m;
+      valid += __builtin_popcount(m) * pl.a.in_cpb;
+    }
+    pl.a.kb_valid = valid;
+  }
   SRB_REQUIRE((!epi.residual.p || epi.residual.dt == out.dt) && (!epi.preact.p || epi.preact.dt == out.dt), SRB_EINVAL,
               "residual / preact must have the dtype of the output");
   SRB_REQUIRE(!epi.mask.p || epi.mask.dt == SRB_F32 || !bf_out, SRB_EUNSUPPORTED, "float relu_mask with bf16 tensors (use relu_bits)");
@@ -1214,9 +1269,9 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
       k_pack_w_c4<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
     else if (bf_in)
       k_pack_w_sl_h<<<blocks, 256, 0, st>>>(w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0,
-                                            perm_C, perm_rr);
+                                            perm_C, perm_rr, wm);
     else
-      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr);
+      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr, wm);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     if (a.c4) {
@@ -1244,7 +1299,8 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
       // in_ps > 1: the map describes the SHUFFLED tensor (C, W*r, H*r, N) and is traversed with element strides (1, r, r, 1):
       // a box of (BW*r) x (BH*r) delivers BW x BH pixels of one sub-pixel phase
       const cuuint64_t r = (cuuint64_t)in_ps;
-      cuuint64_t dims[4] = {(cuuint64_t)(in_ps > 1 ? perm_C : g.Ci), (cuuint64_t)g.Wi * r, (cuuint64_t)g.Hi * r, (cuuint64_t)g.N};
+      cuuint64_t dims[4] = {(cuuint64_t)(in_ps > 1 ? perm_C : g.Ci), (cuuint64_t)(opt.in_w > 0 ? opt.in_w : g.Wi * (int)r),
+                            (cuuint64_t)(opt.in_h > 0 ? opt.in_h : g.Hi * (int)r), (cuuint64_t)g.N};
       const cuuint64_t es = bf_in ? 2 : 4;
       cuuint64_t strides[3] = {(cuuint64_t)in.sw * es, (cuuint64_t)in.sh * es, (cuuint64_t)in.sn * es};
       cuuint32_t box[4] = {(cuuint32_t)a.chunk_elems, (cuuint32_t)(a.BW * in_ps), (cuuint32_t)(a.BH * in_ps), 1};

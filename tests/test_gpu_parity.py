@@ -122,6 +122,9 @@ SWEEP = [
     (64, 3, 9, 1, 4, None, False, 1, 16, 16, 1),       # SRGAN output conv
     (64, 64, 3, 2, 1, "lrelu", False, 1, 16, 16, 2),   # SRGAN D stride-2
     (128, 128, 3, 2, 1, "lrelu", False, 1, 8, 8, 2),
+    (64, 64, 3, 2, 1, "relu", False, 1, 17, 15, 2),    # stride 2 on odd sizes (phase images of unequal size)
+    (32, 64, 4, 2, 1, None, False, 1, 12, 12, 1),      # ConvBlock defaults k4 s2 p1 (base_networks.py:40)
+    (64, 32, 5, 3, 2, "lrelu", False, 1, 14, 13, 1),   # stride 3
     (56, 12, 1, 1, 0, "prelu", False, 1, 10, 10, 2),   # FSRCNN shrink
     (12, 12, 3, 1, 1, None, False, 1, 10, 10, 2),      # FSRCNN map
     (12, 56, 1, 1, 0, "prelu", False, 1, 10, 10, 2),   # FSRCNN expand
@@ -206,8 +209,12 @@ def test_fused_conv_vs_oracle(case, math, cl):
 
 
 @pytest.mark.parametrize("math", ["fp32", "auto"])
-@pytest.mark.parametrize("k,s,p,op,Ci,Co", [(9, 4, 3, 1, 56, 3), (4, 2, 1, 0, 16, 8), (3, 1, 1, 0, 8, 8), (5, 3, 2, 2, 6, 5)])
-def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co, math):
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("k,s,p,op,Ci,Co", [(9, 4, 3, 1, 56, 3), (4, 2, 1, 0, 16, 8), (3, 1, 1, 0, 8, 8), (5, 3, 2, 2, 6, 5),
+                                            (4, 2, 1, 0, 64, 64), (3, 2, 1, 1, 32, 16), (2, 2, 0, 0, 16, 16), (9, 4, 3, 1, 64, 32)])
+def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co, math, cl):
+    """ConvTranspose2d forward / backward.  channels_last inputs with Cin % 4 == 0 run as st x st output-phase convolutions on
+    the tcgen05 kernel in 'auto' mode (csrc/strided.cu); everything else on the CUDA-core scatter kernel."""
     _need_gpu()
     srb200.set_math(math)
     # fp32 mode: exact-order-independent fp32; auto: NHWC outputs with C % 4 == 0 are stored tf32-rounded (2^-11 relative)
@@ -220,7 +227,11 @@ def test_conv_transpose_vs_oracle(k, s, p, op, Ci, Co, math):
     yref = TF.conv_transpose2d(xr, wr, br, s, p, op)
     gy = torch.randn(yref.shape, generator=gen)
     yref.backward(gy)
-    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    xg = x.to(DEV)
+    if cl:
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_(True)
+    wg, bg = (t.to(DEV).requires_grad_(True) for t in (w, b))
     y = srb200.conv_transpose2d(xg, wg, bg, s, p, op)
     y.backward(gy.to(DEV))
     assert rel_l2(y.detach(), yref.detach()) < tol
