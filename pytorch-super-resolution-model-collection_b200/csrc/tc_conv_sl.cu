@@ -505,11 +505,13 @@ __device__ __forceinline__ void mma_band_generic(const SlArgs &a, MmaState &ms, 
     mbar_wait(&a_full[ms.a_buf], ms.a_phase);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t a_tap = (((a_base + ms.a_buf * (uint32_t)a.a_buf_bytes) >> 4) & 0x3FFF) | lbo;
-    const uint32_t tmask = a.in_ps > 1 ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0xffffffffu;
+    // phase masks only exist for interleaved inputs (<= 16 taps); plain convs have up to 16 x 16 taps and no mask
+    const bool masked = a.in_ps > 1;
+    const uint32_t tmask = masked ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0u;
     for (int r = 0; r < a.kh; ++r) {
       for (int s = 0; s < a.kw; ++s) {
         uint32_t b_lo;
-        if (!((tmask >> (r * a.kw + s)) & 1u)) {  // this tap does not exist for this input phase (strided conv)
+        if (masked && !((tmask >> (r * a.kw + s)) & 1u)) {  // this tap does not exist for this input phase (strided conv)
           if (a.b_resident) b_res += b_stage16;
           a_tap += 8u;
           continue;
@@ -703,9 +705,10 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         __syncwarp();
         if (valid) ++ac;
         if (!a.c4 && !a.b_resident) {
-          const uint32_t tmask = a.in_ps > 1 ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0xffffffffu;
+          const bool masked = a.in_ps > 1;
+          const uint32_t tmask = masked ? (uint32_t)a.phase_mask[c / a.in_cpb] : 0u;
           for (int tap = 0; tap < taps; ++tap) {
-            if (!((tmask >> tap) & 1u)) continue;
+            if (masked && !((tmask >> tap) & 1u)) continue;
             const uint32_t st = kb++ % (uint32_t)a.b_stages;
             mbar_wait(&b_empty[st], ((((kb - 1u) / (uint32_t)a.b_stages)) & 1u) ^ 1u);  // released by every CTA that shares the ring
             if (elect_one()) {
