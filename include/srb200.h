@@ -211,6 +211,42 @@ int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int
 int srb_round_tf32(const float *x, float *y, int64_t n, void *stream);
 
 /*
+ * The layers around the conv stacks of SRGAN.  Dense fp32 tensors; reductions are deterministic.
+ *
+ * BatchNorm2d over a dense channels_last tensor of P = N*H*W pixels x C channels (base_networks.py:46,117,137,145,161), fused
+ * with what follows it in the blocks:   y = act(gamma * (x - mean) * invstd + beta) + residual
+ *   training != 0: batch statistics (biased variance), running_mean / running_var updated with `momentum` (unbiased variance),
+ *   like nn.BatchNorm2d; training == 0: the running statistics.  save_mean / save_invstd (C floats each) feed the backward.
+ *   act: srb_act (PReLU: alpha = the single slope); residual: NULL or a tensor like y (ResnetBlock's `bn(conv2(.)) + x`).
+ * Backward: dx, dgamma, dbeta (scaled / accumulated like srb_conv_wgrad), *dalpha += PReLU slope gradient; the gradient of
+ * the residual is dy itself.  Workspace: srb_bn_workspace_bytes(C).
+ */
+size_t srb_bn_workspace_bytes(int32_t C);
+int srb_bn_fwd(const float *x, float *y, int64_t P, int32_t C, const float *gamma, const float *beta, float *running_mean,
+               float *running_var, int training, float momentum, float eps, float *save_mean, float *save_invstd, int act,
+               float slope, const float *alpha, const float *residual, int round_to_tf32, void *ws, size_t ws_bytes, void *stream);
+int srb_bn_bwd(const float *x, const float *dy, float *dx, int64_t P, int32_t C, const float *gamma, const float *beta,
+               const float *save_mean, const float *save_invstd, int act, float slope, const float *alpha, float *dgamma,
+               float *dbeta, float *dalpha, float scale, int accumulate, int round_to_tf32, void *ws, size_t ws_bytes, void *stream);
+
+/* nn.Linear (DenseBlock, base_networks.py:7,29-31; srgan.py:66-70): y[B,O] = x[B,I] w[O,I]^T + bias.  The weight matrix is
+ * streamed once per 16 batch rows (HBM-bound: 8 flop/byte); I % 4 == 0.  Backward: dx (may be NULL), dw / db (may be NULL)
+ * scaled / accumulated like srb_conv_wgrad.  Workspace: srb_linear_workspace_bytes(I, O). */
+size_t srb_linear_workspace_bytes(int32_t I, int32_t O);
+int srb_linear_fwd(const float *x, const float *w, const float *bias, float *y, int32_t B, int32_t I, int32_t O, void *ws,
+                   size_t ws_bytes, void *stream);
+int srb_linear_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, float *db, int32_t B, int32_t I, int32_t O,
+                   float scale, int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* nn.MaxPool2d(2) on a dense channels_last tensor (VGG19 features[4], srgan.py:84-90); idx: one byte per output (argmax 0..3). */
+int srb_maxpool2_fwd(const float *x, float *y, uint8_t *idx, int32_t N, int32_t C, int32_t H, int32_t W, void *stream);
+int srb_maxpool2_bwd(const float *dy, const uint8_t *idx, float *dx, int32_t N, int32_t C, int32_t H, int32_t W, void *stream);
+
+/* nn.BCELoss (mean) over n probabilities (srgan.py:157,276-297) and its backward (dy = *grad_loss * d loss / d y). */
+int srb_bce_fwd(const float *y, const float *t, int32_t n, float *loss, void *stream);
+int srb_bce_bwd(const float *y, const float *t, int32_t n, const float *grad_loss, float *dy, void *stream);
+
+/*
  * Data-parallel gradient exchange (the reference has none; BASELINE.json asks for it): in-place sum of
  * the flat fp32 gradient buffer over `world` GPUs of one NVLink/NVSwitch box, ONE kernel per rank, no NCCL on this path.
  *   bufs_dev  device array of `world` device pointers: every rank's flat buffer (peer-mapped symmetric memory, n floats each)

@@ -457,3 +457,84 @@ def with_forced_activations(net, masks):
 
 def count_convs(net):
     return sum(1 for m in net.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)))
+
+
+# --------------------------------------------------------------------------------------------
+# SRGAN remainder: VGG feature extractor, input normalisation and the adversarial step (srgan.py:84-90, 249-310)
+# --------------------------------------------------------------------------------------------
+class FeatureExtractor(nn.Module):  # srgan.py:84-90 over torchvision's vgg19 layout (features[:feature_layer + 1])
+    CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+
+    def __init__(self, feature_layer=8):
+        super().__init__()
+        layers, cin = [], 3
+        for v in self.CFG:  # torchvision.models.vgg.make_layers(cfgs['E'], batch_norm=False)
+            if v == "M":
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            else:
+                layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+                cin = v
+        self.features = nn.Sequential(*layers[:feature_layer + 1])
+
+    def forward(self, x):
+        return self.features(x)
+
+
+def build_feature_extractor(seed=2):
+    """The reference loads ImageNet weights (srgan.py:144, needs network); tests and benches use torchvision's own default
+    initialisation (kaiming_normal_ fan_out / relu, zero bias: torchvision/models/vgg.py _initialize_weights) under a seed."""
+    torch.manual_seed(seed)
+    fe = FeatureExtractor()
+    for m in fe.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            nn.init.constant_(m.bias, 0)
+    return fe
+
+
+VGG_MEAN, VGG_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def norm_vgg(img):
+    """utils.norm(img, vgg=True) (utils.py:219-229) on a 4-D batch: per-channel (x - mean) / std."""
+    mean = torch.tensor(VGG_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(VGG_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    return (img - mean) / std
+
+
+def make_srgan_optimizers(G, D, lr=1e-5):
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr, betas=(0.9, 0.999))                  # srgan.py:147
+    d_opt = torch.optim.SGD(D.parameters(), lr=lr / 100, momentum=0.9, nesterov=True)    # srgan.py:149
+    return g_opt, d_opt
+
+
+def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, mse=TF.mse_loss, bce=None):
+    """One adversarial iteration exactly as written in srgan.py:256-310 (including its redundancies: recon is not detached
+    for the D update, VGG features of recon.data carry no gradient to G), with the two fixes modern torch forces: labels are
+    shaped like the decision (N,1), and `.data` is `.detach()`.  Returns (D_loss, G_loss) detached."""
+    if bce is None:
+        bce = lambda y, t: TF.binary_cross_entropy(y, t.reshape(y.shape))  # noqa: E731
+    x_, y_ = norm_vgg(hr_img), norm_vgg(lr_img)                             # :256-257
+    n = x_.shape[0]
+    real_label = torch.ones(n, device=x_.device)
+    fake_label = torch.zeros(n, device=x_.device)
+    d_opt.zero_grad()                                                      # :272
+    D_real_loss = bce(D(x_), real_label)                                   # :275-276
+    recon = G(y_)                                                          # :279
+    D_fake_loss = bce(D(recon), fake_label)                                # :280-281
+    D_loss = D_real_loss + D_fake_loss
+    D_loss.backward()                                                      # :286
+    d_opt.step()
+    g_opt.zero_grad()                                                      # :290
+    recon = G(y_)                                                          # :293
+    GAN_loss = bce(D(recon), real_label)                                   # :294-297
+    mse_loss = mse(recon, x_)                                              # :300
+    x_VGG = norm_vgg(hr_img)
+    recon_VGG = norm_vgg(recon.detach())                                   # :302 (recon_image.data)
+    real_feature = FE(x_VGG)
+    fake_feature = FE(recon_VGG)
+    vgg_loss = mse(fake_feature, real_feature.detach())                    # :305
+    G_loss = mse_loss + 6e-3 * vgg_loss + 1e-3 * GAN_loss                  # :308
+    G_loss.backward()
+    g_opt.step()
+    return D_loss.detach(), G_loss.detach()

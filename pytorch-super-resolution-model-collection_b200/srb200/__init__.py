@@ -12,6 +12,8 @@ from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBl
 from .convert import convert, PReLU, ConvTranspose2d, Conv2d
 from .ddp import GradBucket
 from .graphs import TrainStepGraphs
+from . import nn_ops
+from .nn_ops import batch_norm_act, linear, max_pool2, bce_loss
 from . import models, host
 
 __version__ = "0.1.0"

@@ -59,6 +59,20 @@ SYMBOLS = {
     "srb_loss_workspace_bytes": (ctypes.c_size_t, []),
     "srb_loss_fwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_size_t, _vp]),
     "srb_loss_bwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
+    "srb_bn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32]),
+    "srb_bn_fwd": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_float,
+                                  ctypes.c_float, _vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, ctypes.c_int, _vp,
+                                  ctypes.c_size_t, _vp]),
+    "srb_bn_bwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_float,
+                                  _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
+    "srb_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "srb_linear_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_size_t, _vp]),
+    "srb_linear_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+                                      ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
+    "srb_maxpool2_fwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp]),
+    "srb_maxpool2_bwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp]),
+    "srb_bce_fwd": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp]),
+    "srb_bce_bwd": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp]),
     "srb_allreduce_inplace": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _vp, _vp]),
     "srb_launch_count": (ctypes.c_int64, []),
 }

@@ -15,6 +15,7 @@ only their forward is bypassed.  BatchNorm / InstanceNorm / Linear / tanh / sigm
 import torch  # re-exported on purpose: the model files get `torch` through the star import (srcnn.py:13)
 
 from . import functional as F
+from . import nn_ops as N
 
 __all__ = ["torch", "DenseBlock", "ConvBlock", "DeconvBlock", "ResnetBlock", "PSBlock", "Upsample2xBlock"]  # (prepare() is not star-exported: the model files never call it)
 
@@ -69,6 +70,23 @@ class _ActMixin:
             return self.activation, (self.act.weight if self.activation == "prelu" else None)
         return None, None
 
+    def _norm_act(self, out, residual=None, with_act=True):
+        """norm -> activation (-> + residual) after a conv.  BatchNorm2d on CUDA runs as libsrb200's fused kernels
+        (statistics, normalise + activation + residual in one pass; backward likewise); InstanceNorm and tanh / sigmoid
+        stay on torch."""
+        act = self.activation if with_act else None
+        bn = self.bn
+        if isinstance(bn, torch.nn.BatchNorm2d) and out.is_cuda and out.dtype == torch.float32 and out.shape[1] % 4 == 0:
+            fus = act if act in _FUSABLE else None
+            out = N.batch_norm_act(out, bn, activation=fus, alpha=self.act.weight if fus == "prelu" else None, residual=residual)
+            if act is not None and fus is None:
+                out = self.act(out)
+            return out
+        out = bn(out)
+        if act is not None:
+            out = self._post(out, fused=False)
+        return out if residual is None else torch.add(out, residual)
+
     def _post(self, out, fused):
         # activation the conv kernel could not fuse (after a norm layer, or tanh/sigmoid)
         if self.activation is not None and not fused:
@@ -82,7 +100,7 @@ class _ActMixin:
 
 
 class DenseBlock(torch.nn.Module):
-    """base_networks.py:4-36 -- Linear (+BN1d) (+act); stays on torch."""
+    """base_networks.py:4-36 -- Linear (+BN1d) (+act); the Linear runs on libsrb200 (nn_ops.linear), BatchNorm1d on torch."""
 
     def __init__(self, input_size, output_size, bias=True, activation='relu', norm='batch'):
         super(DenseBlock, self).__init__()
@@ -98,7 +116,12 @@ class DenseBlock(torch.nn.Module):
             self.act = act
 
     def forward(self, x):
-        out = self.bn(self.fc(x)) if self.norm is not None else self.fc(x)
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0:
+            out = N.linear(x, self.fc.weight, self.fc.bias)  # weights streamed once by libsrb200 (HBM-bound GEMV-like layer)
+        else:
+            out = self.fc(x)
+        if self.norm is not None:
+            out = self.bn(out)
         if self.activation is None:
             return out
         out = self.act(out)
@@ -130,8 +153,7 @@ class ConvBlock(torch.nn.Module, _ActMixin):
             if fused is not None:
                 return fused
         if self.norm is not None:
-            out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0]))
-            return self._layout(self._post(out, fused=False))
+            return self._layout(self._norm_act(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0])))
         a, alpha = self._fused_act()
         out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha)
         return self._layout(self._post(out, fused=self.activation in _FUSABLE))
@@ -156,8 +178,7 @@ class DeconvBlock(torch.nn.Module, _ActMixin):
     def forward(self, x):
         d = self.deconv
         if self.norm is not None:
-            out = self.bn(F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0]))
-            return self._layout(self._post(out, fused=False))
+            return self._layout(self._norm_act(F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0])))
         a, alpha = self._fused_act()
         out = F.conv_transpose2d(x, d.weight, d.bias, d.stride[0], d.padding[0], d.output_padding[0],
                                  activation=a, alpha=alpha)
@@ -185,10 +206,10 @@ class ResnetBlock(torch.nn.Module, _ActMixin):
     def forward(self, x):
         c1, c2 = self.conv1, self.conv2
         if self.norm is not None:
-            out = self.bn(F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0]))
-            out = self._post(out, fused=False)
-            out = self.bn(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0]))
-            return self._layout(torch.add(out, x))
+            # conv1 -> bn -> act -> conv2 -> bn (the SAME module, :137,145) -> + x; the add rides in the second norm kernel
+            out = self._norm_act(F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0]))
+            out = self._norm_act(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0]), residual=x, with_act=False)
+            return self._layout(out)
         a, alpha = self._fused_act()
         out = F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0], activation=a, alpha=alpha)
         out = self._post(out, fused=self.activation in _FUSABLE)
@@ -223,8 +244,7 @@ class PSBlock(torch.nn.Module, _ActMixin):
             if fused is not None:
                 return fused
         if self.norm is not None:
-            out = self.bn(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], pixel_shuffle=r))
-            return self._layout(self._post(out, fused=False))
+            return self._layout(self._norm_act(F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], pixel_shuffle=r)))
         a, alpha = self._fused_act()
         out = F.conv2d(x, c.weight, c.bias, c.stride[0], c.padding[0], activation=a, alpha=alpha, pixel_shuffle=r)
         return self._layout(self._post(out, fused=self.activation in _FUSABLE))

@@ -58,6 +58,13 @@ def convert(net):
 def _convert(net):
     for name, child in list(net.named_children()):
         tname = type(child).__name__
+        if tname == "FeatureExtractor" and type(child).__module__ != "srb200.models":
+            from .models import FeatureExtractor  # srgan.py:84-90: same `features` Sequential, fused forward
+            new = FeatureExtractor.__new__(FeatureExtractor)
+            torch.nn.Module.__init__(new)
+            new.features = child.features
+            setattr(net, name, new)
+            continue
         if tname in _BLOCKS and not _is_ours(child):
             new = _swap_block(child)
             _convert(new)  # Upsample2xBlock holds nested blocks

@@ -79,3 +79,69 @@ def loss_for(name, fused=False):
 
 
 VDSR_CLIP = 0.4
+
+
+# ---- SRGAN (srgan.py:136-157, 249-310): optimizers, input normalisation and the adversarial step, restated because the
+# reference driver no longer runs on torch 2.x; every layer inside G, D and the VGG feature extractor runs on libsrb200
+VGG_MEAN, VGG_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def norm_vgg(img):
+    """utils.norm(img, vgg=True) (utils.py:219-229) on a 4-D batch (host-side pre-processing in the reference)."""
+    mean = torch.tensor(VGG_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(VGG_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    return (img - mean) / std
+
+
+def make_srgan_optimizers(G, D, lr=1e-5, capturable=False):
+    """Adam for G (srgan.py:147), SGD momentum 0.9 Nesterov lr/100 for D (srgan.py:149); torch's single-kernel implementations."""
+    gp, dp = list(G.parameters()), list(D.parameters())
+    fused = {"fused": True} if (gp and gp[0].is_cuda) else {}
+    adam = dict(fused, capturable=True) if (capturable and fused) else fused
+    return (torch.optim.Adam(gp, lr=lr, betas=(0.9, 0.999), **adam),
+            torch.optim.SGD(dp, lr=lr / 100, momentum=0.9, nesterov=True, **fused))
+
+
+def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=None):
+    """One adversarial iteration as written in srgan.py:256-310 (labels shaped like the decision; `.data` -> `.detach()`).
+    With GradBuckets (data parallel) the D gradients are exchanged before D's step and the G gradients before G's step.
+    Returns (D_loss, G_loss), detached device scalars."""
+    from . import functional as F
+    from . import nn_ops
+    x_, y_ = norm_vgg(hr_img), norm_vgg(lr_img)
+    n = x_.shape[0]
+    real_label = torch.ones(n, device=x_.device)
+    fake_label = torch.zeros(n, device=x_.device)
+    # ---- discriminator (srgan.py:272-287); recon is NOT detached in the reference: G's gradients are computed and discarded
+    if bucket_d is not None:
+        bucket_d.begin_step()
+        if bucket_g is not None:
+            bucket_g.begin_step()
+    else:
+        d_opt.zero_grad()
+    D_real_loss = nn_ops.bce_loss(D(x_), real_label)
+    recon = G(y_)
+    D_fake_loss = nn_ops.bce_loss(D(recon), fake_label)
+    D_loss = D_real_loss + D_fake_loss
+    D_loss.backward()
+    if bucket_d is not None:
+        bucket_d.all_reduce()
+    d_opt.step()
+    # ---- generator (srgan.py:290-310); D's gradients are computed again and cleared by the next iteration's zero_grad
+    if bucket_g is not None:
+        bucket_g.begin_step()
+        bucket_d.begin_step()
+    else:
+        g_opt.zero_grad()
+    recon = G(y_)
+    GAN_loss = nn_ops.bce_loss(D(recon), real_label)
+    mse_loss = F.mse_loss(recon, x_)
+    real_feature = FE(norm_vgg(hr_img))
+    fake_feature = FE(norm_vgg(recon.detach()))
+    vgg_loss = F.mse_loss(fake_feature, real_feature.detach())
+    G_loss = mse_loss + 6e-3 * vgg_loss + 1e-3 * GAN_loss
+    G_loss.backward()
+    if bucket_g is not None:
+        bucket_g.all_reduce()
+    g_opt.step()
+    return D_loss.detach(), G_loss.detach()

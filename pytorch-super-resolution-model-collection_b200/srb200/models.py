@@ -156,5 +156,61 @@ class SRGANDiscriminator(nn.Module):
         return self.dense_layers(out)
 
 
+class MaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d(2, 2) on libsrb200 (class name unchanged: the reference never matches on it)."""
+
+    def forward(self, x):
+        from . import nn_ops
+        if self.kernel_size not in (2, (2, 2)) or self.stride not in (2, (2, 2)) or self.padding not in (0, (0, 0)):
+            raise RuntimeError("srb200.MaxPool2d implements MaxPool2d(2, 2) (VGG19 features[4])")
+        return nn_ops.max_pool2(x)
+
+
+class FeatureExtractor(nn.Module):
+    """srgan.py:84-90  vgg19.features[:feature_layer + 1] (conv3-64, ReLU, conv3-64, ReLU, maxpool, conv3-128, ReLU,
+    conv3-128, ReLU for the default 8).  Child indices -- and so the state_dict keys features.{0,2,5,7}.* of a torchvision
+    checkpoint -- are kept; every Conv2d + ReLU pair runs as one fused libsrb200 kernel, the pool as srb_maxpool2.
+    `netVGG`: a torchvision vgg19 (its layers are shared, not copied) or None for freshly initialised layers (the reference
+    downloads ImageNet weights, srgan.py:144; no network here)."""
+    CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+
+    def __init__(self, netVGG=None, feature_layer=8):
+        super().__init__()
+        if netVGG is not None:
+            layers = list(netVGG.features.children())[:feature_layer + 1]
+        else:
+            layers, cin = [], 3
+            for v in self.CFG:
+                if v == "M":
+                    layers.append(nn.MaxPool2d(2, 2))
+                else:
+                    layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(True)]
+                    cin = v
+            layers = layers[:feature_layer + 1]
+        self.features = nn.Sequential(*layers)
+
+    def forward(self, x):
+        from . import functional as F
+        from . import nn_ops
+        mods = list(self.features.children())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                x = F.conv2d(x, m.weight, m.bias, m.stride[0], m.padding[0], activation="relu" if relu else None)
+                i += 2 if relu else 1
+            elif isinstance(m, nn.MaxPool2d):
+                x = nn_ops.max_pool2(x)
+                i += 1
+            elif isinstance(m, nn.ReLU):
+                x = torch.relu(x)
+                i += 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+
 MODELS = {"srcnn": SRCNN, "espcn": ESPCN, "fsrcnn": FSRCNN, "vdsr": VDSR, "edsr": EDSR,
-          "srgan_g": SRGANGenerator, "srgan_d": SRGANDiscriminator}
+          "srgan_g": SRGANGenerator, "srgan_d": SRGANDiscriminator, "srgan_fe": FeatureExtractor}

@@ -58,7 +58,7 @@ def run_against_oracle(name, args, loss_kind, x, tgt, math, ref=None):
 def tolerances(math, n_convs):
     if math == "exact" or math == "fp32":
         return 1e-3, 1e-3
-    ty = max(1e-3, 4e-4 * n_convs ** 0.5)
+    ty = max(1e-3, 4.5e-4 * n_convs ** 0.5)
     return ty, 2 * ty
 
 

@@ -1,0 +1,165 @@
+"""GPU suite (-m gpu): the non-conv layers of SRGAN on libsrb200 -- BatchNorm2d (+activation, +residual), Linear, MaxPool2d(2),
+BCELoss -- against torch on CPU (fp32 arithmetic on both sides: 1e-5 class), the VGG feature extractor and one full SRGAN
+adversarial step (srgan.py:256-310) against the CPU oracle."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as TF
+
+pytestmark = pytest.mark.gpu
+
+import srb200
+from srb200 import models as M, host, nn_ops
+from oracle import torch_ref as R
+from util import rel_l2
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    srb200.set_math("fp32")
+    srb200.set_grad_scale(1.0)
+    yield
+    srb200.set_math("auto")
+
+
+@pytest.mark.parametrize("act", [None, "relu", "lrelu", "prelu"])
+@pytest.mark.parametrize("res", [False, True])
+@pytest.mark.parametrize("shape", [(4, 64, 9, 7), (2, 128, 5, 5), (3, 8, 6, 6)])
+def test_batch_norm_act_matches_torch(act, res, shape):
+    assert torch.cuda.is_available()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(shape, generator=gen) * 2 + 0.5
+    r = torch.randn(shape, generator=gen) if res else None
+    gy = torch.randn(shape, generator=gen)
+    C = shape[1]
+    bn_ref = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn_ref.weight.normal_(1.0, 0.2, generator=gen)
+        bn_ref.bias.normal_(0.0, 0.2, generator=gen)
+    bn = copy.deepcopy(bn_ref).to(DEV)
+    alpha_ref = torch.tensor([0.25], requires_grad=True)
+    alpha = alpha_ref.detach().clone().to(DEV).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True) if res else None
+    z = bn_ref(xr)
+    if act == "relu":
+        z = TF.relu(z)
+    elif act == "lrelu":
+        z = TF.leaky_relu(z, 0.2)
+    elif act == "prelu":
+        z = TF.prelu(z, alpha_ref)
+    if res:
+        z = z + rr
+    z.backward(gy)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    rg = r.to(DEV).requires_grad_(True) if res else None
+    y = srb200.batch_norm_act(xg, bn, activation=act, alpha=alpha, residual=rg)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y.detach(), z.detach()) < 2e-5
+    assert rel_l2(xg.grad, xr.grad) < 5e-5
+    assert rel_l2(bn.weight.grad, bn_ref.weight.grad) < 5e-5
+    assert rel_l2(bn.bias.grad, bn_ref.bias.grad) < 5e-5
+    assert rel_l2(bn.running_mean, bn_ref.running_mean) < 1e-5 and rel_l2(bn.running_var, bn_ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked) == 1
+    if act == "prelu":
+        assert abs(alpha.grad.item() - alpha_ref.grad.item()) < 1e-4 * max(1.0, abs(alpha_ref.grad.item()))
+    if res:
+        assert torch.equal(rg.grad.cpu(), gy)
+    # eval mode uses the running statistics
+    bn.eval(); bn_ref.eval()
+    assert rel_l2(srb200.batch_norm_act(xg.detach(), bn), bn_ref(x)) < 2e-5
+
+
+@pytest.mark.parametrize("B,I,O", [(16, 32768, 1024), (16, 1024, 1), (5, 2048, 37), (20, 512, 64)])
+def test_linear_matches_torch(B, I, O):
+    assert torch.cuda.is_available()
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(B, I, generator=gen)
+    w = torch.randn(O, I, generator=gen) / I ** 0.5
+    b = torch.randn(O, generator=gen)
+    gy = torch.randn(B, O, generator=gen)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    TF.linear(xr, wr, br).backward(gy)
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = srb200.linear(xg, wg, bg)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y.detach(), TF.linear(x, w, b)) < 2e-5
+    assert rel_l2(xg.grad, xr.grad) < 2e-5
+    assert rel_l2(wg.grad, wr.grad) < 2e-5
+    assert rel_l2(bg.grad, br.grad) < 2e-5
+
+
+def test_max_pool_and_bce_match_torch():
+    assert torch.cuda.is_available()
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 64, 10, 12, generator=gen)
+    x[0, 0, 0, 0] = x[0, 0, 0, 1] = 5.0  # a tie: the first maximum wins
+    gy = torch.randn(3, 64, 5, 6, generator=gen)
+    xr = x.clone().requires_grad_(True)
+    TF.max_pool2d(xr, 2).backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    y = srb200.max_pool2(xg)
+    y.backward(gy.to(DEV))
+    assert torch.equal(y.detach().cpu(), TF.max_pool2d(x, 2))
+    assert torch.equal(xg.grad.cpu(), xr.grad)
+    p = torch.rand(16, 1, generator=gen) * 0.98 + 0.01
+    t = (torch.rand(16, generator=gen) > 0.5).float()
+    pr = p.clone().requires_grad_(True)
+    (3.0 * TF.binary_cross_entropy(pr, t.reshape(16, 1))).backward()
+    pg = p.to(DEV).requires_grad_(True)
+    l = srb200.bce_loss(pg, t.to(DEV))
+    (3.0 * l).backward()
+    assert abs(l.item() - TF.binary_cross_entropy(p, t.reshape(16, 1)).item()) < 1e-6
+    assert rel_l2(pg.grad, pr.grad) < 1e-6
+
+
+def test_feature_extractor_matches_oracle():
+    assert torch.cuda.is_available()
+    ref = R.build_feature_extractor()
+    fe = M.FeatureExtractor()
+    fe.load_state_dict(ref.state_dict())
+    fe.to(DEV)
+    x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    xr = x.clone().requires_grad_(True)
+    gy = torch.randn(2, 128, 16, 16, generator=torch.Generator().manual_seed(7))
+    ref(xr).backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    y = fe(xg)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y.detach(), ref(x).detach()) < 1e-4
+    assert rel_l2(xg.grad, xr.grad) < 1e-4
+    for (k, p), (_, q) in zip(fe.named_parameters(), ref.named_parameters()):
+        assert rel_l2(p.grad, q.grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("math", ["fp32", "auto"])
+def test_srgan_adversarial_step_tracks_the_oracle(math):
+    """srgan.py:256-310 on the engine: both losses and every parameter of G and D after one step against the CPU oracle."""
+    assert torch.cuda.is_available()
+    srb200.set_math(math)
+    Gr, Dr, FEr = R.build("srgan_g", (3, 32, 2), seed=0), R.build("srgan_d", (3, 16, 32), seed=1), R.build_feature_extractor()
+    G, D, FE = M.SRGANGenerator(3, 32, 2), M.SRGANDiscriminator(3, 16, 32), M.FeatureExtractor()
+    G.load_state_dict(Gr.state_dict()); D.load_state_dict(Dr.state_dict()); FE.load_state_dict(FEr.state_dict())
+    for m in (G, D, FE):
+        m.to(DEV).train()
+    lr_ = 1e-3
+    gor, dor = R.make_srgan_optimizers(Gr, Dr, lr=lr_)
+    go, do = host.make_srgan_optimizers(G, D, lr=lr_)
+    gen = torch.Generator().manual_seed(8)
+    lr_img, hr_img = torch.rand(4, 3, 8, 8, generator=gen), torch.rand(4, 3, 32, 32, generator=gen)
+    dl_r, gl_r = R.srgan_step(Gr, Dr, FEr, gor, dor, lr_img, hr_img)
+    l0 = srb200.launch_count()
+    dl, gl = host.srgan_step(G, D, FE, go, do, lr_img.to(DEV), hr_img.to(DEV))
+    assert srb200.launch_count() - l0 > 100
+    tol = 1e-4 if math == "fp32" else 2e-3
+    assert abs(dl.item() - dl_r.item()) < tol * abs(dl_r.item())
+    assert abs(gl.item() - gl_r.item()) < tol * abs(gl_r.item())
+    # D (SGD): parameters move by lr/100 * grad -- compare the updates; G (Adam): sign-like steps of size lr, compared on the
+    # parameters themselves (a rounding-level gradient flips a +-lr step, so the bound is a few lr relative to |p| ~ 0.02)
+    for (k, p), (_, q) in zip(D.named_parameters(), Dr.named_parameters()):
+        assert rel_l2(p.detach(), q.detach()) < 1e-4, k
+    for (k, p), (_, q) in zip(G.named_parameters(), Gr.named_parameters()):
+        assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2.1 * lr_, k
