@@ -40,6 +40,8 @@ WORKLOADS = {
     "edsr64_x4_b32_lr32": ("edsr", (3, 64, 16), 32, (32, 32), "l1", "edsr"),
     "edsr256_x4_b32_lr32": ("edsr", (3, 256, 32), 32, (32, 32), "l1", "edsr"),  # cfg4 (--math bf16 = its dtype; auto = TF32 on fp32 storage)
     "srcnn_x2_b16": ("srcnn", (3, 64), 16, (64, 64), "mse", "srcnn"),
+    # cfg5: SRGAN adversarial iteration as written (srgan.py:256-310): G(3,64,16), D(3,64,128), VGG19[:9] features
+    "srgan_x4_b16": ("srgan", (3, 64, 16), 16, (32, 32), "bce+mse+vgg", "srgan"),
 }
 DEFAULT_WORKLOAD = "espcn_x4_b128_lr64"
 
@@ -66,6 +68,139 @@ def peaks():
     return pk
 
 
+def measure_srgan(ctx, a, workload, steps, warmup):
+    """cfg5: one SRGAN adversarial iteration per step (srb200.host.srgan_step), the whole iteration replayed from one CUDA
+    graph per input slot (two optimizers, BatchNorm statistics and both gradient exchanges included)."""
+    import srb200
+    from srb200 import _lib, host
+    model_key, margs, batch, (h, w), loss_kind, opt_key = WORKLOADS[workload]
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    srb200.set_math(a.math)
+    torch.manual_seed(0)
+    G = srb200.models.SRGANGenerator(*margs)
+    host.init_model("srgan", G)
+    torch.manual_seed(1)
+    D = srb200.models.SRGANDiscriminator(3, 64, 4 * h)
+    host.init_model("srgan", D)
+    torch.manual_seed(2)
+    FE = srb200.models.FeatureExtractor()
+    for m in FE.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            torch.nn.init.constant_(m.bias, 0)
+    for m in (G, D, FE):
+        m.to(dev).train()
+    go, do = host.make_srgan_optimizers(G, D, lr=1e-5, capturable=not a.no_graph)
+    bg = srb200.GradBucket(G, world_size=world) if world > 1 else None
+    bd = srb200.GradBucket(D, world_size=world) if world > 1 else None
+    gen = torch.Generator().manual_seed(1 + rank)
+    host_x = [synth_images(batch, h, w, gen) for _ in range(3)]
+    host_t = [synth_images(batch, 4 * h, 4 * w, gen) for _ in range(3)]
+    stage_x = [torch.empty(t.shape, dtype=torch.uint8, device=dev) for t in host_x]
+    stage_t = [torch.empty(t.shape, dtype=torch.uint8, device=dev) for t in host_t]
+    dev_x = [srb200.image_to_tensor(t.to(dev)) for t in host_x]
+    dev_t = [srb200.image_to_tensor(t.to(dev)) for t in host_t]
+
+    def step(i):
+        return host.srgan_step(G, D, FE, go, do, dev_x[i], dev_t[i], bucket_g=bg, bucket_d=bd)
+
+    for i in range(warmup):
+        step(i % 3)
+    torch.cuda.synchronize()
+    graphs, outs, launches = [], [], 0
+    if not a.no_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.stream(side):
+            for i in range(3):
+                g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    dl, gl = step(i)
+                    out = (dl + gl).clone()
+                launches = _lib.launch_count() - c0
+                graphs.append(g)
+                outs.append(out)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+
+    def run(i):
+        if graphs:
+            graphs[i].replay()
+            return outs[i]
+        dl, gl = step(i)
+        return dl + gl
+
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        s2 = i % 3
+        with torch.cuda.stream(copy_stream):
+            stage_x[s2].copy_(host_x[s2], non_blocking=True)
+            stage_t[s2].copy_(host_t[s2], non_blocking=True)
+            srb200.image_to_tensor(stage_x[s2], out=dev_x[s2])
+            srb200.image_to_tensor(stage_t[s2], out=dev_t[s2])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def timed(n, e2e):
+        ctx.barrier()
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if e2e:
+            copy_stream.wait_event(e0)
+            nxt = prefetch(0)
+        for i in range(n):
+            if e2e:
+                ev = nxt
+                if i + 1 < n:
+                    nxt = prefetch(i + 1)
+                main.wait_event(ev)
+                loss = run(i % 3)
+                loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_evs[i % 2].record(main)
+                if i > 0:
+                    loss_evs[(i - 1) % 2].synchronize()
+            else:
+                run(i % 3)
+        if e2e:
+            loss_evs[(n - 1) % 2].synchronize()
+        e1.record()
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
+
+    for i in range(3):
+        run(i)
+    l0 = _lib.launch_count()
+    with Clocks(ctx.local_rank) as ck:
+        ms = timed(steps, False)
+        n_launch = launches * steps if graphs else _lib.launch_count() - l0
+        ms_e2e = timed(steps, True)
+    imgs = batch * world * steps
+    # algorithmic flops of one iteration as written (SURVEY.md 8d): 2 G fwd + 2 G bwd + 3 D fwd + 3 D bwd + 2 VGG fwd + 1 VGG bwd
+    flops_iter = 1083.8e9 * batch / 16.0
+    pk = peaks()
+    tfl = flops_iter / (ms / steps * 1e-3) / 1e12
+    res = {"workload": workload, "value": imgs / (ms * 1e-3), "ms_per_step": ms / steps, "clocks": ck.summary(), "steps": steps,
+           "gpu_launches": int(n_launch),
+           "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
+                   "h2d_bytes_per_step": int(host_x[0].numel() + host_t[0].numel()), "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / steps, "host_format": "uint8 HWC pixels, pinned; ToTensor on the device"},
+           "roofline": {"bound": "tensor", "achieved": tfl, "peak": pk["tf32_sustained"], "unit": "TFLOP/s",
+                        "frac": tfl / pk["tf32_sustained"], "traffic": None, "kernel": "whole adversarial iteration",
+                        "layer": "G(3,64,16) + D(3,64,128) + VGG19[:9], 1083.8 GFLOP per 16-image iteration as written (SURVEY.md 8d)",
+                        "peak_source": pk["source"] + " sustained; tf32: " + pk["tf32_source"],
+                        "algorithmic_flops": flops_iter},
+           "kernels": [], "comm": None if world == 1 else (bg.comm if bg is not None else None)}
+    graphs.clear()
+    return res
+
+
 def out_shape(model_key, args, n, h, w):
     if model_key == "srcnn":
         return (n, 3, h - 16, w - 16)
@@ -85,6 +220,22 @@ def cpu_reference_run(workload, steps, warmup, budget_s=20.0, sample_batch=None)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     b = sample_batch or batch
+    if model_key == "srgan":
+        G, D, FE = R.build("srgan_g", args, seed=0), R.build("srgan_d", (3, 64, 4 * h), seed=1), R.build_feature_extractor()
+        go, do = R.make_srgan_optimizers(G, D, lr=1e-5)
+        gen = torch.Generator().manual_seed(1)
+        lr_img, hr_img = torch.rand((b, 3, h, w), generator=gen), torch.rand((b, 3, 4 * h, 4 * w), generator=gen)
+        for _ in range(max(1, warmup)):
+            R.srgan_step(G, D, FE, go, do, lr_img, hr_img)
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps and (time.perf_counter() - t0) < budget_s:
+            R.srgan_step(G, D, FE, go, do, lr_img, hr_img)
+            done += 1
+        dt = time.perf_counter() - t0
+        return {"value": b * done / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": "%d adversarial iterations of batch %d (%s, srgan.py:256-310 restated, torch %s CPU/oneDNN)" % (
+                    done, b, workload, torch.__version__), "ms_per_step": 1e3 * dt / max(done, 1), "steps": done}
     net = R.build(model_key, args, seed=0)
     opt = R.make_optimizer(opt_key, net.parameters(), lr=1e-5)
     gen = torch.Generator().manual_seed(1)
@@ -675,7 +826,10 @@ def main():
         finish(ctx)
         return 0
 
-    res = measure_srb(ctx, a, a.workload, a.steps, a.warmup, full=True)
+    if model_key == "srgan":
+        res = measure_srgan(ctx, a, a.workload, a.steps, a.warmup)
+    else:
+        res = measure_srb(ctx, a, a.workload, a.steps, a.warmup, full=True)
     line = {"metric": METRIC, "value": res["value"], "unit": "images/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,

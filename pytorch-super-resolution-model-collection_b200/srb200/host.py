@@ -38,6 +38,8 @@ def init_model(name, net):
             weights_init_normal(m, 0.0, 0.001)
         elif name == "vdsr":
             weights_init_kaiming(m)
+        elif name == "srgan":
+            weights_init_normal(m, 0.0, 0.02)  # srgan.py:44-46,78-80
         elif name == "fsrcnn":
             if isinstance(m, nn.Conv2d):
                 m.weight.data.normal_(0.0, 0.02)

@@ -159,7 +159,12 @@ def test_srgan_adversarial_step_tracks_the_oracle(math):
     assert abs(gl.item() - gl_r.item()) < tol * abs(gl_r.item())
     # D (SGD): parameters move by lr/100 * grad -- compare the updates; G (Adam): sign-like steps of size lr, compared on the
     # parameters themselves (a rounding-level gradient flips a +-lr step, so the bound is a few lr relative to |p| ~ 0.02)
+    d0 = R.build("srgan_d", (3, 16, 32), seed=1).state_dict()
+    upd = {k: (q.detach() - d0[k]) for k, q in Dr.named_parameters()}
+    U = max(u.abs().max().item() for u in upd.values())  # largest SGD update of the step
     for (k, p), (_, q) in zip(D.named_parameters(), Dr.named_parameters()):
-        assert rel_l2(p.detach(), q.detach()) < 1e-4, k
+        # biases start at exactly 0 and the ones in front of a BatchNorm have a mathematically zero gradient: compare the
+        # UPDATES on the scale of the step's largest update instead of relative to the (near-zero) parameter
+        assert (p.detach().cpu() - q.detach()).abs().max().item() <= (5e-3 if math == "fp32" else 5e-2) * U, k
     for (k, p), (_, q) in zip(G.named_parameters(), Gr.named_parameters()):
         assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2.1 * lr_, k
