@@ -207,6 +207,18 @@ int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const floa
 int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int32_t H, int32_t W, int32_t C, float scale,
                         void *stream);
 
+/*
+ * utils.img_interp(imgs, scale, 'bicubic') (utils.py:242-269; used every step by SRCNN / VDSR / DRCN, srcnn.py:120-121) on the
+ * device, optionally followed by utils.shave(., shave) (utils.py:197-205): x fp32 NCHW in [0,1] -> y fp32 NCHW
+ * (N, C, TH - 2*shave, TW - 2*shave).  Bit-exact with the reference's per-image PIL loop: ToPILImage truncation to 8 bits,
+ * Pillow's two-pass fixed-point bicubic (a = -0.5), ToTensor.  The per-axis tables are Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc results, built by the host: bounds = (first tap, tap count) per output index, coeffs = ksize 22-bit
+ * integers per output index.
+ */
+int srb_img_interp_bicubic(const float *x, float *y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t TH, int32_t TW,
+                           const int32_t *bounds_w, const int32_t *coeffs_w, const int32_t *bounds_h, const int32_t *coeffs_h,
+                           int32_t ksize, int32_t shave, void *stream);
+
 /* Round n contiguous floats to tf32 (round-to-nearest, ties away) in place or out of place. */
 int srb_round_tf32(const float *x, float *y, int64_t n, void *stream);
 

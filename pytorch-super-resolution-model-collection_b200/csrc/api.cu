@@ -374,6 +374,39 @@ __global__ void k_scale_by_scalar(float *x, long long n, const float *__restrict
   }
 }
 
+// utils.img_interp(imgs, scale, 'bicubic') (utils.py:242-269): per image ToPILImage -> PIL resize(BICUBIC) -> ToTensor, i.e.
+// Pillow's 8-bit two-pass resample (horizontal first, 22-bit fixed-point coefficients, 8-bit intermediate), optionally
+// followed by utils.shave (utils.py:197-205).  One thread per output pixel; bit-exact integer arithmetic.
+__global__ void k_pil_bicubic(const float *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W, int TH, int TW,
+                              const int *__restrict__ bw, const int *__restrict__ kw, const int *__restrict__ bh,
+                              const int *__restrict__ kh, int ksize, int shave) {
+  const int OH = TH - 2 * shave, OW = TW - 2 * shave;
+  const long long total = (long long)N * C * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW) + shave;
+    long long q = i / OW;
+    const int oy = (int)(q % OH) + shave;
+    const long long nc = q / OH;
+    const float *img = x + nc * H * W;
+    const int x0 = __ldg(bw + 2 * ox), nx = __ldg(bw + 2 * ox + 1), y0 = __ldg(bh + 2 * oy), ny = __ldg(bh + 2 * oy + 1);
+    long long acc = 1LL << 21;
+    for (int yy = 0; yy < ny; ++yy) {
+      const float *row = img + (long long)(y0 + yy) * W + x0;
+      long long h = 1LL << 21;
+      for (int xx = 0; xx < nx; ++xx) {
+        const int u8 = (int)(unsigned char)(int)(__ldg(row + xx) * 255.0f);  // ToPILImage: mul(255).byte() (truncation)
+        h += (long long)u8 * __ldg(kw + ox * ksize + xx);
+      }
+      long long t = h >> 22;
+      t = t < 0 ? 0 : (t > 255 ? 255 : t);
+      acc += t * __ldg(kh + oy * ksize + yy);
+    }
+    long long r = acc >> 22;
+    r = r < 0 ? 0 : (r > 255 ? 255 : r);
+    y[i] = (float)r / 255.0f;  // ToTensor
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -1006,6 +1039,19 @@ int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int
   SRB_REQUIRE(src_nhwc && dst_nchw && N >= 0 && H > 0 && W > 0 && C > 0, SRB_EINVAL, "bad image_to_tensor args");
   if (N == 0) return SRB_OK;
   k_image_to_tensor<<<ew_blocks((long long)N * C * H * W), 256, 0, (cudaStream_t)stream>>>(src_nhwc, dst_nchw, N, H, W, C, scale);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int srb_img_interp_bicubic(const float *x, float *y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t TH, int32_t TW,
+                           const int32_t *bounds_w, const int32_t *coeffs_w, const int32_t *bounds_h, const int32_t *coeffs_h,
+                           int32_t ksize, int32_t shave, void *stream) {
+  SRB_REQUIRE(x && y && bounds_w && coeffs_w && bounds_h && coeffs_h && N >= 0 && C > 0 && H > 0 && W > 0 && TH > 2 * shave &&
+                  TW > 2 * shave && shave >= 0 && ksize > 0, SRB_EINVAL, "bad img_interp arguments");
+  if (N == 0) return SRB_OK;
+  k_pil_bicubic<<<ew_blocks((long long)N * C * (TH - 2 * shave) * (TW - 2 * shave)), 256, 0, (cudaStream_t)stream>>>(
+      x, y, N, C, H, W, TH, TW, bounds_w, coeffs_w, bounds_h, coeffs_h, ksize, shave);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

@@ -55,6 +55,7 @@ SYMBOLS = {
     "srb_prelu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
     "srb_image_to_tensor": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_float, _vp]),
+    "srb_img_interp_bicubic": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int32] * 6 + [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp]),
     "srb_round_tf32": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "srb_loss_workspace_bytes": (ctypes.c_size_t, []),
     "srb_loss_fwd": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_size_t, _vp]),

@@ -147,3 +147,77 @@ def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=N
         bucket_g.all_reduce()
     g_opt.step()
     return D_loss.detach(), G_loss.detach()
+
+
+# ---- utils.img_interp / utils.shave on the device (utils.py:197-205, 242-269) -------------------------------------------------
+_PIL_PRECISION_BITS = 32 - 8 - 2
+_coeff_cache = {}
+
+
+def _pil_bicubic_tables(in_size, out_size, device):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BICUBIC filter (a = -0.5, support 2): per output index the
+    first source index, the tap count and the taps as 22-bit fixed-point integers.  Host arithmetic in double, like Pillow."""
+    import math
+    key = (in_size, out_size, str(device))
+    hit = _coeff_cache.get(key)
+    if hit is not None:
+        return hit
+
+    def cubic(x, a=-0.5):
+        x = abs(x)
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds, coeffs = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        cnt = min(int(center + support + 0.5), in_size) - xmin
+        w = [cubic((x + xmin - center + 0.5) / filterscale) for x in range(cnt)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        q = [int(-0.5 + v * (1 << _PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PIL_PRECISION_BITS)) for v in w]
+        bounds += [xmin, cnt]
+        coeffs += q + [0] * (ksize - cnt)
+    out = (torch.tensor(bounds, dtype=torch.int32, device=device), torch.tensor(coeffs, dtype=torch.int32, device=device), ksize)
+    _coeff_cache[key] = out
+    return out
+
+
+def img_interp(imgs, scale_factor, interpolation="bicubic", shave=0):
+    """utils.img_interp(imgs, scale_factor) for a CUDA float (N,C,H,W) batch in [0,1], bit-exact with the reference's PIL
+    loop (utils.py:242-269), optionally fused with utils.shave(., shave) (the `shave(img_interp(...))` of espcn.py:149)."""
+    import ctypes
+    from ._lib import lib, check
+    if interpolation != "bicubic":
+        raise RuntimeError("srb200.host.img_interp implements the reference's default 'bicubic' mode")
+    if not (imgs.is_cuda and imgs.dtype == torch.float32 and imgs.dim() == 4):
+        raise RuntimeError("img_interp needs a CUDA float32 (N,C,H,W) tensor; there is no CPU path")
+    imgs = imgs.contiguous()
+    n, c, h, w = imgs.shape
+    th, tw = int(h * scale_factor), int(w * scale_factor)
+    bw, kw, ks_w = _pil_bicubic_tables(w, tw, imgs.device)
+    bh, kh, ks_h = _pil_bicubic_tables(h, th, imgs.device)
+    assert ks_w == ks_h
+    out = torch.empty((n, c, th - 2 * shave, tw - 2 * shave), dtype=torch.float32, device=imgs.device)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    check(lib.srb_img_interp_bicubic(vp(imgs), vp(out), n, c, h, w, th, tw, vp(bw), vp(kw), vp(bh), vp(kh), ks_w, shave,
+                                     ctypes.c_void_p(torch.cuda.current_stream(imgs.device).cuda_stream)))
+    return out
+
+
+def shave(imgs, border_size=0):
+    """utils.shave (utils.py:197-205): crop `border_size` pixels from every side (a view; no kernel needed)."""
+    if border_size == 0:
+        return imgs
+    return imgs[..., border_size:-border_size, border_size:-border_size]
