@@ -143,5 +143,31 @@ def main():
         print(name, tuple(y.shape))
 
 
+# utils.img_interp (utils.py:242-269) vectors: square images (see ref_import: Scale/Resize tuple order), the scale factors the
+# drivers use (srcnn.py:121, vdsr.py:137: x scale_factor; 2, 3, 4) and the 1/r downscale of the test loops.
+INTERP_CASES = {"x2": ((2, 3, 16, 16), 2), "x3": ((1, 3, 11, 11), 3), "x4": ((2, 3, 12, 12), 4), "half": ((1, 3, 24, 24), 0.5),
+                "gray_x4": ((2, 1, 9, 9), 4)}
+
+
+def make_interp():
+    mods = ref_import.load()
+    blob = {}
+    for name, (shape, sf) in INTERP_CASES.items():
+        x = torch.rand(shape, generator=torch.Generator().manual_seed(7))
+        if name == "x2":
+            x[0, :, :4] = 1.0  # saturated rows: exercises the clip to 255 on bicubic overshoot
+            x[0, :, 4:8] = 0.0
+        y = mods["utils"].img_interp(x, sf)
+        blob[name + ":x"] = x.numpy()
+        blob[name + ":scale"] = np.float64(sf)
+        blob[name + ":y"] = y.numpy()
+        print("img_interp", name, tuple(x.shape), "->", tuple(y.shape))
+    np.savez_compressed(os.path.join(OUT, "pil_bicubic.npz"), **blob)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "interp":
+        make_interp()
+    else:
+        main()
+        make_interp()

@@ -59,6 +59,12 @@ def load():
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        import torchvision.transforms as _T
+        if not hasattr(_T, "Scale"):
+            # utils.py:255,266 call transforms.Scale, torchvision's pre-0.2 name of Resize (renamed, then removed upstream);
+            # aliasing it is the only way to run the reference's img_interp under the installed torchvision.  Modern Resize
+            # reads a 2-tuple as (h, w) where the reference passes (w, h): identical for the square crops it trains on.
+            _T.Scale = _T.Resize
         for name in ("base_networks", "utils", "srcnn", "espcn", "fsrcnn", "vdsr", "edsr", "srgan"):
             _loaded[name] = importlib.import_module(name)
     return _loaded

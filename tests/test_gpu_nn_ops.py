@@ -3,6 +3,8 @@ BCELoss -- against torch on CPU (fp32 arithmetic on both sides: 1e-5 class), the
 adversarial step (srgan.py:256-310) against the CPU oracle."""
 import copy
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as TF
@@ -168,3 +170,46 @@ def test_srgan_adversarial_step_tracks_the_oracle(math):
         assert (p.detach().cpu() - q.detach()).abs().max().item() <= (5e-3 if math == "fp32" else 5e-2) * U, k
     for (k, p), (_, q) in zip(G.named_parameters(), Gr.named_parameters()):
         assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2.1 * lr_, k
+
+
+# ---- utils.img_interp / utils.shave on the device (utils.py:197-205, 242-269) ---------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["x2", "x3", "x4", "half", "gray_x4"])
+def test_img_interp_matches_reference_golden(case):
+    import os
+    from srb200 import host
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pil_bicubic.npz"))
+    y = host.img_interp(torch.from_numpy(g[case + ":x"]).cuda(), float(g[case + ":scale"]))
+    assert torch.equal(y.cpu(), torch.from_numpy(g[case + ":y"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,sf,border", [((4, 3, 32, 32), 4, 0), ((2, 3, 17, 23), 3, 0), ((3, 3, 24, 24), 2, 6),
+                                             ((2, 1, 40, 28), 0.5, 2), ((0, 3, 8, 8), 2, 0)])
+def test_img_interp_matches_oracle(shape, sf, border):
+    """Bit-exact against the Pillow restatement (non-square, downscale, empty batch), optionally fused with shave."""
+    from oracle import pil_bicubic as PB
+    from srb200 import host
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(5))
+    if shape[0]:
+        x[0, :, : shape[2] // 2] = (x[0, :, : shape[2] // 2] > 0.5).float()  # saturated edges: clip to [0, 255]
+    want = PB.img_interp(x, sf) if shape[0] else torch.empty((0, shape[1], int(shape[2] * sf), int(shape[3] * sf)))
+    if border:
+        want = want[..., border:-border, border:-border]
+    got = host.img_interp(x.cuda(), sf, shave=border)
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    assert torch.equal(host.shave(got, 1).cpu(), want[..., 1:-1, 1:-1])
+
+
+@pytest.mark.gpu
+def test_img_interp_full_size_properties():
+    """cfg3-sized batch (vdsr.py:137: 64 LR crops x4 -> 128^2): constant images stay constant, output lies on the 1/255 grid,
+    and the batch result equals the per-image results (no cross-image reads)."""
+    from srb200 import host
+    x = torch.rand((64, 3, 32, 32), device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    x[1] = 0.5
+    y = host.img_interp(x, 4)
+    assert y.shape == (64, 3, 128, 128)
+    assert torch.equal(y[1], torch.full_like(y[1], float(int(0.5 * 255)) / 255.0))
+    assert torch.equal((y * 255).round() / 255, y)
+    assert torch.equal(host.img_interp(x[5:7].clone(), 4), y[5:7])

@@ -215,3 +215,44 @@ def test_forced_activation_replay_is_identity_on_own_pattern():
     assert rel_l2(y2.detach(), y.detach()) < 1e-6
     for k, p in net.named_parameters():
         assert rel_l2(p.grad, ref[k]) < 1e-5, k
+
+
+# ---- utils.img_interp (utils.py:242-269): the Pillow 8-bit bicubic resample restated in oracle/pil_bicubic.py -------------------
+from oracle import pil_bicubic as PB  # noqa: E402
+
+INTERP_CASES = ["x2", "x3", "x4", "half", "gray_x4"]
+
+
+def _interp_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "pil_bicubic.npz"))
+
+
+@pytest.mark.parametrize("case", INTERP_CASES)
+def test_pil_bicubic_oracle_matches_reference_golden(case):
+    """Bit-exact against vectors produced by the unmodified utils.img_interp (oracle/make_golden.py interp)."""
+    g = _interp_golden()
+    y = PB.img_interp(torch.from_numpy(g[case + ":x"]), float(g[case + ":scale"]))
+    assert torch.equal(y, torch.from_numpy(g[case + ":y"]))
+
+
+@pytest.mark.parametrize("hw,out", [((13, 17), (52, 68)), ((16, 16), (48, 48)), ((31, 9), (15, 27)), ((8, 40), (8, 80))])
+def test_pil_bicubic_oracle_matches_pillow(hw, out):
+    """Non-square and mixed up/down scales straight against Pillow (Image.resize, BICUBIC), uint8 in / uint8 out."""
+    from PIL import Image
+    rng = np.random.default_rng(hw[0] * 100 + hw[1])
+    img = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    img[: hw[0] // 3] = np.where(rng.random((hw[0] // 3, hw[1], 3)) < 0.5, 0, 255)  # hard edges: overshoot + clipping
+    want = np.asarray(Image.fromarray(img).resize((out[1], out[0]), Image.BICUBIC))
+    got = PB.resize_u8(img, out[0], out[1])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_pil_bicubic_oracle_equals_live_reference():
+    u = ref_import.load()["utils"]
+    x = torch.rand((3, 3, 14, 14), generator=torch.Generator().manual_seed(11))
+    for sf in (2, 3, 4):
+        assert torch.equal(PB.img_interp(x, sf), u.img_interp(x, sf))
+    y = torch.rand((2, 3, 20, 20))
+    assert torch.equal(u.shave(y, 3), y[..., 3:-3, 3:-3])  # utils.py:197-205
