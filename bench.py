@@ -40,6 +40,8 @@ WORKLOADS = {
     "edsr64_x4_b32_lr32": ("edsr", (3, 64, 16), 32, (32, 32), "l1", "edsr"),
     "edsr256_x4_b32_lr32": ("edsr", (3, 256, 32), 32, (32, 32), "l1", "edsr"),  # cfg4 (--math bf16 = its dtype; auto = TF32 on fp32 storage)
     "srcnn_x2_b16": ("srcnn", (3, 64), 16, (64, 64), "mse", "srcnn"),
+    # FSRCNN x4 (fsrcnn.py:99 ctor, SURVEY 8a: parity-only net; timed to cover the k9 s4 transposed conv on the tensor path)
+    "fsrcnn_x4_b16_lr32": ("fsrcnn", (3, 4, 56, 12, 4), 16, (32, 32), "mse", "fsrcnn"),
     # cfg5: SRGAN adversarial iteration as written (srgan.py:256-310): G(3,64,16), D(3,64,128), VGG19[:9] features
     "srgan_x4_b16": ("srgan", (3, 64, 16), 16, (32, 32), "bce+mse+vgg", "srgan"),
 }
@@ -109,6 +111,13 @@ def measure_srgan(ctx, a, workload, steps, warmup):
     torch.cuda.synchronize()
     graphs, outs, launches = [], [], 0
     if not a.no_graph:
+        # Gradients left over from the eager warm-up live in the ordinary allocator pool.  srgan_step accumulates into G's
+        # (D_loss.backward() reaches G, srgan.py:283) before g_opt.zero_grad() drops them, so a captured graph would keep raw
+        # pointers to blocks that torch.cuda.graph's own empty_cache() releases when the next capture starts.  Drop them first:
+        # every gradient is then created inside the capture, in the graph's private pool.
+        if bg is None:
+            go.zero_grad(set_to_none=True)
+            do.zero_grad(set_to_none=True)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         pool = torch.cuda.graph_pool_handle()
@@ -208,6 +217,8 @@ def out_shape(model_key, args, n, h, w):
         return (n, 3, (h - 8) * args[2], (w - 8) * args[2])
     if model_key == "vdsr":
         return (n, 3, h, w)
+    if model_key == "fsrcnn":  # conv5 p0, then ConvTranspose2d(k9, s=r, p3, op1): (h-4)*r
+        return (n, 3, (h - 4) * args[1], (w - 4) * args[1])
     return (n, 3, 4 * h, 4 * w)
 
 
@@ -803,6 +814,8 @@ def main():
         return 0
 
     ctx.init_cuda()
+    if os.environ.get("SRB_BENCH_DEBUG"):
+        torch._C._set_print_stack_traces_on_fatal_signal(True)  # C++ backtrace on SIGSEGV/SIGABRT (debugging aid)
     if a.impl == "cudnn":
         variants = (a.variants.split(",") if a.variants else
                     ["as-is", "tuned-cl-graph"] + (["tuned-cl-bf16-graph"] if a.workload.startswith("edsr256") else []))

@@ -1047,9 +1047,10 @@ int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int
 int srb_img_interp_bicubic(const float *x, float *y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t TH, int32_t TW,
                            const int32_t *bounds_w, const int32_t *coeffs_w, const int32_t *bounds_h, const int32_t *coeffs_h,
                            int32_t ksize, int32_t shave, void *stream) {
-  SRB_REQUIRE(x && y && bounds_w && coeffs_w && bounds_h && coeffs_h && N >= 0 && C > 0 && H > 0 && W > 0 && TH > 2 * shave &&
-                  TW > 2 * shave && shave >= 0 && ksize > 0, SRB_EINVAL, "bad img_interp arguments");
-  if (N == 0) return SRB_OK;
+  SRB_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && TH > 2 * shave && TW > 2 * shave && shave >= 0 && ksize > 0, SRB_EINVAL,
+              "bad img_interp sizes");
+  if (N == 0) return SRB_OK;  // empty batch: nothing to read or write (the buffers may be null)
+  SRB_REQUIRE(x && y && bounds_w && coeffs_w && bounds_h && coeffs_h, SRB_EINVAL, "null img_interp buffer");
   k_pil_bicubic<<<ew_blocks((long long)N * C * (TH - 2 * shave) * (TW - 2 * shave)), 256, 0, (cudaStream_t)stream>>>(
       x, y, N, C, H, W, TH, TW, bounds_w, coeffs_w, bounds_h, coeffs_h, ksize, shave);
   count_launch();

@@ -88,11 +88,25 @@ VDSR_CLIP = 0.4
 VGG_MEAN, VGG_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 
+_vgg_consts = {}
+
+
 def norm_vgg(img):
-    """utils.norm(img, vgg=True) (utils.py:219-229) on a 4-D batch (host-side pre-processing in the reference)."""
-    mean = torch.tensor(VGG_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
-    std = torch.tensor(VGG_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    """utils.norm(img, vgg=True) (utils.py:219-229) on a 4-D batch (host-side pre-processing in the reference).  The two
+    constant tensors are built once per (device, dtype): a host->device copy is not allowed inside a CUDA-graph capture."""
+    key = (img.device, img.dtype)
+    if key not in _vgg_consts:
+        if img.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("srb200.host.norm_vgg: call once (or host.prepare_norm_vgg(device)) before capturing a CUDA graph")
+        _vgg_consts[key] = (torch.tensor(VGG_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1),
+                            torch.tensor(VGG_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1))
+    mean, std = _vgg_consts[key]
     return (img - mean) / std
+
+
+def prepare_norm_vgg(device, dtype=torch.float32):
+    """Build norm_vgg's constants ahead of a CUDA-graph capture."""
+    norm_vgg(torch.zeros((1, 3, 1, 1), device=device, dtype=dtype))
 
 
 def make_srgan_optimizers(G, D, lr=1e-5, capturable=False):

@@ -23,9 +23,11 @@ if has bench; then
   echo "bench exit $?"; cat "$OUT/bench_espcn.json"
 fi
 if has bench_more; then
-  for wl in vdsr_b64_128 edsr64_x4_b32_lr32 srcnn_x2_b16 edsr256_x4_b32_lr32; do
-    timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
-    echo "bench $wl exit $?"; cut -c1-600 "$OUT/bench_$wl.json"
+  for spec in "vdsr_b64_128 auto" "edsr64_x4_b32_lr32 auto" "srcnn_x2_b16 auto" "fsrcnn_x4_b16_lr32 auto" "srgan_x4_b16 auto" \
+              "edsr256_x4_b32_lr32 bf16" "edsr256_x4_b32_lr32 auto"; do
+    set -- $spec; wl=$1; mth=$2
+    timeout 600 python bench.py --workload $wl --math $mth --steps 20 --warmup 5 --no-cpu-baseline --no-sub > "$OUT/bench_${wl}_$mth.json" 2> "$OUT/bench_${wl}_$mth.err"
+    echo "bench $wl $mth exit $?"; cut -c1-420 "$OUT/bench_${wl}_$mth.json"; tail -2 "$OUT/bench_${wl}_$mth.err"
   done
 fi
 if has ref; then
