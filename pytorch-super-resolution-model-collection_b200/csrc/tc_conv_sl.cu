@@ -58,6 +58,8 @@ struct SlArgs {
   int in_cpb;        //      sub-pixel phase c / in_cpb, channel block c % in_cpb, fetched through a stride-r TMA traversal
   int kb_valid;      // K-blocks (chunk, tap) that exist: chunks * taps minus the taps the phase masks exclude
   int pad_w;         // horizontal padding (== pad unless a phase launch of a strided / transposed conv says otherwise)
+  int rs;            // row-stacked kernel (k_conv_rs): an M tile is ONE output row of up to 128 / BW images side by side --
+                     // slot q of the tile is pixel q % BW of image n + q / BW (the epilogues read this mapping, nothing else)
   unsigned short phase_mask[16];  // in_ps > 1: bit (r*kw + s) set = tap (r, s) of that input phase exists (others are skipped)
   const float *wpack;  // c4: packed weights (bulk-copied); generic: unused (TMA map)
   int v8;              // out / residual / preact / mask rows are 32-byte aligned: mode-0 epilogue uses 256-bit global accesses
@@ -115,7 +117,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 // (plain conv + bias + act) is ~100 instructions per item, which matters: the epilogue is issue-bound.
 template <int MODE, bool EXTRA>
 __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
-                                               int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid) {
+                                               int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid, int istep = 2) {
   const int act = a.epi.act;
   const float slope = (act == SRB_ACT_PRELU) ? __ldg(a.epi.alpha) : a.epi.slope;
   const bool has_bias = a.epi.bias != nullptr;
@@ -129,13 +131,15 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
   const float *pr = nullptr, *pm = nullptr;
   int pixw = 0;  // first bit word of this thread's pixel (host guarantees N*Ho*Wo*Co/16 < 2^31)
 #pragma unroll 1
-  for (int item = half; item < mtb * ngroups; item += 2) {
+  for (int item = half; item < mtb * ngroups; item += istep) {
     const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
     if (t != t_cur) {
       t_cur = t;
       const int q = t * 128 + m;  // slot of this thread's accumulator row
       const int ty = q / a.BW, tx = q - ty * a.BW;
-      oy = oy0 + ty; ox = ox0 + tx;
+      if (a.rs) { n += ty; oy = oy0; }  // row-stacked tiles (mtb == 1): ty counts images, rows_valid = images present
+      else oy = oy0 + ty;
+      ox = ox0 + tx;
       pix_ok = (ty < rows_valid) && (tx < cols_valid);
       pixw = ((n * a.Ho + oy) * a.Wo + ox) * (a.Co >> 4);
       if (MODE != 3) {
@@ -270,18 +274,20 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
 //   MODE 3: anything with ps == 1: scalar accesses, gradient in y's layout
 template <int MODE>
 __device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
-                                                    int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid, float &lsum) {
+                                                    int n_in, int n0, int oy0, int ox0, int rows_valid, int cols_valid, float &lsum,
+                                                    int istep = 2) {
   const bool has_bias = a.epi.bias != nullptr;
   const bool l1 = a.epi.loss_kind == 2;
   const bool rnd = a.epi.round_tf32 != 0;  // here: round the GRADIENT (it feeds the tensor-core dgrad / wgrad)
   const float coef = a.epi.loss_coef * (l1 ? 1.f : 2.f);
   const int ngroups = a.NT >> 4;
 #pragma unroll 1
-  for (int item = half; item < mtb * ngroups; item += 2) {
+  for (int item = half; item < mtb * ngroups; item += istep) {
     const int t = item / ngroups, j0 = (item - t * ngroups) << 4;
     const int q = t * 128 + m;
     const int ty = q / a.BW, tx = q - ty * a.BW;
-    const int oy = oy0 + ty, ox = ox0 + tx;
+    const int n = a.rs ? n_in + ty : n_in;  // row-stacked tiles: see SlArgs::rs
+    const int oy = a.rs ? oy0 : oy0 + ty, ox = ox0 + tx;
     const bool pix_ok = (ty < rows_valid) && (tx < cols_valid);
     const int cbase = n0 + j0;
     if (cbase >= a.Co) continue;  // warp-uniform
@@ -988,6 +994,341 @@ __global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H,
   }
 }
 
+
+// ================================================================================================================================
+// Row-stacked variant (k_conv_rs) for narrow layers (kh * NT <= 256, all weights resident).
+//
+// The slot-linear kernel above issues one MMA per filter tap with N = Cout: at Cout = 32..64 an SS-mode MMA is bound by
+// re-reading its 4 KB A tile from shared memory (32 + N/4 cycles against N/2 of math, tools/bench_umma.cu).  Here an M tile is
+// ONE INPUT ROW -- 128 pixel slots: G images side by side, BW slots each -- and one MMA multiplies it with the taps of ALL kh
+// filter rows at once: the B operand of horizontal tap s is [kh][NT] filter rows stacked along N (stored r = kh-1 .. 0), and
+// the accumulator of output row o is the TMEM column block o*NT, so input row j accumulates into the CONTIGUOUS column
+// window of output rows j-(kh-1) .. j.  One A read now feeds kh taps: 53 / 60 / 69 cycles per MMA at N = 96 / 144 / 192
+// instead of kh x (40 / 44 / 48) (tools/bench_umma_rows.cu).  Horizontal taps remain shifted views of the same row.
+//
+// Rows stream top to bottom: a CTA owns a contiguous range of the global (image group, column strip, output row) sequence,
+// loads every input row once per 32-channel chunk into a shared-memory ring, and the TMEM column blocks form a ring as well:
+// output row o is complete when input row o+kh-1 has been multiplied, is drained by the epilogue warps and its block is
+// reused R rows later -- no bands, no vertical halo except at the start of a CTA's range.
+constexpr int kRsMaxStages = 8;
+constexpr int kRsMaxBlocks = 16;
+constexpr int kRsPrefetchRows = 6;
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+struct RsArgs {
+  SlArgs e;               // what the epilogues read: N, Ho, Wo, Co, NT, BW (= slots per image), ps, out, epi, v8, rs = 1
+  int chunks, kv_last;    // 32-channel chunks of the input; K steps (of 8 channels) that exist in the last chunk
+  int G, TW, CT;          // images per M tile, output columns per strip, column strips per image
+  int R;                  // TMEM ring: accumulator blocks of NT columns
+  int S, stage_bytes, stage_tx;  // A ring: one stage = one input row, all chunks (chunk_bytes each; stage_tx = TMA bytes per chunk)
+  int chunk_bytes;
+  int bcs_bytes;          // B: bytes of one (chunk, s) operand = kh * NT * 128
+  long long total_rows;   // image groups x column strips x Ho
+};
+
+// debug trace (srb_debug_set_trace): CTA 0 writes globaltimer stamps, 4 roles x 128 events
+#define RS_TRACE(role, idx)                                                                                       \
+  do {                                                                                                            \
+    if (a.e.trace && blockIdx.x == 0 && (idx) < 128) a.e.trace[(role) * 128 + (idx)] = gtime();                   \
+  } while (0)
+
+struct RsSeg {  // a run of output rows inside one (image group, column strip)
+  int img0, ox0, oy0, cnt, imgs_valid, cols_valid;
+};
+__device__ __forceinline__ RsSeg rs_segment(const RsArgs &a, long long row, long long r1) {
+  RsSeg sg;
+  const long long strip = row / a.e.Ho;
+  sg.oy0 = (int)(row - strip * a.e.Ho);
+  const long long left = r1 - row;
+  sg.cnt = (int)(left < (long long)(a.e.Ho - sg.oy0) ? left : (long long)(a.e.Ho - sg.oy0));
+  const int ig = (int)(strip / a.CT), ct = (int)(strip - (long long)ig * a.CT);
+  sg.img0 = ig * a.G;
+  sg.ox0 = ct * a.TW;
+  sg.imgs_valid = min(a.G, a.e.N - sg.img0);
+  sg.cols_valid = min(a.TW, a.e.Wo - sg.ox0);
+  return sg;
+}
+
+struct RsPart { uint32_t tcol, boff, idesc; };  // one MMA: D column, B row offset (16-byte units), instruction descriptor
+// All MMAs of one input row in the steady state (see k_conv_rs): for every chunk, kw horizontal taps x 4 K-steps accumulate into
+// the window of kh output-row blocks starting at TMEM column tc_lo; the very first MMA of the row is split -- the kh-1 older
+// blocks accumulate, the new block (tc_hi, met by filter row 0 = B row block kh-1) is overwritten.  Straight-line issue code.
+template <int KW>
+__device__ __forceinline__ void rs_issue_row_steady(int chunks, uint32_t a_st, uint32_t chunk16, uint32_t b_lo0, uint32_t bcs16, uint32_t tc_lo,
+                                                    uint32_t tc_hi, uint32_t id_full, uint32_t id_win1, uint32_t id_one, uint32_t boff_new) {
+  const uint64_t d_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SWIZZLE_128B, SBO 1024 B
+  umma_tf32_ss(tc_lo, d_hi | (uint64_t)a_st, d_hi | (uint64_t)b_lo0, id_win1, 1u);
+  umma_tf32_ss(tc_hi, d_hi | (uint64_t)a_st, d_hi | (uint64_t)(b_lo0 + boff_new), id_one, 0u);
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    const uint32_t ac = a_st + (uint32_t)c * chunk16, bc = b_lo0 + (uint32_t)(c * KW) * bcs16;
+#pragma unroll
+    for (int s = 0; s < KW; ++s) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        if (s == 0 && k4 == 0) {
+          if (c) umma_tf32_ss(tc_lo, d_hi | (uint64_t)ac, d_hi | (uint64_t)bc, id_full, 1u);
+        } else {
+          umma_tf32_ss(tc_lo, d_hi | (uint64_t)(ac + (uint32_t)(8 * s + 2 * k4)), d_hi | (uint64_t)(bc + (uint32_t)s * bcs16 + (uint32_t)(2 * k4)), id_full,
+                       1u);
+        }
+      }
+    }
+  }
+}
+
+// General version for one (input row, chunk): band edges (partial windows), TMEM ring wrap-around (two column ranges), partial
+// last chunk, any filter width.  `first` (chunk 0, tap 0, K-step 0 of a fresh row): fa0 / fa1 accumulate, fo overwrites.
+__device__ __forceinline__ void rs_issue_chunk(bool chunk0, bool fresh, int kv, int kw, uint32_t a_row, uint32_t b_cs, uint32_t bcs16,
+                                               const RsPart &acc0, const RsPart &acc1, bool two, const RsPart &fa0, const RsPart &fa1,
+                                               uint32_t n1f, uint32_t nf, const RsPart &fo) {
+  const uint64_t d_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+  const bool first = chunk0 && fresh;
+  if (first) {
+    const uint64_t da = d_hi | (uint64_t)a_row;
+    if (n1f) umma_tf32_ss(fa0.tcol, da, d_hi | (uint64_t)(b_cs + fa0.boff), fa0.idesc, 1u);
+    if (nf > n1f) umma_tf32_ss(fa1.tcol, da, d_hi | (uint64_t)(b_cs + fa1.boff), fa1.idesc, 1u);
+    umma_tf32_ss(fo.tcol, da, d_hi | (uint64_t)(b_cs + fo.boff), fo.idesc, 0u);
+  }
+  for (int s = 0; s < kw; ++s) {
+    for (int k4 = 0; k4 < kv; ++k4) {
+      if (s == 0 && k4 == 0 && first) continue;
+      const uint64_t da = d_hi | (uint64_t)(a_row + (uint32_t)(8 * s + 2 * k4));
+      const uint32_t bk = b_cs + (uint32_t)s * bcs16 + (uint32_t)(2 * k4);
+      umma_tf32_ss(acc0.tcol, da, d_hi | (uint64_t)(bk + acc0.boff), acc0.idesc, 1u);
+      if (two) umma_tf32_ss(acc1.tcol, da, d_hi | (uint64_t)(bk + acc1.boff), acc1.idesc, 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, RsArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *a_smem = smem;
+  uint8_t *b_smem = smem + (size_t)a.S * a.stage_bytes + 1024;  // 1 KB gap: the shifted views of the last stage over-read kw-1 slots
+  const int kh = a.e.kh, kw = a.e.kw, NT = a.e.NT;
+  uint64_t *a_full = (uint64_t *)(b_smem + (size_t)a.chunks * kw * a.bcs_bytes);
+  uint64_t *a_empty = a_full + kRsMaxStages;
+  uint64_t *t_full = a_empty + kRsMaxStages;
+  uint64_t *t_empty = t_full + kRsMaxBlocks;
+  uint64_t *b_full = t_empty + kRsMaxBlocks;
+  uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
+  float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < kRsMaxStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kRsMaxBlocks; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // this CTA's share of the global output-row sequence
+  const long long r0 = a.total_rows * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long r1 = a.total_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int ncs = a.chunks * kw;
+      mbar_expect_tx(b_full, (uint32_t)(ncs * a.bcs_bytes));
+      for (int cs = 0; cs < ncs; ++cs) tma_load_3d(&mapB, b_full, b_smem + (size_t)cs * a.bcs_bytes, 0, 0, cs);
+      uint32_t st = 0, ph = 0, nloaded = 0;
+      int tr_i = 0;
+      for (long long row = r0; row < r1;) {
+        const RsSeg sg = rs_segment(a, row, r1);
+        const int nin = sg.cnt + kh - 1;
+        for (int j = 0; j < nin; ++j) {
+          const int iy = sg.oy0 - a.e.pad + j;
+          mbar_wait(&a_empty[st], ph ^ 1u);
+          RS_TRACE(0, tr_i); ++tr_i;
+          if ((a.e.dbg & 2) && nloaded >= (uint32_t)a.S) {
+            mbar_arrive(&a_full[st]);  // debug: operands are loaded only once per stage
+          } else {
+            mbar_expect_tx(&a_full[st], (uint32_t)(a.stage_tx * a.chunks));
+            for (int c = 0; c < a.chunks; ++c)
+              tma_load_4d(&mapA, &a_full[st], a_smem + (size_t)st * a.stage_bytes + (size_t)c * a.chunk_bytes, c * 32, sg.ox0 - a.e.pad_w,
+                          sg.img0, iy);
+          }
+          ++nloaded;
+          if (++st == (uint32_t)a.S) { st = 0; ph ^= 1u; }
+        }
+        row += sg.cnt;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one elected lane runs the whole loop =====================
+    // (scalar state only and straight-line issue code: ptxas then keeps descriptors, TMEM addresses and instruction
+    // descriptors in UNIFORM registers, which is what UTCHMMA reads; per-lane guards or indexed structs cost an R2UR per operand)
+    if (elect_one()) {
+    const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);  // D=f32, A=B=tf32 K-major, M=128; N added per MMA
+    const uint32_t tmem_u = tmem_base;
+    const uint32_t a_base16 = smem_u32(a_smem) >> 4, stage16 = (uint32_t)a.stage_bytes >> 4;
+    const uint32_t b_base16 = smem_u32(b_smem) >> 4, bcs16 = (uint32_t)a.bcs_bytes >> 4;
+    const uint32_t R = (uint32_t)a.R, nt8 = (uint32_t)NT * 8u, chunk16 = (uint32_t)a.chunk_bytes >> 4;
+    const uint32_t b_lo0 = (b_base16 & 0x3FFF) | (1u << 16);
+    const uint32_t id_full = idesc0 | ((((uint32_t)(kh * NT)) >> 3) << 17), id_win1 = idesc0 | ((((uint32_t)((kh - 1) * NT)) >> 3) << 17),
+                   id_one = idesc0 | (((uint32_t)NT >> 3) << 17);
+    mbar_wait(b_full, 0);
+    uint32_t st = 0, ph = 0;
+    uint32_t blk_hi = 0, par_hi = 0;  // ring block / use parity of the next output row to be started
+    uint32_t blk_lo = 0;              // ring block of the oldest incomplete output row
+    int tr_m = 0;
+    for (long long row = r0; row < r1;) {
+      const RsSeg sg = rs_segment(a, row, r1);
+      const int nin = sg.cnt + kh - 1;
+      for (int j = 0; j < nin; ++j) {
+        RS_TRACE(1, tr_m); ++tr_m;
+        const bool fresh = j < sg.cnt;  // output row j is touched for the first time: its block is overwritten
+        if (fresh) {
+          mbar_wait(&t_empty[blk_hi], par_hi ^ 1u);  // drained by the epilogue
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        mbar_wait(&a_full[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_st = ((a_base16 + st * stage16) & 0x3FFF) | (1u << 16);
+        // steady state: a full window of kh blocks that does not wrap around the TMEM ring, no partial last chunk
+        const bool steady = fresh && j >= kh - 1 && blk_lo + (uint32_t)kh <= R && a.kv_last == 4 && kh > 1;
+        if (a.e.dbg & 4) {
+        } else if (steady && kw == 3) {
+          rs_issue_row_steady<3>(a.chunks, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
+                                 id_full, id_win1, id_one, (uint32_t)(kh - 1) * nt8);
+        } else if (steady && kw == 5) {
+          rs_issue_row_steady<5>(a.chunks, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
+                                 id_full, id_win1, id_one, (uint32_t)(kh - 1) * nt8);
+        } else {
+          const int lo = j - (kh - 1) > 0 ? j - (kh - 1) : 0;
+          const uint32_t nb = (uint32_t)((fresh ? j : sg.cnt - 1) - lo + 1);
+          const uint32_t rb_lo = (uint32_t)((kh - 1) - (j - lo));  // B row block (filter row kh-1-rb) that meets output row lo
+          // accumulate window: blocks blk_lo .. blk_lo+nb-1, split where the ring wraps
+          RsPart acc0, acc1, fa0, fa1, fo;
+          const uint32_t n1 = nb < R - blk_lo ? nb : R - blk_lo;
+          acc0.tcol = tmem_u + blk_lo * (uint32_t)NT; acc0.boff = rb_lo * nt8; acc0.idesc = idesc0 | (((n1 * (uint32_t)NT) >> 3) << 17);
+          acc1.tcol = tmem_u; acc1.boff = (rb_lo + n1) * nt8; acc1.idesc = idesc0 | ((((nb - n1) * (uint32_t)NT) >> 3) << 17);
+          const bool two = n1 < nb;
+          // first MMA of a fresh row: the window without the new block accumulates, the new block is overwritten
+          const uint32_t nf = fresh ? nb - 1u : nb;
+          const uint32_t n1f = nf < R - blk_lo ? nf : R - blk_lo;
+          fa0 = acc0; fa0.idesc = idesc0 | (((n1f * (uint32_t)NT) >> 3) << 17);
+          fa1 = acc1; fa1.boff = (rb_lo + n1f) * nt8; fa1.idesc = idesc0 | ((((nf - n1f) * (uint32_t)NT) >> 3) << 17);
+          fo.tcol = tmem_u + blk_hi * (uint32_t)NT; fo.boff = (uint32_t)(kh - 1) * nt8; fo.idesc = id_one;
+          for (int c = 0; c < a.chunks; ++c) {
+            const int kv = (c == a.chunks - 1) ? a.kv_last : 4;
+            rs_issue_chunk(c == 0, fresh, kv, kw, a_st + (uint32_t)c * chunk16, b_lo0 + (uint32_t)(c * kw) * bcs16, bcs16, acc0, acc1, two, fa0,
+                           fa1, n1f, nf, fo);
+          }
+        }
+        if (a.e.dbg & 32) mbar_arrive(&a_empty[st]);  // debug (only meaningful with dbg & 4): plain arrive instead of tcgen05.commit
+        else umma_commit_arrive(&a_empty[st]);
+        if (++st == (uint32_t)a.S) { st = 0; ph ^= 1u; }
+        if (j >= kh - 1) {  // output row j-(kh-1) is complete
+          if (a.e.dbg & 32) mbar_arrive(&t_full[blk_lo]);
+          else umma_commit_arrive(&t_full[blk_lo]);
+          if (++blk_lo == R) blk_lo = 0;
+        }
+        if (fresh && ++blk_hi == R) { blk_hi = 0; par_hi ^= 1u; }
+      }
+      row += sg.cnt;
+    }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31; the two warps of a lane quadrant
+    // take alternate output rows =====================
+    const SlArgs &e = a.e;
+    const int lane_grp = warp & 3, half = (warp - 2) >> 2;
+    for (int j = threadIdx.x - 64; j < NT; j += kThreads - 64) bias_s[j] = (e.epi.bias && j < e.Co) ? __ldg(e.epi.bias + j) : 0.f;
+    const bool lay0 = e.out.sc == 1 && (!e.epi.residual.p || e.epi.residual.sc == 1) &&
+                      (!e.epi.preact.p || e.epi.preact.sc == 1) && (!e.epi.mask.p || e.epi.mask.sc == 1);
+    const bool lay1 = e.out.sw == 1 && (!e.epi.residual.p || e.epi.residual.sw == 1) && (!e.epi.preact.p || e.epi.preact.sw == 1);
+    int fmode = 3;
+    if ((e.Co & 15) == 0) {
+      if (e.ps == 1 && lay0) fmode = 0;
+      else if (e.epi.mask.p) fmode = 3;
+      else if (e.ps == 4 && lay1 && (e.out.sh & 3) == 0) fmode = 1;
+      else if (e.ps == 2 && lay0 && ((e.Co >> 2) & 3) == 0) fmode = 2;
+    }
+    const bool extra = e.epi.residual.p != nullptr || e.epi.preact.p != nullptr || e.epi.mask.p != nullptr;
+    asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");
+    const uint32_t bsa = smem_u32(bias_s);
+    const int m = lane_grp * 32 + lane;
+    float lsum = 0.f;
+    const int lmode = e.epi.loss_kind ? ((e.ps == 4 && e.epi.dz_unshuf) ? 1 : 3) : 0;
+    uint32_t ctr = 0;
+    for (long long row = r0; row < r1;) {
+      const RsSeg sg = rs_segment(a, row, r1);
+      for (int o = 0; o < sg.cnt; ++o, ++ctr) {
+        if ((int)(ctr & 1u) != half) continue;
+        const uint32_t blk = ctr % (uint32_t)a.R;
+        mbar_wait(&t_full[blk], (ctr / (uint32_t)a.R) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane_grp == 2 && lane == 0) RS_TRACE(2 + half, (int)(ctr >> 1));
+        const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + blk * (uint32_t)NT;
+        const int oy = sg.oy0 + o;
+#define RS_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(e, trow, bsa, 0, 1, m, sg.img0, 0, oy, sg.ox0, sg.imgs_valid, sg.cols_valid, 1)
+        if (e.dbg & 1) {}
+        else if (lmode == 1) epilogue_items_loss<1>(e, trow, bsa, 0, 1, m, sg.img0, 0, oy, sg.ox0, sg.imgs_valid, sg.cols_valid, lsum, 1);
+        else if (lmode == 3) epilogue_items_loss<3>(e, trow, bsa, 0, 1, m, sg.img0, 0, oy, sg.ox0, sg.imgs_valid, sg.cols_valid, lsum, 1);
+        else if (fmode == 0) { if (extra) RS_EPI(0, true); else RS_EPI(0, false); }
+        else if (fmode == 1) { if (extra) RS_EPI(1, true); else RS_EPI(1, false); }
+        else if (fmode == 2) { if (extra) RS_EPI(2, true); else RS_EPI(2, false); }
+        else RS_EPI(3, true);
+#undef RS_EPI
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[blk]);
+      }
+      row += sg.cnt;
+    }
+    if (lmode) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      if (lane == 0) e.epi.loss_part[(size_t)blockIdx.x * 8 + (warp - 2)] = lsum;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// B operand of k_conv_rs: out[chunk][s][rr][Npad][32] (tf32 RN), rr = kh-1-r (filter rows stacked along N, last row first)
+__global__ void k_pack_w_rs(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad, int chunks,
+                            int flip) {
+  const long long total = (long long)chunks * kw * kh * Npad * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 31);
+    long long q = i >> 5;
+    const int n = (int)(q % Npad); q /= Npad;
+    const int rr = (int)(q % kh); q /= kh;
+    const int s = (int)(q % kw);
+    const int c = (int)(q / kw);
+    const int k = c * 32 + kk;
+    float v = 0.f;
+    if (n < Nn && k < Kk) v = round_tf32(wval(w, n, k, kh - 1 - rr, s, Nn, Kk, kh, kw, flip));
+    out[i] = v;
+  }
+}
+
 long long *g_sl_trace = nullptr;
 long long g_sl_trace_ctas = 0;
 int g_sl_dbg = 0;
@@ -1123,6 +1464,7 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
   a.in_ps = in_ps;
   a.in_cpb = in_ps > 1 ? g.Ci / (in_ps * in_ps) / celems : 0;
   a.pad_w = g.pad;
+  a.rs = 0;
   a.kb_valid = kblocks;
   for (int i = 0; i < 16; ++i) a.phase_mask[i] = 0xffff;
   pl->Npad = Npad;
@@ -1143,6 +1485,149 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
   pl->wpack_floats = c4 ? (size_t)pl->n_tiles_n * kblocks * NT * 8 : (size_t)kblocks * Npad * 32;
   pl->xpack_floats = c4 ? (size_t)g.N * g.Hi * g.Wi * 4 : 0;
   return true;
+}
+
+
+// ---- row-stacked kernel: plan + launch ------------------------------------------------------------------------------------------
+struct RsPlan {
+  RsArgs a;
+  size_t smem;
+  int grid, Npad, BWs;
+  double lane_eff;
+};
+
+// Layers the row-stacked kernel takes: tf32 operands from an NHWC fp32 tensor (Cin >= 8), stride 1, no input un-shuffle, a single
+// N tile with kh * NT <= 256 and every weight resident in shared memory next to >= 3 row stages.
+bool make_rs_plan(const Geom &g, RsPlan *pl) {
+  if (g_sl_dbg & 128) return false;  // debug: force the slot-linear kernel
+  if (g.st != 1 || g.Ci <= 4 || g.kh > 9 || g.kw > 9) return false;
+  const int NT = round_up_i(g.Co, 16);
+  if (g.kh * NT > 256) return false;
+  const int chunks = (g.Ci + 31) / 32;
+  RsArgs &a = pl->a;
+  memset(&a, 0, sizeof(a));
+  int CT = 1, TW = g.Wo;
+  if (g.Wo > 128) { CT = (g.Wo + 127) / 128; TW = (g.Wo + CT - 1) / CT; }
+  const int BWs = TW + g.kw - 1;
+  int G = 1;
+  if (CT == 1) {
+    G = (128 + g.kw - 1) / BWs;
+    if (G > g.N) G = g.N;
+    if (G < 1) G = 1;
+    while (G > 1 && (G - 1) * BWs + TW > 128) --G;
+  }
+  if (BWs > 256) return false;
+  pl->lane_eff = (double)G * TW / 128.0;
+  if (pl->lane_eff < 0.55) return false;
+  const int slots = G * BWs > 128 ? G * BWs : 128;
+  a.chunk_bytes = round_up_i(slots * 128, 1024);
+  a.stage_bytes = chunks * a.chunk_bytes;
+  a.stage_tx = G * BWs * 128;
+  a.bcs_bytes = g.kh * NT * 128;
+  const long long b_bytes = (long long)chunks * g.kw * a.bcs_bytes;
+  const long long fixed = b_bytes + 1024 /*gap*/ + 1024 /*align*/ + 1024 /*barriers, bias*/;
+  long long S = (226 * 1024 - fixed) / a.stage_bytes;
+  if (S < 2) return false;
+  if (S > kRsMaxStages) S = kRsMaxStages;
+  a.S = (int)S;
+  a.chunks = chunks;
+  a.kv_last = (g.Ci - (chunks - 1) * 32 + 7) / 8;
+  a.G = G; a.TW = TW; a.CT = CT;
+  a.R = 512 / NT < kRsMaxBlocks ? 512 / NT : kRsMaxBlocks;
+  if (a.R < g.kh + 1) return false;
+  const long long IG = (g.N + G - 1) / G;
+  a.total_rows = IG * CT * g.Ho;
+  SlArgs &e = a.e;
+  e.N = g.N; e.Ho = g.Ho; e.Wo = g.Wo; e.Co = g.Co; e.kh = g.kh; e.kw = g.kw; e.pad = g.pad; e.pad_w = g.pad;
+  e.NT = NT; e.BW = BWs; e.ps = g.ps; e.rs = 1; e.MTB = 1; e.chunk_elems = 32;
+  pl->smem = (size_t)a.S * a.stage_bytes + (size_t)fixed;
+  pl->grid = (int)(a.total_rows < 148 ? a.total_rows : 148);
+  pl->Npad = NT;
+  pl->BWs = BWs;
+  return pl->grid >= 1;
+}
+
+bool rs_usable(const Geom &g, const T4 &in, const T4 &out, const Epi &epi, const ConvOpt &opt, RsPlan *pl) {
+  if (in.dt != SRB_F32 || out.dt != SRB_F32) return false;
+  if (opt.in_ps != 1 || opt.wmode != 0 || (opt.pad_w >= 0 && opt.pad_w != g.pad) || opt.in_h > 0 || opt.in_w > 0) return false;
+  (void)epi;
+  return make_rs_plan(g, pl);
+}
+
+int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi_in, void *ws,
+                      size_t ws_bytes, cudaStream_t st, const ConvOpt &opt, RsPlan &pl) {
+  Epi epi = epi_in;
+  RsArgs &a = pl.a;
+  const size_t wpack_floats = (size_t)a.chunks * g.kw * g.kh * pl.Npad * 32;
+  const size_t loss_bytes = epi.loss_kind ? (size_t)kMaxLossCtas * 8 * sizeof(float) + 256 : 0;
+  const size_t need = wpack_floats * sizeof(float) + 512 + loss_bytes;
+  uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+  SRB_REQUIRE(ws && wsp + need <= (uintptr_t)ws + ws_bytes, SRB_EWORKSPACE, "tc_conv_rs workspace: need %zu bytes, have %zu", need + 256,
+              ws_bytes);
+  float *wp = (float *)wsp;
+  if (epi.loss_kind) {
+    SRB_REQUIRE(opt.loss_out != nullptr && pl.grid <= kMaxLossCtas, SRB_EINVAL, "fused loss: bad arguments");
+    SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
+                    epi.target.p && epi.target.dt == SRB_F32,
+                SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
+    if (g.ps == 4 && epi.dz_unshuf) {
+      auto ok = [](const T4 &t) { return !t.p || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0); };
+      SRB_REQUIRE((g.Co & 15) == 0 && ok(out) && ok(epi.target) && (((uintptr_t)epi.dz_unshuf) & 31) == 0, SRB_EUNSUPPORTED,
+                  "fused loss with PixelShuffle(4): NCHW-contiguous y / target, Cout*16 channels");
+    } else {
+      SRB_REQUIRE(g.ps == 1 && epi.dz.p && epi.dz.dt == SRB_F32 && !epi.dz_unshuf, SRB_EUNSUPPORTED,
+                  "fused loss: PixelShuffle(4) with an un-shuffled gradient, or no PixelShuffle with the gradient in y's layout");
+    }
+    epi.loss_part = (float *)(((uintptr_t)wp + wpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
+  }
+  {
+    const long long total = (long long)wpack_floats;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pack_w_rs<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+  }
+  CUtensorMap mapA, mapB;
+  {  // (C, W, N, H): a box of {32, BWs, G, 1} lands as [image][slot][32 ch] = one M tile row
+    cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.N, (cuuint64_t)g.Hi};
+    cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sn * 4, (cuuint64_t)in.sh * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)pl.BWs, (cuuint32_t)a.G, 1};
+    int rc = encode_tiled(&mapA, in.p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {32, (cuuint64_t)(g.kh * pl.Npad), (cuuint64_t)(a.chunks * g.kw)};
+    cuuint64_t strides[2] = {128, (cuuint64_t)g.kh * pl.Npad * 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)(g.kh * pl.Npad), 1};
+    int rc = encode_tiled(&mapB, wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  a.e.out = out;
+  a.e.epi = epi;
+  a.e.dbg = g_sl_dbg;
+  a.e.trace = g_sl_trace_ctas >= 64 ? g_sl_trace : nullptr;
+  {
+    auto ok32 = [](const T4 &t) {
+      return !t.p || ((((uintptr_t)t.p) & 31) == 0 && (t.sn & 7) == 0 && (t.sh & 7) == 0 && (t.sw & 7) == 0);
+    };
+    a.e.v8 = (ok32(out) && ok32(epi.residual) && ok32(epi.preact)) ? 1 : 0;
+  }
+  {
+    static std::atomic<unsigned long long> attr_done{0};
+    int rc = ensure_kernel_attrs(k_conv_rs, attr_done, kMaxSmemBytes, true);
+    if (rc) return rc;
+  }
+  k_conv_rs<<<pl.grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  if (epi.loss_kind) {
+    const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
+    k_sl_loss_finish<<<1, 256, 0, st>>>(epi.loss_part, pl.grid * 8, (float)(1.0 / numel), opt.loss_out);
+    count_launch();
+    SRB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SRB_OK;
 }
 
 }  // namespace
@@ -1194,6 +1679,16 @@ size_t tc_conv_ws_bytes(const Geom &g) {
 }
 
 int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
+  RsPlan rp;
+  if (!bf16 && make_rs_plan(g, &rp)) {
+    const RsArgs &r = rp.a;
+    return snprintf(buf, n,
+                    "conv_rs row-stacked: %d image(s) x %d slots per M tile (%d output columns, lane use %.2f), %d strip(s)/image, N = %d x %d = %d, "
+                    "chunks %d (last: %d K-steps), %d row stages x %d B, weights %d B resident, TMEM ring %d blocks, smem %zu B, "
+                    "%lld output rows on grid %d",
+                    r.G, rp.BWs, r.TW, rp.lane_eff, r.CT, g.kh, r.e.NT, g.kh * r.e.NT, r.chunks, r.kv_last, r.S, r.stage_bytes,
+                    r.chunks * g.kw * r.bcs_bytes, r.R, rp.smem, r.total_rows, rp.grid);
+  }
   SlPlan pl;
   if (!make_sl_plan(g, &pl, bf16)) return snprintf(buf, n, "conv_sl: no plan");
   const SlArgs &a = pl.a;
@@ -1207,6 +1702,10 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi_in,
                    void *ws, size_t ws_bytes, cudaStream_t st, const ConvOpt &opt) {
+  {
+    RsPlan rp;
+    if (rs_usable(g, in, out, epi_in, opt, &rp)) return tc_conv_rs_launch(g, in, w, flip_transpose, out, epi_in, ws, ws_bytes, st, opt, rp);
+  }
   SlPlan pl;
   Epi epi = epi_in;
   const int in_ps = opt.in_ps;

@@ -1,0 +1,54 @@
+"""Debug: time single conv layers (fprop through srb200.conv2d) under the kernel debug flags.
+flags: 0 normal, 1 empty epilogue, 2 operands loaded once, 4 no MMAs, 128 force the slot-linear kernel"""
+import ctypes, sys, os
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pytorch-super-resolution-model-collection_b200"))
+import srb200
+from srb200 import _lib
+
+LAYERS = [("espcn L2 64->32", 128, 64, 60, 60, 32, 3, 0, 1, "relu"), ("espcn L2d 32->64", 128, 32, 58, 58, 64, 3, 2, 1, None),
+          ("espcn L3 32->48 PS4", 128, 32, 58, 58, 3, 3, 0, 4, None), ("vdsr body 64->64", 64, 64, 128, 128, 64, 3, 1, 1, "relu"),
+          ("edsr64 body", 32, 64, 32, 32, 64, 3, 1, 1, "relu")]
+
+def timeit(f, n=10, reps=5):
+    """GPU time per call: n calls captured into one CUDA graph (no host launch overhead), best of `reps` replays."""
+    for _ in range(2):
+        f()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(n):
+                f()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+    return best
+
+if __name__ == "__main__":
+    dbg = _lib.lib.srb_debug_set_flags
+    dbg.argtypes = [ctypes.c_int]
+    dbg.restype = None
+    dev = torch.device("cuda:0")
+    flags = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 4, 3, 7, 128]
+    for name, N, Ci, H, W, Co, k, p, ps, act in LAYERS:
+        x = torch.randn(N, Ci, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(Co * ps * ps, Ci, k, k, device=dev) * 0.05
+        b = torch.randn(Co * ps * ps, device=dev)
+        out = []
+        for fl in flags:
+            dbg(fl)
+            out.append("%d: %6.1f us" % (fl, timeit(lambda: srb200.conv2d(x, w, b, 1, p, activation=act, pixel_shuffle=ps))))
+        dbg(0)
+        print("%-22s %s" % (name, "   ".join(out)), flush=True)
