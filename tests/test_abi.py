@@ -92,6 +92,19 @@ def test_tile_plans_respect_hardware_limits():
             if "no plan" in txt or "CUDA-core" in txt:
                 continue
             seen += 1
+            if txt.startswith("conv_rs"):  # row-stacked kernel: one CTA per SM, the whole 512-column TMEM as a ring of row blocks
+                smem = int(re.search(r"smem (\d+) B", txt).group(1))
+                g_, bw_, tw_ = (int(v) for v in re.search(r"(\d+) image\(s\) x (\d+) slots per M tile \((\d+) output columns", txt).groups())
+                kh_, nt_, n_ = (int(v) for v in re.search(r"N = (\d+) x (\d+) = (\d+)", txt).groups())
+                ring = int(re.search(r"TMEM ring (\d+) blocks", txt).group(1))
+                stages = int(re.search(r"(\d+) row stages", txt).group(1))
+                rows, grid = (int(v) for v in re.search(r"(\d+) output rows on grid (\d+)", txt).groups())
+                assert smem <= 227 * 1024 and stages >= 2, txt
+                assert kh_ == k and n_ == kh_ * nt_ <= 256 and nt_ % 16 == 0 and nt_ >= (co if pas == 0 else c), txt
+                assert ring * nt_ <= 512 and ring > kh_, txt
+                assert (g_ - 1) * bw_ + tw_ <= 128 and bw_ == tw_ + k - 1 and g_ >= 1, txt  # every valid lane inside the 128-slot M tile
+                assert 1 <= grid <= 148 and grid <= rows, txt
+                continue
             smem = int(re.search(r"smem (\d+) B", txt).group(1))
             tmem = int(re.search(r"tmem (\d+) cols", txt).group(1))
             gx, gy = (int(v) for v in re.search(r"grid (\d+) x (\d+)", txt).groups())
