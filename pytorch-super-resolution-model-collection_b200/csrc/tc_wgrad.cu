@@ -46,8 +46,17 @@ struct WgArgs {
   int z_ps, z_cpb;        // z_ps > 1: dz is given as PixelShuffle_r(dz) (y's layout, C = Co / r^2 channels): N-block q of the GEMM is
                           // sub-pixel phase q / z_cpb, channel block q % z_cpb, fetched through a stride-r TMA traversal; the
                           // GEMM's output channel co' = ij * C + c is filter co = c * r^2 + ij (k_wgrad_finish undoes it)
+  int rn;                 // tf32 generic only: the kh FILTER ROWS are stacked along N instead of being separate accumulators:
+                          //   D[(s,ci), (r,co)] = sum_q X[q+s][ci] * dZ[q + (kh-1-r)*BW][co]
+                          // q runs over a band of TH INPUT rows (x tile: TH rows, no halo); the dz tile holds the TH+kh-1 output rows
+                          // those input rows meet (rows outside the image arrive as zeros), and the B operand's N-block kh-1-r is
+                          // that tile viewed kh-1-r rows LATER (LBO = one slot row = BW*128 B) -- one A read feeds kh filter taps.
+                          // An accumulator is (32-channel co block, s-group, ci block) and has acc_cols = kh*32 columns.
+  int acc_cols;           // TMEM columns (= MMA N) per accumulator: NT, or kh*32 in rn mode
+  int Hi;                 // input rows (rn: the bands tile the INPUT rows)
   int dbg;                // debug knobs (srb_debug_set_flags): 2 = stages are TMA-loaded only once, 4 = no MMAs are issued
   int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
+  int acc_boff[kMaxAcc];  // B-descriptor offset (16-byte units) of accumulator j relative to the stage's dz view (rn: its co block)
   float *partial;         // [gridDim.x][gridDim.y][ACC][128][NT]
   float *db_part;         // bias gradient partials [gridDim.x][4 warps][n_cot * NT], or null
 };
@@ -101,15 +110,17 @@ __device__ __forceinline__ void db_rows_h(float (&dbs)[4][8], uint32_t sz, int d
 
 // db partial sums of one dz stage: NB 32-channel blocks, 4 rows per LDS.128 (see the caller for the lane mapping)
 template <int NB>
-__device__ __forceinline__ void db_rows(float4 (&dbs)[8], uint32_t sz, int dz_bytes, int rows, int lane_grp, int lrow, int lchunk) {
-  for (int q0 = lane_grp * 4; q0 < rows; q0 += 16) {
+__device__ __forceinline__ void db_rows(float4 (&dbs)[8], uint32_t sz, int dz_bytes, int rows, int lane_grp, int lrow, int lchunk,
+                                        int row_lo = 0) {
+  for (int q0 = (row_lo & ~3) + lane_grp * 4; q0 < rows; q0 += 16) {
     const int q = q0 + lrow;
     const uint32_t off = sz + (uint32_t)q * 128u + ((uint32_t)(lchunk ^ ((q & 3) << 1)) << 4);
+    const float keep = (q >= row_lo && q < rows) ? 1.f : 0.f;  // rows outside [row_lo, rows) belong to a neighbouring band (or are the zero tail)
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       float4 v;
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(off + (uint32_t)(j * dz_bytes)));
-      dbs[j].x += v.x; dbs[j].y += v.y; dbs[j].z += v.z; dbs[j].w += v.w;
+      dbs[j].x += keep * v.x; dbs[j].y += keep * v.y; dbs[j].z += keep * v.z; dbs[j].w += keep * v.w;
     }
   }
 }
@@ -120,18 +131,19 @@ template <int NACC, bool BF>
 __device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, uint32_t z_lo, uint32_t hi, uint32_t idesc,
                                               uint32_t tmem_base, bool first) {
   constexpr uint32_t KADV = BF ? 128u : 64u;  // one K step = 16 (bf16) / 8 (tf32) pixel rows x 128 B, in 16-byte units
-  uint32_t al[NACC], tc[NACC];
+  uint32_t al[NACC], tc[NACC], bo[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) {
     al[j] = x_lo + (uint32_t)a.acc_off[j];
-    tc[j] = tmem_base + (uint32_t)(j * a.NT);
+    bo[j] = (uint32_t)a.acc_boff[j];
+    tc[j] = tmem_base + (uint32_t)(j * a.acc_cols);
   }
   uint32_t bl = z_lo;
   int ks = 0;
   if (first) {  // very first K-step of this CTA: overwrite the accumulators
 #pragma unroll
     for (int j = 0; j < NACC; ++j) {
-      umma_tf32_lohi<false, BF>(tc[j], al[j], bl, hi, idesc);
+      umma_tf32_lohi<false, BF>(tc[j], al[j], bl + bo[j], hi, idesc);
       al[j] += KADV;
     }
     bl += KADV;
@@ -141,7 +153,7 @@ __device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, ui
   for (; ks < a.ksteps; ++ks) {
 #pragma unroll
     for (int j = 0; j < NACC; ++j) {
-      umma_tf32_lohi<true, BF>(tc[j], al[j], bl, hi, idesc);
+      umma_tf32_lohi<true, BF>(tc[j], al[j], bl + bo[j], hi, idesc);
       al[j] += KADV;
     }
     bl += KADV;
@@ -172,7 +184,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   const int rg_valid = min(a.RG, a.kh - r0);
   const int band0 = blockIdx.x * a.bands_per_cta;
   const int band1 = min(band0 + a.bands_per_cta, a.num_bands);
-  const int ACC = a.RG * a.SG * a.CIB;
+  const int ACC = a.rn ? nb * a.SG * a.CIB : a.RG * a.SG * a.CIB;
   // the CTAs of the first (ci group, filter-row group) also reduce dz over pixels: db[co] = sum_p dz[p][co]
   const bool do_db = a.db_part != nullptr && cig == 0 && rgi == 0;
 
@@ -208,7 +220,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer: one halo band per stage =====================
     {
-      const uint32_t tx_bytes = (uint32_t)(XT * a.BH * a.BW * 128 + nb * a.TH * (a.dz_rowwise ? a.TW : a.BW) * 128);
+      const int z_rows = a.rn ? a.TH + a.kh - 1 : a.TH;  // dz rows per band
+      const uint32_t tx_bytes = (uint32_t)(XT * a.BH * a.BW * 128 + nb * z_rows * (a.dz_rowwise ? a.TW : a.BW) * 128);
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
@@ -231,10 +244,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             tma_load_4d(&mapX, &full_bar[st], sx, 0, 0, oh0, n);  // padded image: no negative coordinates
           } else {
             for (int cb = 0; cb < XT; ++cb)
-              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * XT + cb) * blk_ch, ox0 - a.pad, oh0 - a.pad + r0, n);
+              tma_load_4d(&mapX, &full_bar[st], sx + cb * x_bytes, (cig * XT + cb) * blk_ch, ox0 - a.pad, a.rn ? oh0 : oh0 - a.pad + r0, n);
           }
           for (int j = 0; j < nb; ++j) {
-            int zc = cot * a.NT + j * blk_ch, zx = a.dz_rowwise ? ox0 : 0, zy = oh0, zr = 1;
+            int zc = cot * a.NT + j * blk_ch, zx = a.dz_rowwise ? ox0 : 0, zy = a.rn ? oh0 + a.pad - (a.kh - 1) : oh0, zr = 1;
             if (a.z_ps > 1) {  // pixel-un-shuffle folded into the load (host guarantees NT % blk_ch == 0)
               const int q = zc / blk_ch, ij = q / a.z_cpb;
               zr = a.z_ps;
@@ -243,7 +256,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
               zy = zy * zr + ij / zr;
             }
             if (a.dz_rowwise) {
-              for (int t = 0; t < a.TH; ++t)  // rows past the image (and columns past Wo) arrive as zeros
+              for (int t = 0; t < z_rows; ++t)  // rows past the image (and columns past Wo) arrive as zeros
                 tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, zc, zx, zy + t * zr, n);
             } else {
               tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes, zc, zx, zy, n);
@@ -259,13 +272,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
       // D=f32, A=B=tf32, both MN-major (bits 15,16), N>>3 at bit 17, M=128>>4 at bit 24
       const uint32_t fmt = a.bf16 ? 1u : 2u;  // kind::f16 bf16 operands / kind::tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(a.NT >> 3) << 17) | ((128u >> 4) << 24);
+                             ((uint32_t)(a.acc_cols >> 3) << 17) | ((128u >> 4) << 24);
       // descriptor high words are loop invariant; low word = (addr >> 4) | LBO << 16
       // bf16: standard 128B swizzle (layout type 2), 8 K-rows x 128 B per atom -> SBO = 1024 B
       const uint32_t a_hi = a.bf16 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29)) : (uint32_t)(make_mnmajor_desc(0, 128u) >> 32);
       const uint32_t a_lbo = a.c4 ? ((((uint32_t)a.BW * 128u) >> 4) & 0x3FFF) << 16
                                   : (a.c2 ? (((uint32_t)x_bytes >> 4) & 0x3FFF) << 16 : (128u >> 4) << 16);
-      const uint32_t b_lbo = (((uint32_t)dz_bytes >> 4) & 0x3FFF) << 16;
+      // B: consecutive 32-channel N-blocks are the co blocks of the dz stage, or (rn) the same co block one slot row later
+      const uint32_t b_lbo = ((((uint32_t)(a.rn ? a.BW * 128 : dz_bytes)) >> 4) & 0x3FFF) << 16;
       int it = 0;
       for (int band = band0; band < band1; ++band, ++it) {
         const int st = it % a.stages;
@@ -276,7 +290,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const uint32_t x_lo = ((sx >> 4) & 0x3FFF) | a_lbo;
         const uint32_t z_lo = (((sx + XT * x_bytes) >> 4) & 0x3FFF) | b_lbo;
         if (elect_one()) {
-          const int nacc = a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB;  // a prefix of acc_off (filter-row major)
+          const int nacc = a.rn ? ACC : (a.c4 ? a.RG * a.SG : rg_valid * a.SG * a.CIB);  // a prefix of acc_off (filter-row major)
           const bool first = it == 0;
 #define WG_ISSUE(NA)                                                                         \
   if (a.bf16) wg_issue_band<NA, true>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first);       \
@@ -346,7 +360,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
       // While the MMAs run, these warps walk the same stages and sum the dz tiles over pixels (db).  A warp reads four
       // 128-B rows per LDS.128: lane l takes row q0 + l/8 and the 16-B chunk holding channels 4*(l%8)..+3 of every
       // 32-channel block (128B_ATOM_32B swizzle: 32-byte atom index XOR (row & 3), i.e. 16-B chunk index XOR ((row & 3) << 1)).
-      const int rows = a.TH * a.BW;
+      // rn: the dz tiles of neighbouring bands overlap by kh-1 rows; a band sums the TH rows with its own row indices
+      const int row_lo = a.rn ? (a.kh - 1 - a.pad) * a.BW : 0;
+      const int rows = row_lo + a.TH * a.BW;
       float4 dbs[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) dbs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -359,14 +375,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         if (!(a.dbg & 8)) {
           // rows .. round_up(rows, 8) lie in the tile's zero tail (dz_slots % 8 == 0); warp w takes rows 4w.., 4w+16..
           switch (nb) {
-            case 1: db_rows<1>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 2: db_rows<2>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 3: db_rows<3>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 4: db_rows<4>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 5: db_rows<5>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 6: db_rows<6>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            case 7: db_rows<7>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
-            default: db_rows<8>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk); break;
+            case 1: db_rows<1>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 2: db_rows<2>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 3: db_rows<3>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 4: db_rows<4>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 5: db_rows<5>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 6: db_rows<6>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            case 7: db_rows<7>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
+            default: db_rows<8>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
           }
         }
         __syncwarp();
@@ -395,12 +411,12 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = lane_grp * 32 + lane;
-    float *dst = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * ACC * 128 * a.NT;
+    float *dst = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * ACC * 128 * a.acc_cols;
     for (int acc = 0; acc < ((a.dbg & 32) ? 0 : ACC); ++acc) {
-      const int rl = acc / (a.SG * a.CIB);
-      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.NT);
-      float *row = dst + ((size_t)acc * 128 + m) * a.NT;
-      for (int j0 = 0; j0 < a.NT; j0 += 16) {
+      const int rl = a.rn ? 0 : acc / (a.SG * a.CIB);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.acc_cols);
+      float *row = dst + ((size_t)acc * 128 + m) * a.acc_cols;
+      for (int j0 = 0; j0 < a.acc_cols; j0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)j0, v);
         if (rl >= rg_valid || band0 >= band1) {
@@ -439,6 +455,13 @@ __device__ __forceinline__ void wg_locate(const WgArgs &a, int co, int ci, int r
     by = (cig * a.n_rg + rgi) * a.n_cot + cot;
     acc = (rl * a.SG + sg) * a.CIB + cb;
     m = half * 64 + (ci & 63);
+  } else if (a.rn) {
+    const int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
+    const int sg = s >> 2, sl = s & 3, cob = n >> 5;
+    by = cig * a.n_cot + cot;
+    acc = (cob * a.SG + sg) * a.CIB + cb;
+    m = sl * 32 + (ci & 31);
+    n = (a.kh - 1 - r) * 32 + (n & 31);  // N-block kh-1-r of the accumulator holds filter row r
   } else {
     const int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
     const int rgi = r / a.RG, rl = r - rgi * a.RG;
@@ -469,8 +492,8 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
   const int taps = a.kh * a.kw, total_items = a.Ci * taps, pitch = IPB + 1;
   const int co_tiles = (a.Co + 31) / 32, groups = (total_items + IPB - 1) / IPB;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ACC = a.RG * a.SG * a.CIB;
-  const size_t ss = (size_t)gy * ACC * 128 * a.NT;  // floats between consecutive splits
+  const int ACC = a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB;
+  const size_t ss = (size_t)gy * ACC * 128 * a.acc_cols;  // floats between consecutive splits
   if ((int)blockIdx.x < co_tiles * groups) {
     const int cot32 = blockIdx.x % co_tiles, j0 = (blockIdx.x / co_tiles) * IPB;
     const int co = cot32 * 32 + tx;
@@ -482,7 +505,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
       if (co < a.Co) {
         int by, acc, m, n;
         wg_locate(a, co, ci, r, s, by, acc, m, n);
-        const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.NT + n;
+        const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.acc_cols + n;
         if (lanes8) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           int z = ty;
@@ -583,7 +606,7 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
   a.z_ps = 1; a.z_cpb = 0;
   a.N = g.N; a.Ho = g.Ho; a.Wo = g.Wo; a.Ci = g.Ci; a.Co = g.Co;
   a.kh = g.kh; a.kw = g.kw; a.pad = g.pad;
-  a.c4 = 1; a.bf16 = 0; a.c2 = 0;
+  a.c4 = 1; a.bf16 = 0; a.c2 = 0; a.rn = 0; a.Hi = g.Hi;
   a.TW = g.Wo; a.bands_w = 1; a.dz_rowwise = 0;
   a.BW = g.Wo + g.kw - 1;  // == Wi + 2*pad at stride 1
   if (a.BW > 256 || g.kw > 16 || g.kh > 16) return false;
@@ -612,7 +635,7 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
     break;  // largest band that still double-buffers: least halo re-read
   }
   if (!bestTH) return false;
-  a.NT = NT; a.TH = bestTH; a.BH = bestTH + g.kh - 1;
+  a.NT = NT; a.acc_cols = NT; a.TH = bestTH; a.BH = bestTH + g.kh - 1;
   a.x_slots = best_xs; a.dz_slots = best_zs; a.stages = best_stages;
   a.n_cig = 1; a.n_rg = 1; a.n_cot = co_pad / NT;
   a.bands_per_img = (g.Ho + a.TH - 1) / a.TH;
@@ -641,7 +664,7 @@ bool make_wg_plan_c4(const Geom &g, WgPlan *pl) {
 // bf16 operands: 64-channel blocks, K = 16 pixels per MMA, M = 128 as two 64-lane blocks (WgArgs::bf16 / c2).
 bool make_wg_plan_h(const Geom &g, WgPlan *pl, int z_ps) {
   WgArgs &a = pl->a;
-  a.c4 = 0; a.bf16 = 1;
+  a.c4 = 0; a.bf16 = 1; a.rn = 0; a.Hi = g.Hi;
   a.z_ps = z_ps; a.z_cpb = z_ps > 1 ? g.Co / (z_ps * z_ps) / 64 : 0;
   pl->Hp = pl->Wp = 0;
   pl->xpack_floats = 0;
@@ -716,6 +739,7 @@ bool make_wg_plan_h(const Geom &g, WgPlan *pl, int z_ps) {
   }
   if (best_score < 0) return false;
   a = best;
+  a.acc_cols = a.NT;
   a.bands_per_img = ((g.Ho + a.TH - 1) / a.TH) * a.bands_w;
   a.num_bands = g.N * a.bands_per_img;
   a.ksteps = (a.TH * a.BW + 15) / 16;
@@ -740,7 +764,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
   if (bf16) return make_wg_plan_h(g, pl, z_ps);
   if (g.Ci <= 4) return z_ps == 1 && make_wg_plan_c4(g, pl);
   WgArgs &a = pl->a;
-  a.c4 = 0; a.bf16 = 0; a.c2 = 0;
+  a.c4 = 0; a.bf16 = 0; a.c2 = 0; a.rn = 0; a.Hi = g.Hi;
   a.z_ps = z_ps; a.z_cpb = z_ps > 1 ? g.Co / (z_ps * z_ps) / 32 : 0;
   pl->Hp = pl->Wp = 0;
   pl->xpack_floats = 0;
@@ -752,13 +776,21 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
   double best_score = -1.0;
   WgArgs best = a;
   size_t best_smem = 0;
-  // Enumerate (column split, NT, CIB, RG, TH) and minimise a time model per image row, summed over the CTAs of grid.y:
-  //   MMA cycles  = accumulators * cost(NT) * (pitch / 8 K-steps),   cost(N) = max(32 + N/4, N/2)  [measured, tools/bench_umma.cu:
-  //                 an SS-mode tf32 MMA re-reads its 4 KB A tile and N*32 B of B from shared memory at 128 B/cycle]
+  // Enumerate (row stacking, column split, NT, CIB, RG, TH) and minimise a time model per image row, summed over the CTAs of grid.y:
+  //   MMA cycles  = accumulators * cost(N) * (pitch / 8 K-steps),   cost(N) = max(32 + N/4, N/2) + 15  [measured, tools/bench_umma.cu:
+  //                 an SS-mode tf32 MMA re-reads its 4 KB A tile and N*32 B of B from shared memory at 128 B/cycle; ~15 cycles
+  //                 of every MMA's issue are not hidden behind the previous one (in-kernel traces, tools/trace_rs.py)]
   //   load cycles = TMA bytes (halo rows and halo columns included) / (L2->SM share of one SM ~ 23 B/cycle)
   //   + a fixed hand-off cost per band.
+  // Row stacking (WgArgs::rn): N = kh * 32 per MMA and one accumulator per (co block, s-group, ci block); K runs over the
+  // TH + kh - 1 rows of the x tile, so small bands pay (TH + kh - 1) / TH more K-steps.
   // Column split w: the band covers TW = ceil(Wo / w) output columns; x is fetched as a (TW + kw - 1)-wide halo box and dz
   // row by row at the same pitch.  Wide images (W >= 128) would otherwise be limited to TH = 1 (3x halo re-read).
+  const int dbg_flags = tc_conv_get_dbg();
+  for (int rn = 0; rn <= 1; ++rn) {
+  // (a band owns the output rows with its own input-row indices: needs Ho <= Hi, i.e. 2 * pad <= kh - 1)
+  if (rn && (z_ps != 1 || g.kh < 2 || g.kh * 32 > 256 || 2 * g.pad > g.kh - 1 || (dbg_flags & 256))) continue;
+  if (!rn && (dbg_flags & 512)) continue;
   for (int wsplit = 1; wsplit <= 16; ++wsplit) {
     const int TW = (g.Wo + wsplit - 1) / wsplit;
     if (wsplit > 1 && (TW < 16 || (g.Wo + TW - 1) / TW != wsplit)) continue;
@@ -770,23 +802,27 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
       if (co_pad % NT) continue;
       for (int CIB = cblocks; CIB >= 1; --CIB) {
         if (cblocks % CIB) continue;
-        for (int RG = g.kh; RG >= 1; --RG) {
-          int acc = RG * a.SG * CIB;
-          if (acc * NT > 512 || acc > kMaxAcc) continue;
+        for (int RG = g.kh; RG >= (rn ? g.kh : 1); --RG) {
+          const int acc = rn ? (NT / 32) * a.SG * CIB : RG * a.SG * CIB;
+          const int acc_cols = rn ? g.kh * 32 : NT;
+          if (acc * acc_cols > 512 || acc > kMaxAcc) continue;
           for (int TH = 16; TH >= 1; --TH) {
             if (TH > g.Ho && TH > 1) continue;
-            int BH = TH + RG - 1;
-            if (BH > 256 || TH * z_ps > 256) continue;
+            if (rn && TH > g.Hi && TH > 1) continue;
+            int BH = rn ? TH : TH + RG - 1;  // x box rows: rn bands are TH input rows, the halo is on the dz side
+            if (BH > 256 || TH * z_ps > 256 || TH + g.kh - 1 > 256) continue;
             int x_slots = round_up_i(BH * BW + 4 * a.SG + 8, 8);
-            int dz_slots = round_up_i(TH * BW, 8);
+            // rn: TH + kh - 1 rows of dz, + the slots the last N-block's view reaches past them in the rounded-up last K-step
+            int dz_slots = rn ? round_up_i((TH + g.kh - 1) * BW + 8, 8) : round_up_i(TH * BW, 8);
             size_t stage = (size_t)CIB * x_slots * 128 + (size_t)(NT / 32) * dz_slots * 128;
             int stages = (int)((kMaxSmemBytes - 4096) / stage);
             if (stages < 2) continue;
             if (stages > 4) stages = 4;
             int n_rg = (g.kh + RG - 1) / RG, n_cig = cblocks / CIB, n_cot = co_pad / NT;
-            double costN = (32.0 + NT / 4.0) > NT / 2.0 ? (32.0 + NT / 4.0) : NT / 2.0;
+            double costN = ((32.0 + acc_cols / 4.0) > acc_cols / 2.0 ? (32.0 + acc_cols / 4.0) : acc_cols / 2.0) + 15.0;
             double mma = (double)n_cig * n_rg * n_cot * acc * costN * (bands_w * BW / 8.0);
-            double bytes = ((double)n_cot * n_rg * cblocks * BH / TH * BW + (double)n_cig * n_rg * (co_pad / 32) * TW) * 128.0 * bands_w;
+            const double zrows = rn ? (double)(TH + g.kh - 1) / TH : 1.0;  // dz rows loaded per band row
+            double bytes = ((double)n_cot * n_rg * cblocks * BH / TH * BW + (double)n_cig * n_rg * (co_pad / 32) * TW * zrows) * 128.0 * bands_w;
             double t = mma > bytes / 23.0 ? mma : bytes / 23.0;
             t += 500.0 * bands_w / TH * (n_cig * n_rg * n_cot);  // per-band hand-off (barrier round trips, TMA issue)
             // every TMA instruction costs issue slots and a request round trip; row-wise dz loads issue NT/32 * TH small
@@ -798,6 +834,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
             if (score > best_score) {
               best_score = score;
               best = a;
+              best.rn = rn; best.acc_cols = acc_cols;
               best.TW = TW; best.bands_w = bands_w; best.BW = BW; best.dz_rowwise = bands_w > 1 ? 1 : 0;
               best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
               best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
@@ -809,9 +846,10 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
       }
     }
   }
+  }  // rn
   if (best_score < 0) return false;
   a = best;
-  a.bands_per_img = ((g.Ho + a.TH - 1) / a.TH) * a.bands_w;
+  a.bands_per_img = (((a.rn ? g.Hi : g.Ho) + a.TH - 1) / a.TH) * a.bands_w;
   a.num_bands = g.N * a.bands_per_img;
   a.ksteps = (a.TH * a.BW + 7) / 8;
   int gy = a.n_cig * a.n_rg * a.n_cot;
@@ -820,12 +858,13 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
   a.bands_per_cta = (a.num_bands + target - 1) / target;
   if (a.bands_per_cta < 1) a.bands_per_cta = 1;  // empty batch: plan for the workspace query only
   int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
-  int cols = a.RG * a.SG * a.CIB * a.NT, tc = 32;
+  const int nacc = a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB;
+  int cols = nacc * a.acc_cols, tc = 32;
   while (tc < cols) tc <<= 1;
   a.tmem_cols = tc;
   pl->grid = dim3(gx, gy);
   pl->smem = best_smem;
-  pl->partial_floats = (size_t)gx * gy * a.RG * a.SG * a.CIB * 128 * a.NT;
+  pl->partial_floats = (size_t)gx * gy * nacc * 128 * a.acc_cols;
   pl->db_blocks = 0;
   pl->db_floats = (size_t)gx * 4 * a.n_cot * a.NT;
   return true;
@@ -869,7 +908,7 @@ int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16) {
   return snprintf(buf, n,
                   "tc_wgrad%s: band TH %d TW %d x%d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
                   "stages %d, smem %zu B, tmem %d cols, grid %d x %d, ksteps %d",
-                  a.bf16 ? (a.c2 ? "-bf16(ci pairs)" : "-bf16(tap pairs)") : "", a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
+                  a.bf16 ? (a.c2 ? "-bf16(ci pairs)" : "-bf16(tap pairs)") : (a.rn ? "-rows-stacked" : ""), a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
                   pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
 }
 
@@ -892,8 +931,17 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   WgArgs &a = pl.a;
   {  // A-descriptor offsets of the accumulators, in 16-byte units (one pixel slot = 128 B = 8 units)
     const int row_step = a.BW * 8, x_step = a.x_slots * 8;
-    for (int j = 0; j < kMaxAcc; ++j) a.acc_off[j] = 0;
-    if (a.c4) {
+    for (int j = 0; j < kMaxAcc; ++j) a.acc_off[j] = a.acc_boff[j] = 0;
+    if (a.rn) {
+      // accumulator (co block, sg, cb): A = ci block cb at tap s = 4*sg (un-shifted rows), B = co block's dz view
+      for (int cob = 0; cob < a.NT / 32; ++cob)
+        for (int sg = 0; sg < a.SG; ++sg)
+          for (int cb = 0; cb < a.CIB; ++cb) {
+            const int j = (cob * a.SG + sg) * a.CIB + cb;
+            a.acc_off[j] = sg * 32 + cb * x_step;
+            a.acc_boff[j] = cob * a.dz_slots * 8;
+          }
+    } else if (a.c4) {
       for (int rg = 0; rg < a.RG; ++rg)
         for (int sg = 0; sg < a.SG; ++sg) a.acc_off[rg * a.SG + sg] = 4 * rg * row_step + sg * 64;
     } else if (a.bf16) {
@@ -942,7 +990,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     cuuint64_t dims[4] = {(cuuint64_t)(g.Co / (z_ps * z_ps)), (cuuint64_t)g.Wo * r, (cuuint64_t)g.Ho * r, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)small.sw * es, (cuuint64_t)small.sh * es, (cuuint64_t)small.sn * es};
     cuuint32_t box[4] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)((a.dz_rowwise ? a.TW : a.BW) * z_ps),
-                         (cuuint32_t)((a.dz_rowwise ? 1 : a.TH) * z_ps), 1};
+                         (cuuint32_t)((a.dz_rowwise ? 1 : (a.rn ? a.TH + a.kh - 1 : a.TH)) * z_ps), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)z_ps, (cuuint32_t)z_ps, 1};
     int rc = encode_tiled(&mapZ, small.p, 4, dims, strides, box, bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bf,
                           z_ps > 1 ? estr : nullptr);

@@ -36,7 +36,7 @@ def timeit(f, n=10, reps=5):
         best = min(best, e0.elapsed_time(e1) * 1e3 / n)
     return best
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("WGRAD"):
     dbg = _lib.lib.srb_debug_set_flags
     dbg.argtypes = [ctypes.c_int]
     dbg.restype = None
@@ -52,3 +52,42 @@ if __name__ == "__main__":
             out.append("%d: %6.1f us" % (fl, timeit(lambda: srb200.conv2d(x, w, b, 1, p, activation=act, pixel_shuffle=ps))))
         dbg(0)
         print("%-22s %s" % (name, "   ".join(out)), flush=True)
+
+
+def time_wgrad(flags_list):
+    """srb_conv_wgrad (main kernel + finish) per layer through the C-ABI, under the planner debug flags
+    (256: never stack filter rows along N, 512: always)."""
+    from srb200 import functional as F
+    from srb200._lib import lib, check, t4
+    dbg = _lib.lib.srb_debug_set_flags
+    dbg.argtypes = [ctypes.c_int]
+    dbg.restype = None
+    dev = torch.device("cuda:0")
+    layers = [("espcn L2 wgrad 64->32", 128, 64, 60, 60, 32, 3, 0), ("espcn L3 wgrad 32->48", 128, 32, 58, 58, 48, 3, 0),
+              ("vdsr body wgrad 64->64", 64, 64, 128, 128, 64, 3, 1), ("edsr64 body wgrad", 32, 64, 32, 32, 64, 3, 1),
+              ("vdsr out-like 64->32", 64, 64, 128, 128, 32, 3, 1), ("espcn L1 wgrad 3->64 k5", 128, 3, 64, 64, 64, 5, 0)]
+    for name, N, Ci, H, W, Co, k, p in layers:
+        x = torch.randn(N, Ci, H, W, device=dev)
+        if Ci >= 8:
+            x = x.contiguous(memory_format=torch.channels_last)
+        w = torch.randn(Co, Ci, k, k, device=dev) * 0.05
+        Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+        dz = torch.randn(N, Co, Ho, Wo, device=dev).contiguous(memory_format=torch.channels_last)
+        dw, db = torch.empty_like(w), torch.empty(Co, device=dev)
+        prm = F._params(x, w, 1, p, 0, False, 1, None, 0.2)
+        out = []
+        for fl in flags_list:
+            dbg(fl)
+            ws = torch.empty(lib.srb_conv_workspace_bytes(ctypes.byref(prm), _lib.PASS_WGRAD) + 1024, dtype=torch.uint8, device=dev)
+            tx, tdz = t4(x), t4(dz)
+            def f():
+                st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                check(lib.srb_conv_wgrad(ctypes.byref(prm), ctypes.byref(tx), ctypes.byref(tdz), F._ptr(dw), F._ptr(db), ctypes.c_float(1.0), 0,
+                                         F._ptr(ws), ws.numel(), st))
+            out.append("%d: %6.1f us" % (fl, timeit(f)))
+        dbg(0)
+        print("%-30s %s" % (name, "   ".join(out)), flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("WGRAD"):
+    time_wgrad([0, 256, 512])
