@@ -30,6 +30,7 @@ namespace srb {
 namespace {
 
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kRsEpiPerQuadFwd = 4;  // == kRsEpiPerQuad of k_conv_rs (declared further down)
 constexpr int kMaxLossCtas = 1024;  // fused loss: per-warp partial sums of at most this many CTAs
 constexpr int kMaxBStages = 8;
 
@@ -308,6 +309,13 @@ __device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t tr
       const int c = cbase >> 4;
       const long long yy = (long long)oy * 4, xx = (long long)ox * 4;
       const float *pt = a.epi.target.p + (n * a.epi.target.sn + c * a.epi.target.sc + yy * a.epi.target.sh + xx * a.epi.target.sw);
+      if (a.rs && oy + kRsEpiPerQuadFwd < a.Ho) {
+        // row-stacked kernel: this warp's next output row is oy + kRsEpiPerQuad.  Its target rows are pulled into L2 now: the four
+        // dependent 16-byte loads per item below would otherwise expose the full DRAM latency with ~16 KB in flight per SM.
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (4 * kRsEpiPerQuadFwd + q4) * a.epi.target.sh));
+      }
       float *po = a.out.p ? a.out.p + (n * a.out.sn + c * a.out.sc + yy * a.out.sh + xx * a.out.sw) : nullptr;
       float g[16];
 #pragma unroll
@@ -1013,6 +1021,8 @@ __global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H,
 constexpr int kRsMaxStages = 8;
 constexpr int kRsMaxBlocks = 16;
 constexpr int kRsPrefetchRows = 6;
+constexpr int kRsEpiPerQuad = kRsEpiPerQuadFwd;        // epilogue warps per TMEM lane quadrant
+constexpr int kRsThreads = 64 + 128 * kRsEpiPerQuad;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -1105,7 +1115,7 @@ __device__ __forceinline__ void rs_issue_chunk(bool chunk0, bool fresh, int kv, 
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kRsThreads)
 k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, RsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1249,11 +1259,11 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31; the two warps of a lane quadrant
-    // take alternate output rows =====================
+    // ===================== epilogue: warps 2..; warp w reads TMEM lanes 32*(w%4) .. +31; the kRsEpiPerQuad warps of a lane
+    // quadrant take output rows round-robin (several rows in flight hide the latency of the epilogue's global loads) =====================
     const SlArgs &e = a.e;
     const int lane_grp = warp & 3, half = (warp - 2) >> 2;
-    for (int j = threadIdx.x - 64; j < NT; j += kThreads - 64) bias_s[j] = (e.epi.bias && j < e.Co) ? __ldg(e.epi.bias + j) : 0.f;
+    for (int j = threadIdx.x - 64; j < NT; j += kRsThreads - 64) bias_s[j] = (e.epi.bias && j < e.Co) ? __ldg(e.epi.bias + j) : 0.f;
     const bool lay0 = e.out.sc == 1 && (!e.epi.residual.p || e.epi.residual.sc == 1) &&
                       (!e.epi.preact.p || e.epi.preact.sc == 1) && (!e.epi.mask.p || e.epi.mask.sc == 1);
     const bool lay1 = e.out.sw == 1 && (!e.epi.residual.p || e.epi.residual.sw == 1) && (!e.epi.preact.p || e.epi.preact.sw == 1);
@@ -1265,7 +1275,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       else if (e.ps == 2 && lay0 && ((e.Co >> 2) & 3) == 0) fmode = 2;
     }
     const bool extra = e.epi.residual.p != nullptr || e.epi.preact.p != nullptr || e.epi.mask.p != nullptr;
-    asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(kRsThreads - 64) : "memory");
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;
     float lsum = 0.f;
@@ -1274,11 +1284,11 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     for (long long row = r0; row < r1;) {
       const RsSeg sg = rs_segment(a, row, r1);
       for (int o = 0; o < sg.cnt; ++o, ++ctr) {
-        if ((int)(ctr & 1u) != half) continue;
+        if ((int)(ctr % (uint32_t)kRsEpiPerQuad) != half) continue;
         const uint32_t blk = ctr % (uint32_t)a.R;
         mbar_wait(&t_full[blk], (ctr / (uint32_t)a.R) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane_grp == 2 && lane == 0) RS_TRACE(2 + half, (int)(ctr >> 1));
+        if (lane_grp == 2 && lane == 0 && half < 2) RS_TRACE(2 + half, (int)(ctr / (uint32_t)kRsEpiPerQuad));
         const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + blk * (uint32_t)NT;
         const int oy = sg.oy0 + o;
 #define RS_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(e, trow, bsa, 0, 1, m, sg.img0, 0, oy, sg.ox0, sg.imgs_valid, sg.cols_valid, 1)
@@ -1618,7 +1628,7 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
     int rc = ensure_kernel_attrs(k_conv_rs, attr_done, kMaxSmemBytes, true);
     if (rc) return rc;
   }
-  k_conv_rs<<<pl.grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+  k_conv_rs<<<pl.grid, kRsThreads, pl.smem, st>>>(mapA, mapB, a);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   if (epi.loss_kind) {

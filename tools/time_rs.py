@@ -89,5 +89,29 @@ def time_wgrad(flags_list):
         print("%-30s %s" % (name, "   ".join(out)), flush=True)
 
 
+def time_loss(flags_list):
+    """ESPCN's last layer (32 -> 48, PixelShuffle(4)) fused with the MSE criterion (srb_conv_fprop_loss)."""
+    dbg = _lib.lib.srb_debug_set_flags
+    dbg.argtypes = [ctypes.c_int]
+    dbg.restype = None
+    dev = torch.device("cuda:0")
+    x = torch.randn(128, 32, 58, 58, device=dev).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(48, 32, 3, 3, device=dev) * 0.05
+    b = torch.randn(48, device=dev)
+    t = torch.rand(128, 3, 224, 224, device=dev)
+    out = []
+    for fl in flags_list:
+        dbg(fl)
+        def f():
+            with torch.no_grad():
+                srb200.conv2d_loss(x, w, b, t, "mse", 1, 0, 4)
+        out.append("%d: %6.1f us" % (fl, timeit(f)))
+    dbg(0)
+    print("%-30s %s" % ("espcn L3 + PS4 + MSE", "   ".join(out)), flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("LOSS"):
+    time_loss([8, 9, 11, 12, 13, 14, 15, 128])
+
 if __name__ == "__main__" and os.environ.get("WGRAD"):
     time_wgrad([0, 256, 512])
