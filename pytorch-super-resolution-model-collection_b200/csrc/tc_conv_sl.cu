@@ -620,6 +620,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     SL_TRACE(0);
     if (a.trace) {
@@ -654,6 +655,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (a.cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast into them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();  // everything above overlapped the previous kernel; from here on global memory is touched
   if (threadIdx.x == 0) SL_TRACE(1);
   // every CTA walks the same number of band slots; a slot past the last band only keeps a shared weight ring in lock-step
   const int iters = (num_bands + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -875,6 +877,8 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
 // loss = inv_n * sum of the per-warp partials, in a fixed order (one block)
 __global__ void __launch_bounds__(256) k_sl_loss_finish(const float *__restrict__ partial, int n, float inv_n, float *loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
@@ -923,6 +927,8 @@ __device__ __forceinline__ float wval_phase(const float *__restrict__ w, const W
 
 __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad,
                             int chunks, int flip, int perm_C, int perm_rr, WMap wm) {
+  pdl_trigger();
+  pdl_wait();
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -945,6 +951,8 @@ __global__ void k_pack_w_sl(const float *__restrict__ w, float *__restrict__ out
 // generic B operand for bf16 operands: out[chunk][tap][Npad][64] (bf16 RN), zero for n >= Nn or k >= Kk
 __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__restrict__ out, int Nn, int Kk, int kh, int kw,
                               int Npad, int chunks, int flip, int perm_C, int perm_rr, WMap wm) {
+  pdl_trigger();
+  pdl_wait();
   const int taps = kh * kw;
   const long long total = (long long)chunks * taps * Npad * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -966,6 +974,8 @@ __global__ void k_pack_w_sl_h(const float *__restrict__ w, unsigned short *__res
 // c4 B operand: out[ntile][kb = r*spairs+sp][NT/8][2][8][4]; element (n, k): pixel offset sl = k/4 -> s = 2*sp+sl, channel k%4
 __global__ void k_pack_w_c4(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int NT,
                             int ntiles, int spairs, int flip) {
+  pdl_trigger();
+  pdl_wait();
   const int kblocks = kh * spairs;
   const long long total = (long long)ntiles * kblocks * NT * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -987,6 +997,8 @@ __global__ void k_pack_w_c4(const float *__restrict__ w, float *__restrict__ out
 
 // x (N, C<=4, H, W; any strides) -> NHWC4 image (16 B per pixel, channel >= C zero), tf32-rounded
 __global__ void k_pack_nhwc4(T4 x, float4 *__restrict__ xp, int N, int C, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % W);
@@ -1131,6 +1143,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -1147,6 +1160,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();  // everything above overlapped the previous kernel; from here on global memory is touched
 
   // this CTA's share of the global output-row sequence
   const long long r0 = a.total_rows * (long long)blockIdx.x / (long long)gridDim.x;
@@ -1324,6 +1338,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // B operand of k_conv_rs: out[chunk][s][rr][Npad][32] (tf32 RN), rr = kh-1-r (filter rows stacked along N, last row first)
 __global__ void k_pack_w_rs(const float *__restrict__ w, float *__restrict__ out, int Nn, int Kk, int kh, int kw, int Npad, int chunks,
                             int flip) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)chunks * kw * kh * Npad * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i & 31);
@@ -1594,7 +1610,7 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
     const long long total = (long long)wpack_floats;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_pack_w_rs<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+    launch_pdl(k_pack_w_rs, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
@@ -1628,12 +1644,12 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
     int rc = ensure_kernel_attrs(k_conv_rs, attr_done, kMaxSmemBytes, true);
     if (rc) return rc;
   }
-  k_conv_rs<<<pl.grid, kRsThreads, pl.smem, st>>>(mapA, mapB, a);
+  SRB_CHECK_CUDA(launch_pdl(k_conv_rs, dim3(pl.grid), dim3(kRsThreads), pl.smem, st, mapA, mapB, a));
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   if (epi.loss_kind) {
     const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
-    k_sl_loss_finish<<<1, 256, 0, st>>>(epi.loss_part, pl.grid * 8, (float)(1.0 / numel), opt.loss_out);
+    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, pl.grid * 8, (float)(1.0 / numel), opt.loss_out);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
@@ -1778,19 +1794,19 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (a.c4)
-      k_pack_w_c4<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
+      launch_pdl(k_pack_w_c4, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
     else if (bf_in)
-      k_pack_w_sl_h<<<blocks, 256, 0, st>>>(w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0,
+      launch_pdl(k_pack_w_sl_h, dim3(blocks), dim3(256), 0, st, w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0,
                                             perm_C, perm_rr, wm);
     else
-      k_pack_w_sl<<<blocks, 256, 0, st>>>(w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr, wm);
+      launch_pdl(k_pack_w_sl, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr, wm);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     if (a.c4) {
       const long long px = (long long)g.N * g.Hi * g.Wi;
       int pb = (int)((px + 255) / 256);
       if (pb > 148 * 16) pb = 148 * 16;
-      k_pack_nhwc4<<<pb, 256, 0, st>>>(in, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi);
+      launch_pdl(k_pack_nhwc4, dim3(pb), dim3(256), 0, st, in, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi);
       count_launch();
       SRB_CHECK_CUDA(cudaGetLastError());
     }
@@ -1867,13 +1883,13 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     cfg.numAttrs = 1;
     SRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_sl, mapA, mapB, a));
   } else {
-    k_conv_sl<<<grid, kThreads, pl.smem, st>>>(mapA, mapB, a);
+    SRB_CHECK_CUDA(launch_pdl(k_conv_sl, grid, dim3(kThreads), pl.smem, st, mapA, mapB, a));
   }
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   if (epi.loss_kind) {
     const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
-    k_sl_loss_finish<<<1, 256, 0, st>>>(epi.loss_part, (int)(grid.x * grid.y * 8), (float)(1.0 / numel), loss_out);
+    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, (int)(grid.x * grid.y * 8), (float)(1.0 / numel), loss_out);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }

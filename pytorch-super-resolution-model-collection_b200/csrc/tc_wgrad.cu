@@ -175,6 +175,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   uint32_t *tmem_slot = (uint32_t *)(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   // grid.y -> (ci group, filter-row group, co tile)
   int by = blockIdx.y;
   const int cot = by % a.n_cot; by /= a.n_cot;
@@ -216,6 +217,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();  // the shared-memory zeroing and set-up above overlapped the previous kernel; global memory from here on
 
   if (warp == 0) {
     // ===================== TMA producer: one halo band per stage =====================
@@ -488,6 +490,8 @@ __device__ __forceinline__ int wg_filter_of(const WgArgs &a, int co) {
 // kernel spent 47 us on EDSR-256's 28 MB of partials: 4-byte stores 9 KB apart and 3 loads in flight per thread.)
 __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int gy, int IPB, int lanes8, float *dw, float *db,
                                                       float scale, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float tile[];  // [32][IPB + 1] (+ [8][33] fold buffer when lanes8)
   const int taps = a.kh * a.kw, total_items = a.Ci * taps, pitch = IPB + 1;
   const int co_tiles = (a.Co + 31) / 32, groups = (total_items + IPB - 1) / IPB;
@@ -573,6 +577,8 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
 // padding and the extra right-hand columns are real zeros so that every 8-pixel window of the overlapping view is finite.
 __global__ void k_pack_nhwc4_padded(T4 x, float4 *__restrict__ xp, int N, int C, int H, int W, int pad, int Hp, int Wp,
                                     long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % Wp);
     long long q = i / Wp;
@@ -967,7 +973,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     const long long total = (long long)(pl.xpack_floats / 4);
     int pb = (int)((total + 255) / 256);
     if (pb > 148 * 16) pb = 148 * 16;
-    k_pack_nhwc4_padded<<<pb, 256, 0, st>>>(big, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi, g.pad, pl.Hp, pl.Wp, total);
+    launch_pdl(k_pack_nhwc4_padded, dim3(pb), dim3(256), 0, st, big, (float4 *)xp, g.N, g.Ci, g.Hi, g.Wi, g.pad, pl.Hp, pl.Wp, total);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     // overlapping view: "channel" c of slot x is float 4*x + c of the padded row -> 8 pixels x 4 channels per slot
@@ -1001,7 +1007,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     int rc = ensure_kernel_attrs(k_tc_wgrad, attr_done, kMaxSmemBytes, false);
     if (rc) return rc;
   }
-  k_tc_wgrad<<<pl.grid, kWgThreads, pl.smem, st>>>(mapX, mapZ, a);
+  SRB_CHECK_CUDA(launch_pdl(k_tc_wgrad, pl.grid, dim3(kWgThreads), pl.smem, st, mapX, mapZ, a));
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   {
@@ -1015,7 +1021,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     const int groups = (total_items + IPB - 1) / IPB;
     const unsigned blocks = (unsigned)(co_tiles * groups + (db_small ? co_tiles : 0));
     const size_t fsm = ((size_t)32 * (IPB + 1) + 8 * 33) * sizeof(float);
-    k_wgrad_finish<<<blocks, 256, fsm, st>>>(a, splits, (int)pl.grid.y, IPB, lanes8, dw, db_small, scale, accumulate);
+    launch_pdl(k_wgrad_finish, dim3(blocks), dim3(256), fsm, st, a, splits, (int)pl.grid.y, IPB, lanes8, dw, db_small, scale, accumulate);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
