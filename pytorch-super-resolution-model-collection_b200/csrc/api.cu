@@ -22,6 +22,8 @@ namespace {
 // Iterates in dz's memory order: channels_last -> (n,h,w,c), else (n,c,h,w).
 __global__ void k_act_bwd(T4 dy, T4 ref, T4 dz, int N, int C, int H, int W, int act, float slope_in,
                           const float *__restrict__ alpha, float *dalpha, int cl, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : slope_in;
   long long total = (long long)N * C * H * W;
   float da = 0.f;
@@ -57,6 +59,8 @@ __global__ void k_act_bwd(T4 dy, T4 ref, T4 dz, int N, int C, int H, int W, int 
 
 // out[n, k, h, w] (NHWC) = dz[n, c, h*r+i, w*r+j] with k = c*r*r + i*r + j, rounded to tf32
 __global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int r, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * H * W * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -75,6 +79,8 @@ __global__ void k_pixel_unshuffle(T4 dz, T4 out, int N, int K, int H, int W, int
 // NHWC output row (fully coalesced stores).  Row pitch W*r + 4 keeps the (i, j) gather off a single bank.
 __global__ void __launch_bounds__(256)
 k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float srow[];
   const int n = blockIdx.x / H, h = blockIdx.x - n * H;
   const int Wr = W * r, pitch = Wr + 4, rows = C * r, K = C * r * r;
@@ -119,6 +125,8 @@ k_pixel_unshuffle_rows(T4 dz, T4 out, int N, int C, int H, int W, int r, int rnd
 // Same-layout dense tensors: flat float4 walk (the common case: dy, ref, dz all NHWC- or all NCHW-contiguous)
 __global__ void k_act_bwd_flat(const float4 *__restrict__ dy, const float4 *__restrict__ ref, float4 *dz, long long n4,
                                int act, float slope_in, const float *__restrict__ alpha, float *dalpha, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : (act == SRB_ACT_RELU ? 0.f : slope_in);
   float da = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -147,6 +155,8 @@ __global__ void k_act_bwd_flat(const float4 *__restrict__ dy, const float4 *__re
 }
 
 __global__ void k_prelu_fwd(const float *__restrict__ x, const float *__restrict__ alpha, float *y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const float a = __ldg(alpha);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -156,6 +166,8 @@ __global__ void k_prelu_fwd(const float *__restrict__ x, const float *__restrict
 
 __global__ void k_prelu_bwd(const float *__restrict__ x, const float *__restrict__ dy, const float *__restrict__ alpha,
                             float *dx, float *dalpha, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const float a = __ldg(alpha);
   float da = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -175,6 +187,8 @@ __global__ void k_prelu_bwd(const float *__restrict__ x, const float *__restrict
 }
 
 __global__ void k_round_tf32(const float *__restrict__ x, float *y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = round_tf32(x[i]);
 }
@@ -185,6 +199,8 @@ __global__ void k_round_tf32(const float *__restrict__ x, float *y, long long n)
 __global__ void __launch_bounds__(256) k_loss_partial(const float4 *__restrict__ y, const float4 *__restrict__ t, long long n4,
                                                       const float *__restrict__ ytail, const float *__restrict__ ttail, int ntail,
                                                       int l1, float *__restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = __ldg(y + i), b = __ldg(t + i);
@@ -207,6 +223,8 @@ __global__ void __launch_bounds__(256) k_loss_partial(const float4 *__restrict__
 }
 
 __global__ void __launch_bounds__(256) k_loss_finish(const float *__restrict__ partial, int nblocks, float inv_n, float *loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < nblocks; i += 256) s += partial[i];
@@ -221,6 +239,8 @@ __global__ void __launch_bounds__(256) k_loss_finish(const float *__restrict__ p
 
 __global__ void __launch_bounds__(256) k_loss_bwd(const float *__restrict__ y, const float *__restrict__ t, long long n, int l1,
                                                   float inv_n, const float *__restrict__ g, float *__restrict__ dy) {
+  pdl_trigger();
+  pdl_wait();
   const float c = __ldg(g) * inv_n * (l1 ? 1.f : 2.f);
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -246,6 +266,8 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const float *__restrict__ y, c
 // dz (N, C<=3, H, W; any strides) -> NHWC4 (16 B per pixel, missing channels zero), tf32-rounded: lets the skinny output layers
 // (64->3, 32->3) use the tensor-core wgrad with Co = 4
 __global__ void k_pack_dz4(T4 dz, float4 *__restrict__ out, int N, int C, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
@@ -264,6 +286,8 @@ __global__ void k_pack_dz4(T4 dz, float4 *__restrict__ out, int N, int C, int H,
 // torchvision ToTensor (dataset.py:90,94,98 of the reference): uint8 HWC image in [0,255] -> float CHW in [0,1]
 __global__ void k_image_to_tensor(const unsigned char *__restrict__ src, float *__restrict__ dst, int N, int H, int W, int C,
                                   float scale) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * C * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
@@ -287,6 +311,8 @@ __device__ __forceinline__ unsigned short f2h(float v) {
 __global__ void k_act_bwd_flat_h(const unsigned short *__restrict__ dy, const unsigned short *__restrict__ ref,
                                  unsigned short *dz, long long n, int act, float slope_in, const float *__restrict__ alpha,
                                  float *dalpha) {
+  pdl_trigger();
+  pdl_wait();
   const float slope = (act == SRB_ACT_PRELU) ? __ldg(alpha) : (act == SRB_ACT_RELU ? 0.f : slope_in);
   float da = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -310,6 +336,8 @@ __global__ void k_act_bwd_flat_h(const unsigned short *__restrict__ dy, const un
 // pixel_unshuffle, bf16 NHWC -> bf16 NHWC: out[n,h,w,k = c*r*r + i*r + j] = dz[n, h*r+i, w*r+j, c]; one thread per
 // (pixel, sub-pixel, 8-channel group): one 16-byte load, eight 2-byte stores
 __global__ void k_pixel_unshuffle_h(T4 dz, T4 out, int N, int C, int H, int W, int r) {
+  pdl_trigger();
+  pdl_wait();
   const int rr = r * r, cg = C >> 3;
   const long long total = (long long)N * H * W * rr * cg;
   const unsigned short *src = (const unsigned short *)dz.p;
@@ -333,6 +361,8 @@ __global__ void k_pixel_unshuffle_h(T4 dz, T4 out, int N, int C, int H, int W, i
 
 // bf16 NHWC (N,C,H,W logical) -> dense fp32 NHWC (tf32-representable by construction: bf16 has 8 mantissa bits)
 __global__ void k_h2f_nhwc(T4 x, float *__restrict__ out, int N, int C, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * H * W * C;
   const unsigned short *src = (const unsigned short *)x.p;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -347,6 +377,8 @@ __global__ void k_h2f_nhwc(T4 x, float *__restrict__ out, int N, int C, int H, i
 
 // dz (N, C<=8, H, W; fp32, any strides) -> bf16 NHWC8 (16 B per pixel, missing channels zero)
 __global__ void k_pack_dz8_h(T4 dz, uint4 *__restrict__ out, int N, int C, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
@@ -366,6 +398,8 @@ __global__ void k_pack_dz8_h(T4 dz, uint4 *__restrict__ out, int N, int C, int H
 
 // x *= *g unless *g == 1 (the usual upstream gradient of a scalar loss): every block reads g and leaves early
 __global__ void k_scale_by_scalar(float *x, long long n, const float *__restrict__ g, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const float s = __ldg(g);
   if (s == 1.0f) return;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -380,6 +414,8 @@ __global__ void k_scale_by_scalar(float *x, long long n, const float *__restrict
 __global__ void k_pil_bicubic(const float *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W, int TH, int TW,
                               const int *__restrict__ bw, const int *__restrict__ kw, const int *__restrict__ bh,
                               const int *__restrict__ kh, int ksize, int shave) {
+  pdl_trigger();
+  pdl_wait();
   const int OH = TH - 2 * shave, OW = TW - 2 * shave;
   const long long total = (long long)N * C * OH * OW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -722,7 +758,7 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
 int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream) {
   SRB_REQUIRE(x && g && n >= 0, SRB_EINVAL, "bad scale args");
   if (n == 0) return SRB_OK;
-  k_scale_by_scalar<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n, g, round_to_tf32);
+  launch_pdl(k_scale_by_scalar, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, n, g, round_to_tf32);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -749,7 +785,7 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
     const bool nhwc = tdz.sc == 1 && tdz.sw == C && tdz.sh == (long long)W * C && tdz.sn == (long long)H * W * C;
     const bool nchw = tdz.sw == 1 && tdz.sh == W && tdz.sc == (long long)H * W && tdz.sn == (long long)C * H * W;
     SRB_REQUIRE(same(a) && same(b) && (nhwc || nchw), SRB_EUNSUPPORTED, "bf16 act_bwd needs dy, ref, dz in one dense layout");
-    k_act_bwd_flat_h<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const unsigned short *)a.p, (const unsigned short *)b.p,
+    launch_pdl(k_act_bwd_flat_h, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, (const unsigned short *)a.p, (const unsigned short *)b.p,
                                                                          (unsigned short *)tdz.p, total, p->act, p->slope, alpha, dalpha);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
@@ -765,7 +801,7 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
     int la = dense(a), lb = dense(b), lc = dense(tdz);
     if (la && la == lb && la == lc && (total & 3) == 0 &&
         ((((uintptr_t)a.p) | ((uintptr_t)b.p) | ((uintptr_t)tdz.p)) & 15) == 0) {
-      k_act_bwd_flat<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
+      launch_pdl(k_act_bwd_flat, dim3(ew_blocks(total / 4)), dim3(256), 0, (cudaStream_t)stream, 
           (const float4 *)a.p, (const float4 *)b.p, (float4 *)tdz.p, total / 4, p->act, p->slope, alpha, dalpha,
           want_round(p, tdz, C));
       count_launch();
@@ -774,7 +810,7 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
     }
   }
   int cl = (tdz.sc == 1) ? 1 : 0;
-  k_act_bwd<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dy), to_t4(ref), tdz, p->N, C, H, W, p->act,
+  launch_pdl(k_act_bwd, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, to_t4(dy), to_t4(ref), tdz, p->N, C, H, W, p->act,
                                                                  p->slope, alpha, dalpha, cl,
                                                                  want_round(p, tdz, C));
   count_launch();
@@ -882,7 +918,7 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
       const size_t zb = a256((size_t)g.N * g.Ho * g.Wo * g.Co * sizeof(float));
       SRB_REQUIRE(ws && wsp + zb <= ws_end, SRB_EWORKSPACE, "bf16 wgrad workspace too small");
       float *z32 = (float *)wsp;
-      k_h2f_nhwc<<<ew_blocks((long long)g.N * g.Ho * g.Wo * g.Co), 256, 0, st>>>(tdz, z32, g.N, g.Co, g.Ho, g.Wo);
+      launch_pdl(k_h2f_nhwc, dim3(ew_blocks((long long)g.N * g.Ho * g.Wo * g.Co)), dim3(256), 0, st, tdz, z32, g.N, g.Co, g.Ho, g.Wo);
       count_launch();
       SRB_CHECK_CUDA(cudaGetLastError());
       T4 tz32{z32, (long long)g.Ho * g.Wo * g.Co, 1, (long long)g.Wo * g.Co, g.Co, SRB_F32};
@@ -899,7 +935,7 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
       unsigned short *pack = (unsigned short *)wsp;
       float *dw8 = (float *)(wsp + pb);
       float *dbias8 = dw8 + (size_t)8 * g.Ci * g.kh * g.kw;
-      k_pack_dz8_h<<<ew_blocks((long long)g.N * g.Ho * g.Wo), 256, 0, st>>>(tdz, (uint4 *)pack, g.N, g.Co, g.Ho, g.Wo);
+      launch_pdl(k_pack_dz8_h, dim3(ew_blocks((long long)g.N * g.Ho * g.Wo)), dim3(256), 0, st, tdz, (uint4 *)pack, g.N, g.Co, g.Ho, g.Wo);
       count_launch();
       SRB_CHECK_CUDA(cudaGetLastError());
       T4 tz8{(float *)pack, (long long)g.Ho * g.Wo * 8, 1, (long long)g.Wo * 8, 8, SRB_BF16};
@@ -934,7 +970,7 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
       float *db4 = dw4 + (size_t)4 * g.Ci * g.kh * g.kw;
       void *ws_tc = (void *)(wsp + sk.pack_bytes + sk.dw_bytes);
       const long long px = (long long)g.N * g.Ho * g.Wo;
-      k_pack_dz4<<<ew_blocks(px), 256, 0, st>>>(tdz, (float4 *)pack, g.N, g.Co, g.Ho, g.Wo);
+      launch_pdl(k_pack_dz4, dim3(ew_blocks(px)), dim3(256), 0, st, tdz, (float4 *)pack, g.N, g.Co, g.Ho, g.Wo);
       count_launch();
       SRB_CHECK_CUDA(cudaGetLastError());
       sk.dz4.p = pack;
@@ -967,7 +1003,7 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
                     (dz->sw % 8) == 0 && (dz->sh % 8) == 0 && (dz->sn % 8) == 0 && (((uintptr_t)dz->data) & 15) == 0,
                 SRB_EUNSUPPORTED, "bf16 pixel_unshuffle: both tensors bf16 channels_last, C %% 8 == 0");
     const long long tot = (long long)g.N * g.Ho * g.Wo * g.ps * g.ps * (p->Cout / 8);
-    k_pixel_unshuffle_h<<<ew_blocks(tot), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, p->Cout, g.Ho, g.Wo, g.ps);
+    launch_pdl(k_pixel_unshuffle_h, dim3(ew_blocks(tot)), dim3(256), 0, (cudaStream_t)stream, to_t4(dz), to_t4(out), g.N, p->Cout, g.Ho, g.Wo, g.ps);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     return SRB_OK;
@@ -976,13 +1012,13 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
   const int rnd = is_tf32_math(p->math) ? 1 : 0;  // EXACT / FP32 keep the full fp32 gradient
   const size_t row_smem = (size_t)p->Cout * g.ps * ((size_t)g.Wo * g.ps + 4) * sizeof(float);
   if (dz->sw == 1 && row_smem <= 48 * 1024 && (long long)g.N * g.Ho < (1LL << 31)) {
-    k_pixel_unshuffle_rows<<<(unsigned)(g.N * g.Ho), 256, row_smem, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, p->Cout,
+    launch_pdl(k_pixel_unshuffle_rows, dim3((unsigned)(g.N * g.Ho)), dim3(256), row_smem, (cudaStream_t)stream, to_t4(dz), to_t4(out), g.N, p->Cout,
                                                                                             g.Ho, g.Wo, g.ps, rnd);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     return SRB_OK;
   }
-  k_pixel_unshuffle<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(to_t4(dz), to_t4(out), g.N, g.Co, g.Ho, g.Wo,
+  launch_pdl(k_pixel_unshuffle, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, to_t4(dz), to_t4(out), g.N, g.Co, g.Ho, g.Wo,
                                                                          g.ps, rnd);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
@@ -992,7 +1028,7 @@ int srb_pixel_unshuffle(const srb_conv_params *p, const srb_tensor4 *dz, const s
 int srb_prelu_fwd(const float *x, const float *alpha, float *y, int64_t n, void *stream) {
   SRB_REQUIRE(x && alpha && y && n >= 0, SRB_EINVAL, "bad prelu args");
   if (n == 0) return SRB_OK;
-  k_prelu_fwd<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, alpha, y, n);
+  launch_pdl(k_prelu_fwd, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, alpha, y, n);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -1002,7 +1038,7 @@ int srb_prelu_bwd(const float *x, const float *dy, const float *alpha, float *dx
                   void *stream) {
   SRB_REQUIRE(x && dy && alpha && dx && n >= 0, SRB_EINVAL, "bad prelu args");
   if (n == 0) return SRB_OK;
-  k_prelu_bwd<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, alpha, dx, dalpha, n);
+  launch_pdl(k_prelu_bwd, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, dy, alpha, dx, dalpha, n);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -1016,9 +1052,9 @@ int srb_loss_fwd(int kind, const float *y, const float *t, int64_t n, float *los
   SRB_REQUIRE(((((uintptr_t)y) | ((uintptr_t)t)) & 15) == 0, SRB_EUNSUPPORTED, "loss tensors must be 16-byte aligned");
   const long long n4 = n >> 2;
   const unsigned blocks = ew_blocks(n4 > 0 ? n4 : 1);
-  k_loss_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)y, (const float4 *)t, n4, y + (n4 << 2), t + (n4 << 2),
+  launch_pdl(k_loss_partial, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const float4 *)y, (const float4 *)t, n4, y + (n4 << 2), t + (n4 << 2),
                                                            (int)(n & 3), kind, (float *)ws);
-  k_loss_finish<<<1, 256, 0, (cudaStream_t)stream>>>((const float *)ws, (int)blocks, 1.0f / (float)n, loss);
+  launch_pdl(k_loss_finish, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const float *)ws, (int)blocks, 1.0f / (float)n, loss);
   count_launch(2);
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -1028,7 +1064,7 @@ int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const floa
   SRB_REQUIRE(y && t && grad_loss && dy && n > 0 && (kind == 0 || kind == 1), SRB_EINVAL, "bad loss args");
   SRB_REQUIRE(((((uintptr_t)y) | ((uintptr_t)t) | ((uintptr_t)dy)) & 15) == 0, SRB_EUNSUPPORTED,
               "loss tensors must be 16-byte aligned");
-  k_loss_bwd<<<ew_blocks((n >> 2) > 0 ? (n >> 2) : 1), 256, 0, (cudaStream_t)stream>>>(y, t, n, kind, 1.0f / (float)n, grad_loss, dy);
+  launch_pdl(k_loss_bwd, dim3(ew_blocks((n >> 2) > 0 ? (n >> 2) : 1)), dim3(256), 0, (cudaStream_t)stream, y, t, n, kind, 1.0f / (float)n, grad_loss, dy);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -1038,7 +1074,7 @@ int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int
                         void *stream) {
   SRB_REQUIRE(src_nhwc && dst_nchw && N >= 0 && H > 0 && W > 0 && C > 0, SRB_EINVAL, "bad image_to_tensor args");
   if (N == 0) return SRB_OK;
-  k_image_to_tensor<<<ew_blocks((long long)N * C * H * W), 256, 0, (cudaStream_t)stream>>>(src_nhwc, dst_nchw, N, H, W, C, scale);
+  launch_pdl(k_image_to_tensor, dim3(ew_blocks((long long)N * C * H * W)), dim3(256), 0, (cudaStream_t)stream, src_nhwc, dst_nchw, N, H, W, C, scale);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -1051,7 +1087,7 @@ int srb_img_interp_bicubic(const float *x, float *y, int32_t N, int32_t C, int32
               "bad img_interp sizes");
   if (N == 0) return SRB_OK;  // empty batch: nothing to read or write (the buffers may be null)
   SRB_REQUIRE(x && y && bounds_w && coeffs_w && bounds_h && coeffs_h, SRB_EINVAL, "null img_interp buffer");
-  k_pil_bicubic<<<ew_blocks((long long)N * C * (TH - 2 * shave) * (TW - 2 * shave)), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(k_pil_bicubic, dim3(ew_blocks((long long)N * C * (TH - 2 * shave) * (TW - 2 * shave))), dim3(256), 0, (cudaStream_t)stream, 
       x, y, N, C, H, W, TH, TW, bounds_w, coeffs_w, bounds_h, coeffs_h, ksize, shave);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
@@ -1061,7 +1097,7 @@ int srb_img_interp_bicubic(const float *x, float *y, int32_t N, int32_t C, int32
 int srb_round_tf32(const float *x, float *y, int64_t n, void *stream) {
   SRB_REQUIRE(x && y && n >= 0, SRB_EINVAL, "bad round args");
   if (n == 0) return SRB_OK;
-  k_round_tf32<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  launch_pdl(k_round_tf32, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, y, n);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

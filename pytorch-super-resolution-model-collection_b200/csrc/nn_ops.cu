@@ -31,6 +31,8 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
 // BatchNorm2d, training mode, dense NHWC input (P pixels x C channels).  Block = 64 channels x 4 pixel lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, long long P, int C, double *__restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[2][4][64];
   const int tc = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + tc;
@@ -52,16 +54,48 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, l
   }
 }
 
+// Column sums of the [gx][2][C] double partials: block = 32 channels (x) x 16 row lanes (y).  Lane y adds rows y, y+16, ... with four
+// independent accumulators (the one-thread-per-channel loop this replaces walked up to 592 dependent L2 round trips: 52 us);
+// the 16 lanes are folded through shared memory in a fixed order, so the result does not depend on scheduling.
+constexpr int kBnFinLanes = 16;
+__device__ __forceinline__ void bn_partial_sums(const double *__restrict__ partial, int gx, int C, int c, double &s_out, double &q_out) {
+  __shared__ double fold[2][kBnFinLanes][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+  if (c < C) {
+    int b = ty;
+    for (; b + kBnFinLanes < gx; b += 2 * kBnFinLanes) {
+      s0 += partial[((size_t)b * 2 + 0) * C + c];
+      q0 += partial[((size_t)b * 2 + 1) * C + c];
+      s1 += partial[((size_t)(b + kBnFinLanes) * 2 + 0) * C + c];
+      q1 += partial[((size_t)(b + kBnFinLanes) * 2 + 1) * C + c];
+    }
+    if (b < gx) {
+      s0 += partial[((size_t)b * 2 + 0) * C + c];
+      q0 += partial[((size_t)b * 2 + 1) * C + c];
+    }
+  }
+  fold[0][ty][tx] = s0 + s1;
+  fold[1][ty][tx] = q0 + q1;
+  __syncthreads();
+  double s = 0.0, q = 0.0;
+  if (ty == 0) {
+#pragma unroll
+    for (int y = 0; y < kBnFinLanes; ++y) { s += fold[0][y][tx]; q += fold[1][y][tx]; }
+  }
+  s_out = s;
+  q_out = q;
+}
+
 // mean / biased variance from the partials (fixed order), running statistics updated like nn.BatchNorm2d (unbiased variance)
 __global__ void k_bn_finalize(const double *__restrict__ partial, int gx, int C, double count, float momentum, float eps,
                               float *running_mean, float *running_var, float *save_mean, float *save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < gx; ++b) {
-    s += partial[((size_t)b * 2 + 0) * C + c];
-    q += partial[((size_t)b * 2 + 1) * C + c];
-  }
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  bn_partial_sums(partial, gx, C, c, s, q);
+  if (c >= C || threadIdx.y != 0) return;
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -77,6 +111,8 @@ __global__ void k_bn_finalize(const double *__restrict__ partial, int gx, int C,
 // eval mode: statistics are the running ones
 __global__ void k_bn_eval_stats(const float *__restrict__ running_mean, const float *__restrict__ running_var, int C, float eps,
                                 float *save_mean, float *save_invstd) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   save_mean[c] = running_mean[c];
@@ -89,6 +125,8 @@ __global__ void __launch_bounds__(256) k_bn_apply(const float4 *__restrict__ x, 
                                                   const float4 *__restrict__ gamma, const float4 *__restrict__ beta, int act,
                                                   float slope_in, const float *__restrict__ alpha,
                                                   const float4 *__restrict__ residual, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const float slope = act == SRB_ACT_PRELU ? __ldg(alpha) : slope_in;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -113,6 +151,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(const float *__restrict__ 
                                                       const float *__restrict__ gamma, const float *__restrict__ beta, int act,
                                                       float slope_in, const float *__restrict__ alpha, double *__restrict__ partial,
                                                       double *__restrict__ alpha_partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[3][4][64];
   const float slope = act == SRB_ACT_PRELU ? __ldg(alpha) : slope_in;
   const int tc = threadIdx.x & 63, pl = threadIdx.x >> 6;
@@ -153,13 +193,13 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(const float *__restrict__ 
 __global__ void k_bn_bwd_finalize(const double *__restrict__ partial, int gx, int C, double count, float *dgamma, float *dbeta,
                                   float *mean_dz, float *mean_dzx, const double *__restrict__ alpha_partial, int n_alpha,
                                   float *dalpha, float scale, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  bn_partial_sums(partial, gx, C, c, s, q);
+  if (threadIdx.y != 0) return;
   if (c < C) {
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < gx; ++b) {
-      s += partial[((size_t)b * 2 + 0) * C + c];
-      q += partial[((size_t)b * 2 + 1) * C + c];
-    }
     mean_dz[c] = (float)(s / count);
     mean_dzx[c] = (float)(q / count);
     const float g = (float)q * scale, b2 = (float)s * scale;
@@ -180,6 +220,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float4 *__restrict__
                                                       const float4 *__restrict__ beta, const float4 *__restrict__ mean_dz,
                                                       const float4 *__restrict__ mean_dzx, int act, float slope_in,
                                                       const float *__restrict__ alpha, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   const float slope = act == SRB_ACT_PRELU ? __ldg(alpha) : slope_in;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -208,6 +250,8 @@ constexpr int kLinKC = 512;  // input features staged per step (16 x 512 floats 
 // forward partials: block = 8 warps x 4 outputs; grid (O / 32, K splits); partial[ks][b][o]
 __global__ void __launch_bounds__(256) k_linear_fwd(const float *__restrict__ x, const float *__restrict__ w, int B, int I, int O,
                                                     int k_per_split, float *__restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 xs[kLinB][kLinKC / 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o0 = blockIdx.x * 32 + warp * 4;
@@ -256,6 +300,8 @@ __global__ void __launch_bounds__(256) k_linear_fwd(const float *__restrict__ x,
 // y = act(sum_splits partial + bias): act 0 none, 3 lrelu(slope), 4 sigmoid
 __global__ void k_linear_fwd_finish(const float *__restrict__ partial, int splits, int B, int O, const float *__restrict__ bias,
                                     float *__restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * O) return;
   const int b = i / O, o = i - b * O;
@@ -268,6 +314,8 @@ __global__ void k_linear_fwd_finish(const float *__restrict__ partial, int split
 // dx[b, i] = sum_o dy[b, o] * w[o, i]: thread = one float4 of i, all batch rows; grid (I / 1024, O splits); partial[os][b][i]
 __global__ void __launch_bounds__(256) k_linear_dx(const float *__restrict__ dy, const float *__restrict__ w, int B, int I, int O,
                                                    int o_per_split, float *__restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float dys[];  // [o_per_split][kLinB]
   const int o0 = blockIdx.y * o_per_split, o1 = min(O, o0 + o_per_split);
   for (int e = threadIdx.x; e < (o1 - o0) * kLinB; e += 256) {
@@ -293,6 +341,8 @@ __global__ void __launch_bounds__(256) k_linear_dx(const float *__restrict__ dy,
 }
 
 __global__ void k_linear_dx_finish(const float4 *__restrict__ partial, int splits, int B, long long I4, float4 *__restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * I4) return;
   const long long b = i / I4, q = i - b * I4;
@@ -307,6 +357,8 @@ __global__ void k_linear_dx_finish(const float4 *__restrict__ partial, int split
 // dw[o, i] (=|+=) scale * sum_b dy[b, o] * x[b, i]; db[o] likewise.  Block = 32 outputs x 1024 inputs (thread = one float4 of i)
 __global__ void __launch_bounds__(256) k_linear_dw(const float *__restrict__ x, const float *__restrict__ dy, int B, int I, int O,
                                                    float *__restrict__ dw, float *__restrict__ db, float scale, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float dys[32][kLinB];
   const int o0 = blockIdx.y * 32;
   for (int e = threadIdx.x; e < 32 * kLinB; e += 256) {
@@ -343,6 +395,8 @@ __global__ void __launch_bounds__(256) k_linear_dw(const float *__restrict__ x, 
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void k_maxpool2_fwd(const float *__restrict__ x, float *__restrict__ y, unsigned char *__restrict__ idx, int N, int C,
                                int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -365,6 +419,8 @@ __global__ void k_maxpool2_fwd(const float *__restrict__ x, float *__restrict__ 
 
 __global__ void k_maxpool2_bwd(const float *__restrict__ dy, const unsigned char *__restrict__ idx, float *__restrict__ dx, int N, int C,
                                int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -387,6 +443,8 @@ __global__ void k_maxpool2_bwd(const float *__restrict__ dy, const unsigned char
 // BCELoss (mean): loss = -mean(t * log(y) + (1 - t) * log(1 - y)), logs clamped at -100 (ATen); one block (n is a batch size)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bce_fwd(const float *__restrict__ y, const float *__restrict__ t, int n, float *loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) {
@@ -404,6 +462,8 @@ __global__ void __launch_bounds__(256) k_bce_fwd(const float *__restrict__ y, co
 }
 
 __global__ void k_bce_bwd(const float *__restrict__ y, const float *__restrict__ t, int n, const float *__restrict__ g, float *dy) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float yy = y[i], tt = t[i];
@@ -441,16 +501,16 @@ int srb_bn_fwd(const float *x, float *y, int64_t P, int32_t C, const float *gamm
   if (training) {
     double *partial = (double *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const unsigned gx = bn_gx(P);
-    k_bn_stats<<<dim3(gx, (C + 63) / 64), 256, 0, st>>>(x, P, C, partial);
-    k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(partial, (int)gx, C, (double)P, momentum, eps, running_mean, running_var, save_mean,
+    launch_pdl(k_bn_stats, dim3(dim3(gx, (C + 63) / 64)), dim3(256), 0, st, x, P, C, partial);
+    launch_pdl(k_bn_finalize, dim3((C + 31) / 32), dim3(32, kBnFinLanes), 0, st, partial, (int)gx, C, (double)P, momentum, eps, running_mean, running_var, save_mean,
                                                    save_invstd);
     count_launch(2);
   } else {
-    k_bn_eval_stats<<<(C + 127) / 128, 128, 0, st>>>(running_mean, running_var, C, eps, save_mean, save_invstd);
+    launch_pdl(k_bn_eval_stats, dim3((C + 127) / 128), dim3(128), 0, st, running_mean, running_var, C, eps, save_mean, save_invstd);
     count_launch();
   }
   const long long n4 = P * C / 4;
-  k_bn_apply<<<nblocks(n4, 256 * 4), 256, 0, st>>>((const float4 *)x, (float4 *)y, n4, C / 4, (const float4 *)save_mean,
+  launch_pdl(k_bn_apply, dim3(nblocks(n4, 256 * 4)), dim3(256), 0, st, (const float4 *)x, (float4 *)y, n4, C / 4, (const float4 *)save_mean,
                                                     (const float4 *)save_invstd, (const float4 *)gamma, (const float4 *)beta, act, slope,
                                                     alpha, (const float4 *)residual, round_to_tf32);
   count_launch();
@@ -470,13 +530,13 @@ int srb_bn_bwd(const float *x, const float *dy, float *dx, int64_t P, int32_t C,
   double *partial = (double *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   double *apart = partial + (size_t)148 * 4 * 2 * C;
   float *means = (float *)(apart + (size_t)148 * 4 * gy);
-  k_bn_bwd_stats<<<dim3(gx, gy), 256, 0, st>>>(x, dy, P, C, save_mean, save_invstd, gamma, beta, act, slope, alpha, partial,
+  launch_pdl(k_bn_bwd_stats, dim3(dim3(gx, gy)), dim3(256), 0, st, x, dy, P, C, save_mean, save_invstd, gamma, beta, act, slope, alpha, partial,
                                                (act == SRB_ACT_PRELU && dalpha) ? apart : nullptr);
-  k_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, st>>>(partial, (int)gx, C, (double)P, dgamma, dbeta, means, means + C,
+  launch_pdl(k_bn_bwd_finalize, dim3((C + 31) / 32), dim3(32, kBnFinLanes), 0, st, partial, (int)gx, C, (double)P, dgamma, dbeta, means, means + C,
                                                      (act == SRB_ACT_PRELU && dalpha) ? apart : nullptr, (int)(gx * gy), dalpha, scale,
                                                      accumulate);
   const long long n4 = P * C / 4;
-  k_bn_bwd_apply<<<nblocks(n4, 256 * 4), 256, 0, st>>>((const float4 *)x, (const float4 *)dy, (float4 *)dx, n4, C / 4,
+  launch_pdl(k_bn_bwd_apply, dim3(nblocks(n4, 256 * 4)), dim3(256), 0, st, (const float4 *)x, (const float4 *)dy, (float4 *)dx, n4, C / 4,
                                                         (const float4 *)save_mean, (const float4 *)save_invstd, (const float4 *)gamma,
                                                         (const float4 *)beta, (const float4 *)means, (const float4 *)(means + C), act,
                                                         slope, alpha, round_to_tf32);
@@ -505,8 +565,8 @@ int srb_linear_fwd(const float *x, const float *w, const float *bias, float *y, 
   splits = (I + kps - 1) / kps;
   for (int b0 = 0; b0 < B; b0 += kLinB) {
     const int bn = B - b0 < kLinB ? B - b0 : kLinB;
-    k_linear_fwd<<<dim3(otiles, splits), 256, 0, st>>>(x + (size_t)b0 * I, w, bn, I, O, kps, partial);
-    k_linear_fwd_finish<<<(bn * O + 255) / 256, 256, 0, st>>>(partial, splits, bn, O, bias, y + (size_t)b0 * O);
+    launch_pdl(k_linear_fwd, dim3(dim3(otiles, splits)), dim3(256), 0, st, x + (size_t)b0 * I, w, bn, I, O, kps, partial);
+    launch_pdl(k_linear_fwd_finish, dim3((bn * O + 255) / 256), dim3(256), 0, st, partial, splits, bn, O, bias, y + (size_t)b0 * O);
     count_launch(2);
   }
   SRB_CHECK_CUDA(cudaGetLastError());
@@ -530,13 +590,13 @@ int srb_linear_bwd(const float *x, const float *w, const float *dy, float *dx, f
       if (ops > 512) ops = 512;  // shared memory: ops x 16 floats
       splits = (O + ops - 1) / ops;
       SRB_REQUIRE(splits <= 8, SRB_EUNSUPPORTED, "linear backward: more than 4096 output features");
-      k_linear_dx<<<dim3(itiles, splits), 256, (size_t)ops * kLinB * sizeof(float), st>>>(dy + (size_t)b0 * O, w, bn, I, O, ops, partial);
-      k_linear_dx_finish<<<(unsigned)(((long long)bn * (I / 4) + 255) / 256), 256, 0, st>>>((const float4 *)partial, splits, bn, I / 4,
+      launch_pdl(k_linear_dx, dim3(dim3(itiles, splits)), dim3(256), (size_t)ops * kLinB * sizeof(float), st, dy + (size_t)b0 * O, w, bn, I, O, ops, partial);
+      launch_pdl(k_linear_dx_finish, dim3((unsigned)(((long long)bn * (I / 4) + 255) / 256)), dim3(256), 0, st, (const float4 *)partial, splits, bn, I / 4,
                                                                                          (float4 *)(dx + (size_t)b0 * I));
       count_launch(2);
     }
     if (dw) {
-      k_linear_dw<<<dim3((I / 4 + 255) / 256, (O + 31) / 32), 256, 0, st>>>(x + (size_t)b0 * I, dy + (size_t)b0 * O, bn, I, O, dw, db, scale,
+      launch_pdl(k_linear_dw, dim3(dim3((I / 4 + 255) / 256, (O + 31) / 32)), dim3(256), 0, st, x + (size_t)b0 * I, dy + (size_t)b0 * O, bn, I, O, dw, db, scale,
                                                                            (accumulate || b0 > 0) ? 1 : 0);
       count_launch();
     }
@@ -547,7 +607,7 @@ int srb_linear_bwd(const float *x, const float *w, const float *dy, float *dx, f
 
 int srb_maxpool2_fwd(const float *x, float *y, uint8_t *idx, int32_t N, int32_t C, int32_t H, int32_t W, void *stream) {
   SRB_REQUIRE(x && y && idx && N > 0 && C > 0 && H >= 2 && W >= 2, SRB_EINVAL, "bad maxpool arguments");
-  k_maxpool2_fwd<<<nblocks((long long)N * (H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, idx, N, C, H, W);
+  launch_pdl(k_maxpool2_fwd, dim3(nblocks((long long)N * (H / 2) * (W / 2) * C, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, idx, N, C, H, W);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -556,7 +616,7 @@ int srb_maxpool2_fwd(const float *x, float *y, uint8_t *idx, int32_t N, int32_t 
 int srb_maxpool2_bwd(const float *dy, const uint8_t *idx, float *dx, int32_t N, int32_t C, int32_t H, int32_t W, void *stream) {
   SRB_REQUIRE(dy && dx && idx && N > 0 && C > 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0, SRB_EINVAL,
               "bad maxpool arguments (even H, W)");
-  k_maxpool2_bwd<<<nblocks((long long)N * (H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, idx, dx, N, C, H, W);
+  launch_pdl(k_maxpool2_bwd, dim3(nblocks((long long)N * (H / 2) * (W / 2) * C, 256)), dim3(256), 0, (cudaStream_t)stream, dy, idx, dx, N, C, H, W);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -564,7 +624,7 @@ int srb_maxpool2_bwd(const float *dy, const uint8_t *idx, float *dx, int32_t N, 
 
 int srb_bce_fwd(const float *y, const float *t, int32_t n, float *loss, void *stream) {
   SRB_REQUIRE(y && t && loss && n > 0, SRB_EINVAL, "bad BCE arguments");
-  k_bce_fwd<<<1, 256, 0, (cudaStream_t)stream>>>(y, t, n, loss);
+  launch_pdl(k_bce_fwd, dim3(1), dim3(256), 0, (cudaStream_t)stream, y, t, n, loss);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;
@@ -572,7 +632,7 @@ int srb_bce_fwd(const float *y, const float *t, int32_t n, float *loss, void *st
 
 int srb_bce_bwd(const float *y, const float *t, int32_t n, const float *grad_loss, float *dy, void *stream) {
   SRB_REQUIRE(y && t && grad_loss && dy && n > 0, SRB_EINVAL, "bad BCE arguments");
-  k_bce_bwd<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, t, n, grad_loss, dy);
+  launch_pdl(k_bce_bwd, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, y, t, n, grad_loss, dy);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

@@ -177,29 +177,7 @@ inline int encode_tiled(CUtensorMap *map, void *base, int rank, const cuuint64_t
 
 inline int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
 
-// Programmatic dependent launch (PDL).  Kernels on the hot path call pdl_trigger() first thing -- the NEXT kernel of the stream
-// may then be scheduled as soon as every CTA of this one has started, so its launch latency and prologue (barrier init, TMEM
-// allocation, shared-memory zeroing, tensor-map prefetch) overlap this kernel's execution -- and pdl_wait() before their first
-// access to global memory that an earlier kernel may still be writing or reading (it returns when all prerequisite grids have
-// completed and flushed; a no-op for kernels launched without the attribute).  Captured into CUDA graphs as programmatic edges.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 
 // cudaFuncSetAttribute is PER DEVICE: remember which devices of this process already carry the attributes of a kernel.
 // Two threads racing on the same device both set the (idempotent) attribute; the bit is published afterwards.

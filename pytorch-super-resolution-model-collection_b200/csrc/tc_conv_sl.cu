@@ -1563,6 +1563,9 @@ bool make_rs_plan(const Geom &g, RsPlan *pl) {
   if (a.R < g.kh + 1) return false;
   const long long IG = (g.N + G - 1) / G;
   a.total_rows = IG * CT * g.Ho;
+  // a CTA pays kh-1 halo rows and ~10 us of fixed cost per launch: small problems (EDSR-64 / SRGAN-G bodies: 2-3 rows per CTA)
+  // measured faster on the slot-linear kernel (19.7 vs 20.9 us)
+  if (a.total_rows < 148LL * 8 && !(g_sl_dbg & 1024)) return false;
   SlArgs &e = a.e;
   e.N = g.N; e.Ho = g.Ho; e.Wo = g.Wo; e.Co = g.Co; e.kh = g.kh; e.kw = g.kw; e.pad = g.pad; e.pad_w = g.pad;
   e.NT = NT; e.BW = BWs; e.ps = g.ps; e.rs = 1; e.MTB = 1; e.chunk_elems = 32;
@@ -1728,6 +1731,7 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
 
 int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transpose, const T4 &out, const Epi &epi_in,
                    void *ws, size_t ws_bytes, cudaStream_t st, const ConvOpt &opt) {
+  const PdlScope pdl_scope(2.0 * g.N * g.Ho * g.Wo * (double)g.Co * g.Ci * g.kh * g.kw < 2.0e10);
   {
     RsPlan rp;
     if (rs_usable(g, in, out, epi_in, opt, &rp)) return tc_conv_rs_launch(g, in, w, flip_transpose, out, epi_in, ws, ws_bytes, st, opt, rp);

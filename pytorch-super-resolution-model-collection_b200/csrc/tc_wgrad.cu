@@ -928,6 +928,7 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
                   int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps) {
   WgPlan pl;
   const bool bf = big.dt == SRB_BF16;
+  const PdlScope pdl_scope(2.0 * g.N * g.Ho * g.Wo * (double)g.Co * g.Ci * g.kh * g.kw < 2.0e10);
   SRB_REQUIRE(small.dt == big.dt, SRB_EINVAL, "tc_wgrad: x and dz must have one dtype");
   SRB_REQUIRE(make_wg_plan(g, &pl, bf, z_ps), SRB_EUNSUPPORTED, "tc_wgrad: no plan");
   size_t need = (pl.partial_floats + pl.db_floats + pl.xpack_floats) * sizeof(float) + 256;
