@@ -61,7 +61,7 @@ fi
 if has full; then
   # FULL_WL / FULL_K / FULL_SKIP / FULL_COUNT select the workload, kernel regex and launch window of the --set full capture
   WL=${FULL_WL:-espcn_x4_b128_lr64}
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${FULL_K:-k_conv_sl|k_tc_wgrad}" \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${FULL_K:-k_conv_rs|k_conv_sl|k_tc_wgrad}" \
       --launch-skip ${FULL_SKIP:-16} -c ${FULL_COUNT:-10} -f -o "$OUT/full_$WL" python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-graph > "$OUT/full_run.log" 2>&1
   echo "ncu full exit $?"
   ls -la "$OUT"

@@ -1,4 +1,4 @@
-"""Summarise an `ncu --set full` report of one ESPCN training step (k_conv_sl | k_tc_wgrad instances, in launch order)
+"""Summarise an `ncu --set full` report of one ESPCN training step (k_conv_rs | k_conv_sl | k_tc_wgrad instances, in launch order)
 into profiles/: a JSON keyed by "<C-ABI call>|<layer>" (bench.py reads `traffic` from it) and a markdown table.
 
     python tools/ncu_summary.py <report.ncu-rep> <tag>
@@ -44,7 +44,7 @@ for pos, r in enumerate(data):
         break
     call, layer = (("-", "launch %d" % pos) if GENERIC else ORDER[pos])
     name = r[ix["Kernel Name"]]
-    kern = "k_conv_sl" if "k_conv_sl" in name else ("k_tc_wgrad" if "k_tc_wgrad" in name else name[:30])
+    kern = next((k for k in ("k_conv_rs", "k_conv_sl", "k_tc_wgrad", "k_wgrad_finish") if k in name), name[:30])
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rd = f(r, "dram__bytes_read.sum") * scale.get(unit("dram__bytes_read.sum"), 1.0)
     wr = f(r, "dram__bytes_write.sum") * scale.get(unit("dram__bytes_write.sum"), 1.0)
