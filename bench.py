@@ -469,8 +469,12 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     net = srb200.models.MODELS[model_key](*margs)
     host.init_model(model_key, net)
     net.to(dev).train()
-    opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5, capturable=not a.no_graph)
     bucket = srb200.GradBucket(net, world_size=world)
+    if opt_key in ("espcn", "edsr") and not a.torch_optimizer:
+        # Adam (espcn.py:79, edsr.py:93) as ONE libsrb200 launch over the flat parameter / gradient / moment buffers
+        opt = srb200.FlatAdam(bucket, lr=1e-5, betas=(0.9, 0.999), eps=1e-8)
+    else:
+        opt = host.make_optimizer(opt_key, net.parameters(), lr=1e-5, capturable=not a.no_graph)
     lossf = host.loss_for(model_key, fused=True)
     # criterion evaluated inside the last conv's epilogue where the net allows it (ESPCN, SRCNN, EDSR), plain fused kernels else
     fwd_loss = srb200.FusedLoss(net, "l1" if loss_kind == "l1" else "mse") if not a.no_loss_fusion else (lambda x, t: lossf(net(x), t))
@@ -790,6 +794,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-loss-fusion", action="store_true", help="evaluate the criterion with the stand-alone loss kernels")
+    ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim's fused Adam instead of srb200.FlatAdam (ESPCN / EDSR)")
     ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
     ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")
     a = ap.parse_args()

@@ -141,6 +141,15 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
                         const srb_tensor4 *target, int loss_kind, const srb_tensor4 *y, const srb_tensor4 *dz, int dz_unshuffled,
                         float *loss, void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * torch.optim.Adam.step() (espcn.py:79,131; edsr.py:93,155; amsgrad off) as ONE launch over flat fp32 buffers: p, g, m, v hold all n
+ * parameters / gradients / first / second moments of the model back to back (srb200.FlatAdam builds them as views).  state[0] is the
+ * step count (float, device resident so that CUDA-graph replays advance it), state[1] scratch (both start at 0).  Same arithmetic
+ * as torch's fused Adam: g += wd*p; m += (g-m)(1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ */
+int srb_adam_step_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float *state, void *stream);
+
 /* x[i] *= *g for n contiguous floats unless *g == 1 (device scalar; the upstream gradient of a scalar loss). */
 int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream);
 

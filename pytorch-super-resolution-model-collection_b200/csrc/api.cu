@@ -443,6 +443,40 @@ __global__ void k_pil_bicubic(const float *__restrict__ x, float *__restrict__ y
   }
 }
 
+// torch.optim.Adam (espcn.py:79, edsr.py:93; amsgrad off) over FLAT buffers: every parameter, gradient and moment of the model is a
+// slice of one fp32 array (srb200.GradBucket / srb200.FlatAdam), so the whole optimizer is this one elementwise launch.
+// Same arithmetic and order as torch's fused implementation (fused_adam_utils.cuh adam_math, ADAM mode):
+//   g += wd * p;  m = m + (g - m) * (1 - b1);  v = b2 * v + (1 - b2) * g * g;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// state[0] = step count t (float, on the device: CUDA-graph replays advance it), state[1] = blocks finished (last block commits t+1).
+__global__ void __launch_bounds__(256) k_adam_flat(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                                   float *__restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                                                   float *state) {
+  pdl_trigger();
+  pdl_wait();
+  const float t = state[0] + 1.f;
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi += pi * wd;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const float done = atomicAdd(state + 1, 1.f);
+    if (done == (float)(gridDim.x - 1)) {  // every block has read state[0] (it read it before arriving here)
+      state[0] = t;
+      state[1] = 0.f;
+    }
+  }
+}
+
 inline unsigned ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -753,6 +787,18 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
   ConvOpt lo;
   lo.loss_out = loss;
   return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, (cudaStream_t)stream, lo);
+}
+
+int srb_adam_step_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float *state, void *stream) {
+  SRB_REQUIRE(p && g && m && v && state && n >= 0 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+              SRB_EINVAL, "bad Adam arguments");
+  if (n == 0) return SRB_OK;
+  launch_pdl(k_adam_flat, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long long)n, lr, beta1, beta2, eps, weight_decay,
+             state);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
 }
 
 int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream) {

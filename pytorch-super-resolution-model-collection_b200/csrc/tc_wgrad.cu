@@ -414,10 +414,16 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = lane_grp * 32 + lane;
     float *dst = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * ACC * 128 * a.acc_cols;
+    // The partial tile goes TMEM -> registers -> shared memory (the operand stages are idle: every MMA has completed) and
+    // leaves as a few asynchronous BULK stores (cp.async.bulk shared -> global), instead of 4-byte-granular per-thread
+    // stores that the kernel's exit then waits for.  Falls back to direct stores when the tile does not fit the stages.
+    const size_t dump_bytes = (size_t)ACC * 128 * a.acc_cols * sizeof(float);
+    const bool via_smem = dump_bytes <= (size_t)a.stages * stage_bytes && !(a.dbg & 128);
+    float *sdump = (float *)smem;
     for (int acc = 0; acc < ((a.dbg & 32) ? 0 : ACC); ++acc) {
       const int rl = a.rn ? 0 : acc / (a.SG * a.CIB);
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.acc_cols);
-      float *row = dst + ((size_t)acc * 128 + m) * a.acc_cols;
+      float *row = (via_smem ? sdump : dst) + ((size_t)acc * 128 + m) * a.acc_cols;
       for (int j0 = 0; j0 < a.acc_cols; j0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)j0, v);
@@ -429,6 +435,22 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         for (int j = 0; j < 16; j += 4)
           *(uint4 *)(row + j0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+    }
+    if (via_smem && !(a.dbg & 32)) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the bulk-copy engine
+      asm volatile("bar.sync 1, %0;" ::"r"(kWgThreads - 64) : "memory");  // the four epilogue warps
+      if (warp == 2 && elect_one()) {
+        const uint32_t sbase = smem_u32(sdump);
+        for (size_t off = 0; off < dump_bytes; off += 32768) {
+          const uint32_t nbytes = (uint32_t)(dump_bytes - off < 32768 ? dump_bytes - off : 32768);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((const char *)dst + off), "r"(sbase + (uint32_t)off),
+                       "r"(nbytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the shared memory must outlive the reads (and the writes this kernel's exit publishes)
+      }
+      __syncwarp();
     }
   }
 

@@ -12,6 +12,7 @@ from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBl
 from .convert import convert, PReLU, ConvTranspose2d, Conv2d
 from .ddp import GradBucket
 from .graphs import TrainStepGraphs
+from .optim import FlatAdam
 from . import nn_ops
 from .nn_ops import batch_norm_act, linear, max_pool2, bce_loss
 from . import models, host

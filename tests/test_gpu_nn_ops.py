@@ -217,3 +217,57 @@ def test_img_interp_full_size_properties():
     assert torch.equal(y[1], torch.full_like(y[1], float(int(0.5 * 255)) / 255.0))
     assert ((y * 255) - (y * 255).round()).abs().max().item() < 1e-3
     assert torch.equal(host.img_interp(x[5:7].clone(), 4), y[5:7])
+
+
+# ---- srb200.FlatAdam: torch.optim.Adam (espcn.py:79, edsr.py:93) as one launch over flat buffers -------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_flat_adam_matches_torch_adam(wd):
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.PReLU(), torch.nn.Conv2d(8, 4, 3, bias=False)).to(DEV)
+    ref = copy.deepcopy(net)
+    bucket = srb200.GradBucket(net, world_size=1, direct=False)
+    opt = srb200.FlatAdam(bucket, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    for (p, q) in zip(net.parameters(), ref.parameters()):
+        assert torch.equal(p, q)  # re-seating the parameters as views keeps their values
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(5):
+        x = torch.randn(2, 3, 9, 9, device=DEV, generator=gen)
+        bucket.begin_step()
+        ropt.zero_grad()
+        net(x).square().mean().backward()
+        ref(x).square().mean().backward()
+        opt.step()
+        ropt.step()
+        for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item()), (step, k)
+    assert opt.step_count == 5
+    sd = opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    rs = ropt.state_dict()["state"]
+    for i in range(len(list(net.parameters()))):
+        assert rel_l2(sd["state"][i]["exp_avg"], rs[i]["exp_avg"]) < 1e-4
+        assert rel_l2(sd["state"][i]["exp_avg_sq"], rs[i]["exp_avg_sq"]) < 1e-4  # the two nets' gradients differ at the 1e-6 level (cuDNN vs autograd order)
+
+
+@pytest.mark.gpu
+def test_flat_adam_is_graph_capturable_and_counts_replays():
+    torch.manual_seed(5)
+    lin = torch.nn.Conv2d(2, 2, 1).to(DEV)
+    bucket = srb200.GradBucket(lin, world_size=1, direct=False)
+    opt = srb200.FlatAdam(bucket, lr=1e-3)
+    bucket.flat.fill_(0.5)
+    opt.step()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            opt.step()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert opt.step_count == 4  # one eager step + three replays (the capture itself executes nothing): the counter lives on the device
