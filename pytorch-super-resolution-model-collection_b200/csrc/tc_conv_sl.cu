@@ -1080,18 +1080,21 @@ struct RsPart { uint32_t tcol, boff, idesc; };  // one MMA: D column, B row offs
 // the window of kh output-row blocks starting at TMEM column tc_lo; the very first MMA of the row is split -- the kh-1 older
 // blocks accumulate, the new block (tc_hi, met by filter row 0 = B row block kh-1) is overwritten.  Straight-line issue code.
 template <int KW>
-__device__ __forceinline__ void rs_issue_row_steady(int chunks, uint32_t a_st, uint32_t chunk16, uint32_t b_lo0, uint32_t bcs16, uint32_t tc_lo,
-                                                    uint32_t tc_hi, uint32_t id_full, uint32_t id_win1, uint32_t id_one, uint32_t boff_new) {
+__device__ __forceinline__ void rs_issue_row_steady(int chunks, int kv_last, uint32_t a_st, uint32_t chunk16, uint32_t b_lo0, uint32_t bcs16,
+                                                    uint32_t tc_lo, uint32_t tc_hi, uint32_t id_full, uint32_t id_win1, uint32_t id_one,
+                                                    uint32_t boff_new) {
   const uint64_t d_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SWIZZLE_128B, SBO 1024 B
   umma_tf32_ss(tc_lo, d_hi | (uint64_t)a_st, d_hi | (uint64_t)b_lo0, id_win1, 1u);
   umma_tf32_ss(tc_hi, d_hi | (uint64_t)a_st, d_hi | (uint64_t)(b_lo0 + boff_new), id_one, 0u);
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     const uint32_t ac = a_st + (uint32_t)c * chunk16, bc = b_lo0 + (uint32_t)(c * KW) * bcs16;
+    const int kv = c == chunks - 1 ? kv_last : 4;  // K steps (8 channels each) that exist in this chunk
 #pragma unroll
     for (int s = 0; s < KW; ++s) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
+        if (k4 >= kv) continue;
         if (s == 0 && k4 == 0) {
           if (c) umma_tf32_ss(tc_lo, d_hi | (uint64_t)ac, d_hi | (uint64_t)bc, id_full, 1u);
         } else {
@@ -1228,13 +1231,13 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_st = ((a_base16 + st * stage16) & 0x3FFF) | (1u << 16);
         // steady state: a full window of kh blocks that does not wrap around the TMEM ring, no partial last chunk
-        const bool steady = fresh && j >= kh - 1 && blk_lo + (uint32_t)kh <= R && a.kv_last == 4 && kh > 1;
+        const bool steady = fresh && j >= kh - 1 && blk_lo + (uint32_t)kh <= R && kh > 1;
         if (a.e.dbg & 4) {
         } else if (steady && kw == 3) {
-          rs_issue_row_steady<3>(a.chunks, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
+          rs_issue_row_steady<3>(a.chunks, a.kv_last, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
                                  id_full, id_win1, id_one, (uint32_t)(kh - 1) * nt8);
         } else if (steady && kw == 5) {
-          rs_issue_row_steady<5>(a.chunks, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
+          rs_issue_row_steady<5>(a.chunks, a.kv_last, a_st, chunk16, b_lo0, bcs16, tmem_u + blk_lo * (uint32_t)NT, tmem_u + blk_hi * (uint32_t)NT,
                                  id_full, id_win1, id_one, (uint32_t)(kh - 1) * nt8);
         } else {
           const int lo = j - (kh - 1) > 0 ? j - (kh - 1) : 0;

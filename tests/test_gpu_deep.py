@@ -193,12 +193,23 @@ def test_exact_mode_op_is_fp32_accurate(case):
     ("edsr", (3, 32, 2), (2, 3, 12, 12), "l1"),        # edsr.py:152-153
     ("vdsr", (3, 64, 3), (2, 3, 16, 16), "mse"),       # global residual after the last conv: must fall back, same numbers
 ])
-@pytest.mark.parametrize("math", ["auto", "bf16"])
+@pytest.mark.parametrize("math", ["auto", "bf16", "auto-rowstacked"])
 def test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, math):
     """srb200.FusedLoss (criterion + its backward + the pixel-un-shuffle inside the last conv's epilogue) against the same
     network with the stand-alone loss: loss value and every parameter gradient; and against the CPU oracle's loss."""
     assert torch.cuda.is_available()
     import torch.nn.functional as TF
+    if math == "auto-rowstacked":  # same contract on the row-stacked kernels (the planner skips them for test-sized tensors)
+        import ctypes
+        from srb200 import _lib
+        setf = _lib.lib.srb_debug_set_flags
+        setf.argtypes = [ctypes.c_int]
+        setf.restype = None
+        setf(1024 | 512)
+        try:
+            return test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, "auto")
+        finally:
+            setf(0)
     if math == "bf16" and name in ("espcn", "srcnn"):
         pytest.skip("bf16 storage is specified for the 64+-channel nets (cfg4); ESPCN/SRCNN keep fp32 storage")
     srb200.set_math(math)

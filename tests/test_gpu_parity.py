@@ -159,6 +159,41 @@ def _ref_op(x, w, b, alpha, res, k, s, p, act, ps):
 @pytest.mark.parametrize("math", ["fp32", "auto"])
 @pytest.mark.parametrize("cl", [False, True])
 def test_fused_conv_vs_oracle(case, math, cl):
+    _run_conv_case(case, math, cl)
+
+
+# The planner only picks the row-stacked kernels (k_conv_rs; wgrad with filter rows stacked along N) for layers that give every
+# CTA >= 8 rows, i.e. not for test-sized tensors: debug flag 1024 forces k_conv_rs wherever it is usable, 512 the stacked wgrad.
+#           Cin Cout k  s  p  act      res    ps  H   W   N
+SWEEP_RS = [c for c in SWEEP if c[3] == 1 and c[0] > 4] + [
+    (64, 32, 3, 1, 0, "relu", False, 1, 30, 60, 5),    # two images per M tile, odd batch (last tile half empty)
+    (48, 32, 3, 1, 2, None, False, 1, 28, 56, 3),      # dgrad-like full padding, partial last chunk (48 = 32 + 16 channels)
+    (40, 16, 3, 1, 1, "lrelu", False, 1, 17, 33, 4),   # three images per M tile, 8 channels in the last chunk
+    (40, 16, 3, 1, 1, None, True, 1, 17, 33, 4),       # the same with a residual (the reference never fuses act + residual)
+    (32, 3, 3, 1, 0, None, False, 4, 29, 58, 2),       # PixelShuffle(4) -> NCHW
+    (64, 64, 3, 1, 1, "prelu", False, 2, 16, 16, 8),   # PixelShuffle(2) -> NHWC, N = 4 * 64 * 3 > 256: not row-stacked, must still pass
+    (64, 64, 3, 1, 1, "relu", False, 1, 12, 300, 1),   # three column strips per row
+    (64, 16, 5, 1, 2, "relu", False, 1, 20, 40, 2),    # 5 x 5: N = 80
+    (32, 64, 3, 1, 1, "relu", False, 1, 70, 24, 6),    # long strips: the TMEM ring wraps many times (R = 8 blocks)
+    (64, 48, 3, 1, 1, None, False, 1, 40, 30, 4),      # NT = 48: ring of 10 blocks
+]
+
+
+@pytest.mark.parametrize("case", SWEEP_RS)
+def test_row_stacked_kernels_vs_oracle(case):
+    import ctypes
+    from srb200 import _lib
+    setf = _lib.lib.srb_debug_set_flags
+    setf.argtypes = [ctypes.c_int]
+    setf.restype = None
+    setf(1024 | 512)
+    try:
+        _run_conv_case(case, "auto", True)
+    finally:
+        setf(0)
+
+
+def _run_conv_case(case, math, cl):
     _need_gpu()
     srb200.set_math(math)
     Cin, Cout, k, s, p, act, res, ps, H, W, N = case

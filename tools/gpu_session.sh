@@ -35,7 +35,7 @@ if has ref; then
   cat "$OUT/bench_reference.json"
 fi
 if has cudnn; then
-  for wl in ${CUDNN_WL:-espcn_x4_b128_lr64 vdsr_b64_128 edsr256_x4_b32_lr32}; do
+  for wl in ${CUDNN_WL:-espcn_x4_b128_lr64 vdsr_b64_128 edsr64_x4_b32_lr32 edsr256_x4_b32_lr32}; do
     timeout 600 python bench.py --impl cudnn --workload $wl --steps 30 --warmup 5 > "$OUT/bench_cudnn_$wl.json" 2> "$OUT/bench_cudnn_$wl.err"
     echo "cudnn $wl exit $?"; cut -c1-400 "$OUT/bench_cudnn_$wl.json"
   done
@@ -45,7 +45,7 @@ if has peak; then
 fi
 if has sanitize; then
   # mbarrier / TMEM hand-shake protocols under racecheck + synccheck: a slice of the op sweep
-  SEL=${SAN_K:-"(test_fused_conv_vs_oracle and auto and True) or test_exact_mode_op"}
+  SEL=${SAN_K:-"(test_fused_conv_vs_oracle and auto and True) or test_exact_mode_op or test_golden_net"}
   timeout 420 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests -m gpu -x -q -k "$SEL" > "$OUT/sanitizer_racecheck.log" 2>&1
   echo "racecheck exit $?" >> "$OUT/sanitizer_racecheck.log"; tail -4 "$OUT/sanitizer_racecheck.log"
   timeout 420 compute-sanitizer --tool synccheck --print-limit 20 python -m pytest tests -m gpu -x -q -k "$SEL" > "$OUT/sanitizer_synccheck.log" 2>&1
