@@ -420,6 +420,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const size_t dump_bytes = (size_t)ACC * 128 * a.acc_cols * sizeof(float);
     const bool via_smem = dump_bytes <= (size_t)a.stages * stage_bytes && !(a.dbg & 128);
     float *sdump = (float *)smem;
+    // the other epilogue warps may still be summing the last band's dz tile out of these very stages (db_rows)
+    if (via_smem) asm volatile("bar.sync 1, %0;" ::"r"(kWgThreads - 64) : "memory");
     for (int acc = 0; acc < ((a.dbg & 32) ? 0 : ACC); ++acc) {
       const int rl = a.rn ? 0 : acc / (a.SG * a.CIB);
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * a.acc_cols);
