@@ -627,6 +627,7 @@ int srb_conv_uses_tensor_path(const srb_conv_params *p, int pass, int x_cl, int 
     if (gd.pad < 0) return 0;  // pad > k-1: srb_conv_dgrad takes the CUDA-core scatter kernel
     return (exact ? exact_conv_supported(gd, x) : tc_conv_supported(gd, y, x, true)) ? 1 : 0;
   }
+  if (!exact && g.st > 1) return tc_strided_wgrad_supported(g, y, x) ? 1 : 0;  // phase launches (strided.cu)
   return (exact ? exact_wgrad_supported(g) : tc_wgrad_supported(g, y, x)) ? 1 : 0;
 }
 
@@ -687,6 +688,7 @@ size_t srb_conv_workspace_bytes(const srb_conv_params *p, int pass) {
       if (c1 > b) b = c1;
       if (c2 > b) b = c2;
     }
+    if (g.st > 1 && !p->transposed) { const size_t c = tc_strided_wgrad_ws_bytes(g); if (c > b) b = c; }
     SkinnyWg sk;
     T4 cl{(float *)256, (long long)g.Hi * g.Wi * g.Ci, 1, (long long)g.Wi * g.Ci, g.Ci};  // would-be channels_last x
     if (skinny_wgrad_plan(p, g, cl, &sk) && sk.total > b) b = sk.total;
@@ -1007,6 +1009,8 @@ int srb_conv_wgrad(const srb_conv_params *p, const srb_tensor4 *x, const srb_ten
     }
     if (is_tf32_math(p->math) && tc_wgrad_supported(g, tdz, tx))
       return tc_conv_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
+    if (is_tf32_math(p->math) && g.st > 1 && tc_strided_wgrad_supported(g, tdz, tx))  // SRGAN D (srgan.py:54-63): st*st phase launches
+      return tc_strided_wgrad(g, tdz, tx, dw, db, scale, accumulate, ws, ws_bytes, st);
     SkinnyWg sk;
     uintptr_t wsp = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
     if (!accumulate && ws && skinny_wgrad_plan(p, g, tx, &sk) && wsp + sk.total <= (uintptr_t)ws + ws_bytes) {

@@ -202,8 +202,18 @@ int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16 = false);
 bool tc_wgrad_supported(const Geom &g, const T4 &small, const T4 &big, int z_ps = 1);
 size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16 = false, int z_ps = 1);
 // z_ps > 1: `small` holds PixelShuffle_r of dz (in y's layout); un-shuffled by the TMA traversal, dw/db come out in filter order
+// One input phase of a STRIDED convolution's weight gradient (strided.cu): the launch is a stride-1 wgrad between dz and the phase
+// image x[st*i + a, st*j + b]; its tap (tr, ts) is filter tap r = st * (tr - pad') + a + pad0, s = st * (ts - pad') + b + pad0 of the
+// kh0 x kw0 filter (taps outside the filter are computed and dropped).
+struct WgPhase {
+  int st, a, b, pad0, kh0, kw0;
+};
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
-                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps = 1);
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps = 1, const WgPhase *phase = nullptr);
+bool tc_strided_wgrad_supported(const Geom &g, const T4 &small, const T4 &big);
+size_t tc_strided_wgrad_ws_bytes(const Geom &g);
+int tc_strided_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale, int accumulate,
+                     void *ws, size_t ws_bytes, cudaStream_t st);
 
 
 // 3xTF32 split-operand mode (exact.cu): fp32-accurate results from the same tensor-core kernels.

@@ -138,6 +138,80 @@ int tc_strided_scatter(const Geom &g, const T4 &small, const float *w, const T4 
   return SRB_OK;
 }
 
+// (3) tc_strided_wgrad -- weight gradient of a strided Conv2d: with r - pad = st*d + a the tap reads phase image
+//     P_ab[i, j] = big[st*i + a, st*j + b] at (oy + d_r, ox + d_s): per phase a STRIDE-1 weight gradient between dz and a strided
+//     VIEW of x (T4 strides x st: the TMA map walks it directly), with the sub-filter d in [dmin, dmax] expressed as a k' x k' filter
+//     of padding pad' = -dmin (both taken as the maximum over the two axes and all phases; the surplus taps are computed and dropped
+//     by the finish kernel, which scatters the others to their place in the kh x kw filter).  st*st launches on k_tc_wgrad.
+namespace {
+struct WgradPhases {
+  Geom g2;      // the stride-1 geometry shared by all phases except Hi / Wi (set per phase)
+  int kp, padp;
+};
+bool plan_wgrad_phases(const Geom &g, WgradPhases *wp) {
+  const int st = g.st;
+  if (st < 2 || st > 4 || g.ps != 1) return false;
+  int dmin = 0, dmax = 0;
+  bool any = false;
+  for (int r = 0; r < (g.kh > g.kw ? g.kh : g.kw); ++r) {
+    const int q = r - g.pad;
+    const int d = q >= 0 ? q / st : -((-q + st - 1) / st);  // floor division
+    if (!any || d < dmin) dmin = d;
+    if (!any || d > dmax) dmax = d;
+    any = true;
+  }
+  if (dmin > 0) dmin = 0;  // keep pad' >= 0
+  wp->padp = -dmin;
+  wp->kp = dmax - dmin + 1;
+  if (wp->kp > 16) return false;
+  wp->g2 = Geom{g.N, g.Ci, 0, 0, g.Co, g.Ho, g.Wo, wp->kp, wp->kp, 1, wp->padp, 1};
+  return true;
+}
+}  // namespace
+
+bool tc_strided_wgrad_supported(const Geom &g, const T4 &small, const T4 &big) {
+  WgradPhases wp;
+  if (!plan_wgrad_phases(g, &wp)) return false;
+  if (big.dt != SRB_F32 || small.dt != SRB_F32 || g.Ci <= 4) return false;
+  for (int a = 0; a < g.st; ++a)
+    for (int b = 0; b < g.st; ++b) {
+      Geom g2 = wp.g2;
+      g2.Hi = a < g.Hi ? (g.Hi - a + g.st - 1) / g.st : 0;
+      g2.Wi = b < g.Wi ? (g.Wi - b + g.st - 1) / g.st : 0;
+      if (g2.Hi == 0 || g2.Wi == 0) return false;
+      if (!tc_wgrad_supported(g2, small, phase_view(big, g.st, a, b))) return false;
+    }
+  return true;
+}
+
+size_t tc_strided_wgrad_ws_bytes(const Geom &g) {
+  WgradPhases wp;
+  if (!plan_wgrad_phases(g, &wp)) return 0;
+  Geom g2 = wp.g2;
+  g2.Hi = (g.Hi + g.st - 1) / g.st;
+  g2.Wi = (g.Wi + g.st - 1) / g.st;
+  return tc_wgrad_ws_bytes(g2);
+}
+
+int tc_strided_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale, int accumulate,
+                     void *ws, size_t ws_bytes, cudaStream_t st) {
+  WgradPhases wp;
+  SRB_REQUIRE(plan_wgrad_phases(g, &wp), SRB_EUNSUPPORTED, "strided wgrad: no phase plan");
+  bool first = true;
+  for (int a = 0; a < g.st; ++a)
+    for (int b = 0; b < g.st; ++b) {
+      Geom g2 = wp.g2;
+      g2.Hi = (g.Hi - a + g.st - 1) / g.st;
+      g2.Wi = (g.Wi - b + g.st - 1) / g.st;
+      const WgPhase ph{g.st, a, b, g.pad, g.kh, g.kw};
+      // every phase sees the whole dz: the bias gradient comes from the first one only
+      int rc = tc_conv_wgrad(g2, small, phase_view(big, g.st, a, b), dw, first ? db_small : nullptr, scale, accumulate, ws, ws_bytes, st, 1, &ph);
+      if (rc) return rc;
+      first = false;
+    }
+  return SRB_OK;
+}
+
 size_t tc_strided_ws_bytes(const Geom &g) {
   size_t best = 0;
   GatherPhase gp;

@@ -54,6 +54,8 @@ struct WgArgs {
                           // An accumulator is (32-channel co block, s-group, ci block) and has acc_cols = kh*32 columns.
   int acc_cols;           // TMEM columns (= MMA N) per accumulator: NT, or kh*32 in rn mode
   int Hi;                 // input rows (rn: the bands tile the INPUT rows)
+  int ph_st, ph_a, ph_b, ph_pad0, ph_kh0, ph_kw0;  // ph_st > 0: this launch is one input phase of a strided conv (WgPhase): the
+                          // finish kernel scatters its taps into the kh0 x kw0 filter
   int dbg;                // debug knobs (srb_debug_set_flags): 2 = stages are TMA-loaded only once, 4 = no MMAs are issued
   int acc_off[kMaxAcc];   // A-descriptor offset (16-byte units) of accumulator j relative to the stage's x tile (host-computed)
   int acc_boff[kMaxAcc];  // B-descriptor offset (16-byte units) of accumulator j relative to the stage's dz view (rn: its co block)
@@ -572,7 +574,15 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
       const int col = e / nitems, jj = e - col * nitems;
       const int co2 = cot32 * 32 + col;
       if (co2 < a.Co) {
-        float *d = dw + (size_t)wg_filter_of(a, co2) * total_items + j0 + jj;
+        float *d;
+        if (a.ph_st > 0) {  // phase launch of a strided conv: launch tap (tr, ts) -> filter tap (r, s), or nothing
+          const int j = j0 + jj, ci = j / taps, tap = j - ci * taps, tr = tap / a.kw, ts = tap - tr * a.kw;
+          const int r = a.ph_st * (tr - a.pad) + a.ph_a + a.ph_pad0, s2 = a.ph_st * (ts - a.pad) + a.ph_b + a.ph_pad0;
+          if (r < 0 || r >= a.ph_kh0 || s2 < 0 || s2 >= a.ph_kw0) continue;
+          d = dw + (((size_t)co2 * a.Ci + ci) * a.ph_kh0 + r) * a.ph_kw0 + s2;
+        } else {
+          d = dw + (size_t)wg_filter_of(a, co2) * total_items + j0 + jj;
+        }
         const float t = tile[col * pitch + jj] * scale;
         *d = accumulate ? *d + t : t;
       }
@@ -949,7 +959,7 @@ size_t tc_wgrad_ws_bytes(const Geom &g, bool bf16, int z_ps) {
 }
 
 int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, float *db_small, float scale,
-                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps) {
+                  int accumulate, void *ws, size_t ws_bytes, cudaStream_t st, int z_ps, const WgPhase *phase) {
   WgPlan pl;
   const bool bf = big.dt == SRB_BF16;
   const PdlScope pdl_scope(2.0 * g.N * g.Ho * g.Wo * (double)g.Co * g.Ci * g.kh * g.kw < 2.0e10);
@@ -988,6 +998,11 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
     }
   }
   a.dbg = tc_conv_get_dbg();
+  a.ph_st = 0; a.ph_a = a.ph_b = a.ph_pad0 = a.ph_kh0 = a.ph_kw0 = 0;
+  if (phase) {
+    SRB_REQUIRE(!a.c4 && z_ps == 1, SRB_EUNSUPPORTED, "strided wgrad phases need the generic operand flavour");
+    a.ph_st = phase->st; a.ph_a = phase->a; a.ph_b = phase->b; a.ph_pad0 = phase->pad0; a.ph_kh0 = phase->kh0; a.ph_kw0 = phase->kw0;
+  }
   a.partial = (float *)wsp;
   float *db_part = a.partial + pl.partial_floats;
   a.db_part = db_small ? db_part : nullptr;
