@@ -93,8 +93,9 @@ def measure_srgan(ctx, a, workload, steps, warmup):
     for m in (G, D, FE):
         m.to(dev).train()
     go, do = host.make_srgan_optimizers(G, D, lr=1e-5, capturable=not a.no_graph)
-    bg = srb200.GradBucket(G, world_size=world) if world > 1 else None
-    bd = srb200.GradBucket(D, world_size=world) if world > 1 else None
+    # one GPU: plain autograd accumulation measured marginally faster than the flat buckets (16.8 vs 17.1 ms / iteration)
+    bg = srb200.GradBucket(G, world_size=world) if (world > 1 or a.bucket) else None
+    bd = srb200.GradBucket(D, world_size=world) if (world > 1 or a.bucket) else None
     gen = torch.Generator().manual_seed(1 + rank)
     host_x = [synth_images(batch, h, w, gen) for _ in range(3)]
     host_t = [synth_images(batch, 4 * h, 4 * w, gen) for _ in range(3)]
@@ -794,6 +795,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-loss-fusion", action="store_true", help="evaluate the criterion with the stand-alone loss kernels")
+    ap.add_argument("--bucket", action="store_true", help="SRGAN workload on one GPU: GradBuckets instead of ordinary autograd gradient accumulation")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim's fused Adam instead of srb200.FlatAdam (ESPCN / EDSR)")
     ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
     ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")

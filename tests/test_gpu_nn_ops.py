@@ -271,3 +271,33 @@ def test_flat_adam_is_graph_capturable_and_counts_replays():
         g.replay()
     torch.cuda.synchronize()
     assert opt.step_count == 4  # one eager step + three replays (the capture itself executes nothing): the counter lives on the device
+
+
+@pytest.mark.gpu
+def test_srgan_step_with_grad_buckets_matches_plain_autograd():
+    """srgan.py:256-310 with the flat gradient buckets (direct wgrad writes, modules applied several times before one backward:
+    D sees real, fake and fake again) against the same step with ordinary autograd accumulation: identical parameter updates."""
+    srb200.set_math("fp32")
+
+    def run(with_buckets):
+        torch.manual_seed(0)
+        G, D, FE = M.SRGANGenerator(3, 32, 2), M.SRGANDiscriminator(3, 16, 32), M.FeatureExtractor()
+        host.init_model("srgan", G); host.init_model("srgan", D)
+        for m in (G, D, FE):
+            m.to(DEV).train()
+        go, do = host.make_srgan_optimizers(G, D, lr=1e-3)
+        bg = srb200.GradBucket(G, world_size=1) if with_buckets else None
+        bd = srb200.GradBucket(D, world_size=1) if with_buckets else None
+        gen = torch.Generator().manual_seed(8)
+        lr_img, hr_img = torch.rand(4, 3, 8, 8, generator=gen).to(DEV), torch.rand(4, 3, 32, 32, generator=gen).to(DEV)
+        for _ in range(2):
+            dl, gl = host.srgan_step(G, D, FE, go, do, lr_img, hr_img, bucket_g=bg, bucket_d=bd)
+        if bg is not None:
+            bg.detach(); bd.detach()
+        return dl.item(), gl.item(), [p.detach().clone() for p in list(G.parameters()) + list(D.parameters())]
+
+    dl0, gl0, p0 = run(False)
+    dl1, gl1, p1 = run(True)
+    assert abs(dl0 - dl1) <= 1e-5 * abs(dl0) and abs(gl0 - gl1) <= 1e-5 * abs(gl0)
+    for a, b in zip(p0, p1):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1e-3, a.abs().max().item())
