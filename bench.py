@@ -104,8 +104,13 @@ def measure_srgan(ctx, a, workload, steps, warmup):
     dev_x = [srb200.image_to_tensor(t.to(dev)) for t in host_x]
     dev_t = [srb200.image_to_tensor(t.to(dev)) for t in host_t]
 
+    use_wcache = not a.no_weight_cache
+    if use_wcache:
+        srb200.enable_weight_cache(True)
+    repack = (lambda: srb200.repack_weights(dev)) if use_wcache else None
+
     def step(i):
-        return host.srgan_step(G, D, FE, go, do, dev_x[i], dev_t[i], bucket_g=bg, bucket_d=bd)
+        return host.srgan_step(G, D, FE, go, do, dev_x[i], dev_t[i], bucket_g=bg, bucket_d=bd, after_update=repack)
 
     for i in range(warmup):
         step(i % 3)
@@ -491,6 +496,10 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     dev_t = [srb200.image_to_tensor(t.to(dev)) for t in host_t]
     clip = host.VDSR_CLIP if model_key == "vdsr" else None
 
+    use_wcache = not a.no_weight_cache
+    if use_wcache:
+        srb200.enable_weight_cache(True)  # before the eager warm-up: that is when the cache entries are created
+
     def step(x, t):
         bucket.begin_step()
         loss = fwd_loss(x, t)
@@ -499,6 +508,8 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
         if clip is not None:
             torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
         opt.step()
+        if use_wcache:
+            srb200.repack_weights(dev)  # one launch re-packs every conv filter for the next step
         return loss
 
     graphs = {}
@@ -561,7 +572,8 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     for i in range(warmup):
         step(dev_x[i % 3], dev_t[i % 3])
     if not a.no_graph:
-        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)), clip_norm=clip, forward_loss=fwd_loss)
+        st = srb200.TrainStepGraphs(net, lossf, opt, bucket, slots=list(zip(dev_x, dev_t)), clip_norm=clip, forward_loss=fwd_loss,
+                                    weight_cache=use_wcache)
         graphs.update(stepper=st, launches=st.launches_per_step)
         for i in range(3):
             step_slot(i)
@@ -796,6 +808,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-loss-fusion", action="store_true", help="evaluate the criterion with the stand-alone loss kernels")
     ap.add_argument("--bucket", action="store_true", help="SRGAN workload on one GPU: GradBuckets instead of ordinary autograd gradient accumulation")
+    ap.add_argument("--no-weight-cache", action="store_true", help="re-pack every filter in front of its conv instead of one repack launch per step")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim's fused Adam instead of srb200.FlatAdam (ESPCN / EDSR)")
     ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
     ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")

@@ -150,6 +150,19 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
 int srb_adam_step_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float *state, void *stream);
 
+/*
+ * Opt-in packed-weight cache.  By default every srb_conv_fprop / srb_conv_dgrad / srb_conv_fprop_loss call re-packs its filter into
+ * the kernel's operand layout (a 3-8 us launch in front of the convolution).  After srb_weight_cache_enable(1) the packed copies
+ * persist in buffers the LIBRARY allocates (the one exception to "the caller owns all device memory"; released by
+ * srb_weight_cache_enable(0)), conv calls skip their pack launch, and the caller must call srb_weight_cache_repack(stream) after
+ * EVERY update of the weights (optimizer step, load_state_dict): one launch re-packs every cached filter.  Entries are created
+ * on first use outside stream capture (run one eager step before capturing a CUDA graph); a miss during capture falls back to the
+ * per-call pack.  Keyed by the filter's device pointer and layer geometry; math = EXACT never caches (its launches get temporaries).
+ */
+int srb_weight_cache_enable(int on);
+int srb_weight_cache_repack(void *stream);
+int srb_weight_cache_entries(void);
+
 /* x[i] *= *g for n contiguous floats unless *g == 1 (device scalar; the upstream gradient of a scalar loss). */
 int srb_scale_by_scalar(float *x, int64_t n, const float *g, int round_to_tf32, void *stream);
 

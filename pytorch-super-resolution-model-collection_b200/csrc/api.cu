@@ -725,6 +725,7 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
   int rc = make_geom(p, &g);
   if (rc) return rc;
   if (p->N == 0) return SRB_OK;  // empty batch: nothing to compute
+  const WeightCacheScope wc_scope(p->math != SRB_MATH_EXACT);  // `w` is the caller's filter: its packed copies may be cached
   SRB_REQUIRE(x && x->data && w && y && y->data, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(p->act != SRB_ACT_PRELU || alpha, SRB_EINVAL, "PReLU needs alpha");
   cudaStream_t st = (cudaStream_t)stream;
@@ -765,6 +766,7 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
+  const WeightCacheScope wc_scope(p->math != SRB_MATH_EXACT);  // `w` is the caller's filter: its packed copies may be cached
   SRB_REQUIRE(p->N > 0 && x && x->data && w && target && target->data && dz && dz->data && loss, SRB_EINVAL, "null tensor");
   SRB_REQUIRE(loss_kind == 0 || loss_kind == 1, SRB_EINVAL, "loss kind: 0 = MSE, 1 = L1");
   SRB_REQUIRE(!p->transposed && p->act == SRB_ACT_NONE && (is_tf32_math(p->math) || p->math == SRB_MATH_BF16), SRB_EUNSUPPORTED,
@@ -790,6 +792,10 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
   lo.loss_out = loss;
   return tc_conv_gather(g, tx, w, false, ty, e, ws, ws_bytes, (cudaStream_t)stream, lo);
 }
+
+int srb_weight_cache_enable(int on) { return tc_weight_cache_enable(on); }
+int srb_weight_cache_repack(void *stream) { return tc_weight_cache_repack((cudaStream_t)stream); }
+int srb_weight_cache_entries(void) { return tc_weight_cache_entries(); }
 
 int srb_adam_step_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float *state, void *stream) {
@@ -872,6 +878,7 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   int rc = make_geom(p, &g);
   if (rc) return rc;
   if (p->N == 0) return SRB_OK;
+  const WeightCacheScope wc_scope(p->math != SRB_MATH_EXACT);  // `w` is the caller's filter: its packed copies may be cached
   SRB_REQUIRE(dz && dz->data && w && dx && dx->data, SRB_EINVAL, "null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   T4 tdz = to_t4(dz), tdx = to_t4(dx);

@@ -194,6 +194,19 @@ bool tc_strided_scatter_supported(const Geom &g, const T4 &small, const T4 &big)
 int tc_strided_scatter(const Geom &g, const T4 &small, const float *w, const T4 &big, const Epi &epi, void *ws, size_t ws_bytes,
                        cudaStream_t st);
 size_t tc_strided_ws_bytes(const Geom &g);
+// Packed-weight cache (tc_conv_sl.cu): only filters handed in by the user (not the temporaries of the 3xTF32 mode) may be cached
+inline bool &weight_cache_scope_allowed() {
+  static thread_local bool allowed = false;
+  return allowed;
+}
+struct WeightCacheScope {
+  bool prev;
+  explicit WeightCacheScope(bool allow) : prev(weight_cache_scope_allowed()) { weight_cache_scope_allowed() = allow; }
+  ~WeightCacheScope() { weight_cache_scope_allowed() = prev; }
+};
+int tc_weight_cache_enable(int on);
+int tc_weight_cache_repack(cudaStream_t st);
+int tc_weight_cache_entries();
 void tc_conv_set_trace(long long *buf, long long max_ctas);
 void tc_conv_set_dbg(int flags);
 int tc_conv_get_dbg();

@@ -24,6 +24,8 @@
 // CTAs are sized for two per SM (<= 112 KB smem, <= 256 TMEM columns) so one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
 #include <string.h>
+#include <mutex>
+#include <vector>
 
 namespace srb {
 
@@ -1358,9 +1360,156 @@ __global__ void k_pack_w_rs(const float *__restrict__ w, float *__restrict__ out
   }
 }
 
+
+// ================================================================================================================================
+// Opt-in packed-weight cache (srb_weight_cache_enable / srb_weight_cache_repack).
+//
+// Every fprop / dgrad launch needs its filter in an operand layout that depends on the kernel flavour; by default a small pack
+// kernel in front of the conv writes it into the call's workspace (3-8 us per call plus a dependent-launch gap: 18 % of the
+// EDSR-256 bf16 step, 15 % of EDSR-64, 9 % of the SRGAN iteration).  With the cache enabled the packed copies persist in buffers
+// the LIBRARY allocates (the one exception to "torch owns all device memory"), conv calls skip their pack kernel, and the host
+// promises to call srb_weight_cache_repack(stream) after every weight update (optimizer step, load_state_dict): ONE launch
+// re-packs every cached filter from the current weights.  CUDA-graph friendly: entries are created during the eager warm-up
+// (cudaMalloc + table upload are not capturable; a miss during capture falls back to the per-call pack), the repack launch is
+// captured behind the optimizer.
+struct PackJob {
+  const float *w;
+  void *out;
+  int kind;  // 0: k_pack_w_sl (tf32)  1: k_pack_w_sl_h (bf16)  2: k_pack_w_rs  3: k_pack_w_c4
+  int Nn, Kk, kh, kw, Npad, chunks, flip, perm_C, perm_rr;
+  int NT, ntiles, spairs;
+  WMap wm;
+  long long total;  // elements of `out`
+};
+
+__device__ __forceinline__ void pack_job_element(const PackJob &j, long long i) {
+  if (j.kind == 2) {
+    const int kk = (int)(i & 31);
+    long long q = i >> 5;
+    const int n = (int)(q % j.Npad); q /= j.Npad;
+    const int rr = (int)(q % j.kh); q /= j.kh;
+    const int s = (int)(q % j.kw);
+    const int c = (int)(q / j.kw);
+    const int k = c * 32 + kk;
+    float v = 0.f;
+    if (n < j.Nn && k < j.Kk) v = round_tf32(wval(j.w, n, k, j.kh - 1 - rr, s, j.Nn, j.Kk, j.kh, j.kw, j.flip));
+    ((float *)j.out)[i] = v;
+  } else if (j.kind == 3) {
+    const int kblocks = j.kh * j.spairs;
+    const int k4 = (int)(i & 3), n8 = (int)((i >> 2) & 7), kh2 = (int)((i >> 5) & 1);
+    long long q = i >> 6;
+    const int ng = (int)(q % (j.NT / 8)); q /= (j.NT / 8);
+    const int kb = (int)(q % kblocks);
+    const int t = (int)(q / kblocks);
+    const int n = t * j.NT + ng * 8 + n8;
+    const int r = kb / j.spairs, sp = kb - r * j.spairs;
+    const int s = 2 * sp + kh2;
+    float v = 0.f;
+    if (n < j.Nn && k4 < j.Kk && s < j.kw) v = round_tf32(wval(j.w, n, k4, r, s, j.Nn, j.Kk, j.kh, j.kw, j.flip));
+    ((float *)j.out)[i] = v;
+  } else {
+    const int ce = j.kind == 1 ? 64 : 32, sh = j.kind == 1 ? 6 : 5;
+    const int taps = j.kh * j.kw;
+    const int kk = (int)(i & (ce - 1));
+    long long q = i >> sh;
+    const int n = (int)(q % j.Npad); q /= j.Npad;
+    const int tap = (int)(q % taps);
+    const int c = (int)(q / taps);
+    const int k = c * ce + kk;
+    float v = 0.f;
+    if (n < j.Nn && k < j.Kk) {
+      const int r = tap / j.kw, s = tap - r * j.kw;
+      v = j.wm.wmode ? wval_phase(j.w, j.wm, n, k, r, s, j.Nn, j.Kk) : wval(j.w, n, perm_k(k, j.perm_C, j.perm_rr), r, s, j.Nn, j.Kk, j.kh, j.kw, j.flip);
+    }
+    if (j.kind == 1) ((unsigned short *)j.out)[i] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xffffu);
+    else ((float *)j.out)[i] = round_tf32(v);
+  }
+}
+
+constexpr int kPackChunk = 256 * 16;  // elements of one job a block of the multi-job kernel handles
+// blk[b] = (job index, chunk index inside the job)
+__global__ void __launch_bounds__(256) k_pack_multi(const PackJob *__restrict__ jobs, const int2 *__restrict__ blk) {
+  pdl_trigger();
+  pdl_wait();
+  const int2 bj = blk[blockIdx.x];
+  const PackJob j = jobs[bj.x];
+  const long long i0 = (long long)bj.y * kPackChunk;
+  const long long i1 = i0 + kPackChunk < j.total ? i0 + kPackChunk : j.total;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) pack_job_element(j, i);
+}
+__global__ void __launch_bounds__(256) k_pack_one(PackJob j) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.total; i += (long long)gridDim.x * blockDim.x) pack_job_element(j, i);
+}
+
 long long *g_sl_trace = nullptr;
 long long g_sl_trace_ctas = 0;
 int g_sl_dbg = 0;
+
+struct WCacheDev {
+  std::vector<PackJob> jobs;
+  PackJob *d_jobs = nullptr;
+  int2 *d_blk = nullptr;
+  int n_blk = 0;
+};
+std::mutex g_wc_mu;
+bool g_wc_enabled = false;
+WCacheDev g_wc[64];
+
+inline bool wc_same(const PackJob &a, const PackJob &b) {
+  return a.w == b.w && a.kind == b.kind && a.Nn == b.Nn && a.Kk == b.Kk && a.kh == b.kh && a.kw == b.kw && a.Npad == b.Npad &&
+         a.chunks == b.chunks && a.flip == b.flip && a.perm_C == b.perm_C && a.perm_rr == b.perm_rr && a.NT == b.NT &&
+         a.ntiles == b.ntiles && a.spairs == b.spairs && memcmp(&a.wm, &b.wm, sizeof(WMap)) == 0 && a.total == b.total;
+}
+
+// (re)build the device tables of one device's cache; not capturable (called from the eager warm-up only)
+int wc_upload(WCacheDev &c) {
+  std::vector<int2> blk;
+  for (size_t j = 0; j < c.jobs.size(); ++j) {
+    const long long nchunks = (c.jobs[j].total + kPackChunk - 1) / kPackChunk;
+    for (long long q = 0; q < nchunks; ++q) blk.push_back(make_int2((int)j, (int)q));
+  }
+  if (c.d_jobs) SRB_CHECK_CUDA(cudaFree(c.d_jobs));
+  if (c.d_blk) SRB_CHECK_CUDA(cudaFree(c.d_blk));
+  c.d_jobs = nullptr; c.d_blk = nullptr; c.n_blk = 0;
+  if (c.jobs.empty()) return SRB_OK;
+  SRB_CHECK_CUDA(cudaMalloc(&c.d_jobs, c.jobs.size() * sizeof(PackJob)));
+  SRB_CHECK_CUDA(cudaMalloc(&c.d_blk, blk.size() * sizeof(int2)));
+  SRB_CHECK_CUDA(cudaMemcpy(c.d_jobs, c.jobs.data(), c.jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  SRB_CHECK_CUDA(cudaMemcpy(c.d_blk, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  c.n_blk = (int)blk.size();
+  return SRB_OK;
+}
+
+// Packed copy of job `t` (out unset): the cached buffer when the cache is on (created and packed now on a miss), else null.
+// A miss while the stream is capturing also returns null: the caller packs into its workspace as without the cache.
+int wc_lookup(PackJob t, size_t elem_bytes, cudaStream_t st, void **out) {
+  *out = nullptr;
+  if (!g_wc_enabled || !weight_cache_scope_allowed()) return SRB_OK;
+  int dev = 0;
+  SRB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return SRB_OK;
+  std::lock_guard<std::mutex> lk(g_wc_mu);
+  if (!g_wc_enabled) return SRB_OK;
+  WCacheDev &c = g_wc[dev];
+  for (const PackJob &j : c.jobs)
+    if (wc_same(j, t)) { *out = j.out; return SRB_OK; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  SRB_CHECK_CUDA(cudaStreamIsCapturing(st, &cs));
+  if (cs != cudaStreamCaptureStatusNone) return SRB_OK;
+  SRB_CHECK_CUDA(cudaMalloc(&t.out, (size_t)t.total * elem_bytes + 256));
+  c.jobs.push_back(t);
+  int rc = wc_upload(c);
+  if (rc) return rc;
+  int blocks = (int)((t.total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_pack_one<<<blocks, 256, 0, st>>>(t);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  *out = t.out;
+  return SRB_OK;
+}
 
 struct SlPlan {
   SlArgs a;
@@ -1613,12 +1762,23 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
     epi.loss_part = (float *)(((uintptr_t)wp + wpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
   }
   {
-    const long long total = (long long)wpack_floats;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    launch_pdl(k_pack_w_rs, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
-    count_launch();
-    SRB_CHECK_CUDA(cudaGetLastError());
+    PackJob job;
+    memset(&job, 0, sizeof(job));
+    job.w = w; job.kind = 2; job.Nn = g.Co; job.Kk = g.Ci; job.kh = g.kh; job.kw = g.kw; job.Npad = pl.Npad; job.chunks = a.chunks;
+    job.flip = flip_transpose ? 1 : 0; job.total = (long long)wpack_floats;
+    void *cached = nullptr;
+    int rc_c = wc_lookup(job, 4, st, &cached);
+    if (rc_c) return rc_c;
+    if (cached) {
+      wp = (float *)cached;
+    } else {
+      const long long total = (long long)wpack_floats;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      launch_pdl(k_pack_w_rs, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0);
+      count_launch();
+      SRB_CHECK_CUDA(cudaGetLastError());
+    }
   }
   CUtensorMap mapA, mapB;
   {  // (C, W, N, H): a box of {32, BWs, G, 1} lands as [image][slot][32 ch] = one M tile row
@@ -1667,6 +1827,48 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
 void tc_conv_set_trace(long long *buf, long long max_ctas) { g_sl_trace = buf; g_sl_trace_ctas = max_ctas; }
 void tc_conv_set_dbg(int flags) { g_sl_dbg = flags; }
 int tc_conv_get_dbg() { return g_sl_dbg; }
+
+int tc_weight_cache_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_wc_mu);
+  g_wc_enabled = on != 0;
+  if (!on) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+      WCacheDev &c = g_wc[d];
+      if (c.jobs.empty() && !c.d_jobs) continue;
+      cudaSetDevice(d);
+      cudaDeviceSynchronize();
+      for (PackJob &j : c.jobs) cudaFree(j.out);
+      c.jobs.clear();
+      if (c.d_jobs) cudaFree(c.d_jobs);
+      if (c.d_blk) cudaFree(c.d_blk);
+      c.d_jobs = nullptr; c.d_blk = nullptr; c.n_blk = 0;
+    }
+    cudaSetDevice(cur);
+  }
+  return SRB_OK;
+}
+
+int tc_weight_cache_repack(cudaStream_t st) {
+  int dev = 0;
+  SRB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return SRB_OK;
+  std::lock_guard<std::mutex> lk(g_wc_mu);
+  WCacheDev &c = g_wc[dev];
+  if (!g_wc_enabled || c.n_blk == 0) return SRB_OK;
+  k_pack_multi<<<c.n_blk, 256, 0, st>>>(c.d_jobs, c.d_blk);
+  count_launch();
+  SRB_CHECK_CUDA(cudaGetLastError());
+  return SRB_OK;
+}
+
+int tc_weight_cache_entries() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  std::lock_guard<std::mutex> lk(g_wc_mu);
+  return (int)g_wc[dev].jobs.size();
+}
 
 bool tc_conv_supported(const Geom &g, const T4 &in, const T4 &out, bool /*dgrad*/, int in_ps, int /*pad_w*/) {
   if (g.st != 1 || g.N <= 0) return false;
@@ -1797,17 +1999,28 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
 
   // 1. operands: weights (and, for c4, the NHWC4 image)
   {
+    PackJob job;
+    memset(&job, 0, sizeof(job));
+    job.w = w; job.kind = a.c4 ? 3 : (bf_in ? 1 : 0);
+    job.Nn = g.Co; job.Kk = g.Ci; job.kh = g.kh; job.kw = g.kw; job.Npad = pl.Npad; job.chunks = a.chunks; job.flip = flip_transpose ? 1 : 0;
+    job.perm_C = perm_C; job.perm_rr = perm_rr; job.NT = a.NT; job.ntiles = pl.n_tiles_n; job.spairs = a.spairs; job.wm = wm;
+    job.total = a.c4 ? (long long)pl.wpack_floats : (long long)a.chunks * g.kh * g.kw * pl.Npad * (bf_in ? 64 : 32);
+    void *cached = nullptr;
+    int rc_c = wc_lookup(job, bf_in ? 2 : 4, st, &cached);
+    if (rc_c) return rc_c;
+    if (cached) wp = (float *)cached;
     const long long total = (long long)pl.wpack_floats;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (a.c4)
+    if (cached) {
+    } else if (a.c4)
       launch_pdl(k_pack_w_c4, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, a.NT, pl.n_tiles_n, a.spairs, flip_transpose ? 1 : 0);
     else if (bf_in)
       launch_pdl(k_pack_w_sl_h, dim3(blocks), dim3(256), 0, st, w, (unsigned short *)wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0,
                                             perm_C, perm_rr, wm);
     else
       launch_pdl(k_pack_w_sl, dim3(blocks), dim3(256), 0, st, w, wp, g.Co, g.Ci, g.kh, g.kw, pl.Npad, a.chunks, flip_transpose ? 1 : 0, perm_C, perm_rr, wm);
-    count_launch();
+    if (!cached) count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
     if (a.c4) {
       const long long px = (long long)g.N * g.Hi * g.Wi;

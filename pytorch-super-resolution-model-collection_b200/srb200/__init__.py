@@ -6,7 +6,7 @@ Importing this package loads libsrb200.so; if the CUDA library is not built the 
 from . import _lib  # noqa: F401  (raises ImportError when the engine is missing)
 from ._lib import launch_count, SrbError, LIB_PATH
 from . import functional
-from .functional import conv2d, conv_transpose2d, prelu, set_math, get_math, set_grad_scale, set_fuse_relu_backward, mse_loss, l1_loss, image_to_tensor, conv2d_loss
+from .functional import conv2d, conv_transpose2d, prelu, set_math, get_math, set_grad_scale, set_fuse_relu_backward, mse_loss, l1_loss, image_to_tensor, conv2d_loss, enable_weight_cache, repack_weights, weight_cache_entries
 from . import base_networks
 from .base_networks import DenseBlock, ConvBlock, DeconvBlock, ResnetBlock, PSBlock, Upsample2xBlock, prepare, FusedLoss
 from .convert import convert, PReLU, ConvTranspose2d, Conv2d

@@ -45,6 +45,9 @@ SYMBOLS = {
     "srb_conv_fprop_loss": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _vp, _P(Tensor4), ctypes.c_int, _P(Tensor4),
                                            _P(Tensor4), ctypes.c_int, _vp, _vp, ctypes.c_size_t, _vp]),
     "srb_scale_by_scalar": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
+    "srb_weight_cache_enable": (ctypes.c_int, [ctypes.c_int]),
+    "srb_weight_cache_repack": (ctypes.c_int, [_vp]),
+    "srb_weight_cache_entries": (ctypes.c_int, []),
     "srb_adam_step_flat": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                           ctypes.c_float, _vp, _vp]),
     "srb_act_bwd": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _P(Tensor4), _vp, _vp]),

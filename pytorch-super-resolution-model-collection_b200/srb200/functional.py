@@ -54,6 +54,23 @@ def _record(y, residual=None):
             rec.append(((y - residual) if residual is not None else y) > 0)
 
 
+def enable_weight_cache(on=True):
+    """Opt-in packed-weight cache of libsrb200 (include/srb200.h: srb_weight_cache_enable): conv calls stop re-packing their
+    filters; call `repack_weights()` after EVERY weight update (optimizer.step(), load_state_dict, manual edits).
+    `srb200.TrainStepGraphs(..., weight_cache=True)` does both."""
+    check(lib.srb_weight_cache_enable(1 if on else 0))
+
+
+def repack_weights(device=None):
+    """Refresh every cached packed filter from the current weights: one launch on the current stream."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    check(lib.srb_weight_cache_repack(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
+
+def weight_cache_entries():
+    return int(lib.srb_weight_cache_entries())
+
+
 def set_fuse_relu_backward(on):
     """Fold a ReLU layer's threshold_backward into the dgrad epilogue of its consumer conv (default on).
 

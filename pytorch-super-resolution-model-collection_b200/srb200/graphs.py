@@ -24,8 +24,16 @@ from . import _lib
 
 
 class TrainStepGraphs:
-    def __init__(self, net, loss_fn, optimizer, bucket, slots, clip_norm=None, capture_allreduce=True, forward_loss=None):
+    def __init__(self, net, loss_fn, optimizer, bucket, slots, clip_norm=None, capture_allreduce=True, forward_loss=None,
+                 weight_cache=False):
         self.net, self.loss_fn, self.opt, self.bucket = net, loss_fn, optimizer, bucket
+        # weight_cache: libsrb200 keeps the packed filters of every conv layer and this stepper re-packs them all with ONE launch
+        # behind optimizer.step() (captured into the optimizer graph) instead of one pack launch in front of every conv.
+        # Enable it (srb200.enable_weight_cache()) BEFORE the eager warm-up steps: cache entries cannot be created during capture.
+        self.weight_cache = bool(weight_cache)
+        if self.weight_cache:
+            from . import functional as F
+            F.enable_weight_cache(True)
         # forward_loss(x, t) -> loss replaces loss_fn(net(x), t) (e.g. srb200.FusedLoss: criterion inside the last conv's epilogue)
         self.forward_loss = forward_loss if forward_loss is not None else (lambda x, t: loss_fn(net(x), t))
         self.slots = list(slots)
@@ -64,7 +72,13 @@ class TrainStepGraphs:
         if self.clip_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.clip_norm)
         self.opt.step()
+        self._repack()
         return loss
+
+    def _repack(self):
+        if self.weight_cache:
+            from . import functional as F
+            F.repack_weights(self.dev)
 
     def _capture_once(self, with_comm):
         side = torch.cuda.Stream(device=self.dev)
@@ -91,6 +105,7 @@ class TrainStepGraphs:
                 if self.clip_norm is not None:
                     torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.clip_norm)
                 self.opt.step()
+                self._repack()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.fwd_bwd, self.tail, self.losses = fwd_bwd, tail, losses

@@ -118,9 +118,10 @@ def make_srgan_optimizers(G, D, lr=1e-5, capturable=False):
             torch.optim.SGD(dp, lr=lr / 100, momentum=0.9, nesterov=True, **fused))
 
 
-def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=None):
+def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=None, after_update=None):
     """One adversarial iteration as written in srgan.py:256-310 (labels shaped like the decision; `.data` -> `.detach()`).
     With GradBuckets (data parallel) the D gradients are exchanged before D's step and the G gradients before G's step.
+    `after_update` is called after each of the two optimizer steps (packed-weight cache: srb200.repack_weights).
     Returns (D_loss, G_loss), detached device scalars."""
     from . import functional as F
     from . import nn_ops
@@ -143,6 +144,8 @@ def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=N
     if bucket_d is not None:
         bucket_d.all_reduce()
     d_opt.step()
+    if after_update is not None:
+        after_update()  # e.g. srb200.repack_weights: the generator phase below already runs through the UPDATED discriminator
     # ---- generator (srgan.py:290-310); D's gradients are computed again and cleared by the next iteration's zero_grad
     if bucket_g is not None:
         bucket_g.begin_step()
@@ -160,6 +163,8 @@ def srgan_step(G, D, FE, g_opt, d_opt, lr_img, hr_img, bucket_g=None, bucket_d=N
     if bucket_g is not None:
         bucket_g.all_reduce()
     g_opt.step()
+    if after_update is not None:
+        after_update()
     return D_loss.detach(), G_loss.detach()
 
 

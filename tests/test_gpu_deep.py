@@ -245,3 +245,48 @@ def test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, mat
     for k in g_u:
         assert rel_l2(g_f[k], g_u[k]) < tol, k
     assert abs(l_f - lossf(yref, tgt).item()) < (3e-2 if math == "bf16" else 2e-3) * abs(l_u)
+
+
+# ---- opt-in packed-weight cache (srb_weight_cache_enable / _repack) ----------------------------------------------------------------
+@pytest.mark.parametrize("name,args,xshape,math", [("espcn", (3, 64, 4), (3, 3, 20, 22), "auto"), ("edsr", (3, 32, 2), (2, 3, 12, 12), "auto"),
+                                                   ("edsr", (3, 64, 2), (2, 3, 12, 12), "bf16"), ("srgan_d", (3, 16, 32), (2, 3, 32, 32), "auto"),
+                                                   ("fsrcnn", (3, 4, 56, 12, 4), (2, 3, 20, 20), "auto")])
+def test_weight_cache_training_matches_uncached(name, args, xshape, math):
+    """Three SGD steps with the packed-weight cache (one repack launch after each update) against the same steps without it:
+    identical losses and parameters -- the cached filters follow the weights -- and a stale cache is detectably different."""
+    assert torch.cuda.is_available()
+    srb200.set_math(math)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(xshape, generator=gen).to(DEV)
+
+    def run(cached, repack=True):
+        torch.manual_seed(0)
+        net = M.MODELS[name](*args)
+        srb200.host.init_model(name if name != "srgan_d" else "srgan", net)
+        net.to(DEV).train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.05)
+        srb200.enable_weight_cache(cached)
+        losses = []
+        try:
+            for _ in range(3):
+                opt.zero_grad()
+                loss = net(x).float().square().mean()
+                loss.backward()
+                opt.step()
+                if cached and repack:
+                    srb200.repack_weights(DEV)
+                losses.append(loss.item())
+            n_entries = srb200.weight_cache_entries()
+        finally:
+            srb200.enable_weight_cache(False)
+        return losses, [p.detach().clone() for p in net.parameters()], n_entries
+
+    l0, p0, n0 = run(False)
+    l1, p1, n1 = run(True)
+    assert n0 == 0 and n1 > 0
+    assert l0 == l1
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
+    l2, _, _ = run(True, repack=False)  # the contract matters: without the repack the convs keep using the first step's filters
+    if name != "fsrcnn":  # (FSRCNN's 1e-4 deconv init makes its gradients ~1e-10: three steps do not move the loss at all)
+        assert l2[0] == l0[0] and l2[2] != l0[2]
