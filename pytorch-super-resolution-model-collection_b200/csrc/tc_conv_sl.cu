@@ -1552,6 +1552,8 @@ bool make_sl_plan(const Geom &g, SlPlan *pl, bool bf16 = false, int in_ps = 1) {
     const int col_cap = ctas == 2 ? 256 : 512;
     for (int t_bufs = 2; t_bufs >= 1; --t_bufs) {
       for (int MTB = (col_cap / (t_bufs * NT) < 4 ? col_cap / (t_bufs * NT) : 4); MTB >= 1; --MTB) {
+        if ((g_sl_dbg & 8192) && MTB > 1) continue;   // debug: force the smallest bands
+        if ((g_sl_dbg & 16384) && MTB > 2) continue;
         for (int wsplit = 1; wsplit <= 16; ++wsplit) {
           const int TW = (g.Wo + wsplit - 1) / wsplit;
           const int BW = TW + kextra;

@@ -9,7 +9,9 @@ from srb200 import _lib
 
 LAYERS = [("espcn L2 64->32", 128, 64, 60, 60, 32, 3, 0, 1, "relu"), ("espcn L2d 32->64", 128, 32, 58, 58, 64, 3, 2, 1, None),
           ("espcn L3 32->48 PS4", 128, 32, 58, 58, 3, 3, 0, 4, None), ("vdsr body 64->64", 64, 64, 128, 128, 64, 3, 1, 1, "relu"),
-          ("edsr64 body", 32, 64, 32, 32, 64, 3, 1, 1, "relu"), ("espcn L3d 48->32", 128, 48, 56, 56, 32, 3, 2, 1, None)]
+          ("edsr64 body", 32, 64, 32, 32, 64, 3, 1, 1, "relu"), ("espcn L3d 48->32", 128, 48, 56, 56, 32, 3, 2, 1, None),
+          ("srgan G body b16", 16, 64, 32, 32, 64, 3, 1, 1, "relu"), ("srgan D 128->128 64^2", 16, 128, 64, 64, 128, 3, 1, 1, "lrelu"),
+          ("srgan D 256->256 32^2", 16, 256, 32, 32, 256, 3, 1, 1, "lrelu"), ("edsr64 up 64->256 ps2", 32, 64, 32, 32, 64, 3, 1, 2, None)]
 
 def timeit(f, n=10, reps=5):
     """GPU time per call: n calls captured into one CUDA graph (no host launch overhead), best of `reps` replays."""
