@@ -809,6 +809,7 @@ def main():
     ap.add_argument("--no-loss-fusion", action="store_true", help="evaluate the criterion with the stand-alone loss kernels")
     ap.add_argument("--bucket", action="store_true", help="SRGAN workload on one GPU: GradBuckets instead of ordinary autograd gradient accumulation")
     ap.add_argument("--no-weight-cache", action="store_true", help="re-pack every filter in front of its conv instead of one repack launch per step")
+    ap.add_argument("--debug-flags", type=int, default=0, help="libsrb200 debug / A-B knobs (srb_debug_set_flags; see csrc/tc_conv_sl.cu)")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim's fused Adam instead of srb200.FlatAdam (ESPCN / EDSR)")
     ap.add_argument("--no-sub", action="store_true", help="skip the VDSR cfg3 sub-result (extra key of the default run)")
     ap.add_argument("--variants", default=None, help="--impl cudnn: comma list of as-is,tuned,tuned-cl,tuned-cl-graph,tuned-cl-bf16-graph")
@@ -834,6 +835,12 @@ def main():
         return 0
 
     ctx.init_cuda()
+    if a.debug_flags:
+        import ctypes
+        from srb200 import _lib as _l
+        _l.lib.srb_debug_set_flags.argtypes = [ctypes.c_int]
+        _l.lib.srb_debug_set_flags.restype = None
+        _l.lib.srb_debug_set_flags(a.debug_flags)
     if os.environ.get("SRB_BENCH_DEBUG"):
         torch._C._set_print_stack_traces_on_fatal_signal(True)  # C++ backtrace on SIGSEGV/SIGABRT (debugging aid)
     if a.impl == "cudnn":

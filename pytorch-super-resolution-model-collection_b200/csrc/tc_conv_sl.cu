@@ -31,7 +31,10 @@ namespace srb {
 
 namespace {
 
-constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two CTAs per SM)
+constexpr int kThreadsWide = 576;  // the same with 16 epilogue warps: one CTA per SM, four epilogue warps per TMEM lane quadrant.
+                                   // The store-bound layers (Cin <= 4 edges writing 64 channels, bf16 bodies) were limited by the
+                                   // number of stores in flight: VDSR 3->64 at 128^2 ran at 1.6 TB/s with 8 epilogue warps per SM
 constexpr int kRsEpiPerQuadFwd = 4;  // == kRsEpiPerQuad of k_conv_rs (declared further down)
 constexpr int kMaxLossCtas = 1024;  // fused loss: per-warp partial sums of at most this many CTAs
 constexpr int kMaxBStages = 8;
@@ -375,7 +378,7 @@ __device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t tr
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_items_h(const SlArgs &a, uint32_t trow, uint32_t bias_saddr, int half, int mtb, int m,
-                                                 int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid) {
+                                                 int n, int n0, int oy0, int ox0, int rows_valid, int cols_valid, int istep = 2) {
   typedef unsigned short bf;
   const int act = a.epi.act;
   const float slope = (act == SRB_ACT_PRELU) ? __ldg(a.epi.alpha) : a.epi.slope;
@@ -389,7 +392,7 @@ __device__ __forceinline__ void epilogue_items_h(const SlArgs &a, uint32_t trow,
   const bf *pr = nullptr;
   int pixw = 0;
 #pragma unroll 1
-  for (int item = half; item < mtb * ngroups; item += 2) {
+  for (int item = half; item < mtb * ngroups; item += istep) {
     const int t = item / ngroups, j0 = (item - t * ngroups) * COLS;
     if (t != t_cur) {
       t_cur = t;
@@ -606,7 +609,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Persistent: CTA (x, y) walks bands x, x + gridDim.x, ... of N tile y.  Every ring (A chunk buffers, B stages, TMEM
 // accumulator buffers) is tracked by a running counter, so the TMA producer runs ahead into the next band while the
 // MMAs of the current one are still in flight, and the epilogue of band i overlaps the MMAs of band i+1.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreadsWide)
 k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, SlArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -641,7 +644,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (!a.c4) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
-      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], (kThreads - 64) / 32);
+      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], (blockDim.x - 64) / 32);
     }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], (uint32_t)a.cl); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -803,9 +806,9 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   } else {
     // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31 =====================
     // Two warps share each lane quadrant and alternate over the (M-tile, 16-column group) work items.
-    const int lane_grp = warp & 3, half = (warp - 2) >> 2;
+    const int lane_grp = warp & 3, half = (warp - 2) >> 2, halves = ((int)blockDim.x - 64) / 128;  // epilogue warps per lane quadrant
     // bias -> shared memory while the first MMAs run (zero when absent or beyond Co)
-    for (int j = threadIdx.x - 64; j < a.NT; j += kThreads - 64) {
+    for (int j = threadIdx.x - 64; j < a.NT; j += (int)blockDim.x - 64) {
       const int co = n0 + j;
       bias_s[j] = (a.epi.bias && co < a.Co) ? __ldg(a.epi.bias + co) : 0.f;
     }
@@ -826,7 +829,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       else if (a.ps == 2 && lay0 && ((a.Co >> 2) & 3) == 0) fmode = 2;
     }
     const bool extra = a.epi.residual.p != nullptr || a.epi.preact.p != nullptr || a.epi.mask.p != nullptr;
-    asm volatile("bar.sync 1, %0;" ::"r"(kThreads - 64) : "memory");  // bias_s visible to all epilogue warps
+    asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 64) : "memory");  // bias_s visible to all epilogue warps
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;
     float lsum = 0.f;  // this thread's share of the fused loss sum
@@ -839,11 +842,11 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (wi == 0 && warp == 2 && lane == 0) SL_TRACE(4);
       const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + tb * (uint32_t)acc_cols;
-#define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
-#define SL_EPIH(MODE) epilogue_items_h<MODE>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid)
+#define SL_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, halves)
+#define SL_EPIH(MODE) epilogue_items_h<MODE>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, halves)
       if (a.dbg & 1) {}
-      else if (lmode == 1) epilogue_items_loss<1>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum);
-      else if (lmode == 3) epilogue_items_loss<3>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum);
+      else if (lmode == 1) epilogue_items_loss<1>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum, halves);
+      else if (lmode == 3) epilogue_items_loss<3>(a, trow, bsa, half, mtb, m, img, n0, oy0, ox0, rows_valid, cols_valid, lsum, halves);
       else if (a.out_bf16 && hmode == 0) SL_EPIH(0);
       else if (a.out_bf16 && hmode == 2) SL_EPIH(2);
       else if (fmode == 0) { if (extra) SL_EPI(0, true); else SL_EPI(0, false); }
@@ -861,7 +864,7 @@ k_conv_sl(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (lmode) {  // one partial per epilogue warp, summed over the lanes in a fixed (butterfly) order
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-      if (lane == 0) a.epi.loss_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (warp - 2)] = lsum;
+      if (lane == 0) a.epi.loss_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((blockDim.x - 64) / 32) + (warp - 2)] = lsum;
     }
   }
 #undef SL_BAND_GEOM
@@ -1328,7 +1331,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (lmode) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-      if (lane == 0) e.epi.loss_part[(size_t)blockIdx.x * 8 + (warp - 2)] = lsum;
+      if (lane == 0) e.epi.loss_part[(size_t)blockIdx.x * (4 * kRsEpiPerQuad) + (warp - 2)] = lsum;  // one slot per epilogue warp
     }
   }
 
@@ -1749,7 +1752,7 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
               ws_bytes);
   float *wp = (float *)wsp;
   if (epi.loss_kind) {
-    SRB_REQUIRE(opt.loss_out != nullptr && pl.grid <= kMaxLossCtas, SRB_EINVAL, "fused loss: bad arguments");
+    SRB_REQUIRE(opt.loss_out != nullptr && pl.grid * 4 * kRsEpiPerQuad <= kMaxLossCtas * 8, SRB_EINVAL, "fused loss: bad arguments");
     SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
                     epi.target.p && epi.target.dt == SRB_F32,
                 SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
@@ -1817,7 +1820,7 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
   SRB_CHECK_CUDA(cudaGetLastError());
   if (epi.loss_kind) {
     const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
-    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, pl.grid * 8, (float)(1.0 / numel), opt.loss_out);
+    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, pl.grid * 4 * kRsEpiPerQuad, (float)(1.0 / numel), opt.loss_out);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }
@@ -1984,7 +1987,7 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   float *wp = (float *)wsp;
   float *xp = (float *)((wsp + pl.wpack_floats * sizeof(float) + 255) & ~(uintptr_t)255);
   if (epi.loss_kind) {
-    SRB_REQUIRE(loss_out != nullptr && (long long)pl.grid_x * pl.n_tiles_n <= kMaxLossCtas, SRB_EINVAL, "fused loss: bad arguments");
+    SRB_REQUIRE(loss_out != nullptr && (long long)pl.grid_x * pl.n_tiles_n * 16 <= kMaxLossCtas * 8, SRB_EINVAL, "fused loss: bad arguments");
     SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
                     out.dt == SRB_F32 && epi.target.p && epi.target.dt == SRB_F32,
                 SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
@@ -2089,11 +2092,13 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     if (rc) return rc;
   }
   dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles_n);
+  // one CTA per SM: 16 epilogue warps (more stores in flight); two per SM: 8 each (registers: 96 x 576 x 2 would not fit)
+  const int sl_threads = (pl.ctas_per_sm == 1 && !(g_sl_dbg & 32768)) ? kThreadsWide : kThreads;
   if (a.cl > 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(sl_threads);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -2105,13 +2110,13 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
     cfg.numAttrs = 1;
     SRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_sl, mapA, mapB, a));
   } else {
-    SRB_CHECK_CUDA(launch_pdl(k_conv_sl, grid, dim3(kThreads), pl.smem, st, mapA, mapB, a));
+    SRB_CHECK_CUDA(launch_pdl(k_conv_sl, grid, dim3(sl_threads), pl.smem, st, mapA, mapB, a));
   }
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   if (epi.loss_kind) {
     const double numel = (double)g.N * g.Ho * g.Wo * g.Co;
-    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, (int)(grid.x * grid.y * 8), (float)(1.0 / numel), loss_out);
+    launch_pdl(k_sl_loss_finish, dim3(1), dim3(256), 0, st, epi.loss_part, (int)(grid.x * grid.y * ((sl_threads - 64) / 32)), (float)(1.0 / numel), loss_out);
     count_launch();
     SRB_CHECK_CUDA(cudaGetLastError());
   }

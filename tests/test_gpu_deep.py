@@ -290,3 +290,23 @@ def test_weight_cache_training_matches_uncached(name, args, xshape, math):
     l2, _, _ = run(True, repack=False)  # the contract matters: without the repack the convs keep using the first step's filters
     if name != "fsrcnn":  # (FSRCNN's 1e-4 deconv init makes its gradients ~1e-10: three steps do not move the loss at all)
         assert l2[0] == l0[0] and l2[2] != l0[2]
+
+
+def test_fused_loss_value_at_cfg2_size():
+    """ESPCN cfg2's last layer (128 x 32 x 58 x 58 -> PixelShuffle(4) -> 3 x 224 x 224) fused with MSE: every CTA works on ~25 rows
+    and all of its epilogue warps carry partial loss sums -- the value and the gradient must equal the unfused conv + loss."""
+    assert torch.cuda.is_available()
+    srb200.set_math("auto")
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(128, 32, 58, 58, generator=gen).to(DEV).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(48, 32, 3, 3, generator=gen) * 0.05).to(DEV).requires_grad_(True)
+    b = (torch.randn(48, generator=gen) * 0.1).to(DEV).requires_grad_(True)
+    t = torch.rand(128, 3, 224, 224, generator=gen).to(DEV)
+    loss_f = srb200.conv2d_loss(x, w, b, t, "mse", 1, 0, 4)
+    loss_f.backward()
+    gw_f, gb_f = w.grad.clone(), b.grad.clone()
+    w.grad = b.grad = None
+    loss_u = srb200.mse_loss(srb200.conv2d(x, w, b, 1, 0, activation=None, pixel_shuffle=4), t)
+    loss_u.backward()
+    assert abs(loss_f.item() - loss_u.item()) <= 2e-6 * abs(loss_u.item())
+    assert rel_l2(gw_f, w.grad) < 2e-4 and rel_l2(gb_f, b.grad) < 2e-4
