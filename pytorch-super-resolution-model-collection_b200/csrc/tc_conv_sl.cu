@@ -1039,7 +1039,11 @@ constexpr int kRsMaxStages = 8;
 constexpr int kRsMaxBlocks = 16;
 constexpr int kRsPrefetchRows = 6;
 constexpr int kRsEpiPerQuad = kRsEpiPerQuadFwd;        // epilogue warps per TMEM lane quadrant
-constexpr int kRsThreads = 64 + 128 * kRsEpiPerQuad;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
+// Warps 0-1: TMA producers, warps 2-3: MMA issuers (one of each per row STREAM), then the epilogue warps.  With two streams a CTA
+// walks two halves of its row range concurrently -- each stream has its own operand ring, half of the TMEM ring and half of the
+// epilogue warps; the resident weights are shared -- so that one issuing thread's per-row bookkeeping (barrier waits, commits,
+// descriptor updates: ~0.25 us per row that the tensor pipe otherwise idles through) overlaps the other stream's MMAs.
+constexpr int kRsThreads = 128 + 128 * kRsEpiPerQuad;
 
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -1050,7 +1054,8 @@ struct RsArgs {
   SlArgs e;               // what the epilogues read: N, Ho, Wo, Co, NT, BW (= slots per image), ps, out, epi, v8, rs = 1
   int chunks, kv_last;    // 32-channel chunks of the input; K steps (of 8 channels) that exist in the last chunk
   int G, TW, CT;          // images per M tile, output columns per strip, column strips per image
-  int R;                  // TMEM ring: accumulator blocks of NT columns
+  int R;                  // TMEM ring: accumulator blocks of NT columns (per stream)
+  int streams;            // 1 or 2 concurrent row streams per CTA (S and R are per stream)
   int S, stage_bytes, stage_tx;  // A ring: one stage = one input row, all chunks (chunk_bytes each; stage_tx = TMA bytes per chunk)
   int chunk_bytes;
   int bcs_bytes;          // B: bytes of one (chunk, s) operand = kh * NT * 128
@@ -1140,13 +1145,13 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *a_smem = smem;
-  uint8_t *b_smem = smem + (size_t)a.S * a.stage_bytes + 1024;  // 1 KB gap: the shifted views of the last stage over-read kw-1 slots
+  uint8_t *b_smem = smem + (size_t)a.streams * a.S * a.stage_bytes + 1024;  // 1 KB gap: the shifted views of the last stage over-read kw-1 slots
   const int kh = a.e.kh, kw = a.e.kw, NT = a.e.NT;
-  uint64_t *a_full = (uint64_t *)(b_smem + (size_t)a.chunks * kw * a.bcs_bytes);
-  uint64_t *a_empty = a_full + kRsMaxStages;
-  uint64_t *t_full = a_empty + kRsMaxStages;
-  uint64_t *t_empty = t_full + kRsMaxBlocks;
-  uint64_t *b_full = t_empty + kRsMaxBlocks;
+  uint64_t *a_full0 = (uint64_t *)(b_smem + (size_t)a.chunks * kw * a.bcs_bytes);  // [stream][kRsMaxStages]
+  uint64_t *a_empty0 = a_full0 + 2 * kRsMaxStages;
+  uint64_t *t_full0 = a_empty0 + 2 * kRsMaxStages;                                  // [stream][kRsMaxBlocks]
+  uint64_t *t_empty0 = t_full0 + 2 * kRsMaxBlocks;
+  uint64_t *b_full = t_empty0 + 2 * kRsMaxBlocks;
   uint32_t *tmem_slot = (uint32_t *)(b_full + 1);
   float *bias_s = (float *)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);  // NT floats
 
@@ -1155,31 +1160,43 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-    for (int s = 0; s < kRsMaxStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < kRsMaxBlocks; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    for (int s = 0; s < 2 * kRsMaxStages; ++s) { mbar_init(&a_full0[s], 1); mbar_init(&a_empty0[s], 1); }
+    for (int s = 0; s < 2 * kRsMaxBlocks; ++s) { mbar_init(&t_full0[s], 1); mbar_init(&t_empty0[s], 4); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t tmem_base0 = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();  // everything above overlapped the previous kernel; from here on global memory is touched
 
-  // this CTA's share of the global output-row sequence
-  const long long r0 = a.total_rows * (long long)blockIdx.x / (long long)gridDim.x;
-  const long long r1 = a.total_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  // this CTA's share of the global output-row sequence, and this warp's stream's share of that
+  const long long c0 = a.total_rows * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long c1 = a.total_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  // role -> stream: producers 0/1, issuers 2/3; epilogue warp e = warp - 4: with two streams e / 4 alternates between them
+  const int q = a.streams == 1 ? 0 : (warp < 4 ? (warp & 1) : (((warp - 4) >> 2) & 1));
+  const long long cm = a.streams == 1 ? c1 : c0 + (c1 - c0 + 1) / 2;
+  const long long r0 = q == 0 ? c0 : cm, r1 = q == 0 ? cm : c1;
+  uint64_t *a_full = a_full0 + q * kRsMaxStages, *a_empty = a_empty0 + q * kRsMaxStages;
+  uint64_t *t_full = t_full0 + q * kRsMaxBlocks, *t_empty = t_empty0 + q * kRsMaxBlocks;
+  a_smem += (size_t)q * a.S * a.stage_bytes;
+  const uint32_t tmem_base = tmem_base0 + (uint32_t)(q * a.R * NT);  // this stream's half of the accumulator ring
+  const bool idle_role = a.streams == 1 && (warp == 1 || warp == 3);
 
-  if (warp == 0) {
+  if (idle_role) {
+  } else if (warp < 2) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       const int ncs = a.chunks * kw;
-      mbar_expect_tx(b_full, (uint32_t)(ncs * a.bcs_bytes));
-      for (int cs = 0; cs < ncs; ++cs) tma_load_3d(&mapB, b_full, b_smem + (size_t)cs * a.bcs_bytes, 0, 0, cs);
+      if (warp == 0) {  // the resident weights, shared by both streams
+        mbar_expect_tx(b_full, (uint32_t)(ncs * a.bcs_bytes));
+        for (int cs = 0; cs < ncs; ++cs) tma_load_3d(&mapB, b_full, b_smem + (size_t)cs * a.bcs_bytes, 0, 0, cs);
+      }
       uint32_t st = 0, ph = 0, nloaded = 0;
       int tr_i = 0;
       for (long long row = r0; row < r1;) {
@@ -1188,7 +1205,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         for (int j = 0; j < nin; ++j) {
           const int iy = sg.oy0 - a.e.pad + j;
           mbar_wait(&a_empty[st], ph ^ 1u);
-          RS_TRACE(0, tr_i); ++tr_i;
+          if (q == 0) RS_TRACE(0, tr_i);
+          ++tr_i;
           if ((a.e.dbg & 2) && nloaded >= (uint32_t)a.S) {
             mbar_arrive(&a_full[st]);  // debug: operands are loaded only once per stage
           } else {
@@ -1204,7 +1222,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp < 4) {
     // ===================== MMA issuer: one elected lane runs the whole loop =====================
     // (scalar state only and straight-line issue code: ptxas then keeps descriptors, TMEM addresses and instruction
     // descriptors in UNIFORM registers, which is what UTCHMMA reads; per-lane guards or indexed structs cost an R2UR per operand)
@@ -1226,7 +1244,8 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       const RsSeg sg = rs_segment(a, row, r1);
       const int nin = sg.cnt + kh - 1;
       for (int j = 0; j < nin; ++j) {
-        RS_TRACE(1, tr_m); ++tr_m;
+        if (q == 0) RS_TRACE(1, tr_m);
+        ++tr_m;
         const bool fresh = j < sg.cnt;  // output row j is touched for the first time: its block is overwritten
         if (fresh) {
           mbar_wait(&t_empty[blk_hi], par_hi ^ 1u);  // drained by the epilogue
@@ -1284,8 +1303,10 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // ===================== epilogue: warps 2..; warp w reads TMEM lanes 32*(w%4) .. +31; the kRsEpiPerQuad warps of a lane
     // quadrant take output rows round-robin (several rows in flight hide the latency of the epilogue's global loads) =====================
     const SlArgs &e = a.e;
-    const int lane_grp = warp & 3, half = (warp - 2) >> 2;
-    for (int j = threadIdx.x - 64; j < NT; j += kRsThreads - 64) bias_s[j] = (e.epi.bias && j < e.Co) ? __ldg(e.epi.bias + j) : 0.f;
+    const int lane_grp = warp & 3;
+    // rows of a stream go round-robin over its `halves` epilogue warps per lane quadrant
+    const int halves = kRsEpiPerQuad / a.streams, half = a.streams == 1 ? (warp - 4) >> 2 : (warp - 4) >> 3;
+    for (int j = threadIdx.x - 128; j < NT; j += kRsThreads - 128) bias_s[j] = (e.epi.bias && j < e.Co) ? __ldg(e.epi.bias + j) : 0.f;
     const bool lay0 = e.out.sc == 1 && (!e.epi.residual.p || e.epi.residual.sc == 1) &&
                       (!e.epi.preact.p || e.epi.preact.sc == 1) && (!e.epi.mask.p || e.epi.mask.sc == 1);
     const bool lay1 = e.out.sw == 1 && (!e.epi.residual.p || e.epi.residual.sw == 1) && (!e.epi.preact.p || e.epi.preact.sw == 1);
@@ -1297,7 +1318,7 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       else if (e.ps == 2 && lay0 && ((e.Co >> 2) & 3) == 0) fmode = 2;
     }
     const bool extra = e.epi.residual.p != nullptr || e.epi.preact.p != nullptr || e.epi.mask.p != nullptr;
-    asm volatile("bar.sync 1, %0;" ::"r"(kRsThreads - 64) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(kRsThreads - 128) : "memory");
     const uint32_t bsa = smem_u32(bias_s);
     const int m = lane_grp * 32 + lane;
     float lsum = 0.f;
@@ -1306,11 +1327,11 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     for (long long row = r0; row < r1;) {
       const RsSeg sg = rs_segment(a, row, r1);
       for (int o = 0; o < sg.cnt; ++o, ++ctr) {
-        if ((int)(ctr % (uint32_t)kRsEpiPerQuad) != half) continue;
+        if ((int)(ctr % (uint32_t)halves) != half) continue;
         const uint32_t blk = ctr % (uint32_t)a.R;
         mbar_wait(&t_full[blk], (ctr / (uint32_t)a.R) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane_grp == 2 && lane == 0 && half < 2) RS_TRACE(2 + half, (int)(ctr / (uint32_t)kRsEpiPerQuad));
+        if (lane_grp == 2 && lane == 0 && half < 2 && q == 0) RS_TRACE(2 + half, (int)(ctr / (uint32_t)halves));
         const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + blk * (uint32_t)NT;
         const int oy = sg.oy0 + o;
 #define RS_EPI(MODE, EXTRA) epilogue_items<MODE, EXTRA>(e, trow, bsa, 0, 1, m, sg.img0, 0, oy, sg.ox0, sg.imgs_valid, sg.cols_valid, 1)
@@ -1331,15 +1352,15 @@ k_conv_rs(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (lmode) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-      if (lane == 0) e.epi.loss_part[(size_t)blockIdx.x * (4 * kRsEpiPerQuad) + (warp - 2)] = lsum;  // one slot per epilogue warp
+      if (lane == 0) e.epi.loss_part[(size_t)blockIdx.x * (4 * kRsEpiPerQuad) + (warp - 4)] = lsum;  // one slot per epilogue warp
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base0), "r"(512u) : "memory");
   }
 }
 
@@ -1708,15 +1729,18 @@ bool make_rs_plan(const Geom &g, RsPlan *pl) {
   a.stage_tx = G * BWs * 128;
   a.bcs_bytes = g.kh * NT * 128;
   const long long b_bytes = (long long)chunks * g.kw * a.bcs_bytes;
-  const long long fixed = b_bytes + 1024 /*gap*/ + 1024 /*align*/ + 1024 /*barriers, bias*/;
-  long long S = (226 * 1024 - fixed) / a.stage_bytes;
+  const long long fixed = b_bytes + 1024 /*gap*/ + 1024 /*align*/ + 2048 /*barriers, bias*/;
+  // two row streams when each still gets >= 2 row stages and a TMEM ring of >= 2 * kh blocks (else the window wraps too often)
+  const int r_all = 512 / NT;
+  a.streams = (!(g_sl_dbg & 65536) && (r_all / 2) >= 2 * g.kh && (226 * 1024 - fixed) / (2 * a.stage_bytes) >= 2) ? 2 : 1;
+  long long S = (226 * 1024 - fixed) / ((long long)a.streams * a.stage_bytes);
   if (S < 2) return false;
   if (S > kRsMaxStages) S = kRsMaxStages;
   a.S = (int)S;
   a.chunks = chunks;
   a.kv_last = (g.Ci - (chunks - 1) * 32 + 7) / 8;
   a.G = G; a.TW = TW; a.CT = CT;
-  a.R = 512 / NT < kRsMaxBlocks ? 512 / NT : kRsMaxBlocks;
+  a.R = r_all / a.streams < kRsMaxBlocks ? r_all / a.streams : kRsMaxBlocks;
   if (a.R < g.kh + 1) return false;
   const long long IG = (g.N + G - 1) / G;
   a.total_rows = IG * CT * g.Ho;
@@ -1726,7 +1750,7 @@ bool make_rs_plan(const Geom &g, RsPlan *pl) {
   SlArgs &e = a.e;
   e.N = g.N; e.Ho = g.Ho; e.Wo = g.Wo; e.Co = g.Co; e.kh = g.kh; e.kw = g.kw; e.pad = g.pad; e.pad_w = g.pad;
   e.NT = NT; e.BW = BWs; e.ps = g.ps; e.rs = 1; e.MTB = 1; e.chunk_elems = 32;
-  pl->smem = (size_t)a.S * a.stage_bytes + (size_t)fixed;
+  pl->smem = (size_t)a.streams * a.S * a.stage_bytes + (size_t)fixed;
   pl->grid = (int)(a.total_rows < 148 ? a.total_rows : 148);
   pl->Npad = NT;
   pl->BWs = BWs;
@@ -1923,9 +1947,9 @@ int tc_conv_describe(const Geom &g, char *buf, size_t n, bool bf16) {
     const RsArgs &r = rp.a;
     return snprintf(buf, n,
                     "conv_rs row-stacked: %d image(s) x %d slots per M tile (%d output columns, lane use %.2f), %d strip(s)/image, N = %d x %d = %d, "
-                    "chunks %d (last: %d K-steps), %d row stages x %d B, weights %d B resident, TMEM ring %d blocks, smem %zu B, "
+                    "chunks %d (last: %d K-steps), %d stream(s) x %d row stages x %d B, weights %d B resident, TMEM ring %d blocks, smem %zu B, "
                     "%lld output rows on grid %d",
-                    r.G, rp.BWs, r.TW, rp.lane_eff, r.CT, g.kh, r.e.NT, g.kh * r.e.NT, r.chunks, r.kv_last, r.S, r.stage_bytes,
+                    r.G, rp.BWs, r.TW, rp.lane_eff, r.CT, g.kh, r.e.NT, g.kh * r.e.NT, r.chunks, r.kv_last, r.streams, r.S, r.stage_bytes,
                     r.chunks * g.kw * r.bcs_bytes, r.R, rp.smem, r.total_rows, rp.grid);
   }
   SlPlan pl;

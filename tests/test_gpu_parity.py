@@ -176,17 +176,22 @@ SWEEP_RS = [c for c in SWEEP if c[3] == 1 and c[0] > 4] + [
     (64, 16, 5, 1, 2, "relu", False, 1, 20, 40, 2),    # 5 x 5: N = 80
     (32, 64, 3, 1, 1, "relu", False, 1, 70, 24, 6),    # long strips: the TMEM ring wraps many times (R = 8 blocks)
     (64, 48, 3, 1, 1, None, False, 1, 40, 30, 4),      # NT = 48: ring of 10 blocks
+    (64, 32, 3, 1, 1, "relu", False, 1, 5, 20, 1),     # one row per CTA: the second row stream of every CTA is empty
+    (64, 32, 3, 1, 1, "relu", False, 1, 61, 20, 5),    # 305 rows over 148 CTAs: 2-3 rows per CTA, streams of unequal length
 ]
 
 
+@pytest.mark.parametrize("one_stream", [False, True], ids=["streams-auto", "one-stream"])
 @pytest.mark.parametrize("case", SWEEP_RS)
-def test_row_stacked_kernels_vs_oracle(case):
+def test_row_stacked_kernels_vs_oracle(case, one_stream):
+    """k_conv_rs (forced regardless of problem size) + row-stacked wgrad; NT <= 32 layers run two row streams per CTA unless
+    flag 65536 forces one."""
     import ctypes
     from srb200 import _lib
     setf = _lib.lib.srb_debug_set_flags
     setf.argtypes = [ctypes.c_int]
     setf.restype = None
-    setf(1024 | 512)
+    setf(1024 | 512 | (65536 if one_stream else 0))
     try:
         _run_conv_case(case, "auto", True)
     finally:
