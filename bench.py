@@ -177,9 +177,10 @@ def measure_srgan(ctx, a, workload, steps, warmup):
                     nxt = prefetch(i + 1)
                 main.wait_event(ev)
                 loss = run(i % 3)
-                loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                if "loss" not in E2E_SKIP:
+                    loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
                 loss_evs[i % 2].record(main)
-                if i > 0:
+                if i > 0 and "sync" not in E2E_SKIP:
                     loss_evs[(i - 1) % 2].synchronize()
             else:
                 run(i % 3)
@@ -457,6 +458,10 @@ class Ctx:
         return t.item()
 
 
+# diagnostic only (the e2e number of such a run is not an e2e number): SRB_E2E_SKIP=copy,convert,loss,sync drops parts of the e2e leg
+E2E_SKIP = set(filter(None, os.environ.get("SRB_E2E_SKIP", "").split(",")))
+
+
 def synth_images(batch, h, w, gen):
     """Synthetic uint8 HWC image batch (what a decoder hands to dataset.py:90's ToTensor), pinned."""
     return torch.randint(0, 256, (batch, h, w, 3), generator=gen, dtype=torch.uint8).pin_memory()
@@ -522,20 +527,30 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
-        """Step i's batch: pinned uint8 -> device staging (PCIe) -> fp32 NCHW slot (ToTensor on the device), all on the copy
-        stream, overlapping the previous step's kernels.  Slot i%3 was last read by step i-3 (host-synchronised since)."""
+        """Step i's batch: pinned uint8 -> device staging (PCIe) on the copy stream, overlapping the previous step's kernels.
+        Staging slot i%3 was last read by step i-3 (host-synchronised since)."""
         s = i % 3
         with torch.cuda.stream(copy_stream):
-            stage_x[s].copy_(host_x[s], non_blocking=True)
-            stage_t[s].copy_(host_t[s], non_blocking=True)
-            srb200.image_to_tensor(stage_x[s], out=dev_x[s])
-            srb200.image_to_tensor(stage_t[s], out=dev_t[s])
+            if "copy" not in E2E_SKIP:
+                stage_x[s].copy_(host_x[s], non_blocking=True)
+                stage_t[s].copy_(host_t[s], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return ev
 
+    def to_tensor(i):
+        """ToTensor on the device (uint8 HWC staging -> the fp32 NCHW slot the step reads), on the MAIN stream in front of the step:
+        beside the training kernels (on the copy stream) it cost 75 us per step -- the one-CTA-per-SM conv kernels own the whole
+        register file, so a concurrent elementwise grid and the convs take turns on every SM -- in line it costs its own ~20 us."""
+        s = i % 3
+        if "convert" not in E2E_SKIP:
+            srb200.image_to_tensor(stage_x[s], out=dev_x[s])
+            srb200.image_to_tensor(stage_t[s], out=dev_t[s])
+
     loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
+    step_done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_stream = torch.cuda.Stream(device=dev)
 
     def timed(nsteps, e2e):
         ctx.barrier()
@@ -554,10 +569,17 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
                 if i + 1 < nsteps:
                     nxt = prefetch(i + 1)
                 main.wait_event(ev)
+                to_tensor(i)
                 loss = step_slot(i % 3)
-                loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
-                loss_evs[i % 2].record(main)
-                if i > 0:
+                # the 4-byte read-back runs on its own stream behind an event: a memcpy node on the main stream would sit between
+                # two steps' kernels (slot i%3's loss tensor is not rewritten before step i+3; the host has read it by then)
+                step_done[i % 2].record(main)
+                d2h_stream.wait_event(step_done[i % 2])
+                with torch.cuda.stream(d2h_stream):
+                    if "loss" not in E2E_SKIP:
+                        loss_hosts[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                    loss_evs[i % 2].record(d2h_stream)
+                if i > 0 and "sync" not in E2E_SKIP:
                     loss_evs[(i - 1) % 2].synchronize()
                     seen += float(loss_hosts[(i - 1) % 2][0])
             else:

@@ -299,6 +299,34 @@ __global__ void k_image_to_tensor(const unsigned char *__restrict__ src, float *
   }
 }
 
+// The same for C <= 4 channels, W % 4 == 0 and 4-byte aligned buffers: a thread takes FOUR consecutive pixels of one row -- 4*C
+// bytes = C aligned 32-bit loads -- and writes one float4 into each channel plane (the scalar kernel above does a strided byte load,
+// three 64-bit divisions and a 4-byte store per element: 75 us of every ESPCN e2e step when it ran beside the training kernels).
+template <int C>
+__global__ void __launch_bounds__(256) k_image_to_tensor_v4(const uint32_t *__restrict__ src, float4 *__restrict__ dst, int N, int H, int W4,
+                                                            float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const long long groups = (long long)N * H * W4;  // groups of 4 pixels
+  const long long plane4 = (long long)H * W4;      // float4s per channel plane
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const long long n = gidx / plane4, hw4 = gidx - n * plane4;
+    uint32_t wd[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) wd[j] = __ldg(src + gidx * C + j);  // 4 pixels x C bytes, pixel-major
+    float v[C][4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int b = px * C + c;
+        v[c][px] = (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu) * scale;
+      }
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[(n * C + c) * plane4 + hw4] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+  }
+}
+
 // ---- bf16 storage mode helpers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float h2f(unsigned short h) { return __uint_as_float((uint32_t)h << 16); }
 __device__ __forceinline__ unsigned short f2h(float v) {
@@ -1129,9 +1157,17 @@ int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const floa
 
 int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int32_t H, int32_t W, int32_t C, float scale,
                         void *stream) {
-  SRB_REQUIRE(src_nhwc && dst_nchw && N >= 0 && H > 0 && W > 0 && C > 0, SRB_EINVAL, "bad image_to_tensor args");
-  if (N == 0) return SRB_OK;
-  launch_pdl(k_image_to_tensor, dim3(ew_blocks((long long)N * C * H * W)), dim3(256), 0, (cudaStream_t)stream, src_nhwc, dst_nchw, N, H, W, C, scale);
+  SRB_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0, SRB_EINVAL, "bad image_to_tensor args");
+  if (N == 0) return SRB_OK;  // an empty batch has no storage behind it
+  SRB_REQUIRE(src_nhwc && dst_nchw, SRB_EINVAL, "null image_to_tensor buffer");
+  const bool v4 = C <= 4 && (W & 3) == 0 && ((uintptr_t)src_nhwc & 3) == 0 && ((uintptr_t)dst_nchw & 15) == 0;
+  const long long groups = (long long)N * H * (W / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v4 && C == 1) launch_pdl(k_image_to_tensor_v4<1>, dim3(ew_blocks(groups)), dim3(256), 0, st, (const uint32_t *)src_nhwc, (float4 *)dst_nchw, N, H, W / 4, scale);
+  else if (v4 && C == 2) launch_pdl(k_image_to_tensor_v4<2>, dim3(ew_blocks(groups)), dim3(256), 0, st, (const uint32_t *)src_nhwc, (float4 *)dst_nchw, N, H, W / 4, scale);
+  else if (v4 && C == 3) launch_pdl(k_image_to_tensor_v4<3>, dim3(ew_blocks(groups)), dim3(256), 0, st, (const uint32_t *)src_nhwc, (float4 *)dst_nchw, N, H, W / 4, scale);
+  else if (v4 && C == 4) launch_pdl(k_image_to_tensor_v4<4>, dim3(ew_blocks(groups)), dim3(256), 0, st, (const uint32_t *)src_nhwc, (float4 *)dst_nchw, N, H, W / 4, scale);
+  else launch_pdl(k_image_to_tensor, dim3(ew_blocks((long long)N * C * H * W)), dim3(256), 0, st, src_nhwc, dst_nchw, N, H, W, C, scale);
   count_launch();
   SRB_CHECK_CUDA(cudaGetLastError());
   return SRB_OK;

@@ -537,13 +537,21 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
         wg_locate(a, co, ci, r, s, by, acc, m, n);
         const float *p = a.partial + (((size_t)by * ACC + acc) * 128 + m) * a.acc_cols + n;
         if (lanes8) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          // 8 independent loads in flight per thread: a 148-way split is 2-3 round trips to L2 instead of 5
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
           int z = ty;
-          for (; z + 24 < splits; z += 32) {
+          for (; z + 56 < splits; z += 64) {
             s0 += p[(size_t)z * ss]; s1 += p[(size_t)(z + 8) * ss]; s2 += p[(size_t)(z + 16) * ss]; s3 += p[(size_t)(z + 24) * ss];
+            s4 += p[(size_t)(z + 32) * ss]; s5 += p[(size_t)(z + 40) * ss]; s6 += p[(size_t)(z + 48) * ss]; s7 += p[(size_t)(z + 56) * ss];
           }
-          for (; z < splits; z += 8) s0 += p[(size_t)z * ss];
-          sum = (s0 + s1) + (s2 + s3);
+          if (z < splits) s0 += p[(size_t)z * ss];
+          if (z + 8 < splits) s1 += p[(size_t)(z + 8) * ss];
+          if (z + 16 < splits) s2 += p[(size_t)(z + 16) * ss];
+          if (z + 24 < splits) s3 += p[(size_t)(z + 24) * ss];
+          if (z + 32 < splits) s4 += p[(size_t)(z + 32) * ss];
+          if (z + 40 < splits) s5 += p[(size_t)(z + 40) * ss];
+          if (z + 48 < splits) s6 += p[(size_t)(z + 48) * ss];
+          sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
         } else {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
           int z = 0;
