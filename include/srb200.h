@@ -59,7 +59,8 @@ typedef enum srb_math {
                         contract at the BASELINE depths (VDSR-20, EDSR-256x32), where single-pass TF32 reaches ~1.5e-3. */
 } srb_math;
 
-typedef enum srb_dtype { SRB_F32 = 0, SRB_BF16 = 1 } srb_dtype;
+/* SRB_U8: image bytes; accepted only where a function says so (the target of srb_conv_fprop_loss) */
+typedef enum srb_dtype { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2 } srb_dtype;
 
 /* Logical NCHW view with element strides (like torch.Tensor.stride()); dtype = srb_dtype of the elements. */
 typedef struct srb_tensor4 {
@@ -136,6 +137,9 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
  * dz is the conv's own dense NHWC tensor (N, Cout*ps*ps, Ho, Wo), ready for srb_conv_dgrad/wgrad with ps = 1 geometry;
  * dz_unshuffled == 0 (requires ps == 1): dz has y's shape and strides of its own.  The loss sum is deterministic
  * (per-warp partials folded in a fixed order).  Layers with an activation or a residual are SRB_EUNSUPPORTED.
+ * target->dtype may be SRB_U8: the decoded image itself (strides in bytes; for an (N,H,W,C) HWC buffer sn = H*W*C, sc = 1,
+ * sh = W*C, sw = C), read as t = byte * (1/255) -- torchvision's ToTensor (dataset.py:90) -- so the fp32 copy of the HR target,
+ * 4x its bytes, never exists on the device.
  */
 int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
                         const srb_tensor4 *target, int loss_kind, const srb_tensor4 *y, const srb_tensor4 *dz, int dz_unshuffled,

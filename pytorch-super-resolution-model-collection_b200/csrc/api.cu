@@ -800,7 +800,14 @@ int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const fl
   SRB_REQUIRE(!p->transposed && p->act == SRB_ACT_NONE && (is_tf32_math(p->math) || p->math == SRB_MATH_BF16), SRB_EUNSUPPORTED,
               "fused loss: Conv2d without activation on the tensor path (math auto / tf32 / bf16)");
   T4 tx = to_t4(x), ty = to_t4(y), tt = to_t4(target), tdz = to_t4(dz);
-  if (!ty.p) { ty = tt; ty.p = nullptr; }  // geometry of y (= target's) without storing it
+  SRB_REQUIRE(tt.dt == SRB_F32 || tt.dt == SRB_U8, SRB_EUNSUPPORTED, "fused loss: the target is fp32, or uint8 image bytes (t = byte / 255)");
+  if (!ty.p) {  // geometry of y without storing it: the target's if that is fp32, a dense NCHW one beside a uint8 target
+    ty = tt; ty.p = nullptr;
+    if (tt.dt == SRB_U8) {
+      const long long Wy = (long long)g.Wo * g.ps, Hy = (long long)g.Ho * g.ps, Cy = g.Co / (g.ps * g.ps);
+      ty.dt = SRB_F32; ty.sw = 1; ty.sh = Wy; ty.sc = Hy * Wy; ty.sn = Cy * Hy * Wy;
+    }
+  }
   T4 probe = ty;
   probe.p = (float *)256;
   SRB_REQUIRE(tc_conv_supported(g, tx, probe, false), SRB_EUNSUPPORTED, "fused loss: this layer does not run on the tensor path");

@@ -274,6 +274,9 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
 }
 
 
+// one pixel byte as torchvision's ToTensor maps it (k_image_to_tensor computes the same product)
+__device__ __forceinline__ float u8_unit(const unsigned char *p) { return (float)__ldg(p) * (1.0f / 255.0f); }
+
 // ---- loss-fused epilogue of the network's last conv (no activation, no residual; fp32 outputs) --------------------------------
 //   MODE 1: PixelShuffle(4) into NCHW (ESPCN): y/target addressed like epilogue_items MODE 1; the gradient is written
 //           un-shuffled -- 16 consecutive conv channels of this pixel = 64 contiguous bytes of the (N,Ho,Wo,Co) tensor
@@ -313,19 +316,30 @@ __device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t tr
     if (MODE == 1) {
       const int c = cbase >> 4;
       const long long yy = (long long)oy * 4, xx = (long long)ox * 4;
-      const float *pt = a.epi.target.p + (n * a.epi.target.sn + c * a.epi.target.sc + yy * a.epi.target.sh + xx * a.epi.target.sw);
+      const long long toff = n * a.epi.target.sn + c * a.epi.target.sc + yy * a.epi.target.sh + xx * a.epi.target.sw;
+      const float *pt = a.epi.target.p + toff;
+      const unsigned char *pb = (const unsigned char *)a.epi.target.p + toff;  // SRB_U8 target: the strides count bytes
+      const bool tu8 = a.epi.target.dt == SRB_U8;
       if (a.rs && oy + kRsEpiPerQuadFwd < a.Ho) {
         // row-stacked kernel: this warp's next output row is oy + kRsEpiPerQuad.  Its target rows are pulled into L2 now: the four
         // dependent 16-byte loads per item below would otherwise expose the full DRAM latency with ~16 KB in flight per SM.
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (4 * kRsEpiPerQuadFwd + q4) * a.epi.target.sh));
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (tu8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (4 * kRsEpiPerQuadFwd + q4) * a.epi.target.sh));
+          else asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (4 * kRsEpiPerQuadFwd + q4) * a.epi.target.sh));
+        }
       }
       float *po = a.out.p ? a.out.p + (n * a.out.sn + c * a.out.sc + yy * a.out.sh + xx * a.out.sw) : nullptr;
       float g[16];
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const float4 tt = __ldg((const float4 *)(pt + q4 * a.epi.target.sh));
+        float4 tt;
+        if (tu8) {  // raw image bytes (any pixel stride: HWC as decoded, or planar); t = byte / 255 as ToTensor computes it
+          const unsigned char *pr = pb + q4 * a.epi.target.sh;
+          tt = make_float4(u8_unit(pr), u8_unit(pr + a.epi.target.sw), u8_unit(pr + 2 * a.epi.target.sw), u8_unit(pr + 3 * a.epi.target.sw));
+        } else {
+          tt = __ldg((const float4 *)(pt + q4 * a.epi.target.sh));
+        }
         const float d0 = z[4 * q4] - tt.x, d1 = z[4 * q4 + 1] - tt.y, d2 = z[4 * q4 + 2] - tt.z, d3 = z[4 * q4 + 3] - tt.w;
         if (l1) {
           lsum += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
@@ -349,7 +363,8 @@ __device__ __forceinline__ void epilogue_items_loss(const SlArgs &a, uint32_t tr
       for (int j = 0; j < 16; ++j) {
         const int co = cbase + j;
         if (co < a.Co) {
-          const float tt = __ldg(a.epi.target.p + ps_offset(a.epi.target, 1, n, co, oy, ox));
+          const long long toff = ps_offset(a.epi.target, 1, n, co, oy, ox);
+          const float tt = a.epi.target.dt == SRB_U8 ? u8_unit((const unsigned char *)a.epi.target.p + toff) : __ldg(a.epi.target.p + toff);
           const float d = z[j] - tt;
           float g;
           if (l1) { lsum += fabsf(d); g = d > 0.f ? coef : (d < 0.f ? -coef : 0.f); }
@@ -1778,10 +1793,12 @@ int tc_conv_rs_launch(const Geom &g, const T4 &in, const float *w, bool flip_tra
   if (epi.loss_kind) {
     SRB_REQUIRE(opt.loss_out != nullptr && pl.grid * 4 * kRsEpiPerQuad <= kMaxLossCtas * 8, SRB_EINVAL, "fused loss: bad arguments");
     SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
-                    epi.target.p && epi.target.dt == SRB_F32,
+                    epi.target.p && (epi.target.dt == SRB_F32 || epi.target.dt == SRB_U8),
                 SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
     if (g.ps == 4 && epi.dz_unshuf) {
-      auto ok = [](const T4 &t) { return !t.p || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0); };
+      auto ok = [](const T4 &t) {
+        return !t.p || t.dt == SRB_U8 || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0);
+      };
       SRB_REQUIRE((g.Co & 15) == 0 && ok(out) && ok(epi.target) && (((uintptr_t)epi.dz_unshuf) & 31) == 0, SRB_EUNSUPPORTED,
                   "fused loss with PixelShuffle(4): NCHW-contiguous y / target, Cout*16 channels");
     } else {
@@ -2013,10 +2030,12 @@ int tc_conv_gather(const Geom &g, const T4 &in, const float *w, bool flip_transp
   if (epi.loss_kind) {
     SRB_REQUIRE(loss_out != nullptr && (long long)pl.grid_x * pl.n_tiles_n * 16 <= kMaxLossCtas * 8, SRB_EINVAL, "fused loss: bad arguments");
     SRB_REQUIRE(epi.act == SRB_ACT_NONE && !epi.residual.p && !epi.preact.p && !epi.mask.p && !epi.bits_out && !epi.bits_in &&
-                    out.dt == SRB_F32 && epi.target.p && epi.target.dt == SRB_F32,
+                    out.dt == SRB_F32 && epi.target.p && (epi.target.dt == SRB_F32 || epi.target.dt == SRB_U8),
                 SRB_EUNSUPPORTED, "fused loss: the last conv must have fp32 output, no activation and no residual");
     if (g.ps == 4 && epi.dz_unshuf) {
-      auto ok = [](const T4 &t) { return !t.p || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0); };
+      auto ok = [](const T4 &t) {
+        return !t.p || t.dt == SRB_U8 || (t.sw == 1 && (t.sh & 3) == 0 && (t.sc & 3) == 0 && (t.sn & 3) == 0 && (((uintptr_t)t.p) & 15) == 0);
+      };
       SRB_REQUIRE((g.Co & 15) == 0 && ok(out) && ok(epi.target) && (((uintptr_t)epi.dz_unshuf) & 31) == 0, SRB_EUNSUPPORTED,
                   "fused loss with PixelShuffle(4): NCHW-contiguous y / target, Cout*16 channels");
     } else {

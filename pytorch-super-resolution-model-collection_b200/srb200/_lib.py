@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LRELU = 0, 1, 2, 3
 MATH_FP32, MATH_TF32, MATH_AUTO, MATH_EXACT, MATH_BF16 = 0, 1, 2, 3, 4
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 PASS_FPROP, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 
 
@@ -112,7 +112,9 @@ def check(rc):
 def t4(t):
     """torch.Tensor (4-D, fp32 or bf16, CUDA) -> Tensor4 (logical NCHW + element strides + dtype)."""
     s = t.stride()
-    return Tensor4(t.data_ptr(), s[0], s[1], s[2], s[3], BF16 if t.dtype == _torch_bf16() else F32)
+    import torch
+    dt = BF16 if t.dtype == torch.bfloat16 else (U8 if t.dtype == torch.uint8 else F32)
+    return Tensor4(t.data_ptr(), s[0], s[1], s[2], s[3], dt)
 
 
 def _torch_bf16():

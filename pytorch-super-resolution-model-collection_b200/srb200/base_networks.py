@@ -316,8 +316,11 @@ class FusedLoss(torch.nn.Module):
         return (F.l1_loss if self.kind == "l1" else F.mse_loss)(y, target)
 
     def forward(self, x, target):
+        """target: the fp32 (N,C,H,W) tensor of the reference loops, or the decoded uint8 (N,H,W,C) image batch itself -- the
+        fused epilogue then applies ToTensor's byte/255 on the fly (dataset.py:90) and the fp32 HR tensor never exists."""
+        u8 = target.dtype == torch.uint8
         if self.mode == "plain" or self.last is None:
-            return self._plain(x, target)
+            return self._plain(x, F.image_to_tensor(target) if u8 else target)
         holder = {}
         self.last._loss_req = (target, self.kind, holder)
         try:
@@ -327,6 +330,8 @@ class FusedLoss(torch.nn.Module):
         if "loss" in holder and y is holder["y"]:
             self.mode = "fused"
             return holder["loss"]
+        if u8:
+            target = F.image_to_tensor(target)
         if "loss" in holder:
             # the network post-processes its last block's output: the fused loss would be wrong -- never use it here again
             self.mode = "plain"

@@ -478,7 +478,9 @@ class _FusedConvLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, target, kind, stride, pad, ps, need_output):
-        _require_cuda(weight, bias, target)
+        _require_cuda(weight, bias, None if target.dtype == torch.uint8 else target)
+        if not target.is_cuda:
+            raise RuntimeError("srb200 kernels need CUDA tensors (target on %s); there is no CPU path" % target.device)
         x = _as_act(x)
         weight = weight.contiguous()
         target = target.contiguous()
@@ -486,6 +488,10 @@ class _FusedConvLoss(torch.autograd.Function):
         ho, wo = ctypes.c_int32(), ctypes.c_int32()
         check(lib.srb_conv_out_hw(ctypes.byref(p), ctypes.byref(ho), ctypes.byref(wo)))
         oshape = (p.N, p.Cout, ho.value * ps, wo.value * ps)
+        if target.dtype == torch.uint8:
+            # the decoded image batch itself, (N,H,W,C) bytes: the epilogue reads t = byte/255 (ToTensor) through this NCHW view
+            assert tuple(target.shape) == (oshape[0], oshape[2], oshape[3], oshape[1]), "uint8 target must be the (N,H,W,C) image"
+            target = target.permute(0, 3, 1, 2)
         assert tuple(target.shape) == oshape, "target must have the shape of the network output"
         dev = x.device
         y = torch.empty(oshape, dtype=torch.float32, device=dev) if need_output else None

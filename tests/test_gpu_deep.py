@@ -310,3 +310,72 @@ def test_fused_loss_value_at_cfg2_size():
     loss_u.backward()
     assert abs(loss_f.item() - loss_u.item()) <= 2e-6 * abs(loss_u.item())
     assert rel_l2(gw_f, w.grad) < 2e-4 and rel_l2(gb_f, b.grad) < 2e-4
+
+
+@pytest.mark.parametrize("kernel", ["auto", "slot-linear"])
+@pytest.mark.parametrize("case", [
+    # (N, Cin, H, W, Cout_conv, k, pad, ps, kind, math)
+    (128, 32, 58, 58, 48, 3, 0, 4, "mse", "auto"),   # ESPCN cfg2's last layer: PixelShuffle(4) -> NCHW, 3 image channels
+    (6, 32, 19, 23, 16, 3, 1, 4, "l1", "auto"),      # one image channel, odd sizes
+    (5, 64, 20, 24, 3, 5, 2, 1, "mse", "auto"),      # SRCNN-like tail (no shuffle): the scalar loss epilogue
+    (4, 64, 16, 16, 3, 3, 1, 1, "l1", "bf16"),       # EDSR's output conv in bf16 storage mode
+], ids=lambda c: "N%d_C%d_%dx%d_Co%d_k%d_p%d_ps%d_%s_%s" % c)
+def test_fused_loss_uint8_target_equals_fp32_target(case, kernel):
+    """The decoded (N,H,W,C) uint8 image as the fused loss's target == ToTensor of it as an fp32 (N,C,H,W) target: loss, the
+    network output and both parameter gradients are bit-identical (the epilogue computes the same byte * (1/255) product that
+    srb200.image_to_tensor stores)."""
+    import ctypes
+    from srb200 import _lib
+    N, Cin, H, W, Co, k, pad, ps, kind, math = case
+    srb200.set_math(math)
+    setf = _lib.lib.srb_debug_set_flags
+    setf.argtypes = [ctypes.c_int]
+    setf.restype = None
+    setf(128 if kernel == "slot-linear" else 0)
+    try:
+        gen = torch.Generator().manual_seed(21)
+        x = torch.randn(N, Cin, H, W, generator=gen).to(DEV).contiguous(memory_format=torch.channels_last)
+        if math == "bf16":
+            x = x.to(torch.bfloat16)
+        w = (torch.randn(Co, Cin, k, k, generator=gen) * 0.05).to(DEV).requires_grad_(True)
+        b = (torch.randn(Co, generator=gen) * 0.1).to(DEV).requires_grad_(True)
+        Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+        img = torch.randint(0, 256, (N, Ho * ps, Wo * ps, Co // (ps * ps)), generator=gen, dtype=torch.uint8).to(DEV)
+        res = []
+        for t in (srb200.image_to_tensor(img), img):
+            w.grad = b.grad = None
+            loss, y = srb200.conv2d_loss(x, w, b, t, kind, 1, pad, ps, need_output=True)
+            loss.backward()
+            res.append((loss.detach().clone(), y.clone(), w.grad.clone(), b.grad.clone()))
+        for a_, b_ in zip(*res):
+            assert torch.equal(a_, b_)
+        assert float(res[0][0]) > 0
+    finally:
+        setf(0)
+        srb200.set_math("auto")
+
+
+def test_fused_loss_module_takes_uint8_images():
+    """srb200.FusedLoss(net, kind)(x, uint8 HWC target): fused for ESPCN, converted (image_to_tensor) and unfused for VDSR."""
+    from srb200 import models as M2, host as H2
+    srb200.set_math("auto")
+    gen = torch.Generator().manual_seed(5)
+    for name, args, shape, ps in (("espcn", (1, 64, 4), (4, 1, 16, 16), 4), ("vdsr", (1, 64, 4), (2, 1, 16, 16), 1)):
+        torch.manual_seed(0)
+        net = M2.MODELS[name](*args)
+        H2.init_model(name, net)
+        net.to(DEV).train()
+        x = torch.rand(shape, generator=gen).to(DEV)
+        with torch.no_grad():
+            oshape = net(x).shape
+        img = torch.randint(0, 256, (oshape[0], oshape[2], oshape[3], oshape[1]), generator=gen, dtype=torch.uint8).to(DEV)
+        fl = srb200.FusedLoss(net, "mse")
+        outs = []
+        for t in (srb200.image_to_tensor(img), img):
+            net.zero_grad(set_to_none=True)
+            loss = fl(x, t)
+            loss.backward()
+            outs.append([loss.detach().clone()] + [p.grad.clone() for p in net.parameters()])
+        assert fl.mode == ("fused" if name == "espcn" else "plain")
+        for a_, b_ in zip(*outs):
+            assert torch.equal(a_, b_)
