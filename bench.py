@@ -423,6 +423,31 @@ def make_config(workload, world, no_graph, math):
             "launch": "eager" if no_graph else "cuda-graph replay (srb200.TrainStepGraphs: fwd+loss+bwd[+allreduce] graph per input slot, optimizer graph)"}
 
 
+def bind_to_gpu_numa(index):
+    """Run this process (and therefore first-touch its pinned staging buffers) on the NUMA node the GPU's PCIe root port
+    belongs to: the e2e leg's host->device copies then do not cross the inter-socket link.  Returns a small record for the
+    JSON line; a no-op (with the reason) where sysfs does not say.  SRB_NO_NUMA_BIND=1 disables it (A/B)."""
+    if os.environ.get("SRB_NO_NUMA_BIND") == "1":
+        return {"bound": False, "why": "SRB_NO_NUMA_BIND"}
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"bound": False, "why": "numa_node -1 for " + bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "no allowed cpu on node %d" % node}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus), "pci": bus}
+    except Exception as e:  # sysfs layout, permissions: measurement proceeds unbound
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 class Ctx:
     """Process-wide state shared by the measured workloads: rank / world / device / barrier."""
 
@@ -438,6 +463,7 @@ class Ctx:
             raise SystemExit("bench.py needs a CUDA device for this --impl: the engine has no CPU path")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa(self.local_rank)
         if self.world > 1 and need_dist:
             import torch.distributed as dist
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -625,7 +651,7 @@ def measure_srb(ctx, a, workload, steps, warmup, full):
         return res
     res["e2e"] = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
                   "h2d_bytes_per_step": int(host_x[0].numel() + host_t[0].numel()), "d2h_bytes_per_step": 4,
-                  "ms_per_step": ms_e2e / steps,
+                  "ms_per_step": ms_e2e / steps, "numa": ctx.numa,
                   "host_format": "uint8 HWC pixels, pinned; ToTensor (x/255, HWC->CHW) runs on the device: a kernel for the LR input, "
                                  "inside the fused loss epilogue for the HR target" if t_u8 else
                                  "uint8 HWC pixels, pinned; ToTensor (x/255, HWC->CHW) runs on the device"}
