@@ -11,7 +11,10 @@ LAYERS = [("espcn L2 64->32", 128, 64, 60, 60, 32, 3, 0, 1, "relu"), ("espcn L2d
           ("espcn L3 32->48 PS4", 128, 32, 58, 58, 3, 3, 0, 4, None), ("vdsr body 64->64", 64, 64, 128, 128, 64, 3, 1, 1, "relu"),
           ("edsr64 body", 32, 64, 32, 32, 64, 3, 1, 1, "relu"), ("espcn L3d 48->32", 128, 48, 56, 56, 32, 3, 2, 1, None),
           ("srgan G body b16", 16, 64, 32, 32, 64, 3, 1, 1, "relu"), ("srgan D 128->128 64^2", 16, 128, 64, 64, 128, 3, 1, 1, "lrelu"),
-          ("srgan D 256->256 32^2", 16, 256, 32, 32, 256, 3, 1, 1, "lrelu"), ("edsr64 up 64->256 ps2", 32, 64, 32, 32, 64, 3, 1, 2, None)]
+          ("srgan D 256->256 32^2", 16, 256, 32, 32, 256, 3, 1, 1, "lrelu"), ("edsr64 up 64->256 ps2", 32, 64, 32, 32, 64, 3, 1, 2, None),
+          ("espcn L1 3->64 k5", 128, 3, 64, 64, 64, 5, 0, 1, "relu")]
+if os.environ.get("ONLY"):  # e.g. ONLY="espcn L1" under ncu
+    LAYERS = [l for l in LAYERS if l[0].startswith(os.environ["ONLY"])]
 
 def timeit(f, n=10, reps=5):
     """GPU time per call: n calls captured into one CUDA graph (no host launch overhead), best of `reps` replays."""
@@ -45,7 +48,9 @@ if __name__ == "__main__" and not os.environ.get("WGRAD"):
     dev = torch.device("cuda:0")
     flags = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 4, 3, 7, 128]
     for name, N, Ci, H, W, Co, k, p, ps, act in LAYERS:
-        x = torch.randn(N, Ci, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+        x = torch.randn(N, Ci, H, W, device=dev)
+        if Ci > 4:
+            x = x.contiguous(memory_format=torch.channels_last)
         w = torch.randn(Co * ps * ps, Ci, k, k, device=dev) * 0.05
         b = torch.randn(Co * ps * ps, device=dev)
         out = []
