@@ -52,7 +52,12 @@ struct WgArgs {
                           // those input rows meet (rows outside the image arrive as zeros), and the B operand's N-block kh-1-r is
                           // that tile viewed kh-1-r rows LATER (LBO = one slot row = BW*128 B) -- one A read feeds kh filter taps.
                           // An accumulator is (32-channel co block, s-group, ci block) and has acc_cols = kh*32 columns.
-  int acc_cols;           // TMEM columns (= MMA N) per accumulator: NT, or kh*32 in rn mode
+                          // rn == 2: the co blocks of the tile are stacked along N as well (N = kh * NT <= 256, e.g. 3 x 64 = 192: one
+                          // MMA of cost max(32 + N/4, N/2) instead of NT/32 of them): the dz tile is laid out [row][co block][BW slots]
+                          // (one TMA per row and co block), so that N-block (kh-1-r) * NT/32 + cob sits (that many) * BW slots after
+                          // the view's start -- a single LBO.  K then walks the band row by row (BW % 8 == 0: no K-step straddles
+                          // two rows) and B skips the other co blocks' slots at every row end.  Accumulator = (s-group, ci block).
+  int acc_cols;           // TMEM columns (= MMA N) per accumulator: NT, kh*32 (rn == 1) or kh*NT (rn == 2)
   int Hi;                 // input rows (rn: the bands tile the INPUT rows)
   int ph_st, ph_a, ph_b, ph_pad0, ph_kh0, ph_kw0;  // ph_st > 0: this launch is one input phase of a strided conv (WgPhase): the
                           // finish kernel scatters its taps into the kh0 x kw0 filter
@@ -129,9 +134,42 @@ __device__ __forceinline__ void db_rows(float4 (&dbs)[8], uint32_t sz, int dz_by
 
 // All MMAs of one band (one pipeline stage) for NACC accumulators: straight-line issue code per K-step -- one add and one
 // MMA per accumulator.  (The previous runtime-predicated loop spent ~24 instructions per MMA and was issue bound.)
-template <int NACC, bool BF>
+template <int NACC, bool BF, bool ROWS = false>
 __device__ __forceinline__ void wg_issue_band(const WgArgs &a, uint32_t x_lo, uint32_t z_lo, uint32_t hi, uint32_t idesc,
                                               uint32_t tmem_base, bool first) {
+  if (ROWS) {  // rn == 2: K-steps row by row; at a row end the dz descriptor skips the other co blocks' slots of that row
+    const uint32_t ks_row = (uint32_t)a.BW >> 3, b_skip = (uint32_t)((a.NT >> 5) - 1) * (uint32_t)a.BW * 8u;
+    uint32_t al[NACC], tc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) {
+      al[j] = x_lo + (uint32_t)a.acc_off[j];
+      tc[j] = tmem_base + (uint32_t)(j * a.acc_cols);
+    }
+    uint32_t bl = z_lo;
+    for (int row = 0; row < a.TH; ++row) {
+      uint32_t k = 0;
+      if (first && row == 0) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          umma_tf32_lohi<false, false>(tc[j], al[j], bl, hi, idesc);
+          al[j] += 64u;
+        }
+        bl += 64u;
+        k = 1;
+      }
+#pragma unroll 3
+      for (; k < ks_row; ++k) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          umma_tf32_lohi<true, false>(tc[j], al[j], bl, hi, idesc);
+          al[j] += 64u;
+        }
+        bl += 64u;
+      }
+      bl += b_skip;
+    }
+    return;
+  }
   constexpr uint32_t KADV = BF ? 128u : 64u;  // one K step = 16 (bf16) / 8 (tf32) pixel rows x 128 B, in 16-byte units
   uint32_t al[NACC], tc[NACC], bo[NACC];
 #pragma unroll
@@ -187,7 +225,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
   const int rg_valid = min(a.RG, a.kh - r0);
   const int band0 = blockIdx.x * a.bands_per_cta;
   const int band1 = min(band0 + a.bands_per_cta, a.num_bands);
-  const int ACC = a.rn ? nb * a.SG * a.CIB : a.RG * a.SG * a.CIB;
+  const int ACC = a.rn == 2 ? a.SG * a.CIB : (a.rn ? nb * a.SG * a.CIB : a.RG * a.SG * a.CIB);
   // the CTAs of the first (ci group, filter-row group) also reduce dz over pixels: db[co] = sum_p dz[p][co]
   const bool do_db = a.db_part != nullptr && cig == 0 && rgi == 0;
 
@@ -259,7 +297,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
               zx = zx * zr + ij % zr;
               zy = zy * zr + ij / zr;
             }
-            if (a.dz_rowwise) {
+            if (a.rn == 2) {
+              for (int t = 0; t < z_rows; ++t)  // tile layout [row][co block][BW slots]
+                tma_load_4d(&mapZ, &full_bar[st], sz + (size_t)((t * nb + j) * a.BW) * 128, zc, zx, zy + t * zr, n);
+            } else if (a.dz_rowwise) {
               for (int t = 0; t < z_rows; ++t)  // rows past the image (and columns past Wo) arrive as zeros
                 tma_load_4d(&mapZ, &full_bar[st], sz + j * dz_bytes + t * a.BW * 128, zc, zx, zy + t * zr, n);
             } else {
@@ -298,6 +339,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
           const bool first = it == 0;
 #define WG_ISSUE(NA)                                                                         \
   if (a.bf16) wg_issue_band<NA, true>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first);       \
+  else if (a.rn == 2) wg_issue_band<NA, false, true>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first); \
   else wg_issue_band<NA, false>(a, x_lo, z_lo, a_hi, idesc, tmem_base, first);             \
   break
           switch ((a.dbg & 4) ? 0 : nacc) {
@@ -376,7 +418,24 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int st = it % a.stages;
         mbar_wait(&full_bar[st], (uint32_t)(it / a.stages) & 1u);
         const uint32_t sz = smem_u32(smem + (size_t)st * stage_bytes + (size_t)XT * x_bytes);
-        if (!(a.dbg & 8)) {
+        if (a.rn == 2) {
+          // tile [row][co block][BW slots]: the band owns the TH tile rows from kh-1-pad on (BW % 8 == 0: whole 4-slot groups)
+          for (int t = a.kh - 1 - a.pad; t < a.kh - 1 - a.pad + a.TH; ++t) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nb) {
+                const int q_lo = (t * nb + j) * a.BW;
+                for (int q0 = q_lo + lane_grp * 4; q0 < q_lo + a.BW; q0 += 16) {
+                  const int q = q0 + lrow;
+                  const uint32_t off = sz + (uint32_t)q * 128u + ((uint32_t)(lchunk ^ ((q & 3) << 1)) << 4);
+                  float4 v;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(off));
+                  dbs[j].x += v.x; dbs[j].y += v.y; dbs[j].z += v.z; dbs[j].w += v.w;
+                }
+              }
+            }
+          }
+        } else if (!(a.dbg & 8)) {
           // rows .. round_up(rows, 8) lie in the tile's zero tail (dz_slots % 8 == 0); warp w takes rows 4w.., 4w+16..
           switch (nb) {
             case 1: db_rows<1>(dbs, sz, dz_bytes, rows, lane_grp, lrow, lchunk, row_lo); break;
@@ -483,6 +542,13 @@ __device__ __forceinline__ void wg_locate(const WgArgs &a, int co, int ci, int r
     by = (cig * a.n_rg + rgi) * a.n_cot + cot;
     acc = (rl * a.SG + sg) * a.CIB + cb;
     m = half * 64 + (ci & 63);
+  } else if (a.rn == 2) {
+    const int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
+    const int sg = s >> 2, sl = s & 3, cob = n >> 5;
+    by = cig * a.n_cot + cot;
+    acc = sg * a.CIB + cb;
+    m = sl * 32 + (ci & 31);
+    n = ((a.kh - 1 - r) * (a.NT >> 5) + cob) * 32 + (n & 31);  // N-block (kh-1-r) * NT/32 + cob
   } else if (a.rn) {
     const int cblk = ci >> 5, cig = cblk / a.CIB, cb = cblk - cig * a.CIB;
     const int sg = s >> 2, sl = s & 3, cob = n >> 5;
@@ -522,7 +588,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finish(WgArgs a, int splits, int 
   const int taps = a.kh * a.kw, total_items = a.Ci * taps, pitch = IPB + 1;
   const int co_tiles = (a.Co + 31) / 32, groups = (total_items + IPB - 1) / IPB;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ACC = a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB;
+  const int ACC = a.rn == 2 ? a.SG * a.CIB : (a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB);
   const size_t ss = (size_t)gy * ACC * 128 * a.acc_cols;  // floats between consecutive splits
   if ((int)blockIdx.x < co_tiles * groups) {
     const int cot32 = blockIdx.x % co_tiles, j0 = (blockIdx.x / co_tiles) * IPB;
@@ -835,28 +901,39 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
   // Column split w: the band covers TW = ceil(Wo / w) output columns; x is fetched as a (TW + kw - 1)-wide halo box and dz
   // row by row at the same pitch.  Wide images (W >= 128) would otherwise be limited to TH = 1 (3x halo re-read).
   const int dbg_flags = tc_conv_get_dbg();
-  for (int rn = 0; rn <= 1; ++rn) {
+  // experiments only: SRB_WG_FORCE="TH,wsplit" pins the band shape of the generic tf32 planner (0 = free)
+  static const int force_th = [] { const char *e = getenv("SRB_WG_FORCE"); return e ? atoi(e) : 0; }();
+  static const int force_ws = [] { const char *e = getenv("SRB_WG_FORCE"); const char *c = e ? strchr(e, ',') : nullptr; return c ? atoi(c + 1) : 0; }();
+  const bool force2 = (dbg_flags & 524288) != 0;  // tests: take the rows+co-stacked flavour wherever it has a plan
+  for (int rni = 0; rni <= 2; ++rni) {
+  const int rn = force2 ? 2 - rni : rni;
+  if (force2 && rn != 2 && best_score >= 0) continue;
   // (a band owns the output rows with its own input-row indices: needs Ho <= Hi, i.e. 2 * pad <= kh - 1)
   if (rn && (z_ps != 1 || g.kh < 2 || g.kh * 32 > 256 || 2 * g.pad > g.kh - 1 || (dbg_flags & 256))) continue;
   if (!rn && (dbg_flags & 512)) continue;
+  if (rn == 2 && (dbg_flags & 262144)) continue;
   for (int wsplit = 1; wsplit <= 16; ++wsplit) {
     const int TW = (g.Wo + wsplit - 1) / wsplit;
     if (wsplit > 1 && (TW < 16 || (g.Wo + TW - 1) / TW != wsplit)) continue;
+    if (force_ws && wsplit != force_ws) continue;
     const int bands_w = (g.Wo + TW - 1) / TW;
     // row-wise dz loads land at t * BW * 128 B: keep every row on the 512-B period of the 32B-atom swizzle
-    const int BW = bands_w > 1 ? round_up_i(TW + g.kw - 1, 4) : g.Wo + g.kw - 1;
+    // rn == 2: K walks row by row, so a row is a whole number of 8-slot K-steps
+    const int BW = rn == 2 ? round_up_i(TW + g.kw - 1, 8) : (bands_w > 1 ? round_up_i(TW + g.kw - 1, 4) : g.Wo + g.kw - 1);
     if (BW * z_ps > 256) continue;
     for (int NT = (co_pad < 256 ? co_pad : 256); NT >= 32; NT -= 32) {
       if (co_pad % NT) continue;
+      if (rn == 2 && (NT < 64 || NT * g.kh > 256)) continue;  // NT == 32 is rn == 1; the MMA's N is at most 256
       for (int CIB = cblocks; CIB >= 1; --CIB) {
         if (cblocks % CIB) continue;
         for (int RG = g.kh; RG >= (rn ? g.kh : 1); --RG) {
-          const int acc = rn ? (NT / 32) * a.SG * CIB : RG * a.SG * CIB;
-          const int acc_cols = rn ? g.kh * 32 : NT;
+          const int acc = rn == 2 ? a.SG * CIB : (rn ? (NT / 32) * a.SG * CIB : RG * a.SG * CIB);
+          const int acc_cols = rn == 2 ? g.kh * NT : (rn ? g.kh * 32 : NT);
           if (acc * acc_cols > 512 || acc > kMaxAcc) continue;
           for (int TH = 16; TH >= 1; --TH) {
             if (TH > g.Ho && TH > 1) continue;
             if (rn && TH > g.Hi && TH > 1) continue;
+            if (force_th && TH != force_th) continue;
             int BH = rn ? TH : TH + RG - 1;  // x box rows: rn bands are TH input rows, the halo is on the dz side
             if (BH > 256 || TH * z_ps > 256 || TH + g.kh - 1 > 256) continue;
             int x_slots = round_up_i(BH * BW + 4 * a.SG + 8, 8);
@@ -875,7 +952,8 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
             t += 500.0 * bands_w / TH * (n_cig * n_rg * n_cot);  // per-band hand-off (barrier round trips, TMA issue)
             // every TMA instruction costs issue slots and a request round trip; row-wise dz loads issue NT/32 * TH small
             // boxes per band (edsr256: 32 x 2 KB), which measurably starves the pipeline
-            const double n_tma = CIB + (bands_w > 1 ? (double)(NT / 32) * TH : (double)(NT / 32));
+            const double n_tma = CIB + (rn == 2 ? (double)(NT / 32) * (TH + g.kh - 1)
+                                                : (bands_w > 1 ? (double)(NT / 32) * TH : (double)(NT / 32)));
             t += 40.0 * n_tma * bands_w / TH * (n_cig * n_rg * n_cot);
             if (stages == 2) t *= 1.08;                            // less slack for the TMA latency
             double score = 1e9 / t + TH * 1e-3;
@@ -883,7 +961,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
               best_score = score;
               best = a;
               best.rn = rn; best.acc_cols = acc_cols;
-              best.TW = TW; best.bands_w = bands_w; best.BW = BW; best.dz_rowwise = bands_w > 1 ? 1 : 0;
+              best.TW = TW; best.bands_w = bands_w; best.BW = BW; best.dz_rowwise = (bands_w > 1 || rn == 2) ? 1 : 0;
               best.NT = NT; best.CIB = CIB; best.RG = RG; best.TH = TH; best.BH = BH;
               best.x_slots = x_slots; best.dz_slots = dz_slots; best.stages = stages;
               best.n_cig = n_cig; best.n_rg = n_rg; best.n_cot = n_cot;
@@ -906,7 +984,7 @@ bool make_wg_plan(const Geom &g, WgPlan *pl, bool bf16 = false, int z_ps = 1) {
   a.bands_per_cta = (a.num_bands + target - 1) / target;
   if (a.bands_per_cta < 1) a.bands_per_cta = 1;  // empty batch: plan for the workspace query only
   int gx = (a.num_bands + a.bands_per_cta - 1) / a.bands_per_cta;
-  const int nacc = a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB;
+  const int nacc = a.rn == 2 ? a.SG * a.CIB : (a.rn ? (a.NT / 32) * a.SG * a.CIB : a.RG * a.SG * a.CIB);
   int cols = nacc * a.acc_cols, tc = 32;
   while (tc < cols) tc <<= 1;
   a.tmem_cols = tc;
@@ -956,7 +1034,7 @@ int tc_wgrad_describe(const Geom &g, char *buf, size_t n, bool bf16) {
   return snprintf(buf, n,
                   "tc_wgrad%s: band TH %d TW %d x%d BW %d BH %d, bands %d (%d per CTA), CIB %d RG %d SG %d NT %d, groups ci %d r %d co %d, "
                   "stages %d, smem %zu B, tmem %d cols, grid %d x %d, ksteps %d",
-                  a.bf16 ? (a.c2 ? "-bf16(ci pairs)" : "-bf16(tap pairs)") : (a.rn ? "-rows-stacked" : ""), a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
+                  a.bf16 ? (a.c2 ? "-bf16(ci pairs)" : "-bf16(tap pairs)") : (a.rn == 2 ? "-rows+co-stacked" : (a.rn ? "-rows-stacked" : "")), a.TH, a.TW, a.bands_w, a.BW, a.BH, a.num_bands, a.bands_per_cta, a.CIB, a.RG, a.SG, a.NT, a.n_cig, a.n_rg, a.n_cot, a.stages,
                   pl.smem, a.tmem_cols, pl.grid.x, pl.grid.y, a.ksteps);
 }
 
@@ -981,7 +1059,11 @@ int tc_conv_wgrad(const Geom &g, const T4 &small, const T4 &big, float *dw, floa
   {  // A-descriptor offsets of the accumulators, in 16-byte units (one pixel slot = 128 B = 8 units)
     const int row_step = a.BW * 8, x_step = a.x_slots * 8;
     for (int j = 0; j < kMaxAcc; ++j) a.acc_off[j] = a.acc_boff[j] = 0;
-    if (a.rn) {
+    if (a.rn == 2) {
+      // accumulator (sg, cb): A = ci block cb at tap s = 4*sg, B = the whole [row][co block] tile (all co blocks in one MMA)
+      for (int sg = 0; sg < a.SG; ++sg)
+        for (int cb = 0; cb < a.CIB; ++cb) a.acc_off[sg * a.CIB + cb] = sg * 32 + cb * x_step;
+    } else if (a.rn) {
       // accumulator (co block, sg, cb): A = ci block cb at tap s = 4*sg (un-shifted rows), B = co block's dz view
       for (int cob = 0; cob < a.NT / 32; ++cob)
         for (int sg = 0; sg < a.SG; ++sg)

@@ -200,11 +200,7 @@ def test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, mat
     assert torch.cuda.is_available()
     import torch.nn.functional as TF
     if math == "auto-rowstacked":  # same contract on the row-stacked kernels (the planner skips them for test-sized tensors)
-        import ctypes
-        from srb200 import _lib
-        setf = _lib.lib.srb_debug_set_flags
-        setf.argtypes = [ctypes.c_int]
-        setf.restype = None
+        from util import set_debug_flags as setf
         setf(1024 | 512)
         try:
             return test_loss_fused_into_last_conv_matches_unfused(name, args, xshape, kind, "auto")
@@ -324,13 +320,9 @@ def test_fused_loss_uint8_target_equals_fp32_target(case, kernel):
     """The decoded (N,H,W,C) uint8 image as the fused loss's target == ToTensor of it as an fp32 (N,C,H,W) target: loss, the
     network output and both parameter gradients are bit-identical (the epilogue computes the same byte * (1/255) product that
     srb200.image_to_tensor stores)."""
-    import ctypes
-    from srb200 import _lib
     N, Cin, H, W, Co, k, pad, ps, kind, math = case
     srb200.set_math(math)
-    setf = _lib.lib.srb_debug_set_flags
-    setf.argtypes = [ctypes.c_int]
-    setf.restype = None
+    from util import set_debug_flags as setf
     setf(128 if kernel == "slot-linear" else 0)
     try:
         gen = torch.Generator().manual_seed(21)

@@ -178,6 +178,9 @@ SWEEP_RS = [c for c in SWEEP if c[3] == 1 and c[0] > 4] + [
     (64, 48, 3, 1, 1, None, False, 1, 40, 30, 4),      # NT = 48: ring of 10 blocks
     (64, 32, 3, 1, 1, "relu", False, 1, 5, 20, 1),     # one row per CTA: the second row stream of every CTA is empty
     (64, 32, 3, 1, 1, "relu", False, 1, 61, 20, 5),    # 305 rows over 148 CTAs: 2-3 rows per CTA, streams of unequal length
+    (64, 64, 3, 1, 1, "relu", False, 1, 37, 150, 2),   # wide image: three column strips, Cout 64 (wgrad N = 192 when forced)
+    (32, 80, 3, 1, 0, None, False, 1, 21, 45, 3),      # Cout 80 (padded to 96 = 3 co blocks: no NT = 64 tiling, the wgrad stays rows-stacked)
+    (32, 128, 2, 1, 0, None, False, 1, 18, 26, 3),     # 2 x 2 filter: N = 2 x 128 = 256
 ]
 
 
@@ -185,13 +188,10 @@ SWEEP_RS = [c for c in SWEEP if c[3] == 1 and c[0] > 4] + [
 @pytest.mark.parametrize("case", SWEEP_RS)
 def test_row_stacked_kernels_vs_oracle(case, one_stream):
     """k_conv_rs (forced regardless of problem size) + row-stacked wgrad; NT <= 32 layers run two row streams per CTA unless
-    flag 65536 forces one."""
-    import ctypes
-    from srb200 import _lib
-    setf = _lib.lib.srb_debug_set_flags
-    setf.argtypes = [ctypes.c_int]
-    setf.restype = None
-    setf(1024 | 512 | (65536 if one_stream else 0))
+    flag 65536 forces one.  The one-stream variant also forces the rows+co-stacked wgrad flavour (N = kh * NT, flag 524288)
+    wherever it has a plan (Cout >= 64 with kh * 64 <= 256)."""
+    from util import set_debug_flags as setf
+    setf(1024 | 512 | ((65536 | 524288) if one_stream else 0))
     try:
         _run_conv_case(case, "auto", True)
     finally:

@@ -68,3 +68,15 @@ def loss_of(kind, y, tgt):
     if kind == "bce":
         return TF.binary_cross_entropy(y, tgt)
     return TF.mse_loss(y, tgt)
+
+
+def set_debug_flags(flags):
+    """srb_debug_set_flags + drop srb200's cached workspace sizes: the planner's choice (and therefore the workspace a call
+    needs) depends on the flags, and the Python side caches srb_conv_workspace_bytes per layer."""
+    import ctypes
+    from srb200 import _lib, functional
+    f = _lib.lib.srb_debug_set_flags
+    f.argtypes = [ctypes.c_int]
+    f.restype = None
+    f(int(flags))
+    functional._ws_cache.clear()

@@ -1,9 +1,9 @@
+# compute-sanitizer over the kernels added late in round 2: two-stream k_conv_rs, rows+co-stacked wgrad (flag 524288 in the
+# one-stream variant of the sweep), uint8-target loss epilogue.  Usage (GPU box): bash tools/sanitize_new_kernels.sh [outdir]
 set -u
-OUT=gpurun_out/r4b; mkdir -p $OUT
-SEL="(test_row_stacked_kernels_vs_oracle and streams-auto) or uint8_target"
-timeout 300 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_deep.py -m gpu -x -q -k "$SEL" > $OUT/sanitizer_racecheck.log 2>&1
-echo "racecheck exit $?" >> $OUT/sanitizer_racecheck.log; tail -4 $OUT/sanitizer_racecheck.log
-timeout 300 compute-sanitizer --tool synccheck --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_deep.py -m gpu -x -q -k "$SEL" > $OUT/sanitizer_synccheck.log 2>&1
-echo "synccheck exit $?" >> $OUT/sanitizer_synccheck.log; tail -4 $OUT/sanitizer_synccheck.log
-timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_deep.py -m gpu -x -q -k "$SEL" > $OUT/sanitizer_memcheck.log 2>&1
-echo "memcheck exit $?" >> $OUT/sanitizer_memcheck.log; tail -4 $OUT/sanitizer_memcheck.log
+OUT=${1:-gpurun_out/sanitize}; mkdir -p $OUT
+SEL="test_row_stacked_kernels_vs_oracle or uint8_target"
+for tool in racecheck synccheck memcheck; do
+  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_deep.py -m gpu -x -q -k "$SEL" > $OUT/sanitizer_$tool.log 2>&1
+  echo "$tool exit $?" >> $OUT/sanitizer_$tool.log; tail -4 $OUT/sanitizer_$tool.log
+done

@@ -121,4 +121,4 @@ if __name__ == "__main__" and os.environ.get("LOSS"):
     time_loss([8, 9, 11, 12, 13, 14, 15, 128])
 
 if __name__ == "__main__" and os.environ.get("WGRAD"):
-    time_wgrad([int(v) for v in os.environ.get("WGRAD").split(",")] if "," in os.environ.get("WGRAD") else [0, 256, 512])
+    time_wgrad([int(v) for v in os.environ.get("WGRAD").split(",") if v] if "," in os.environ.get("WGRAD") else [0, 256, 512])
