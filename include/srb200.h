@@ -194,6 +194,17 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
                    const uint16_t *relu_bits, const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream);
 
 /*
+ * The same with a second gradient folded in: dx = dgrad(dz) + add (then the ReLU mask, if any).  `add` has dx's shape and dtype.
+ * This is the fan-out sum autograd performs at the input of a ResnetBlock (`torch.add(out, residual)`, base_networks.py:149:
+ * x feeds conv1 AND the skip connection, so dL/dx = dgrad_conv1 + dL/dy) done in the dgrad kernel's epilogue instead of a
+ * separate add pass over dx.  Stride-1 Conv2d without PixelShuffle on the tensor path (math auto / tf32 / bf16) only; anything
+ * else returns SRB_EUNSUPPORTED before launching (the caller then adds the two tensors itself).  add == NULL: srb_conv_dgrad.
+ */
+int srb_conv_dgrad_add(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
+                       const uint16_t *relu_bits, const srb_tensor4 *add, const srb_tensor4 *dx, void *ws, size_t ws_bytes,
+                       void *stream);
+
+/*
  * Weight + bias gradient.  Replaces cudnn_convolution_backward_weight + the bias aten::sum.
  *   dw   same shape as w (fp32, contiguous), overwritten (accumulate == 0) or added to (accumulate != 0)
  *   db   (Cout*ps*ps) or NULL, same accumulate rule

@@ -909,6 +909,12 @@ int srb_act_bwd(const srb_conv_params *p, const srb_tensor4 *dy, const srb_tenso
 
 int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
                    const uint16_t *relu_bits, const srb_tensor4 *dx, void *ws, size_t ws_bytes, void *stream) {
+  return srb_conv_dgrad_add(p, dz, w, relu_mask, relu_bits, nullptr, dx, ws, ws_bytes, stream);
+}
+
+int srb_conv_dgrad_add(const srb_conv_params *p, const srb_tensor4 *dz, const float *w, const srb_tensor4 *relu_mask,
+                       const uint16_t *relu_bits, const srb_tensor4 *add, const srb_tensor4 *dx, void *ws, size_t ws_bytes,
+                       void *stream) {
   Geom g;
   int rc = make_geom(p, &g);
   if (rc) return rc;
@@ -924,6 +930,18 @@ int srb_conv_dgrad(const srb_conv_params *p, const srb_tensor4 *dz, const float 
   e.bits_out = nullptr;
   e.bits_in = relu_bits;
   e.round_tf32 = want_round(p, tdx, p->Cin);
+  if (add && add->data) {
+    // dx = dgrad(dz) + add through the epilogue's residual operand (added before the ReLU mask): stride-1 Conv2d without
+    // PixelShuffle on the tensor path only -- decided before anything is launched
+    T4 tadd = to_t4(add);
+    Geom gd{g.N, g.Co, g.Ho, g.Wo, g.Ci, g.Hi, g.Wi, g.kh, g.kw, 1, g.kh - 1 - g.pad, 1};
+    const bool tensor_ok = !p->transposed && g.ps == 1 && g.st == 1 && g.kh == g.kw && gd.pad >= 0 &&
+                           (is_tf32_math(p->math) || p->math == SRB_MATH_BF16) && tadd.dt == tdx.dt &&
+                           (p->math == SRB_MATH_BF16 || (tdz.dt == SRB_F32 && tdx.dt == SRB_F32)) &&
+                           tc_conv_supported(gd, tdz, tdx, true, 1);
+    SRB_REQUIRE(tensor_ok, SRB_EUNSUPPORTED, "dgrad with an added gradient: stride-1 Conv2d on the tensor path (math auto / tf32 / bf16)");
+    e.residual = tadd;
+  }
   if (p->math == SRB_MATH_BF16) {
     SRB_REQUIRE(!p->transposed && g.st == 1 && g.kh == g.kw, SRB_EUNSUPPORTED,
                 "bf16 storage mode: dgrad needs a stride-1 square-kernel Conv2d");

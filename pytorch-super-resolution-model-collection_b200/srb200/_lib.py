@@ -53,6 +53,8 @@ SYMBOLS = {
     "srb_act_bwd": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _P(Tensor4), _vp, _vp]),
     "srb_conv_dgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _vp, _P(Tensor4), _vp, ctypes.c_size_t,
                                       _vp]),
+    "srb_conv_dgrad_add": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _vp, _P(Tensor4), _vp, _P(Tensor4), _P(Tensor4), _vp,
+                                          ctypes.c_size_t, _vp]),
     "srb_conv_wgrad": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp, _vp, ctypes.c_float,
                                       ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
     "srb_pixel_unshuffle": (ctypes.c_int, [_P(ConvParams), _P(Tensor4), _P(Tensor4), _vp]),
@@ -102,6 +104,9 @@ lib = _load()
 
 class SrbError(RuntimeError):
     pass
+
+
+EUNSUPPORTED = -2  # SRB_EUNSUPPORTED (include/srb200.h)
 
 
 def check(rc):

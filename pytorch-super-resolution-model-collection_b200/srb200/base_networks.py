@@ -12,6 +12,8 @@ utils.weights_init_* (class-name matching, utils.py:76-113), optimizers and chec
 only their forward is bypassed.  BatchNorm / InstanceNorm / Linear / tanh / sigmoid stay on torch
 (SURVEY.md 8f "next" rows).
 """
+import os
+
 import torch  # re-exported on purpose: the model files get `torch` through the star import (srcnn.py:13)
 
 from . import functional as F
@@ -211,9 +213,11 @@ class ResnetBlock(torch.nn.Module, _ActMixin):
             out = self._norm_act(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0]), residual=x, with_act=False)
             return self._layout(out)
         a, alpha = self._fused_act()
-        out = F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0], activation=a, alpha=alpha)
+        # x feeds conv1 and the skip: its two gradients are summed in conv1's dgrad epilogue (F.SkipGrad), not by an add kernel
+        tok = F.SkipGrad() if (_SKIPGRAD and x.requires_grad and torch.is_grad_enabled() and x.is_cuda) else None
+        out = F.conv2d(x, c1.weight, c1.bias, c1.stride[0], c1.padding[0], activation=a, alpha=alpha, skip_sink=tok)
         out = self._post(out, fused=self.activation in _FUSABLE)
-        return self._layout(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0], residual=x))
+        return self._layout(F.conv2d(out, c2.weight, c2.bias, c2.stride[0], c2.padding[0], residual=x, skip_src=tok))
 
 
 class PSBlock(torch.nn.Module, _ActMixin):
@@ -291,6 +295,10 @@ def prepare(net):
         if name in _CONV_BLOCK_NAMES and type(m).__module__ == __name__:
             last_conv = m
     return net
+
+
+# SRB_NO_SKIPGRAD=1: leave the residual blocks' fan-out sum to autograd (A/B measurements)
+_SKIPGRAD = os.environ.get("SRB_NO_SKIPGRAD") != "1"
 
 
 class FusedLoss(torch.nn.Module):

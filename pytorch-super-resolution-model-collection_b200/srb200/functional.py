@@ -215,12 +215,24 @@ def _params(x, weight, stride, pad, out_pad, transposed, ps, act, slope):
                       1 if transposed else 0, ps, _ACT_CODES[act], float(slope), _state["math"])
 
 
+class SkipGrad(object):
+    """Hand-over of the skip connection's gradient inside a residual block (`torch.add(out, residual)`, base_networks.py:149):
+    x feeds conv1 AND the skip, so autograd would sum dL/dx = dgrad_conv1(dh) + dL/dy with an extra add pass over dx.  The
+    block passes one SkipGrad to both convs: conv2's backward parks dL/dy here instead of returning it as the residual's
+    gradient, conv1's backward (which always runs after it) folds it into its dgrad epilogue (srb_conv_dgrad_add)."""
+    __slots__ = ("grad", "armed")
+
+    def __init__(self):
+        self.grad = None     # dL/dy parked by the block's last conv during backward
+        self.armed = False   # set by conv1's forward when it will compute dL/dx
+
+
 class _FusedConv(torch.autograd.Function):
     """y = PixelShuffle_ps(act(conv(x, w) + b)) + residual   (one kernel forward; act_bwd + wgrad + dgrad backward)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
-                out_token):
+                out_token, skip_sink=None, skip_src=None):
         _require_cuda(weight, bias, alpha)
         if not x.is_cuda:
             raise RuntimeError("srb200 kernels need CUDA tensors (got %s); there is no CPU path" % x.device)
@@ -257,6 +269,10 @@ class _FusedConv(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.params = (weight, bias)  # GradBucket direct-write targets (ddp.py)
         ctx.in_token, ctx.out_token = in_token, out_token
+        ctx.skip_sink, ctx.skip_src = skip_sink, skip_src
+        if skip_sink is not None:  # this conv's backward will compute dL/dx: the skip's gradient can ride in its epilogue
+            skip_sink.armed = bool(ctx.needs_input_grad[0])
+            skip_sink.grad = None
         ctx.save_for_backward(x, weight, alpha, preact if need_preact else (y if act is not None else None))
         return y
 
@@ -272,6 +288,9 @@ class _FusedConv(torch.autograd.Function):
             tok.premasked = None
         dy = _as_act(dy)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        if dres is not None and ctx.skip_src is not None and ctx.skip_src.armed:
+            ctx.skip_src.grad = dres  # the block's first conv adds it to its dgrad (SkipGrad)
+            dres = None
         dalpha = None
         if premasked:
             dz = dy  # the consumer's dgrad epilogue already applied this layer's ReLU mask (and the tf32 rounding)
@@ -338,15 +357,37 @@ class _FusedConv(torch.autograd.Function):
                 fuse = False  # bf16 storage mode folds the mask only in its packed form
             tmask = t4(x) if (fuse and bits is None) else None
             ws = _workspace(dev, _ws_bytes(p, _lib.PASS_DGRAD))
-            check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
-                                     ctypes.byref(tmask) if tmask is not None else None, _ptr(bits), ctypes.byref(tdx),
-                                     _ptr(ws), ws.numel(), st))
+            skip = None
+            if ctx.skip_sink is not None and ctx.skip_sink.grad is not None:
+                skip, ctx.skip_sink.grad = ctx.skip_sink.grad, None
+            if skip is not None and tuple(skip.shape) == tuple(dx.shape) and skip.dtype == dx.dtype:
+                tadd = t4(skip)
+                rc = lib.srb_conv_dgrad_add(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
+                                            ctypes.byref(tmask) if tmask is not None else None, _ptr(bits),
+                                            ctypes.byref(tadd), ctypes.byref(tdx), _ptr(ws), ws.numel(), st)
+                if rc == _lib.EUNSUPPORTED:  # nothing was launched: plain dgrad (no mask folded in), then the sum
+                    fuse = False
+                    check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight), None, None, ctypes.byref(tdx),
+                                             _ptr(ws), ws.numel(), st))
+                    dx = dx + skip
+                else:
+                    check(rc)
+            else:
+                if skip is not None:
+                    fuse, tmask, bits = False, None, None
+                check(lib.srb_conv_dgrad(ctypes.byref(p), ctypes.byref(tdz), _ptr(weight),
+                                         ctypes.byref(tmask) if tmask is not None else None, _ptr(bits), ctypes.byref(tdx),
+                                         _ptr(ws), ws.numel(), st))
+                if skip is not None:
+                    dx = dx + skip.to(dx.dtype)
             if fuse:
                 itok.premasked = (dx.data_ptr(), dx._version, tuple(dx.shape), tuple(dx.stride()))
-        return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None, None, None
+        elif ctx.skip_sink is not None and ctx.skip_sink.grad is not None:
+            ctx.skip_sink.grad = None  # unreachable by construction (armed == needs_input_grad[0]); never leak a stale gradient
+        return dx, dw, db, dalpha, dres, None, None, None, None, None, None, None, None, None, None, None
 
 
-def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope):
+def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, skip_sink=None, skip_src=None):
     """_FusedConv.apply plus the ReLU-backward handshake (see _ReluToken)."""
     in_token = getattr(x, "_srb_relu", None) if x.requires_grad else None
     if in_token is not None:
@@ -358,7 +399,7 @@ def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, p
     # y = ReLU(z) exactly (no residual on top); only worth it when a gradient will flow back into this layer
     out_token = _ReluToken() if (act == "relu" and residual is None and torch.is_grad_enabled()) else None
     y = _FusedConv.apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, ps, act, slope, in_token,
-                         out_token)
+                         out_token, skip_sink, skip_src)
     if out_token is not None and y.requires_grad:
         y._srb_relu = out_token
     if act is not None and _state["act_recorder"] is not None:
@@ -367,15 +408,17 @@ def _apply(x, weight, bias, alpha, residual, stride, pad, out_pad, transposed, p
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, activation=None, alpha=None, slope=0.2, residual=None,
-           pixel_shuffle=1):
+           pixel_shuffle=1, skip_sink=None, skip_src=None):
     """Fused Conv2d -> +bias -> act -> PixelShuffle(r) -> +residual.
 
     activation: None | 'relu' | 'prelu' (alpha = the nn.PReLU weight, shape (1,)) | 'lrelu' (slope).
+    skip_sink / skip_src: one shared SkipGrad for the first (sink: its input x is also the block's skip) and the last (src: its
+    `residual` is that x) conv of a residual block -- the skip's gradient is then added inside the first conv's dgrad kernel.
     """
     if activation == "prelu":
         assert alpha is not None and alpha.numel() == 1, "base_networks.py uses nn.PReLU() with one shared slope"
     return _apply(x, weight, bias, alpha if activation == "prelu" else None, residual,
-                  int(stride), int(padding), 0, False, int(pixel_shuffle), activation, slope)
+                  int(stride), int(padding), 0, False, int(pixel_shuffle), activation, slope, skip_sink, skip_src)
 
 
 def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, activation=None, alpha=None,
