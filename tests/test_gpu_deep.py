@@ -371,3 +371,51 @@ def test_fused_loss_module_takes_uint8_images():
         assert fl.mode == ("fused" if name == "espcn" else "plain")
         for a_, b_ in zip(*outs):
             assert torch.equal(a_, b_)
+
+
+@pytest.mark.parametrize("math", ["auto", "exact", "bf16"])
+def test_resnet_block_skip_gradient_folded_into_dgrad(math):
+    """ResnetBlock backward: dL/dx = dgrad_conv1 + dL/dy (the skip) comes out of conv1's dgrad kernel (srb_conv_dgrad_add through
+    functional.SkipGrad) -- same gradients as leaving the sum to autograd, also when x has further consumers; `exact` has no
+    fused form (SRB_EUNSUPPORTED -> the sum is done after the kernel) and must agree to rounding."""
+    from srb200 import base_networks as BN
+    srb200.set_math(math)
+    try:
+        torch.manual_seed(0)
+        blk = BN.ResnetBlock(64, kernel_size=3, stride=1, padding=1, bias=True, activation="relu", norm=None).to(DEV)
+        gen = torch.Generator().manual_seed(3)
+        x0 = torch.randn(4, 64, 20, 24, generator=gen).to(DEV).contiguous(memory_format=torch.channels_last)
+        gy = torch.randn(4, 64, 20, 24, generator=gen).to(DEV).contiguous(memory_format=torch.channels_last)
+        if math == "bf16":  # bf16 storage mode: 64-channel activations and their gradients are bf16 tensors
+            x0, gy = x0.to(torch.bfloat16), gy.to(torch.bfloat16)
+        res = []
+        for fused in (True, False):
+            BN._SKIPGRAD = fused
+            x = x0.clone().requires_grad_(True)
+            blk.zero_grad(set_to_none=True)
+            xin = x * 1.0                       # a non-leaf input, as inside a network
+            y = blk(xin) + 0.5 * xin            # x has a third consumer besides conv1 and the block's skip
+            y.backward(gy)
+            res.append([x.grad.float().clone()] + [p.grad.clone() for p in blk.parameters()])
+        ab = max(float(rel_l2(a_, b_)) for a_, b_ in zip(*res))
+        # and against fp32 torch on the CPU (cuDNN's own convs would be TF32) with the same weights
+        xr = x0.detach().float().cpu().requires_grad_(True)
+        w1, b1, w2, b2 = [p.detach().float().cpu() for p in (blk.conv1.weight, blk.conv1.bias, blk.conv2.weight, blk.conv2.bias)]
+        xin = xr * 1.0
+        yr = TF_conv(TF_relu(TF_conv(xin, w1, b1)), w2, b2) + xin + 0.5 * xin
+        yr.backward(gy.float().cpu())
+        ref = float(rel_l2(res[0][0].cpu(), xr.grad))
+        print("skip-gradient fusion math=%s: fused vs autograd sum %.3e, fused vs fp32 CPU %.3e" % (math, ab, ref))
+        assert ab < {"auto": 1e-3, "exact": 1e-6, "bf16": 1e-2}[math]  # measured 1.4e-4 / 5e-8 / 3.2e-3
+        assert ref < {"auto": 8e-3, "exact": 1e-5, "bf16": 2e-2}[math]  # measured 3.5e-3 (ReLU mask flips under tf32) / 1.7e-6 / 5.8e-3
+    finally:
+        BN._SKIPGRAD = True
+        srb200.set_math("auto")
+
+
+def TF_conv(x, w, b):
+    return torch.nn.functional.conv2d(x, w, b, 1, 1)
+
+
+def TF_relu(x):
+    return torch.nn.functional.relu(x)
