@@ -466,8 +466,11 @@ class Ctx:
         self.numa = bind_to_gpu_numa(self.local_rank)
         if self.world > 1 and need_dist:
             import torch.distributed as dist
+            # rank 0 prints exactly ONE JSON line on stdout: NCCL's log (its version banner appears from WARN level up) goes
+            # to stderr unless the user pointed it somewhere else
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+                os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
 
