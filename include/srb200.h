@@ -138,8 +138,8 @@ int srb_conv_fprop(const srb_conv_params *p, const srb_tensor4 *x, const float *
  * dz_unshuffled == 0 (requires ps == 1): dz has y's shape and strides of its own.  The loss sum is deterministic
  * (per-warp partials folded in a fixed order).  Layers with an activation or a residual are SRB_EUNSUPPORTED.
  * target->dtype may be SRB_U8: the decoded image itself (strides in bytes; for an (N,H,W,C) HWC buffer sn = H*W*C, sc = 1,
- * sh = W*C, sw = C), read as t = byte * (1/255) -- torchvision's ToTensor (dataset.py:90) -- so the fp32 copy of the HR target,
- * 4x its bytes, never exists on the device.
+ * sh = W*C, sw = C), read as t = byte / 255 (correctly rounded: bit-identical to torchvision's ToTensor, dataset.py:90, and to
+ * srb_image_to_tensor with scale 1/255) -- so the fp32 copy of the HR target, 4x its bytes, never exists on the device.
  */
 int srb_conv_fprop_loss(const srb_conv_params *p, const srb_tensor4 *x, const float *w, const float *bias,
                         const srb_tensor4 *target, int loss_kind, const srb_tensor4 *y, const srb_tensor4 *dz, int dz_unshuffled,
@@ -238,7 +238,8 @@ int srb_loss_bwd(int kind, const float *y, const float *t, int64_t n, const floa
 
 /*
  * ToTensor on the device (torchvision.transforms.ToTensor, dataset.py:90,94,98): uint8 NHWC image batch -> fp32 NCHW,
- * dst = src * scale (scale = 1/255).  Lets the host ship the 1-byte pixels its decoder produced instead of floats
+ * dst = src * scale; with scale == 1/255 (as a float) the result is the correctly rounded src / 255, i.e. bit-identical to
+ * ToTensor's `.div(255)` (a plain multiply by 1/255 is 1 ulp off for 126 of the 256 byte values).  Lets the host ship the 1-byte pixels its decoder produced instead of floats
  * (4x fewer PCIe bytes per training step).
  */
 int srb_image_to_tensor(const uint8_t *src_nhwc, float *dst_nchw, int32_t N, int32_t H, int32_t W, int32_t C, float scale,

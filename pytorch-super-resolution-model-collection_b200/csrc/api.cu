@@ -295,7 +295,8 @@ __global__ void k_image_to_tensor(const unsigned char *__restrict__ src, float *
     const int h = (int)(q % H); q /= H;
     const int c = (int)(q % C);
     const long long n = q / C;
-    dst[i] = (float)__ldg(src + ((n * H + h) * W + w) * C + c) * scale;
+    const unsigned int b = __ldg(src + ((n * H + h) * W + w) * C + c);
+    dst[i] = scale == (1.0f / 255.0f) ? byte_over_255(b) : (float)b * scale;  // 1/255: ToTensor's exact division
   }
 }
 
@@ -314,13 +315,15 @@ __global__ void __launch_bounds__(256) k_image_to_tensor_v4(const uint32_t *__re
     uint32_t wd[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) wd[j] = __ldg(src + gidx * C + j);  // 4 pixels x C bytes, pixel-major
+    const bool exact = scale == (1.0f / 255.0f);  // ToTensor: the correctly rounded byte / 255
     float v[C][4];
 #pragma unroll
     for (int px = 0; px < 4; ++px)
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int b = px * C + c;
-        v[c][px] = (float)((wd[b >> 2] >> ((b & 3) * 8)) & 0xffu) * scale;
+        const unsigned int byte = (wd[b >> 2] >> ((b & 3) * 8)) & 0xffu;
+        v[c][px] = exact ? byte_over_255(byte) : (float)byte * scale;
       }
 #pragma unroll
     for (int c = 0; c < C; ++c) dst[(n * C + c) * plane4 + hw4] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);

@@ -86,6 +86,18 @@ struct Epi {
   float *loss_part;
 };
 
+#ifdef __CUDACC__
+// byte / 255 as torchvision's ToTensor computes it (`img.float().div(255)`, dataset.py:90): the correctly rounded quotient from one
+// multiply by RN(1/255) and two FMAs (remainder, correction) -- bit-identical to the IEEE division for all 256 byte values
+// (checked exhaustively, tests/test_oracle.py), while b * (1/255) alone is 1 ulp off for 126 of them.
+__device__ __forceinline__ float byte_over_255(unsigned int b) {
+  const float r = 1.0f / 255.0f, bf = (float)b;
+  const float q0 = bf * r;
+  const float rem = __fmaf_rn(-q0, 255.0f, bf);
+  return __fmaf_rn(rem, r, q0);
+}
+#endif
+
 // Programmatic dependent launch (PDL).  Kernels on the hot path call pdl_trigger() first thing -- the NEXT kernel of the stream
 // may then be scheduled as soon as every CTA of this one has started, so its launch latency and prologue (barrier init, TMEM
 // allocation, shared-memory zeroing, tensor-map prefetch) overlap this kernel's execution -- and pdl_wait() before their first

@@ -277,8 +277,8 @@ __device__ __forceinline__ void epilogue_items(const SlArgs &a, uint32_t trow, u
 }
 
 
-// one pixel byte as torchvision's ToTensor maps it (k_image_to_tensor computes the same product)
-__device__ __forceinline__ float u8_unit(const unsigned char *p) { return (float)__ldg(p) * (1.0f / 255.0f); }
+// one pixel byte as torchvision's ToTensor maps it (byte / 255, correctly rounded; k_image_to_tensor computes the same)
+__device__ __forceinline__ float u8_unit(const unsigned char *p) { return byte_over_255((unsigned int)__ldg(p)); }
 
 // ---- loss-fused epilogue of the network's last conv (no activation, no residual; fp32 outputs) --------------------------------
 //   MODE 1: PixelShuffle(4) into NCHW (ESPCN): y/target addressed like epilogue_items MODE 1; the gradient is written

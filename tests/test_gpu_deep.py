@@ -318,7 +318,7 @@ def test_fused_loss_value_at_cfg2_size():
 ], ids=lambda c: "N%d_C%d_%dx%d_Co%d_k%d_p%d_ps%d_%s_%s" % c)
 def test_fused_loss_uint8_target_equals_fp32_target(case, kernel):
     """The decoded (N,H,W,C) uint8 image as the fused loss's target == ToTensor of it as an fp32 (N,C,H,W) target: loss, the
-    network output and both parameter gradients are bit-identical (the epilogue computes the same byte * (1/255) product that
+    network output and both parameter gradients are bit-identical (the epilogue computes the same correctly rounded byte / 255 that
     srb200.image_to_tensor stores)."""
     N, Cin, H, W, Co, k, pad, ps, kind, math = case
     srb200.set_math(math)

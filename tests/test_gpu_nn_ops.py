@@ -306,11 +306,13 @@ def test_srgan_step_with_grad_buckets_matches_plain_autograd():
 @pytest.mark.parametrize("shape", [(5, 16, 24, 3), (3, 9, 8, 1), (2, 7, 12, 4), (2, 6, 20, 2), (4, 10, 13, 3), (1, 4, 4, 5), (0, 8, 8, 3)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_image_to_tensor_matches_totensor(shape):
-    """srb200.image_to_tensor == torchvision ToTensor (dataset.py:90 of the reference): uint8 HWC -> float CHW * (1/255);
+    """srb200.image_to_tensor == torchvision ToTensor (dataset.py:90 of the reference), bit for bit: uint8 HWC -> float CHW / 255;
     W % 4 == 0 with C <= 4 takes the 4-pixels-per-thread kernel, everything else (odd W, C = 5, unaligned views) the scalar one."""
     g = torch.Generator().manual_seed(3)
     img = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(DEV)
-    want = (img.permute(0, 3, 1, 2).float() * np.float32(1.0 / 255.0)).contiguous()
+    # exactly what ToTensor does ON THE HOST (dataset.py:90): a true division (torch's CUDA div-by-scalar multiplies by 1/255
+    # and is 1 ulp off for 126 byte values -- the library kernel is not)
+    want = img.cpu().permute(0, 3, 1, 2).float().div(255).contiguous().to(DEV)
     got = srb200.image_to_tensor(img)
     assert got.shape == want.shape and torch.equal(got, want)
     if shape[0] > 1:  # a batch slice that starts at an odd byte offset when N*H*W*C is odd: falls back, still exact

@@ -256,3 +256,31 @@ def test_pil_bicubic_oracle_equals_live_reference():
         assert torch.equal(PB.img_interp(x, sf), u.img_interp(x, sf))
     y = torch.rand((2, 3, 20, 20))
     assert torch.equal(u.shave(y, 3), y[..., 3:-3, 3:-3])  # utils.py:197-205
+
+
+def test_byte_over_255_sequence_is_the_exact_division():
+    """The device computes ToTensor's byte / 255 as q0 = b * RN(1/255); rem = fma(-q0, 255, b); q = fma(rem, RN(1/255), q0)
+    (csrc/srb_common.cuh byte_over_255).  Exhaustive check in exact rational arithmetic that this is the correctly rounded
+    quotient -- i.e. torch's `.div(255)` -- for every byte, and that the plain product is not."""
+    from fractions import Fraction as Fr
+    import torch
+
+    def rn32(x):
+        c = np.float32(float(x))
+        cands = sorted([c, np.nextafter(c, np.float32(np.inf)), np.nextafter(c, np.float32(-np.inf))], key=lambda v: abs(Fr(float(v)) - x))
+        a, b = cands[0], cands[1]
+        if abs(Fr(float(a)) - x) == abs(Fr(float(b)) - x):
+            return a if int(np.array([a]).view(np.uint32)[0]) % 2 == 0 else b
+        return a
+
+    r = np.float32(1.0 / 255.0)
+    assert rn32(Fr(1, 255)) == r
+    ref = torch.arange(256, dtype=torch.uint8).float().div(255).numpy()
+    plain_off = 0
+    for b in range(256):
+        q0 = rn32(Fr(b) * Fr(float(r)))
+        rem = rn32(Fr(b) - Fr(float(q0)) * 255)
+        q = rn32(Fr(float(rem)) * Fr(float(r)) + Fr(float(q0)))
+        assert q == rn32(Fr(b, 255)) == ref[b]
+        plain_off += int(q0 != ref[b])
+    assert plain_off == 126
