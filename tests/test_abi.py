@@ -179,3 +179,43 @@ def test_out_hw_matches_torch_shapes(seed):
         ho, wo = ctypes.c_int32(), ctypes.c_int32()
         assert lib.srb_conv_out_hw(ctypes.byref(prm), ctypes.byref(ho), ctypes.byref(wo)) == 0
         assert (ho.value, wo.value) == tuple(y.shape[2:]), (k, s, p, op, h, w, tr)
+
+
+def test_wgrad_plan_invariants():
+    """Weight-gradient plans (tf32, Cin > 4): the band geometry covers the image, the accumulators fit TMEM for the flavour the
+    planner chose (separate filter rows / rows stacked along N / rows and co blocks stacked), and the rows+co-stacked flavour keeps
+    its two structural requirements: BW % 8 == 0 (no K-step straddles two rows) and N = kh * NT <= 256."""
+    buf = ctypes.create_string_buffer(1024)
+    flavours = {"": 0, "-rows-stacked": 0, "-rows+co-stacked": 0}
+    shapes = _PLAN_SHAPES + [(64, 64, 128, 128, 64, 3, 1), (16, 64, 37, 150, 64, 3, 1), (8, 128, 40, 40, 128, 2, 0)]
+    for (n, c, h, w, co, k, p) in shapes:
+        if c <= 4 or c % 32 or co % 4 or h + 2 * p < k or w + 2 * p < k:
+            continue
+        ho, wo = h + 2 * p - k + 1, w + 2 * p - k + 1
+        prm = _lib.ConvParams(n, c, h, w, co, k, k, 1, p, 0, 0, 1, _lib.ACT_NONE, 0.2, _lib.MATH_AUTO)
+        assert lib.srb_conv_describe_plan(ctypes.byref(prm), 2, buf, 1024) == 0
+        txt = buf.value.decode()
+        m = re.match(r"tc_wgrad(\S*): band TH (\d+) TW (\d+) x(\d+) BW (\d+) BH (\d+), bands (\d+) \((\d+) per CTA\), CIB (\d+) RG (\d+) "
+                     r"SG (\d+) NT (\d+), groups ci (\d+) r (\d+) co (\d+), stages (\d+), smem (\d+) B, tmem (\d+) cols, grid (\d+) x (\d+), "
+                     r"ksteps (\d+)", txt)
+        if not m:
+            assert "no plan" in txt or "CUDA-core" in txt or "bf16" in txt, txt
+            continue
+        fl = m.group(1)
+        th, tw, xw, bw, bh, bands, per_cta, cib, rg, sg, nt, gci, gr, gco, stages, smem, tmem, gx, gy, ksteps = (int(v) for v in m.groups()[1:])
+        assert fl in flavours, txt
+        flavours[fl] += 1
+        assert xw * tw >= wo and (xw - 1) * tw < wo and bw >= tw + k - 1, txt
+        assert sg == (k + 3) // 4 and nt % 32 == 0 and gco * nt >= co and gci * cib * 32 == c, txt
+        rows = h if fl else ho  # the stacked flavours tile the INPUT rows
+        assert bands == n * ((rows + th - 1) // th) * xw and gx * per_cta >= bands and gx * gy <= 148, txt
+        assert ksteps == (th * bw + 7) // 8 and stages >= 2 and smem <= 227 * 1024, txt
+        if fl == "-rows+co-stacked":
+            assert bw % 8 == 0 and k * nt <= 256 and nt >= 64 and rg == k, txt
+            assert sg * cib * k * nt <= tmem <= 512, txt
+        elif fl == "-rows-stacked":
+            assert k * 32 <= 256 and rg == k and bh == th, txt
+            assert (nt // 32) * sg * cib * k * 32 <= tmem <= 512, txt
+        else:
+            assert bh == th + rg - 1 and rg * sg * cib * nt <= tmem <= 512, txt
+    assert all(v > 0 for v in flavours.values()), flavours
