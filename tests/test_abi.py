@@ -98,6 +98,11 @@ def test_tile_plans_respect_hardware_limits():
                 kh_, nt_, n_ = (int(v) for v in re.search(r"N = (\d+) x (\d+) = (\d+)", txt).groups())
                 ring = int(re.search(r"TMEM ring (\d+) blocks", txt).group(1))
                 stages = int(re.search(r"(\d+) row stages", txt).group(1))
+                streams = int(re.search(r"(\d+) stream\(s\)", txt).group(1))
+                stage_b = int(re.search(r"row stages x (\d+) B", txt).group(1))
+                assert streams in (1, 2) and streams * stages * stage_b < smem, txt
+                if streams == 2:  # each stream owns half of TMEM: a ring of >= 2 * kh blocks, else the window wraps too often
+                    assert 2 * ring * int(re.search(r"N = \d+ x (\d+)", txt).group(1)) <= 512 and ring >= 2 * k, txt
                 rows, grid = (int(v) for v in re.search(r"(\d+) output rows on grid (\d+)", txt).groups())
                 assert smem <= 227 * 1024 and stages >= 2, txt
                 assert kh_ == k and n_ == kh_ * nt_ <= 256 and nt_ % 16 == 0 and nt_ >= (co if pas == 0 else c), txt
