@@ -679,6 +679,13 @@ int srb_conv_backward_folds_ps(const srb_conv_params *p, int x_cl, int dz_cl) {
 
 /* Debug only (not in the public header): per-CTA phase timestamps of the next k_conv_sl launches go to buf (8 x int64 per CTA). */
 void srb_debug_set_trace(void *buf, long long max_ctas) { tc_conv_set_trace((long long *)buf, max_ctas); }
+/* Debug / A-B knobs (not in the public header; tests and tools/ only).  Bits:
+ *      1  empty epilogue            2  operands loaded only once       4  no MMAs issued            8  no db column sums
+ *     16  skip a fence (sl) / the smem zeroing (wgrad)                 32  plain arrive instead of commit (rs) / no dump (wgrad)
+ *     64  cluster multicast ring   128  force k_conv_sl (no row-stacked kernel) / wgrad direct dump
+ *    256  never stack filter rows in wgrad        512  always stack them        1024  row-stacked fprop/dgrad regardless of size
+ *   8192 / 16384  cap MTB          32768  narrow (320-thread) k_conv_sl        65536  one row stream per CTA in k_conv_rs
+ * 262144  no rows+co stacking (rn = 2) in wgrad   524288  prefer it wherever it has a plan */
 void srb_debug_set_flags(int flags) { tc_conv_set_dbg(flags); }
 
 int srb_conv_describe_plan(const srb_conv_params *p, int pass, char *buf, size_t n) {
