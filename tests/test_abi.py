@@ -224,3 +224,36 @@ def test_wgrad_plan_invariants():
         else:
             assert bh == th + rg - 1 and rg * sg * cib * nt <= tmem <= 512, txt
     assert all(v > 0 for v in flavours.values()), flavours
+
+
+def test_shipped_library_carries_tcgen05_tma_tmem_sass():
+    """The built libsrb200.so really is a Blackwell tensor-core library: the three hot kernels contain tcgen05.mma (UTCHMMA), TMA
+    tensor loads (UTMALDG), TMEM loads (LDTM), tcgen05.commit (UTCBAR) and mbarrier (SYNCS) SASS, and nothing in it is a legacy
+    mma.sync (HMMA) kernel.  (`tools/sass_census.py` writes the full per-kernel table into profiles/.)"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(os.path.dirname(_lib.__file__), "libsrb200.so")
+    out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    counts, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = {}
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            op = m.group(1)
+            for k in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "HMMA"):
+                if op.startswith(k):
+                    counts[cur][k] = counts[cur].get(k, 0) + 1
+    assert "sm_100a" in out or "sm_100" in out
+    for kern in ("k_conv_rs", "k_conv_sl", "k_tc_wgrad"):
+        fn = [f for f in counts if kern + "E" in f or kern + "I" in f]
+        assert fn, kern
+        c = counts[fn[0]]
+        for k in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS"):
+            assert c.get(k, 0) > 0, (kern, k, c)
+    assert sum(c.get("HMMA", 0) for c in counts.values()) == 0
